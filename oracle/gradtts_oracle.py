@@ -1,0 +1,148 @@
+"""CPU ORACLE (test infrastructure, not product) for the Grad-TTS reverse-diffusion sampler.
+
+A functional, state_dict-driven restatement of the reference algorithm in plain
+PyTorch CPU fp32 ops.  Only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs may import this file; the product path
+(speech-backbones_b200/) never does.
+
+Pinned: `scripts/make_golden.py` runs THIS file and the unmodified reference
+modules (imported from /root/reference) on identical weights/inputs and asserts
+agreement before writing tests/golden/*.pt; tests/test_oracle.py re-checks the
+oracle against those committed reference outputs on every run.  The reference
+itself holds no golden vectors for this path, so the imported
+reference module is the anchor.
+
+Every function cites the reference lines it restates (paths relative to
+/root/reference/Grad-TTS/).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+HEADS = 4          # model/diffusion.py:83
+GROUPS = 8         # model/diffusion.py:50
+
+
+def mish(x):
+    """model/diffusion.py:16-18: x * tanh(softplus(x))."""
+    return x * torch.tanh(F.softplus(x))
+
+
+def conv_gn_mish(p, pre, x, mask):
+    """Block.forward, model/diffusion.py:56-58: Mish(GN8(Conv3x3(x*mask)))*mask."""
+    y = F.conv2d(x * mask, p[f"{pre}.block.0.weight"], p[f"{pre}.block.0.bias"], padding=1)
+    y = F.group_norm(y, GROUPS, p[f"{pre}.block.1.weight"], p[f"{pre}.block.1.bias"], eps=1e-5)
+    return mish(y) * mask
+
+
+def resnet(p, pre, x, mask, temb):
+    """ResnetBlock.forward, model/diffusion.py:74-79.  The time projection is added
+    AFTER block1's output mask (so padded columns become non-zero)."""
+    h = conv_gn_mish(p, f"{pre}.block1", x, mask)
+    h = h + F.linear(mish(temb), p[f"{pre}.mlp.1.weight"], p[f"{pre}.mlp.1.bias"])[:, :, None, None]
+    h = conv_gn_mish(p, f"{pre}.block2", h, mask)
+    wname = f"{pre}.res_conv.weight"
+    xm = x * mask
+    res = F.conv2d(xm, p[wname], p[f"{pre}.res_conv.bias"]) if wname in p else xm
+    return h + res
+
+
+def rezero_linear_attention(p, pre, x):
+    """Residual(Rezero(LinearAttention)), model/diffusion.py:39-46,82-110.
+    softmax over ALL H*W positions of k (no mask); context = k v^T; out = context^T q."""
+    b, c, h, w = x.shape
+    qkv = F.conv2d(x, p[f"{pre}.fn.fn.to_qkv.weight"])
+    qkv = qkv.reshape(b, 3, HEADS, -1, h * w)            # 'b (qkv heads c) h w -> qkv b heads c (h w)'
+    q, k, v = qkv[:, 0], qkv[:, 1], qkv[:, 2]
+    k = k.softmax(dim=-1)
+    ctx = torch.einsum("bhdn,bhen->bhde", k, v)
+    out = torch.einsum("bhde,bhdn->bhen", ctx, q).reshape(b, -1, h, w)
+    out = F.conv2d(out, p[f"{pre}.fn.fn.to_out.weight"], p[f"{pre}.fn.fn.to_out.bias"])
+    return out * p[f"{pre}.fn.g"] + x
+
+
+def sinusoid(t, dim, scale):
+    """SinusoidalPosEmb.forward, model/diffusion.py:118-125."""
+    half = dim // 2
+    f = math.log(10000) / (half - 1)
+    f = torch.exp(torch.arange(half, device=t.device).float() * -f)
+    e = scale * t[:, None] * f[None, :]
+    return torch.cat((e.sin(), e.cos()), dim=-1)
+
+
+def estimator(p, cfg, x, mask, mu, t, spk=None):
+    """GradLogPEstimator2d.forward, model/diffusion.py:174-216.
+    x, mu: [B,80,T]; mask: [B,1,T]; t: [B]; spk: None or [B,spk_emb_dim] -> [B,80,T]."""
+    pre = "estimator"
+    temb = sinusoid(t, cfg.dim, cfg.pe_scale)
+    temb = F.linear(temb, p[f"{pre}.mlp.0.weight"], p[f"{pre}.mlp.0.bias"])
+    temb = F.linear(mish(temb), p[f"{pre}.mlp.2.weight"], p[f"{pre}.mlp.2.bias"])
+    if cfg.n_spks < 2:
+        h = torch.stack([mu, x], 1)
+    else:
+        s = F.linear(spk, p[f"{pre}.spk_mlp.0.weight"], p[f"{pre}.spk_mlp.0.bias"])
+        s = F.linear(mish(s), p[f"{pre}.spk_mlp.2.weight"], p[f"{pre}.spk_mlp.2.bias"])
+        h = torch.stack([mu, x, s[:, :, None].repeat(1, 1, x.shape[-1])], 1)
+    m = mask[:, None]                                       # [B,1,1,T]
+    skips, masks = [], [m]
+    for l in range(3):
+        mk = masks[-1]
+        h = resnet(p, f"{pre}.downs.{l}.0", h, mk, temb)
+        h = resnet(p, f"{pre}.downs.{l}.1", h, mk, temb)
+        h = rezero_linear_attention(p, f"{pre}.downs.{l}.2", h)
+        skips.append(h)
+        if l < 2:
+            h = F.conv2d(h * mk, p[f"{pre}.downs.{l}.3.conv.weight"],
+                         p[f"{pre}.downs.{l}.3.conv.bias"], stride=2, padding=1)
+        else:
+            h = h * mk                                      # Identity()(x * mask_down), :196
+        masks.append(mk[:, :, :, ::2])
+    masks = masks[:-1]
+    mk = masks[-1]
+    h = resnet(p, f"{pre}.mid_block1", h, mk, temb)
+    h = rezero_linear_attention(p, f"{pre}.mid_attn", h)
+    h = resnet(p, f"{pre}.mid_block2", h, mk, temb)
+    for j in range(2):
+        mk = masks.pop()
+        h = torch.cat((h, skips.pop()), dim=1)
+        h = resnet(p, f"{pre}.ups.{j}.0", h, mk, temb)
+        h = resnet(p, f"{pre}.ups.{j}.1", h, mk, temb)
+        h = rezero_linear_attention(p, f"{pre}.ups.{j}.2", h)
+        h = F.conv_transpose2d(h * mk, p[f"{pre}.ups.{j}.3.conv.weight"],
+                               p[f"{pre}.ups.{j}.3.conv.bias"], stride=2, padding=1)
+    h = conv_gn_mish(p, f"{pre}.final_block", h, m)
+    out = F.conv2d(h * m, p[f"{pre}.final_conv.weight"], p[f"{pre}.final_conv.bias"])
+    return (out * m).squeeze(1)
+
+
+def beta_t(t, beta_min, beta_max):
+    """get_noise(cumulative=False), model/diffusion.py:219-224."""
+    return beta_min + (beta_max - beta_min) * t
+
+
+@torch.no_grad()
+def reverse_diffusion(p, cfg, z, mask, mu, n_timesteps, stoc=False, spk=None, noise=None):
+    """Diffusion.reverse_diffusion, model/diffusion.py:254-275.
+
+    stoc=False: xt <- (xt - 0.5*(mu - xt - est)*beta*h)*mask
+    stoc=True : xt <- (xt - ((0.5*(mu - xt) - est)*beta*h + eps*sqrt(beta*h)))*mask
+                (est is NOT halved on this branch, :265).
+    `noise` [N,B,80,T] supplies eps per step; if None it is drawn with torch.randn
+    from the global generator in the reference's order (:267)."""
+    h = 1.0 / n_timesteps
+    xt = z * mask
+    for i in range(n_timesteps):
+        t = (1.0 - (i + 0.5) * h) * torch.ones(z.shape[0], dtype=z.dtype, device=z.device)
+        bt = beta_t(t[:, None, None], cfg.beta_min, cfg.beta_max)
+        est = estimator(p, cfg, xt, mask, mu, t, spk)
+        if stoc:
+            det = (0.5 * (mu - xt) - est) * bt * h
+            eps = noise[i] if noise is not None else torch.randn(z.shape, dtype=z.dtype, device=z.device)
+            dxt = det + eps * torch.sqrt(bt * h)
+        else:
+            dxt = 0.5 * (mu - xt - est) * bt * h
+        xt = (xt - dxt) * mask
+    return xt
