@@ -1,0 +1,111 @@
+/*
+ * sbk.h - C ABI of the B200-native score-based mel sampler (libsbk.so).
+ *
+ * The reference (huawei-noah/Speech-Backbones) has no FFI layer: its boundary for this
+ * path is the Python class `Diffusion` (Grad-TTS/model/diffusion.py:227-279) and its
+ * estimator `GradLogPEstimator2d` (:128-216).  This header is the boundary a binding
+ * for that class would call; every entry point cites the reference interface it replaces.
+ * Plain pointers and sizes only; no torch types.  All tensors are contiguous fp32 in the
+ * reference's own layouts ([B,n_feats,T], [B,1,T], [B], [B,spk_emb_dim]).
+ *
+ * Ownership: the caller owns every buffer passed in/out and the CUDA stream; the library
+ * owns packed weights, workspaces and CUDA graphs.  Calls on one handle are not re-entrant.
+ * Work is enqueued asynchronously on `stream` (stream-ordered with the caller's next op)
+ * except for the *_host entry points, which synchronise before returning.
+ * Errors: 0 on success, non-zero otherwise; text via sbk_last_error().  No exceptions.
+ */
+#ifndef SBK_H_
+#define SBK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sbk_handle sbk_handle;
+
+enum { SBK_OK = 0, SBK_ERR_ARG = 1, SBK_ERR_CUDA = 2, SBK_ERR_STATE = 3, SBK_ERR_UNSUPPORTED = 4 };
+
+/* arithmetic of the dense contractions (3x3/1x1 convs); GN / softmax / Mish / Euler are always fp32 */
+enum { SBK_PREC_FP32 = 0,   /* CUDA-core FFMA, fp32 operands (bit-faithful class of the CPU reference)   */
+       SBK_PREC_TF32 = 1,   /* tcgen05 kind::tf32, fp32 accumulate in TMEM (PyTorch's default GPU class) */
+       SBK_PREC_BF16 = 2 }; /* tcgen05 kind::f16 bf16 operands, fp32 accumulate                          */
+
+enum { SBK_MODEL_GRADTTS = 0, SBK_MODEL_DIFFVC = 1 };
+
+/* Constructor arguments of Diffusion.__init__ (Grad-TTS/model/diffusion.py:228-230). */
+typedef struct sbk_config {
+    int32_t model;        /* SBK_MODEL_*                                                    */
+    int32_t n_feats;      /* 80                                                             */
+    int32_t dim;          /* 64 (Grad-TTS dec_dim, params.py:40)                            */
+    int32_t n_spks;       /* 1 => no speaker channel; >1 => spk_mlp + third input channel   */
+    int32_t spk_emb_dim;  /* 64                                                             */
+    float beta_min;       /* 0.05                                                           */
+    float beta_max;       /* 20.0                                                           */
+    float pe_scale;       /* 1000.0                                                         */
+    int32_t device;       /* CUDA device ordinal                                            */
+    int32_t precision;    /* SBK_PREC_*                                                     */
+    int32_t use_graph;    /* 1: capture one reverse step as a CUDA graph and replay it      */
+} sbk_config;
+
+/* Diffusion.__init__ / GradLogPEstimator2d.__init__ (diffusion.py:128-172,228-242). */
+int sbk_create(const sbk_config* cfg, sbk_handle** out);
+void sbk_destroy(sbk_handle* h);
+
+/* nn.Module.load_state_dict(strict=True) (Grad-TTS/inference.py:53): one call per state_dict
+ * entry under `estimator.` with the reference name (e.g. "estimator.downs.0.0.block1.block.0.weight")
+ * and shape.  `data` may be a host or device pointer to contiguous fp32.  sbk_pack() then checks
+ * that every expected tensor was supplied (strict) and builds the kernel layouts. */
+int sbk_set_weight(sbk_handle* h, const char* ref_name, const void* data, const int64_t* shape, int ndim);
+int sbk_pack(sbk_handle* h);
+/* number of tensors the strict loader expects / name of the i-th one (host logic; no GPU work) */
+int sbk_num_weights(const sbk_handle* h);
+const char* sbk_weight_name(const sbk_handle* h, int i);
+
+/* bytes of device workspace a (B,T) problem needs (activations, statistics, time tables) */
+size_t sbk_workspace_bytes(const sbk_handle* h, int B, int T);
+
+/* GradLogPEstimator2d.forward(x, mask, mu, t, spk) (diffusion.py:174-216).
+ * x, mu, out: [B,n_feats,T]; mask: [B,1,T] in {0,1}; t: [B]; spk: NULL or [B,spk_emb_dim]. Device pointers. */
+int sbk_estimator(sbk_handle* h, const float* x, const float* mask, const float* mu, const float* t,
+                  const float* spk, float* out, int B, int T, void* stream);
+
+/* Diffusion.reverse_diffusion(z, mask, mu, n_timesteps, stoc, spk) (diffusion.py:254-275).
+ * noise: NULL when stoc==0, else [N,B,n_feats,T] pre-drawn N(0,1) (the reference draws it with
+ * torch.randn inside the loop, :267; the binding draws it in the same order and passes it in).
+ * out may alias z.  Device pointers. */
+int sbk_reverse_diffusion(sbk_handle* h, const float* z, const float* mask, const float* mu, const float* spk,
+                          const float* noise, float* out, int B, int T, int n_timesteps, int stoc, void* stream);
+
+/* The same loop in slices: runs steps [step_begin, step_end) of an n_timesteps-step trajectory in place
+ * on xt (which must already hold z*mask at step 0, or the previous slice's result).  noise, when stoc,
+ * holds (step_end-step_begin) slabs of [B,n_feats,T].  Lets a caller stream noise for large N. */
+int sbk_reverse_steps(sbk_handle* h, float* xt, const float* mask, const float* mu, const float* spk,
+                      const float* noise, int B, int T, int n_timesteps, int step_begin, int step_end,
+                      int stoc, void* stream);
+
+/* Diffusion.forward with HOST buffers (the call `GradTTS.forward` makes at tts.py:96 when the caller's
+ * tensors live on the CPU): copies z/mask/mu(/spk/noise) to the device, runs the loop, copies the result
+ * back into out, and synchronises.  Pinned host memory gives asynchronous copies. */
+int sbk_reverse_diffusion_host(sbk_handle* h, const float* z, const float* mask, const float* mu, const float* spk,
+                               const float* noise, float* out, int B, int T, int n_timesteps, int stoc);
+
+/* number of kernel launches the last sbk_estimator / sbk_reverse_* call enqueued (graph nodes count) */
+int64_t sbk_last_launch_count(const sbk_handle* h);
+
+/* test hook: copy a named intermediate of the last sbk_estimator call (NHWC fp32) to `dst` (host or device).
+ * Returns the element count through *numel; dst may be NULL to query the size only. */
+int sbk_debug_read(sbk_handle* h, const char* name, float* dst, int64_t* numel);
+/* test hook: enumerate intermediate names */
+int sbk_debug_num(const sbk_handle* h);
+const char* sbk_debug_name(const sbk_handle* h, int i);
+
+const char* sbk_last_error(void);
+const char* sbk_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SBK_H_ */

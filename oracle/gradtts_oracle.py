@@ -31,26 +31,34 @@ def mish(x):
     return x * torch.tanh(F.softplus(x))
 
 
-def conv_gn_mish(p, pre, x, mask):
+def _tap(taps, name, value):
+    """test hook: record an intermediate (NCHW) under the name libsbk's debug reader uses"""
+    if taps is not None:
+        taps[name] = value.detach().clone()
+
+
+def conv_gn_mish(p, pre, x, mask, taps=None):
     """Block.forward, model/diffusion.py:56-58: Mish(GN8(Conv3x3(x*mask)))*mask."""
     y = F.conv2d(x * mask, p[f"{pre}.block.0.weight"], p[f"{pre}.block.0.bias"], padding=1)
+    _tap(taps, f"{pre}.raw", y)
     y = F.group_norm(y, GROUPS, p[f"{pre}.block.1.weight"], p[f"{pre}.block.1.bias"], eps=1e-5)
     return mish(y) * mask
 
 
-def resnet(p, pre, x, mask, temb):
+def resnet(p, pre, x, mask, temb, taps=None):
     """ResnetBlock.forward, model/diffusion.py:74-79.  The time projection is added
     AFTER block1's output mask (so padded columns become non-zero)."""
-    h = conv_gn_mish(p, f"{pre}.block1", x, mask)
+    h = conv_gn_mish(p, f"{pre}.block1", x, mask, taps)
     h = h + F.linear(mish(temb), p[f"{pre}.mlp.1.weight"], p[f"{pre}.mlp.1.bias"])[:, :, None, None]
-    h = conv_gn_mish(p, f"{pre}.block2", h, mask)
+    h = conv_gn_mish(p, f"{pre}.block2", h, mask, taps)
     wname = f"{pre}.res_conv.weight"
     xm = x * mask
     res = F.conv2d(xm, p[wname], p[f"{pre}.res_conv.bias"]) if wname in p else xm
+    _tap(taps, f"{pre}.out", h + res)
     return h + res
 
 
-def rezero_linear_attention(p, pre, x):
+def rezero_linear_attention(p, pre, x, taps=None):
     """Residual(Rezero(LinearAttention)), model/diffusion.py:39-46,82-110.
     softmax over ALL H*W positions of k (no mask); context = k v^T; out = context^T q."""
     b, c, h, w = x.shape
@@ -59,8 +67,10 @@ def rezero_linear_attention(p, pre, x):
     q, k, v = qkv[:, 0], qkv[:, 1], qkv[:, 2]
     k = k.softmax(dim=-1)
     ctx = torch.einsum("bhdn,bhen->bhde", k, v)
+    _tap(taps, f"{pre}.ctx", ctx)
     out = torch.einsum("bhde,bhdn->bhen", ctx, q).reshape(b, -1, h, w)
     out = F.conv2d(out, p[f"{pre}.fn.fn.to_out.weight"], p[f"{pre}.fn.fn.to_out.bias"])
+    _tap(taps, f"{pre}.out", out * p[f"{pre}.fn.g"] + x)
     return out * p[f"{pre}.fn.g"] + x
 
 
@@ -73,7 +83,7 @@ def sinusoid(t, dim, scale):
     return torch.cat((e.sin(), e.cos()), dim=-1)
 
 
-def estimator(p, cfg, x, mask, mu, t, spk=None):
+def estimator(p, cfg, x, mask, mu, t, spk=None, taps=None):
     """GradLogPEstimator2d.forward, model/diffusion.py:174-216.
     x, mu: [B,80,T]; mask: [B,1,T]; t: [B]; spk: None or [B,spk_emb_dim] -> [B,80,T]."""
     pre = "estimator"
@@ -90,30 +100,32 @@ def estimator(p, cfg, x, mask, mu, t, spk=None):
     skips, masks = [], [m]
     for l in range(3):
         mk = masks[-1]
-        h = resnet(p, f"{pre}.downs.{l}.0", h, mk, temb)
-        h = resnet(p, f"{pre}.downs.{l}.1", h, mk, temb)
-        h = rezero_linear_attention(p, f"{pre}.downs.{l}.2", h)
+        h = resnet(p, f"{pre}.downs.{l}.0", h, mk, temb, taps)
+        h = resnet(p, f"{pre}.downs.{l}.1", h, mk, temb, taps)
+        h = rezero_linear_attention(p, f"{pre}.downs.{l}.2", h, taps)
         skips.append(h)
         if l < 2:
             h = F.conv2d(h * mk, p[f"{pre}.downs.{l}.3.conv.weight"],
                          p[f"{pre}.downs.{l}.3.conv.bias"], stride=2, padding=1)
+            _tap(taps, f"{pre}.downs.{l}.3.out", h)
         else:
             h = h * mk                                      # Identity()(x * mask_down), :196
         masks.append(mk[:, :, :, ::2])
     masks = masks[:-1]
     mk = masks[-1]
-    h = resnet(p, f"{pre}.mid_block1", h, mk, temb)
-    h = rezero_linear_attention(p, f"{pre}.mid_attn", h)
-    h = resnet(p, f"{pre}.mid_block2", h, mk, temb)
+    h = resnet(p, f"{pre}.mid_block1", h, mk, temb, taps)
+    h = rezero_linear_attention(p, f"{pre}.mid_attn", h, taps)
+    h = resnet(p, f"{pre}.mid_block2", h, mk, temb, taps)
     for j in range(2):
         mk = masks.pop()
         h = torch.cat((h, skips.pop()), dim=1)
-        h = resnet(p, f"{pre}.ups.{j}.0", h, mk, temb)
-        h = resnet(p, f"{pre}.ups.{j}.1", h, mk, temb)
-        h = rezero_linear_attention(p, f"{pre}.ups.{j}.2", h)
+        h = resnet(p, f"{pre}.ups.{j}.0", h, mk, temb, taps)
+        h = resnet(p, f"{pre}.ups.{j}.1", h, mk, temb, taps)
+        h = rezero_linear_attention(p, f"{pre}.ups.{j}.2", h, taps)
         h = F.conv_transpose2d(h * mk, p[f"{pre}.ups.{j}.3.conv.weight"],
                                p[f"{pre}.ups.{j}.3.conv.bias"], stride=2, padding=1)
-    h = conv_gn_mish(p, f"{pre}.final_block", h, m)
+        _tap(taps, f"{pre}.ups.{j}.3.out", h)
+    h = conv_gn_mish(p, f"{pre}.final_block", h, m, taps)
     out = F.conv2d(h * m, p[f"{pre}.final_conv.weight"], p[f"{pre}.final_conv.bias"])
     return (out * m).squeeze(1)
 

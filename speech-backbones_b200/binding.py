@@ -1,0 +1,208 @@
+"""ctypes binding of libsbk.so (include/sbk.h).  No CPU fallback: if the library is missing or
+the call fails, a RuntimeError is raised."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsbk.so")
+
+PREC = {"fp32": 0, "tf32": 1, "bf16": 2}
+MODEL = {"gradtts": 0, "diffvc": 1}
+
+EXPORTS = [
+    "sbk_create", "sbk_destroy", "sbk_set_weight", "sbk_pack", "sbk_num_weights", "sbk_weight_name",
+    "sbk_workspace_bytes", "sbk_estimator", "sbk_reverse_diffusion", "sbk_reverse_steps",
+    "sbk_reverse_diffusion_host", "sbk_last_launch_count", "sbk_debug_read", "sbk_debug_num",
+    "sbk_debug_name", "sbk_last_error", "sbk_version",
+]
+
+
+class SbkConfig(C.Structure):
+    _fields_ = [("model", C.c_int32), ("n_feats", C.c_int32), ("dim", C.c_int32), ("n_spks", C.c_int32),
+                ("spk_emb_dim", C.c_int32), ("beta_min", C.c_float), ("beta_max", C.c_float),
+                ("pe_scale", C.c_float), ("device", C.c_int32), ("precision", C.c_int32),
+                ("use_graph", C.c_int32)]
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} not found: build it with `python __graft_entry__.py` (nvcc, sm_100a). "
+                           "There is no CPU fallback for the sampler.")
+    lib = C.CDLL(LIB_PATH)
+    P, I, F = C.c_void_p, C.c_int, C.c_void_p
+    lib.sbk_create.argtypes = [C.POINTER(SbkConfig), C.POINTER(P)]
+    lib.sbk_destroy.argtypes = [P]
+    lib.sbk_destroy.restype = None
+    lib.sbk_set_weight.argtypes = [P, C.c_char_p, F, C.POINTER(C.c_int64), I]
+    lib.sbk_pack.argtypes = [P]
+    lib.sbk_num_weights.argtypes = [P]
+    lib.sbk_weight_name.argtypes = [P, I]
+    lib.sbk_weight_name.restype = C.c_char_p
+    lib.sbk_workspace_bytes.argtypes = [P, I, I]
+    lib.sbk_workspace_bytes.restype = C.c_size_t
+    lib.sbk_estimator.argtypes = [P, F, F, F, F, F, F, I, I, P]
+    lib.sbk_reverse_diffusion.argtypes = [P, F, F, F, F, F, F, I, I, I, I, P]
+    lib.sbk_reverse_steps.argtypes = [P, F, F, F, F, F, I, I, I, I, I, I, P]
+    lib.sbk_reverse_diffusion_host.argtypes = [P, F, F, F, F, F, F, I, I, I, I]
+    lib.sbk_last_launch_count.argtypes = [P]
+    lib.sbk_last_launch_count.restype = C.c_int64
+    lib.sbk_debug_read.argtypes = [P, C.c_char_p, F, C.POINTER(C.c_int64)]
+    lib.sbk_debug_num.argtypes = [P]
+    lib.sbk_debug_name.argtypes = [P, I]
+    lib.sbk_debug_name.restype = C.c_char_p
+    lib.sbk_last_error.restype = C.c_char_p
+    lib.sbk_version.restype = C.c_char_p
+    _lib = lib
+    return lib
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed (code {rc}): {load_library().sbk_last_error().decode()}")
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"{name}: expected float32, got {t.dtype}")
+    return t.contiguous()
+
+
+class Engine:
+    """One sbk_handle: a (device, configuration) pair owning packed weights, workspace and graphs."""
+
+    def __init__(self, n_feats=80, dim=64, n_spks=1, spk_emb_dim=64, beta_min=0.05, beta_max=20.0,
+                 pe_scale=1000.0, device=0, precision="fp32", use_graph=True, model="gradtts"):
+        self.lib = load_library()
+        self.cfg = SbkConfig(MODEL[model], n_feats, dim, n_spks, spk_emb_dim, beta_min, beta_max, pe_scale,
+                             device, PREC[precision], 1 if use_graph else 0)
+        self.h = C.c_void_p()
+        _check(self.lib.sbk_create(C.byref(self.cfg), C.byref(self.h)), "sbk_create")
+        self.device = device
+        self.n_feats = n_feats
+        self.n_spks = n_spks
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.lib.sbk_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- strict state_dict loading (Grad-TTS/inference.py:53)
+    def weight_names(self):
+        return [self.lib.sbk_weight_name(self.h, i).decode() for i in range(self.lib.sbk_num_weights(self.h))]
+
+    def load_state_dict(self, sd, prefix=""):
+        """`sd` maps reference names (optionally under `prefix`, e.g. 'decoder.') to tensors (CPU or CUDA)."""
+        for name in self.weight_names():
+            key = prefix + name
+            if key not in sd:
+                raise RuntimeError(f"missing key '{key}' in state_dict (strict)")
+            t = sd[key].detach().to(torch.float32).contiguous()
+            shape = (C.c_int64 * t.dim())(*t.shape)
+            _check(self.lib.sbk_set_weight(self.h, name.encode(), C.c_void_p(t.data_ptr()), shape, t.dim()),
+                   f"sbk_set_weight({name})")
+        _check(self.lib.sbk_pack(self.h), "sbk_pack")
+
+    def workspace_bytes(self, B, T):
+        return int(self.lib.sbk_workspace_bytes(self.h, B, T))
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _check_inputs(self, x, mask, mu, spk):
+        for n, t in (("x", x), ("mask", mask), ("mu", mu)):
+            if not t.is_cuda:
+                raise RuntimeError(f"{n} must be a CUDA tensor: the sampler has no CPU path")
+        B, F, T = x.shape
+        if F != self.n_feats or mu.shape != x.shape or mask.shape != (B, 1, T):
+            raise RuntimeError(f"shape mismatch: x {tuple(x.shape)}, mu {tuple(mu.shape)}, mask {tuple(mask.shape)}")
+        if self.n_spks > 1 and spk is None:
+            raise RuntimeError("spk embedding required for a multi-speaker model")
+        return B, T
+
+    def estimator(self, x, mask, mu, t, spk=None):
+        B, T = self._check_inputs(x, mask, mu, spk)
+        x, mask, mu, t = _f32c(x, "x"), _f32c(mask, "mask"), _f32c(mu, "mu"), _f32c(t, "t")
+        spk = _f32c(spk, "spk") if (spk is not None and self.n_spks > 1) else None
+        out = torch.empty_like(x)
+        _check(self.lib.sbk_estimator(self.h, _ptr(x), _ptr(mask), _ptr(mu), _ptr(t), _ptr(spk), _ptr(out), B, T,
+                                      self._stream()), "sbk_estimator")
+        return out
+
+    def reverse_diffusion(self, z, mask, mu, n_timesteps, stoc=False, spk=None, noise=None):
+        B, T = self._check_inputs(z, mask, mu, spk)
+        z, mask, mu = _f32c(z, "z"), _f32c(mask, "mask"), _f32c(mu, "mu")
+        spk = _f32c(spk, "spk") if (spk is not None and self.n_spks > 1) else None
+        if stoc:
+            if noise is None:
+                raise RuntimeError("stoc=True needs pre-drawn noise [N,B,n_feats,T]")
+            noise = _f32c(noise, "noise")
+            if tuple(noise.shape) != (n_timesteps, B, self.n_feats, T):
+                raise RuntimeError(f"noise shape {tuple(noise.shape)} != {(n_timesteps, B, self.n_feats, T)}")
+        out = torch.empty_like(z)
+        _check(self.lib.sbk_reverse_diffusion(self.h, _ptr(z), _ptr(mask), _ptr(mu), _ptr(spk),
+                                              _ptr(noise) if stoc else None, _ptr(out), B, T, int(n_timesteps),
+                                              1 if stoc else 0, self._stream()), "sbk_reverse_diffusion")
+        return out
+
+    def reverse_steps(self, xt, mask, mu, n_timesteps, step_begin, step_end, stoc=False, spk=None, noise=None):
+        B, T = self._check_inputs(xt, mask, mu, spk)
+        assert xt.is_contiguous() and xt.dtype == torch.float32
+        mask, mu = _f32c(mask, "mask"), _f32c(mu, "mu")
+        spk = _f32c(spk, "spk") if (spk is not None and self.n_spks > 1) else None
+        noise = _f32c(noise, "noise") if stoc else None
+        _check(self.lib.sbk_reverse_steps(self.h, _ptr(xt), _ptr(mask), _ptr(mu), _ptr(spk), _ptr(noise), B, T,
+                                          int(n_timesteps), int(step_begin), int(step_end), 1 if stoc else 0,
+                                          self._stream()), "sbk_reverse_steps")
+        return xt
+
+    def reverse_diffusion_host(self, z, mask, mu, n_timesteps, stoc=False, spk=None, noise=None, out=None):
+        """Host-buffer entry point: CPU (ideally pinned) tensors in, CPU tensor out; copies are inside the call."""
+        for n, t in (("z", z), ("mask", mask), ("mu", mu)):
+            if t.is_cuda:
+                raise RuntimeError(f"{n}: reverse_diffusion_host takes host tensors")
+        B, _, T = z.shape
+        z, mask, mu = _f32c(z, "z"), _f32c(mask, "mask"), _f32c(mu, "mu")
+        spk = _f32c(spk, "spk") if (spk is not None and self.n_spks > 1) else None
+        noise = _f32c(noise, "noise") if stoc else None
+        if out is None:
+            out = torch.empty_like(z, pin_memory=z.is_pinned())
+        _check(self.lib.sbk_reverse_diffusion_host(self.h, _ptr(z), _ptr(mask), _ptr(mu), _ptr(spk), _ptr(noise),
+                                                   _ptr(out), B, T, int(n_timesteps), 1 if stoc else 0),
+               "sbk_reverse_diffusion_host")
+        return out
+
+    def last_launch_count(self):
+        return int(self.lib.sbk_last_launch_count(self.h))
+
+    # ---- test hooks
+    def debug_names(self):
+        return [self.lib.sbk_debug_name(self.h, i).decode() for i in range(self.lib.sbk_debug_num(self.h))]
+
+    def debug_read(self, name):
+        n = C.c_int64(0)
+        _check(self.lib.sbk_debug_read(self.h, name.encode(), None, C.byref(n)), "sbk_debug_read")
+        if n.value == 0:
+            return None
+        out = torch.empty(n.value, dtype=torch.float32)
+        _check(self.lib.sbk_debug_read(self.h, name.encode(), C.c_void_p(out.data_ptr()), C.byref(n)), "sbk_debug_read")
+        return out

@@ -1,0 +1,779 @@
+// Host side of libsbk.so: strict weight loading + packing, workspace arena, the per-step launch
+// plan of the Grad-TTS score U-Net, CUDA-graph replay of the Euler(-Maruyama) loop, and the C ABI.
+// Mirrors Diffusion / GradLogPEstimator2d (Grad-TTS/model/diffusion.py:128-279); see include/sbk.h.
+#include "../../include/sbk.h"
+#include "sbk_internal.h"
+
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace sbk;
+
+static thread_local char g_err[1024] = "";
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CU(x)                                                                                          \
+    do {                                                                                               \
+        cudaError_t e_ = (x);                                                                          \
+        if (e_ != cudaSuccess)                                                                         \
+            return fail(SBK_ERR_CUDA, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+namespace {
+
+struct WSpec { std::string name; std::vector<int64_t> shape; };
+struct ResnetInfo { std::string prefix; int cin, cout; };
+struct AttnInfo { std::string prefix; int c; };
+
+__global__ void k_set_int(int* p, int v) { *p = v; }
+__global__ void k_set_ptr(const float** p, const float* v) { *p = v; }
+
+struct Arena {
+    char* base = nullptr; size_t cap = 0, off = 0;
+    void* take(size_t bytes) {
+        off = (off + 255) & ~size_t(255);
+        void* r = base ? base + off : nullptr;
+        off += bytes;
+        return r;
+    }
+};
+
+enum OpKind { OP_FIRST, OP_IGEMM, OP_RESFINAL, OP_CTX, OP_MIX, OP_FINAL };
+struct Op {
+    OpKind kind; std::string name;
+    FirstConvParams fc; IgemmParams ig; ResFinalParams rf; AttnCtxParams cx; AttnMixParams mx; FinalParams fn;
+    const float* dbg_ptr = nullptr; int64_t dbg_numel = 0;
+};
+
+struct Plan {
+    int B = 0, T = 0, tb_rows = 0, noise_cap_steps = 0;
+    void* mem = nullptr; size_t bytes = 0;
+    std::vector<Op> ops;
+    int final_op = -1;
+    // owned buffers
+    float *xt = nullptr, *mu = nullptr, *mask = nullptr, *spk_s = nullptr, *spk_in = nullptr;
+    double* stats = nullptr; int n_stat_doubles = 0;
+    float *tb = nullptr, *t_rows = nullptr; float4* coef = nullptr;
+    int* step_cur = nullptr; int* step_next = nullptr;
+    const float** noise_pp = nullptr;
+    int tb_stride = 0;
+    cudaGraphExec_t gexec[3] = {nullptr, nullptr, nullptr};   // per FinalParams.mode
+    int launches_per_step = 0;
+};
+
+}  // namespace
+
+struct sbk_handle {
+    sbk_config cfg;
+    std::vector<WSpec> spec;
+    std::vector<ResnetInfo> resnets;
+    std::vector<AttnInfo> attns;
+    std::map<std::string, float*> raw;        // device copies, reference layout
+    std::map<std::string, float*> packed;     // kernel layouts
+    std::vector<void*> owned;
+    float* d_freqs = nullptr;
+    bool is_packed = false;
+    Plan plan;
+    cudaStream_t cap_stream = nullptr;
+    int64_t last_launches = 0;
+    int tb_off[16];
+    int tb_total = 0;
+};
+
+// ------------------------------------------------------------------------------------------------
+// parameter inventory (GradLogPEstimator2d.__init__, diffusion.py:128-172)
+// ------------------------------------------------------------------------------------------------
+static void build_spec(sbk_handle* h) {
+    const sbk_config& c = h->cfg;
+    const int dim = c.dim;
+    const int d[4] = {2 + (c.n_spks > 1 ? 1 : 0), dim, dim * 2, dim * 4};
+    auto add = [&](const std::string& n, std::vector<int64_t> s) { h->spec.push_back({n, s}); };
+    auto resnet = [&](const std::string& p, int cin, int cout) {
+        add(p + ".mlp.1.weight", {cout, dim});
+        add(p + ".mlp.1.bias", {cout});
+        const char* blk[2] = {"block1", "block2"};
+        for (int k = 0; k < 2; ++k) {
+            const int ci = k == 0 ? cin : cout;
+            add(p + "." + blk[k] + ".block.0.weight", {cout, ci, 3, 3});
+            add(p + "." + blk[k] + ".block.0.bias", {cout});
+            add(p + "." + blk[k] + ".block.1.weight", {cout});
+            add(p + "." + blk[k] + ".block.1.bias", {cout});
+        }
+        if (cin != cout) {
+            add(p + ".res_conv.weight", {cout, cin, 1, 1});
+            add(p + ".res_conv.bias", {cout});
+        }
+        h->resnets.push_back({p, cin, cout});
+    };
+    auto attn = [&](const std::string& p, int ch) {
+        add(p + ".fn.g", {1});
+        add(p + ".fn.fn.to_qkv.weight", {kAttnHidden * 3, ch, 1, 1});
+        add(p + ".fn.fn.to_out.weight", {ch, kAttnHidden, 1, 1});
+        add(p + ".fn.fn.to_out.bias", {ch});
+        h->attns.push_back({p, ch});
+    };
+    if (c.n_spks > 1) {
+        add("estimator.spk_mlp.0.weight", {c.spk_emb_dim * 4, c.spk_emb_dim});
+        add("estimator.spk_mlp.0.bias", {c.spk_emb_dim * 4});
+        add("estimator.spk_mlp.2.weight", {c.n_feats, c.spk_emb_dim * 4});
+        add("estimator.spk_mlp.2.bias", {c.n_feats});
+    }
+    add("estimator.mlp.0.weight", {dim * 4, dim});
+    add("estimator.mlp.0.bias", {dim * 4});
+    add("estimator.mlp.2.weight", {dim, dim * 4});
+    add("estimator.mlp.2.bias", {dim});
+    for (int l = 0; l < 3; ++l) {
+        const std::string p = "estimator.downs." + std::to_string(l);
+        resnet(p + ".0", d[l], d[l + 1]);
+        resnet(p + ".1", d[l + 1], d[l + 1]);
+        attn(p + ".2", d[l + 1]);
+        if (l < 2) {
+            add(p + ".3.conv.weight", {d[l + 1], d[l + 1], 3, 3});
+            add(p + ".3.conv.bias", {d[l + 1]});
+        }
+    }
+    resnet("estimator.mid_block1", d[3], d[3]);
+    attn("estimator.mid_attn", d[3]);
+    resnet("estimator.mid_block2", d[3], d[3]);
+    const int up_in[2] = {d[2], d[1]}, up_out[2] = {d[3], d[2]};
+    for (int j = 0; j < 2; ++j) {
+        const std::string p = "estimator.ups." + std::to_string(j);
+        resnet(p + ".0", up_out[j] * 2, up_in[j]);
+        resnet(p + ".1", up_in[j], up_in[j]);
+        attn(p + ".2", up_in[j]);
+        add(p + ".3.conv.weight", {up_in[j], up_in[j], 4, 4});
+        add(p + ".3.conv.bias", {up_in[j]});
+    }
+    add("estimator.final_block.block.0.weight", {dim, dim, 3, 3});
+    add("estimator.final_block.block.0.bias", {dim});
+    add("estimator.final_block.block.1.weight", {dim});
+    add("estimator.final_block.block.1.bias", {dim});
+    add("estimator.final_conv.weight", {1, dim, 1, 1});
+    add("estimator.final_conv.bias", {1});
+    int off = 0;
+    for (size_t k = 0; k < h->resnets.size(); ++k) { h->tb_off[k] = off; off += h->resnets[k].cout; }
+    h->tb_total = off;
+}
+
+static int64_t numel_of(const std::vector<int64_t>& s) { int64_t n = 1; for (auto v : s) n *= v; return n; }
+
+// ------------------------------------------------------------------------------------------------
+// C ABI: lifecycle + strict loading
+// ------------------------------------------------------------------------------------------------
+extern "C" const char* sbk_last_error(void) { return g_err; }
+extern "C" const char* sbk_version(void) { return "sbk 0.1 (sm_100a)"; }
+
+extern "C" int sbk_create(const sbk_config* cfg, sbk_handle** out) {
+    if (!cfg || !out) return fail(SBK_ERR_ARG, "sbk_create: null argument");
+    if (cfg->model != SBK_MODEL_GRADTTS) return fail(SBK_ERR_UNSUPPORTED, "sbk_create: model %d not supported", cfg->model);
+    if (cfg->dim <= 0 || cfg->dim % 64 != 0) return fail(SBK_ERR_ARG, "sbk_create: dim must be a positive multiple of 64 (got %d)", cfg->dim);
+    if (cfg->n_feats <= 0 || cfg->n_feats % 4 != 0) return fail(SBK_ERR_ARG, "sbk_create: n_feats must be a multiple of 4 (two stride-2 levels), got %d", cfg->n_feats);
+    if (cfg->n_spks < 1 || cfg->spk_emb_dim <= 0) return fail(SBK_ERR_ARG, "sbk_create: bad speaker configuration");
+    if (cfg->precision != SBK_PREC_FP32) return fail(SBK_ERR_UNSUPPORTED, "sbk_create: precision %d not built yet", cfg->precision);
+    sbk_handle* h = new sbk_handle();
+    h->cfg = *cfg;
+    build_spec(h);
+    *out = h;
+    return SBK_OK;
+}
+
+static void free_plan(sbk_handle* h) {
+    Plan& p = h->plan;
+    for (int i = 0; i < 3; ++i) if (p.gexec[i]) { cudaGraphExecDestroy(p.gexec[i]); p.gexec[i] = nullptr; }
+    if (p.mem) cudaFree(p.mem);
+    p = Plan();
+}
+
+extern "C" void sbk_destroy(sbk_handle* h) {
+    if (!h) return;
+    free_plan(h);
+    for (auto& kv : h->raw) cudaFree(kv.second);
+    for (void* p : h->owned) cudaFree(p);
+    if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
+    delete h;
+}
+
+extern "C" int sbk_num_weights(const sbk_handle* h) { return h ? (int)h->spec.size() : 0; }
+extern "C" const char* sbk_weight_name(const sbk_handle* h, int i) {
+    if (!h || i < 0 || i >= (int)h->spec.size()) return nullptr;
+    return h->spec[i].name.c_str();
+}
+
+extern "C" int sbk_set_weight(sbk_handle* h, const char* name, const void* data, const int64_t* shape, int ndim) {
+    if (!h || !name || !data || !shape) return fail(SBK_ERR_ARG, "sbk_set_weight: null argument");
+    const WSpec* ws = nullptr;
+    for (auto& s : h->spec) if (s.name == name) { ws = &s; break; }
+    if (!ws) return fail(SBK_ERR_ARG, "sbk_set_weight: unexpected key '%s' (strict)", name);
+    if ((int)ws->shape.size() != ndim) return fail(SBK_ERR_ARG, "sbk_set_weight: '%s' rank %d, expected %d", name, ndim, (int)ws->shape.size());
+    for (int i = 0; i < ndim; ++i)
+        if (ws->shape[i] != shape[i]) return fail(SBK_ERR_ARG, "sbk_set_weight: '%s' dim %d is %lld, expected %lld", name, i, (long long)shape[i], (long long)ws->shape[i]);
+    CU(cudaSetDevice(h->cfg.device));
+    const size_t bytes = numel_of(ws->shape) * sizeof(float);
+    float*& dst = h->raw[name];
+    if (!dst) CU(cudaMalloc(&dst, bytes));
+    CU(cudaMemcpy(dst, data, bytes, cudaMemcpyDefault));
+    h->is_packed = false;
+    return SBK_OK;
+}
+
+// copy a raw tensor to the host, repack with `f(dst, src)`, upload under `key`
+template <class F>
+static int repack(sbk_handle* h, const std::string& src, const std::string& key, size_t out_floats, F f) {
+    const WSpec* ws = nullptr;
+    for (auto& s : h->spec) if (s.name == src) { ws = &s; break; }
+    if (!ws) return fail(SBK_ERR_STATE, "repack: no spec for %s", src.c_str());
+    std::vector<float> hs(numel_of(ws->shape)), hd(out_floats);
+    CU(cudaMemcpy(hs.data(), h->raw[src], hs.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    f(hd.data(), hs.data(), ws->shape);
+    float*& d = h->packed[key];
+    if (!d) { CU(cudaMalloc(&d, out_floats * sizeof(float))); h->owned.push_back(d); }
+    CU(cudaMemcpy(d, hd.data(), out_floats * sizeof(float), cudaMemcpyHostToDevice));
+    return SBK_OK;
+}
+
+#define TRY(x) do { int rc_ = (x); if (rc_ != SBK_OK) return rc_; } while (0)
+
+extern "C" int sbk_pack(sbk_handle* h) {
+    if (!h) return fail(SBK_ERR_ARG, "sbk_pack: null handle");
+    for (auto& s : h->spec)
+        if (!h->raw.count(s.name)) return fail(SBK_ERR_STATE, "sbk_pack: missing key '%s' (strict)", s.name.c_str());
+    CU(cudaSetDevice(h->cfg.device));
+    // conv KxK [co][ci][r][s] -> [r*K+s][ci][co]
+    auto conv_pack = [](float* d, const float* s, const std::vector<int64_t>& sh) {
+        const int64_t co = sh[0], ci = sh[1], kk = sh[2] * sh[3];
+        for (int64_t o = 0; o < co; ++o) for (int64_t i = 0; i < ci; ++i) for (int64_t t = 0; t < kk; ++t)
+            d[(t * ci + i) * co + o] = s[(o * ci + i) * kk + t];
+    };
+    // ConvTranspose2d [ci][co][kh][kw] -> [kh*4+kw][ci][co]
+    auto convt_pack = [](float* d, const float* s, const std::vector<int64_t>& sh) {
+        const int64_t ci = sh[0], co = sh[1], kk = sh[2] * sh[3];
+        for (int64_t i = 0; i < ci; ++i) for (int64_t o = 0; o < co; ++o) for (int64_t t = 0; t < kk; ++t)
+            d[(t * ci + i) * co + o] = s[(i * co + o) * kk + t];
+    };
+    // first conv [co][ci][3][3] -> [ci*9+t][co]
+    auto first_pack = [](float* d, const float* s, const std::vector<int64_t>& sh) {
+        const int64_t co = sh[0], ci = sh[1];
+        for (int64_t o = 0; o < co; ++o) for (int64_t i = 0; i < ci; ++i) for (int64_t t = 0; t < 9; ++t)
+            d[(i * 9 + t) * co + o] = s[(o * ci + i) * 9 + t];
+    };
+    // to_qkv [384][C] -> k/v part as [ci][head*64 + {d | 32+e}]
+    auto kv_pack = [](float* d, const float* s, const std::vector<int64_t>& sh) {
+        const int64_t C = sh[1];
+        for (int64_t ci = 0; ci < C; ++ci) for (int hd = 0; hd < kHeads; ++hd) for (int x = 0; x < 32; ++x) {
+            d[ci * 256 + hd * 64 + x] = s[(128 + hd * 32 + x) * C + ci];
+            d[ci * 256 + hd * 64 + 32 + x] = s[(256 + hd * 32 + x) * C + ci];
+        }
+    };
+    for (size_t k = 0; k < h->resnets.size(); ++k) {
+        const ResnetInfo& r = h->resnets[k];
+        if (k == 0) TRY(repack(h, r.prefix + ".block1.block.0.weight", r.prefix + ".block1.w", (size_t)r.cin * 9 * r.cout, first_pack));
+        else TRY(repack(h, r.prefix + ".block1.block.0.weight", r.prefix + ".block1.w", (size_t)r.cin * 9 * r.cout, conv_pack));
+        TRY(repack(h, r.prefix + ".block2.block.0.weight", r.prefix + ".block2.w", (size_t)r.cout * 9 * r.cout, conv_pack));
+        if (r.cin != r.cout) TRY(repack(h, r.prefix + ".res_conv.weight", r.prefix + ".res.w", (size_t)r.cin * r.cout, conv_pack));
+    }
+    for (auto& a : h->attns) TRY(repack(h, a.prefix + ".fn.fn.to_qkv.weight", a.prefix + ".kv.w", (size_t)a.c * 256, kv_pack));
+    for (int l = 0; l < 2; ++l) {
+        const std::string p = "estimator.downs." + std::to_string(l) + ".3.conv";
+        const int c = h->cfg.dim << l;
+        TRY(repack(h, p + ".weight", p + ".w", (size_t)c * c * 9, conv_pack));
+    }
+    for (int j = 0; j < 2; ++j) {
+        const std::string p = "estimator.ups." + std::to_string(j) + ".3.conv";
+        const int c = h->cfg.dim << (1 - j);
+        TRY(repack(h, p + ".weight", p + ".w", (size_t)c * c * 16, convt_pack));
+    }
+    TRY(repack(h, "estimator.final_block.block.0.weight", "estimator.final_block.w", (size_t)h->cfg.dim * h->cfg.dim * 9, conv_pack));
+    // sinusoid frequencies, SinusoidalPosEmb.forward (diffusion.py:121-122): fp32 exp of fp32(j) * fp32(-ln(1e4)/(half-1))
+    {
+        const int half = h->cfg.dim / 2;
+        std::vector<float> f(half);
+        const float neg = (float)(-(log(10000.0) / (double)(half - 1)));
+        for (int j = 0; j < half; ++j) f[j] = expf((float)j * neg);
+        if (!h->d_freqs) { CU(cudaMalloc(&h->d_freqs, half * sizeof(float))); h->owned.push_back(h->d_freqs); }
+        CU(cudaMemcpy(h->d_freqs, f.data(), half * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    free_plan(h);   // packed pointers may have changed
+    h->is_packed = true;
+    return SBK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// workspace layout + launch plan
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct Bufs {
+    float *A[3], *Bf[3], *X[3], *Y[3], *S[3], *D[3], *U1;
+    float *kv_part, *ctx, *w_eff, *b_eff;
+};
+}
+
+static size_t layout(const sbk_handle* h, int B, int T, int tb_rows, Arena& ar, Bufs* bf, Plan* pl) {
+    const sbk_config& c = h->cfg;
+    const int dim = c.dim, H = c.n_feats;
+    const size_t P[3] = {(size_t)H * T, (size_t)(H / 2) * (T / 2), (size_t)(H / 4) * (T / 4)};
+    const int C[3] = {dim, dim * 2, dim * 4};
+    auto f = [&](size_t n) { return (float*)ar.take(n * sizeof(float)); };
+    Bufs b{};
+    for (int l = 0; l < 3; ++l) {
+        const size_t n = (size_t)B * P[l] * C[l];
+        b.A[l] = f(n); b.Bf[l] = f(n); b.X[l] = f(n); b.Y[l] = f(n);
+        b.S[l] = l > 0 ? f(n) : nullptr;
+        b.D[l] = l > 0 ? f((size_t)B * P[l] * C[l - 1]) : nullptr;
+    }
+    b.U1 = f((size_t)B * P[1] * C[1]);
+    const size_t mt0 = (P[0] + 127) / 128;
+    b.kv_part = f((size_t)B * mt0 * kHeads * kKvPartFloats);
+    b.ctx = f((size_t)B * kHeads * 1024);
+    b.w_eff = f((size_t)B * C[2] * C[2]);
+    b.b_eff = f(C[2]);
+    if (bf) *bf = b;
+    Plan dummy;
+    Plan& p = pl ? *pl : dummy;
+    p.xt = f((size_t)B * H * T); p.mu = f((size_t)B * H * T); p.mask = f((size_t)B * T);
+    p.spk_s = f((size_t)B * H); p.spk_in = f((size_t)B * c.spk_emb_dim);
+    p.n_stat_doubles = 25 * B * kGroups * 2;
+    p.stats = (double*)ar.take(p.n_stat_doubles * sizeof(double));
+    p.tb_stride = h->tb_total;
+    p.tb = f((size_t)tb_rows * h->tb_total);
+    p.t_rows = f(tb_rows);
+    p.coef = (float4*)ar.take((size_t)tb_rows * sizeof(float4));
+    p.step_cur = (int*)ar.take(sizeof(int));
+    p.step_next = (int*)ar.take(sizeof(int));
+    p.noise_pp = (const float**)ar.take(sizeof(float*));
+    return ar.off + 256;
+}
+
+extern "C" size_t sbk_workspace_bytes(const sbk_handle* h, int B, int T) {
+    if (!h || B <= 0 || T <= 0 || T % 4 != 0) return 0;
+    Arena ar;
+    return layout(h, B, T, B > 1024 ? B : 1024, ar, nullptr, nullptr);
+}
+
+static int build_plan(sbk_handle* h, int B, int T, int tb_rows) {
+    free_plan(h);
+    Plan& pl = h->plan;
+    const sbk_config& c = h->cfg;
+    Arena probe;
+    const size_t bytes = layout(h, B, T, tb_rows, probe, nullptr, nullptr);
+    CU(cudaMalloc(&pl.mem, bytes));
+    pl.bytes = bytes;
+    Arena ar; ar.base = (char*)pl.mem; ar.cap = bytes;
+    Bufs bf;
+    layout(h, B, T, tb_rows, ar, &bf, &pl);
+    pl.B = B; pl.T = T; pl.tb_rows = tb_rows;
+
+    const int dim = c.dim, H0 = c.n_feats;
+    const int Hs[3] = {H0, H0 / 2, H0 / 4}, Ws[3] = {T, T / 2, T / 4};
+    const int cin0 = 2 + (c.n_spks > 1 ? 1 : 0);
+    int gn_slot = 0;
+    auto stats_slot = [&]() { return pl.stats + (size_t)(gn_slot++) * B * kGroups * 2; };
+    auto W = [&](const std::string& k) -> const float* {
+        auto it = h->packed.find(k);
+        if (it != h->packed.end()) return it->second;
+        auto it2 = h->raw.find(k);
+        return it2 != h->raw.end() ? it2->second : nullptr;
+    };
+    auto gnref = [&](const double* st, const std::string& blk, int C, int lvl) {
+        GnRef g; g.stats = st; g.gamma = W(blk + ".block.1.weight"); g.beta = W(blk + ".block.1.bias");
+        g.inv_count = 1.0f / ((float)(C / kGroups) * (float)Hs[lvl] * (float)Ws[lvl]);
+        return g;
+    };
+    auto base_ig = [&](int geom, int lvl_in, int lvl_out) {
+        IgemmParams p; memset(&p, 0, sizeof(p));
+        p.geom = geom; p.B = B; p.T = T;
+        p.Hin = Hs[lvl_in]; p.Win = Ws[lvl_in]; p.Hout = Hs[lvl_out]; p.Wout = Ws[lvl_out];
+        p.in_lvl = lvl_in; p.out_lvl = lvl_out; p.mask = pl.mask; p.step = pl.step_cur;
+        return p;
+    };
+    auto push = [&](Op& op, const float* dbg, int64_t numel) { op.dbg_ptr = dbg; op.dbg_numel = numel; pl.ops.push_back(op); };
+    auto npix = [&](int lvl) { return (int64_t)B * Hs[lvl] * Ws[lvl]; };
+
+    // ResnetBlock (diffusion.py:74-79) at level lvl: in (in0|in1) -> out
+    auto resnet = [&](int k, int lvl, const float* in0, int c0, const float* in1, int c1, float* out) {
+        const ResnetInfo& r = h->resnets[k];
+        float* A = bf.A[lvl]; float* Bb = bf.Bf[lvl];
+        double* st1 = stats_slot(); double* st2 = stats_slot();
+        if (k == 0) {
+            Op op; op.kind = OP_FIRST; op.name = r.prefix + ".block1.raw";
+            FirstConvParams& p = op.fc; memset(&p, 0, sizeof(p));
+            p.mu = pl.mu; p.xt = pl.xt; p.spk_s = pl.spk_s; p.mask = pl.mask;
+            p.w = W(r.prefix + ".block1.w"); p.bias = W(r.prefix + ".block1.block.0.bias");
+            p.out = A; p.ostats = st1; p.B = B; p.H = H0; p.T = T; p.cin = cin0; p.C = r.cout;
+            push(op, A, npix(lvl) * r.cout);
+        } else {
+            Op op; op.kind = OP_IGEMM; op.name = r.prefix + ".block1.raw";
+            op.ig = base_ig(G_C3, lvl, lvl);
+            IgemmParams& p = op.ig;
+            p.in0 = in0; p.c0 = c0; p.in1 = in1; p.c1 = c1;
+            p.w = W(r.prefix + ".block1.w"); p.bias = W(r.prefix + ".block1.block.0.bias");
+            p.out = A; p.Cout = r.cout; p.pro = PRO_MASK; p.epi = EPI_PLAIN; p.ostats = st1;
+            push(op, A, npix(lvl) * r.cout);
+        }
+        {
+            Op op; op.kind = OP_IGEMM; op.name = r.prefix + ".block2.raw";
+            op.ig = base_ig(G_C3, lvl, lvl);
+            IgemmParams& p = op.ig;
+            p.in0 = A; p.c0 = r.cout; p.w = W(r.prefix + ".block2.w"); p.bias = W(r.prefix + ".block2.block.0.bias");
+            p.out = Bb; p.Cout = r.cout; p.pro = PRO_GN; p.pgn = gnref(st1, r.prefix + ".block1", r.cout, lvl);
+            p.tb = pl.tb + h->tb_off[k]; p.tb_stride = pl.tb_stride;
+            p.epi = EPI_PLAIN; p.ostats = st2;
+            push(op, Bb, npix(lvl) * r.cout);
+        }
+        if (k == 0 || r.cin == r.cout) {
+            Op op; op.kind = OP_RESFINAL; op.name = r.prefix + ".out";
+            ResFinalParams& p = op.rf; memset(&p, 0, sizeof(p));
+            p.h2raw = Bb; p.gn = gnref(st2, r.prefix + ".block2", r.cout, lvl);
+            p.mask = pl.mask; p.T = T; p.lvl = lvl; p.out = out; p.B = B; p.H = Hs[lvl]; p.W = Ws[lvl]; p.C = r.cout;
+            if (k == 0) {
+                p.x = nullptr; p.mu = pl.mu; p.xt = pl.xt; p.spk_s = pl.spk_s; p.cin = cin0;
+                p.wres = W(r.prefix + ".res.w"); p.bres = W(r.prefix + ".res_conv.bias");
+            } else {
+                p.x = in0;
+            }
+            push(op, out, npix(lvl) * r.cout);
+        } else {
+            Op op; op.kind = OP_IGEMM; op.name = r.prefix + ".out";
+            op.ig = base_ig(G_PW, lvl, lvl);
+            IgemmParams& p = op.ig;
+            p.in0 = in0; p.c0 = c0; p.in1 = in1; p.c1 = c1;
+            p.w = W(r.prefix + ".res.w"); p.bias = W(r.prefix + ".res_conv.bias");
+            p.out = out; p.Cout = r.cout; p.pro = PRO_MASK; p.epi = EPI_RES;
+            p.rraw = Bb; p.rgn = gnref(st2, r.prefix + ".block2", r.cout, lvl);
+            push(op, out, npix(lvl) * r.cout);
+        }
+    };
+    // Residual(Rezero(LinearAttention)) (diffusion.py:39-46,82-110)
+    auto attention = [&](int k, int lvl, const float* x, float* out) {
+        const AttnInfo& a = h->attns[k];
+        const int mt = igemm_mtiles(G_PW, Hs[lvl], Ws[lvl], Hs[lvl], Ws[lvl]);
+        {
+            Op op; op.kind = OP_IGEMM; op.name = a.prefix + ".kvpart";
+            op.ig = base_ig(G_PW, lvl, lvl);
+            IgemmParams& p = op.ig;
+            p.in0 = x; p.c0 = a.c; p.w = W(a.prefix + ".kv.w"); p.Cout = 256; p.pro = PRO_NONE; p.epi = EPI_KV;
+            p.kv_part = bf.kv_part; p.out = nullptr;
+            push(op, nullptr, 0);
+        }
+        {
+            Op op; op.kind = OP_CTX; op.name = a.prefix + ".ctx";
+            op.cx.kv_part = bf.kv_part; op.cx.mtiles = mt; op.cx.ctx = bf.ctx; op.cx.B = B;
+            push(op, bf.ctx, (int64_t)B * kHeads * 1024);
+        }
+        {
+            Op op; op.kind = OP_MIX; op.name = a.prefix + ".mix";
+            AttnMixParams& p = op.mx;
+            p.ctx = bf.ctx; p.wq = W(a.prefix + ".fn.fn.to_qkv.weight"); p.wout = W(a.prefix + ".fn.fn.to_out.weight");
+            p.bout = W(a.prefix + ".fn.fn.to_out.bias"); p.g = W(a.prefix + ".fn.g");
+            p.w_eff = bf.w_eff; p.b_eff = bf.b_eff; p.B = B; p.C = a.c;
+            push(op, nullptr, 0);
+        }
+        {
+            Op op; op.kind = OP_IGEMM; op.name = a.prefix + ".out";
+            op.ig = base_ig(G_PW, lvl, lvl);
+            IgemmParams& p = op.ig;
+            p.in0 = x; p.c0 = a.c; p.w = bf.w_eff; p.w_bstride = (long long)a.c * a.c; p.bias = bf.b_eff;
+            p.out = out; p.Cout = a.c; p.pro = PRO_NONE; p.epi = EPI_PLAIN;
+            push(op, out, npix(lvl) * a.c);
+        }
+    };
+    auto resample = [&](int geom, const std::string& pre, int lvl_in, int lvl_out, const float* x, int C, float* out) {
+        Op op; op.kind = OP_IGEMM; op.name = pre + ".out";
+        op.ig = base_ig(geom, lvl_in, lvl_out);
+        IgemmParams& p = op.ig;
+        p.in0 = x; p.c0 = C; p.w = W(pre + ".conv.w"); p.bias = W(pre + ".conv.bias");
+        p.out = out; p.Cout = C; p.pro = PRO_MASK; p.epi = EPI_PLAIN;
+        push(op, out, npix(lvl_out) * C);
+    };
+
+    const int C1 = dim, C2 = dim * 2, C3 = dim * 4;
+    // downs (diffusion.py:190-197)
+    resnet(0, 0, nullptr, cin0, nullptr, 0, bf.X[0]);
+    resnet(1, 0, bf.X[0], C1, nullptr, 0, bf.Y[0]);
+    attention(0, 0, bf.Y[0], bf.X[0]);
+    resample(G_DOWN, "estimator.downs.0.3", 0, 1, bf.X[0], C1, bf.D[1]);
+    resnet(2, 1, bf.D[1], C1, nullptr, 0, bf.X[1]);
+    resnet(3, 1, bf.X[1], C2, nullptr, 0, bf.Y[1]);
+    attention(1, 1, bf.Y[1], bf.S[1]);
+    resample(G_DOWN, "estimator.downs.1.3", 1, 2, bf.S[1], C2, bf.D[2]);
+    resnet(4, 2, bf.D[2], C2, nullptr, 0, bf.X[2]);
+    resnet(5, 2, bf.X[2], C3, nullptr, 0, bf.Y[2]);
+    attention(2, 2, bf.Y[2], bf.S[2]);
+    // mid (:199-203); Identity()(x*mask) is absorbed by the consumers' mask prologue
+    resnet(6, 2, bf.S[2], C3, nullptr, 0, bf.X[2]);
+    attention(3, 2, bf.X[2], bf.Y[2]);
+    resnet(7, 2, bf.Y[2], C3, nullptr, 0, bf.X[2]);
+    // ups (:205-211): cat(x, skip) is pure addressing (two input pointers)
+    resnet(8, 2, bf.X[2], C3, bf.S[2], C3, bf.Y[2]);
+    resnet(9, 2, bf.Y[2], C2, nullptr, 0, bf.X[2]);
+    attention(4, 2, bf.X[2], bf.Y[2]);
+    resample(G_UP, "estimator.ups.0.3", 2, 1, bf.Y[2], C2, bf.U1);
+    resnet(10, 1, bf.U1, C2, bf.S[1], C2, bf.X[1]);
+    resnet(11, 1, bf.X[1], C1, nullptr, 0, bf.Y[1]);
+    attention(5, 1, bf.Y[1], bf.X[1]);
+    resample(G_UP, "estimator.ups.1.3", 1, 0, bf.X[1], C1, bf.Y[0]);
+    // final_block + final_conv + update (:213-216)
+    double* stf = stats_slot();
+    {
+        Op op; op.kind = OP_IGEMM; op.name = "estimator.final_block.raw";
+        op.ig = base_ig(G_C3, 0, 0);
+        IgemmParams& p = op.ig;
+        p.in0 = bf.Y[0]; p.c0 = C1; p.w = W("estimator.final_block.w"); p.bias = W("estimator.final_block.block.0.bias");
+        p.out = bf.A[0]; p.Cout = C1; p.pro = PRO_MASK; p.epi = EPI_PLAIN; p.ostats = stf;
+        push(op, bf.A[0], npix(0) * C1);
+    }
+    {
+        Op op; op.kind = OP_FINAL; op.name = "estimator.out";
+        FinalParams& p = op.fn; memset(&p, 0, sizeof(p));
+        p.raw = bf.A[0]; p.gn = gnref(stf, "estimator.final_block", C1, 0);
+        p.wfin = W("estimator.final_conv.weight"); p.bfin = W("estimator.final_conv.bias");
+        p.mask = pl.mask; p.mu = pl.mu; p.xt_in = pl.xt; p.xt_out = pl.xt;
+        p.coef = pl.coef; p.step = pl.step_cur; p.B = B; p.H = H0; p.T = T; p.C = C1;
+        pl.final_op = (int)pl.ops.size();
+        push(op, nullptr, 0);
+    }
+    pl.launches_per_step = (int)pl.ops.size() + 1;
+    return SBK_OK;
+}
+
+static int run_ops(sbk_handle* h, cudaStream_t s) {
+    Plan& pl = h->plan;
+    StepBeginParams sb{pl.stats, pl.n_stat_doubles, pl.step_cur, pl.step_next};
+    int n = launch_step_begin(sb, s);
+    for (auto& op : pl.ops) {
+        switch (op.kind) {
+            case OP_FIRST: n += launch_first_conv(op.fc, s); break;
+            case OP_IGEMM: n += launch_igemm(op.ig, s); break;
+            case OP_RESFINAL: n += launch_resfinal(op.rf, s); break;
+            case OP_CTX: n += launch_attn_ctx(op.cx, s); break;
+            case OP_MIX: n += launch_attn_mix(op.mx, s); break;
+            case OP_FINAL: n += launch_final(op.fn, s); break;
+        }
+    }
+    return n;
+}
+
+static int ensure_plan(sbk_handle* h, int B, int T, int rows) {
+    if (!h->is_packed) return fail(SBK_ERR_STATE, "weights not packed: call sbk_set_weight for every key, then sbk_pack");
+    if (B <= 0 || T <= 0 || T % 4 != 0) return fail(SBK_ERR_ARG, "B must be > 0 and T a positive multiple of 4 (fix_len_compatibility), got B=%d T=%d", B, T);
+    CU(cudaSetDevice(h->cfg.device));
+    Plan& pl = h->plan;
+    if (pl.mem && pl.B == B && pl.T == T && pl.tb_rows >= rows) return SBK_OK;
+    int cap = rows < 64 ? 64 : rows;
+    if (pl.mem && pl.B == B && pl.T == T && cap < pl.tb_rows) cap = pl.tb_rows;
+    return build_plan(h, B, T, cap);
+}
+
+static int time_table(sbk_handle* h, int rows, cudaStream_t s) {
+    Plan& pl = h->plan;
+    TimeTableParams p; memset(&p, 0, sizeof(p));
+    p.t_rows = pl.t_rows; p.rows = rows; p.freqs = h->d_freqs; p.pe_scale = h->cfg.pe_scale; p.dim = h->cfg.dim;
+    p.w0 = h->raw["estimator.mlp.0.weight"]; p.b0 = h->raw["estimator.mlp.0.bias"];
+    p.w2 = h->raw["estimator.mlp.2.weight"]; p.b2 = h->raw["estimator.mlp.2.bias"];
+    p.nproj = (int)h->resnets.size();
+    for (int k = 0; k < p.nproj; ++k) {
+        p.pw[k] = h->raw[h->resnets[k].prefix + ".mlp.1.weight"];
+        p.pb[k] = h->raw[h->resnets[k].prefix + ".mlp.1.bias"];
+        p.pc[k] = h->resnets[k].cout; p.poff[k] = h->tb_off[k];
+    }
+    p.tb = pl.tb; p.tb_stride = pl.tb_stride;
+    return launch_time_table(p, s);
+}
+
+static int speaker(sbk_handle* h, const float* spk, int B, cudaStream_t s) {
+    if (h->cfg.n_spks < 2) return 0;
+    Plan& pl = h->plan;
+    SpkParams p; p.spk = spk; p.B = B; p.E = h->cfg.spk_emb_dim; p.n_feats = h->cfg.n_feats; p.out = pl.spk_s;
+    p.w0 = h->raw["estimator.spk_mlp.0.weight"]; p.b0 = h->raw["estimator.spk_mlp.0.bias"];
+    p.w2 = h->raw["estimator.spk_mlp.2.weight"]; p.b2 = h->raw["estimator.spk_mlp.2.bias"];
+    return launch_spk(p, s);
+}
+
+static void set_mode(Plan& pl, int mode, bool per_sample_t, float* out) {
+    for (auto& op : pl.ops)
+        if (op.kind == OP_IGEMM && op.ig.pro == PRO_GN) op.ig.tb_per_sample = per_sample_t ? 1 : 0;
+    FinalParams& f = pl.ops[pl.final_op].fn;
+    f.mode = mode; f.xt_out = out; f.noise_pp = pl.noise_pp;
+}
+
+extern "C" int sbk_estimator(sbk_handle* h, const float* x, const float* mask, const float* mu, const float* t,
+                             const float* spk, float* out, int B, int T, void* stream) {
+    if (!h || !x || !mask || !mu || !t || !out) return fail(SBK_ERR_ARG, "sbk_estimator: null argument");
+    if (h->cfg.n_spks > 1 && !spk) return fail(SBK_ERR_ARG, "sbk_estimator: spk is required when n_spks > 1");
+    TRY(ensure_plan(h, B, T, B));
+    cudaStream_t s = (cudaStream_t)stream;
+    Plan& pl = h->plan;
+    const size_t nb = (size_t)B * h->cfg.n_feats * T * sizeof(float);
+    CU(cudaMemcpyAsync(pl.xt, x, nb, cudaMemcpyDeviceToDevice, s));
+    CU(cudaMemcpyAsync(pl.mu, mu, nb, cudaMemcpyDeviceToDevice, s));
+    CU(cudaMemcpyAsync(pl.mask, mask, (size_t)B * T * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    CU(cudaMemcpyAsync(pl.t_rows, t, (size_t)B * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    int64_t n = 0;
+    n += speaker(h, spk, B, s);
+    n += time_table(h, B, s);
+    set_mode(pl, 0, true, out);
+    k_set_int<<<1, 1, 0, s>>>(pl.step_next, 0); ++n;
+    n += run_ops(h, s);
+    CU(cudaGetLastError());
+    h->last_launches = n;
+    return SBK_OK;
+}
+
+// host-side coefficients of step i, with the reference's fp32 rounding order (diffusion.py:259-263,269,273)
+static void step_coefs(const sbk_config& c, int n_timesteps, int i, float* t_out, float4* cf) {
+    const double hd = 1.0 / n_timesteps;
+    const float t = (float)(1.0 - (i + 0.5) * hd);             // python double scalar * ones(fp32)
+    const float beta = c.beta_min + (float)((double)c.beta_max - (double)c.beta_min) * t;
+    const float hf = (float)hd;
+    *t_out = t;
+    *cf = make_float4(beta, hf, sqrtf(beta * hf), 0.f);
+}
+
+static int run_steps(sbk_handle* h, const float* noise, int B, int T, int N, int s0, int s1, int stoc, cudaStream_t s, int64_t* launches) {
+    Plan& pl = h->plan;
+    const int mode = stoc ? 2 : 1;
+    set_mode(pl, mode, false, pl.xt);
+    // the kernel indexes noise by absolute step: bias the base so slab s0 is the first one supplied
+    const float* nbase = noise ? noise - (long long)s0 * B * h->cfg.n_feats * T : nullptr;
+    k_set_int<<<1, 1, 0, s>>>(pl.step_next, s0);
+    k_set_ptr<<<1, 1, 0, s>>>(pl.noise_pp, nbase);
+    *launches += 2;
+    if (h->cfg.use_graph) {
+        if (!pl.gexec[mode]) {
+            if (!h->cap_stream) CU(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+            cudaGraph_t g = nullptr;
+            CU(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+            run_ops(h, h->cap_stream);
+            CU(cudaStreamEndCapture(h->cap_stream, &g));
+            CU(cudaGraphInstantiate(&pl.gexec[mode], g, 0));
+            CU(cudaGraphDestroy(g));
+        }
+        for (int i = s0; i < s1; ++i) CU(cudaGraphLaunch(pl.gexec[mode], s));
+        *launches += (int64_t)(s1 - s0) * pl.launches_per_step;
+    } else {
+        for (int i = s0; i < s1; ++i) *launches += run_ops(h, s);
+    }
+    CU(cudaGetLastError());
+    (void)N;
+    return SBK_OK;
+}
+
+static int prepare_loop(sbk_handle* h, const float* mask, const float* mu, const float* spk, int B, int T, int N,
+                        cudaStream_t s, int64_t* launches) {
+    Plan& pl = h->plan;
+    const size_t nb = (size_t)B * h->cfg.n_feats * T * sizeof(float);
+    if (mu != pl.mu) CU(cudaMemcpyAsync(pl.mu, mu, nb, cudaMemcpyDeviceToDevice, s));
+    if (mask != pl.mask) CU(cudaMemcpyAsync(pl.mask, mask, (size_t)B * T * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    std::vector<float> tr(N); std::vector<float4> cf(N);
+    for (int i = 0; i < N; ++i) step_coefs(h->cfg, N, i, &tr[i], &cf[i]);
+    // pageable-source async copies are staged before returning, so the vectors may die at scope exit
+    CU(cudaMemcpyAsync(pl.t_rows, tr.data(), N * sizeof(float), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(pl.coef, cf.data(), N * sizeof(float4), cudaMemcpyHostToDevice, s));
+    *launches += speaker(h, spk, B, s);
+    *launches += time_table(h, N, s);
+    return SBK_OK;
+}
+
+extern "C" int sbk_reverse_steps(sbk_handle* h, float* xt, const float* mask, const float* mu, const float* spk,
+                                 const float* noise, int B, int T, int n_timesteps, int step_begin, int step_end,
+                                 int stoc, void* stream) {
+    if (!h || !xt || !mask || !mu) return fail(SBK_ERR_ARG, "sbk_reverse_steps: null argument");
+    if (n_timesteps < 1 || step_begin < 0 || step_end > n_timesteps || step_begin > step_end)
+        return fail(SBK_ERR_ARG, "sbk_reverse_steps: bad step range [%d,%d) of %d", step_begin, step_end, n_timesteps);
+    if (stoc && !noise) return fail(SBK_ERR_ARG, "sbk_reverse_steps: stoc=1 needs a noise buffer");
+    if (h->cfg.n_spks > 1 && !spk) return fail(SBK_ERR_ARG, "sbk_reverse_steps: spk is required when n_spks > 1");
+    TRY(ensure_plan(h, B, T, n_timesteps));
+    cudaStream_t s = (cudaStream_t)stream;
+    Plan& pl = h->plan;
+    int64_t n = 0;
+    const size_t nb = (size_t)B * h->cfg.n_feats * T * sizeof(float);
+    CU(cudaMemcpyAsync(pl.xt, xt, nb, cudaMemcpyDeviceToDevice, s));
+    TRY(prepare_loop(h, mask, mu, spk, B, T, n_timesteps, s, &n));
+    TRY(run_steps(h, noise, B, T, n_timesteps, step_begin, step_end, stoc, s, &n));
+    CU(cudaMemcpyAsync(xt, pl.xt, nb, cudaMemcpyDeviceToDevice, s));
+    h->last_launches = n;
+    return SBK_OK;
+}
+
+extern "C" int sbk_reverse_diffusion(sbk_handle* h, const float* z, const float* mask, const float* mu, const float* spk,
+                                     const float* noise, float* out, int B, int T, int n_timesteps, int stoc, void* stream) {
+    if (!h || !z || !mask || !mu || !out) return fail(SBK_ERR_ARG, "sbk_reverse_diffusion: null argument");
+    if (n_timesteps < 1) return fail(SBK_ERR_ARG, "sbk_reverse_diffusion: n_timesteps must be >= 1");
+    if (stoc && !noise) return fail(SBK_ERR_ARG, "sbk_reverse_diffusion: stoc=1 needs a noise buffer");
+    if (h->cfg.n_spks > 1 && !spk) return fail(SBK_ERR_ARG, "sbk_reverse_diffusion: spk is required when n_spks > 1");
+    TRY(ensure_plan(h, B, T, n_timesteps));
+    cudaStream_t s = (cudaStream_t)stream;
+    Plan& pl = h->plan;
+    int64_t n = 0;
+    const size_t nb = (size_t)B * h->cfg.n_feats * T * sizeof(float);
+    TRY(prepare_loop(h, mask, mu, spk, B, T, n_timesteps, s, &n));
+    n += launch_scale_mask(z, pl.mask, pl.xt, 0, B, h->cfg.n_feats, T, s);     // xt = z * mask (:256)
+    TRY(run_steps(h, noise, B, T, n_timesteps, 0, n_timesteps, stoc, s, &n));
+    CU(cudaMemcpyAsync(out, pl.xt, nb, cudaMemcpyDeviceToDevice, s));
+    h->last_launches = n;
+    return SBK_OK;
+}
+
+extern "C" int sbk_reverse_diffusion_host(sbk_handle* h, const float* z, const float* mask, const float* mu, const float* spk,
+                                          const float* noise, float* out, int B, int T, int n_timesteps, int stoc) {
+    if (!h || !z || !mask || !mu || !out) return fail(SBK_ERR_ARG, "sbk_reverse_diffusion_host: null argument");
+    if (n_timesteps < 1) return fail(SBK_ERR_ARG, "sbk_reverse_diffusion_host: n_timesteps must be >= 1");
+    if (stoc && !noise) return fail(SBK_ERR_ARG, "sbk_reverse_diffusion_host: stoc=1 needs a noise buffer");
+    if (h->cfg.n_spks > 1 && !spk) return fail(SBK_ERR_ARG, "sbk_reverse_diffusion_host: spk is required when n_spks > 1");
+    TRY(ensure_plan(h, B, T, n_timesteps));
+    if (!h->cap_stream) CU(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+    cudaStream_t s = h->cap_stream;
+    Plan& pl = h->plan;
+    const size_t nb = (size_t)B * h->cfg.n_feats * T * sizeof(float);
+    float* d_z = nullptr; float* d_noise = nullptr;
+    CU(cudaMallocAsync(&d_z, nb, s));
+    CU(cudaMemcpyAsync(d_z, z, nb, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(pl.mu, mu, nb, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(pl.mask, mask, (size_t)B * T * sizeof(float), cudaMemcpyHostToDevice, s));
+    if (spk) CU(cudaMemcpyAsync(pl.spk_in, spk, (size_t)B * h->cfg.spk_emb_dim * sizeof(float), cudaMemcpyHostToDevice, s));
+    if (stoc) {
+        CU(cudaMallocAsync(&d_noise, nb * n_timesteps, s));
+        CU(cudaMemcpyAsync(d_noise, noise, nb * n_timesteps, cudaMemcpyHostToDevice, s));
+    }
+    int64_t n = 0;
+    TRY(prepare_loop(h, pl.mask, pl.mu, spk ? pl.spk_in : nullptr, B, T, n_timesteps, s, &n));
+    n += launch_scale_mask(d_z, pl.mask, pl.xt, 0, B, h->cfg.n_feats, T, s);
+    TRY(run_steps(h, d_noise, B, T, n_timesteps, 0, n_timesteps, stoc, s, &n));
+    CU(cudaMemcpyAsync(out, pl.xt, nb, cudaMemcpyDeviceToHost, s));
+    CU(cudaFreeAsync(d_z, s));
+    if (d_noise) CU(cudaFreeAsync(d_noise, s));
+    CU(cudaStreamSynchronize(s));
+    h->last_launches = n;
+    return SBK_OK;
+}
+
+extern "C" int64_t sbk_last_launch_count(const sbk_handle* h) { return h ? h->last_launches : 0; }
+
+extern "C" int sbk_debug_num(const sbk_handle* h) { return h ? (int)h->plan.ops.size() : 0; }
+extern "C" const char* sbk_debug_name(const sbk_handle* h, int i) {
+    if (!h || i < 0 || i >= (int)h->plan.ops.size()) return nullptr;
+    return h->plan.ops[i].name.c_str();
+}
+extern "C" int sbk_debug_read(sbk_handle* h, const char* name, float* dst, int64_t* numel) {
+    if (!h || !name) return fail(SBK_ERR_ARG, "sbk_debug_read: null argument");
+    for (auto& op : h->plan.ops) {
+        if (op.name != name) continue;
+        if (numel) *numel = op.dbg_numel;
+        if (dst && op.dbg_ptr && op.dbg_numel > 0) {
+            CU(cudaDeviceSynchronize());
+            CU(cudaMemcpy(dst, op.dbg_ptr, op.dbg_numel * sizeof(float), cudaMemcpyDefault));
+        }
+        return SBK_OK;
+    }
+    return fail(SBK_ERR_ARG, "sbk_debug_read: no intermediate named '%s'", name);
+}

@@ -1,0 +1,131 @@
+// Internal declarations shared by the kernel translation units and the host-side planner.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sbk {
+
+constexpr int kGroups = 8;        // GroupNorm groups (Grad-TTS/model/diffusion.py:50)
+constexpr int kHeads = 4;         // LinearAttention heads (:83)
+constexpr int kDimHead = 32;
+constexpr int kAttnHidden = 128;  // heads * dim_head
+constexpr int kKvPartFloats = 32 + 32 + 32 * 32;   // per (tile, head): max[32], sum[32], S[32][32]
+
+enum Geom { G_PW = 0, G_C3 = 1, G_DOWN = 2, G_UP = 3 };
+enum Pro { PRO_NONE = 0, PRO_MASK = 1, PRO_GN = 2 };
+enum Epi { EPI_PLAIN = 0, EPI_RES = 1, EPI_KV = 2 };
+
+// GroupNorm statistics of one conv output: per (sample, group) {sum, sum of squares} in fp64.
+struct GnRef {
+    const double* stats;   // [B][8][2]
+    const float* gamma;    // [C]
+    const float* beta;     // [C]
+    float inv_count;       // 1 / ((C/8) * H * W)
+};
+
+// Implicit-GEMM convolution over NHWC fp32 activations.
+//   out[b][m][co] = epilogue( sum_{tap, ci} prologue(in[b][pix(m,tap)][ci]) * w[tap][ci][co] )
+struct IgemmParams {
+    int geom;
+    // input(s): channel concat of in0 (c0 channels) and in1 (c1 channels, may be 0)
+    const float* in0; const float* in1; int c0, c1;
+    int Hin, Win, Hout, Wout;
+    int B;
+    const float* w; long long w_bstride;          // packed [ntaps][Cin][Cout] (+ optional per-sample stride)
+    const float* bias; long long bias_bstride;    // [Cout] or nullptr
+    float* out; int Cout;
+    // prologue
+    int pro;
+    const float* mask; int T; int in_lvl;         // mask[b*T + (wi << in_lvl)]
+    GnRef pgn;                                    // PRO_GN: statistics of in0
+    const float* tb; int tb_stride; int tb_per_sample; const int* step;   // PRO_GN: + time projection row
+    // epilogue
+    int epi;
+    double* ostats;                               // EPI_PLAIN: accumulate GN statistics of `out` (nullable)
+    const float* rraw; GnRef rgn; int out_lvl;    // EPI_RES: out = acc + bias + Mish(GN(rraw))*mask
+    float* kv_part;                               // EPI_KV: [B][mtiles][4][kKvPartFloats]
+};
+
+struct FirstConvParams {        // Block.conv of downs.0.0.block1 on the planar stack([mu, xt(, s)]) * mask
+    const float* mu; const float* xt; const float* spk_s;   // [B][H][T], [B][H][T], [B][H] or nullptr
+    const float* mask;          // [B][T]
+    const float* w;             // packed [cin*9 + r*3 + s][64]
+    const float* bias;
+    float* out; double* ostats; // [B][H][T][C], [B][8][2]
+    int B, H, T, cin, C;
+};
+
+struct ResFinalParams {         // out = Mish(GN(h2raw))*mask + res(x*mask)
+    const float* h2raw; GnRef gn;
+    const float* x;             // identity residual source (NHWC, same C) or nullptr for the planar first block
+    const float* mu; const float* xt; const float* spk_s;   // planar inputs for downs.0.0.res_conv
+    const float* wres; const float* bres; int cin;          // [cin][C], [C]
+    const float* mask; int T; int lvl;
+    float* out;
+    int B, H, W, C;
+};
+
+struct AttnCtxParams {          // merge per-tile softmax partials -> normalised context [B][4][32][32]
+    const float* kv_part; int mtiles; float* ctx; int B;
+};
+
+struct AttnMixParams {          // A_b = I + g * Wout * blockdiag(ctx^T) * Wq ; packed as [ci][co]; bias' = g*bout
+    const float* ctx;           // [B][4][32][32]
+    const float* wq;            // [128][C]   (rows 0..127 of to_qkv)
+    const float* wout;          // [C][128]
+    const float* bout;          // [C]
+    const float* g;             // [1]
+    float* w_eff;               // [B][C(ci)][C(co)]
+    float* b_eff;               // [C]
+    int B, C;
+};
+
+struct FinalParams {            // final_block GN+Mish, final_conv 1x1 -> 1, mask, Euler(-Maruyama) update
+    const float* raw; GnRef gn; // [B][H][T][C]
+    const float* wfin; const float* bfin;
+    const float* mask; const float* mu;
+    const float* xt_in; float* xt_out;   // Euler mode: xt_out = (xt - dxt)*mask ; estimator mode: xt_out = est
+    const float* const* noise_pp;   // stoc: device cell holding a base such that step i's slab is base + i*B*H*T
+    const float4* coef;         // per step {beta, h, sqrt(beta*h), 0}
+    const int* step;
+    int mode;                   // 0: estimator output, 1: deterministic Euler, 2: Euler-Maruyama
+    int B, H, T, C;
+};
+
+struct TimeTableParams {        // SinusoidalPosEmb + mlp + the 12 per-ResnetBlock projections
+    const float* t_rows; int rows;     // t value per row
+    const float* freqs;                // [dim/2] host-computed exp(-j*ln(1e4)/(dim/2-1))
+    float pe_scale; int dim;
+    const float* w0; const float* b0;  // [4*dim][dim], [4*dim]
+    const float* w2; const float* b2;  // [dim][4*dim], [dim]
+    int nproj;
+    const float* pw[16]; const float* pb[16]; int pc[16]; int poff[16];   // Linear(dim -> pc[k]) per ResnetBlock
+    float* tb; int tb_stride;
+};
+
+struct SpkParams {              // spk_mlp: Linear(E,4E) -> Mish -> Linear(4E, n_feats)
+    const float* spk; const float* w0; const float* b0; const float* w2; const float* b2;
+    float* out; int B, E, n_feats;
+};
+
+struct StepBeginParams { double* stats; int n_doubles; int* step_cur; int* step_next; };
+
+// launchers (all asynchronous on `s`); return the number of kernels launched
+int launch_igemm(const IgemmParams& p, cudaStream_t s);
+int launch_first_conv(const FirstConvParams& p, cudaStream_t s);
+int launch_resfinal(const ResFinalParams& p, cudaStream_t s);
+int launch_attn_ctx(const AttnCtxParams& p, cudaStream_t s);
+int launch_attn_mix(const AttnMixParams& p, cudaStream_t s);
+int launch_final(const FinalParams& p, cudaStream_t s);
+int launch_time_table(const TimeTableParams& p, cudaStream_t s);
+int launch_spk(const SpkParams& p, cudaStream_t s);
+int launch_step_begin(const StepBeginParams& p, cudaStream_t s);
+int launch_scale_mask(const float* z, const float* mask, float* out, long long n_per_b_row, int B, int H, int T, cudaStream_t s);
+
+inline int igemm_mtiles(int geom, int Hout, int Wout, int Hin, int Win) {
+    const int TM = 128;
+    if (geom == G_UP) return 4 * ((Hin * Win + TM - 1) / TM);
+    return (Hout * Wout + TM - 1) / TM;
+}
+
+}  // namespace sbk
