@@ -95,9 +95,17 @@ int sbk_reverse_diffusion_host(sbk_handle* h, const float* z, const float* mask,
 /* number of kernel launches the last sbk_estimator / sbk_reverse_* call enqueued (graph nodes count) */
 int64_t sbk_last_launch_count(const sbk_handle* h);
 
+/* measurement hook: run ONE step of the current plan (the (B,T) of the last call) launch by launch with a CUDA
+ * event between launches, on the library's stream, and return per-launch milliseconds plus the algorithmic
+ * FLOPs / HBM bytes of each launch (names via sbk_debug_name).  Advances the library's xt copy by one step. */
+int sbk_profile_ops(sbk_handle* h, float* ms, double* flops, double* bytes, int cap, int* n_ops);
+
 /* test hook: copy a named intermediate of the last sbk_estimator call (NHWC fp32) to `dst` (host or device).
  * Returns the element count through *numel; dst may be NULL to query the size only. */
 int sbk_debug_read(sbk_handle* h, const char* name, float* dst, int64_t* numel);
+/* test hook: when on, sbk_estimator snapshots every launch's output right after the launch (workspace buffers
+ * are reused across stages, so later stages would otherwise overwrite earlier intermediates) */
+int sbk_debug_capture(sbk_handle* h, int on);
 /* test hook: enumerate intermediate names */
 int sbk_debug_num(const sbk_handle* h);
 const char* sbk_debug_name(const sbk_handle* h, int i);

@@ -7,6 +7,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -49,11 +50,13 @@ struct Arena {
     }
 };
 
-enum OpKind { OP_FIRST, OP_IGEMM, OP_RESFINAL, OP_CTX, OP_MIX, OP_FINAL };
+enum OpKind { OP_FIRST, OP_IGEMM, OP_RESFINAL, OP_CTX, OP_MIX, OP_FINAL, OP_CONVTC };
 struct Op {
     OpKind kind; std::string name;
-    FirstConvParams fc; IgemmParams ig; ResFinalParams rf; AttnCtxParams cx; AttnMixParams mx; FinalParams fn;
+    FirstConvParams fc; IgemmParams ig; ConvTcParams tc; ResFinalParams rf; AttnCtxParams cx; AttnMixParams mx; FinalParams fn;
     const float* dbg_ptr = nullptr; int64_t dbg_numel = 0;
+    double flops = 0, bytes = 0;   // algorithmic work of this launch
+    float* dbg_copy = nullptr;     // snapshot taken right after the launch when debug capture is on
 };
 
 struct Plan {
@@ -87,6 +90,7 @@ struct sbk_handle {
     Plan plan;
     cudaStream_t cap_stream = nullptr;
     int64_t last_launches = 0;
+    bool capture = false;
     int tb_off[16];
     int tb_total = 0;
 };
@@ -180,7 +184,7 @@ extern "C" int sbk_create(const sbk_config* cfg, sbk_handle** out) {
     if (cfg->dim <= 0 || cfg->dim % 64 != 0) return fail(SBK_ERR_ARG, "sbk_create: dim must be a positive multiple of 64 (got %d)", cfg->dim);
     if (cfg->n_feats <= 0 || cfg->n_feats % 4 != 0) return fail(SBK_ERR_ARG, "sbk_create: n_feats must be a multiple of 4 (two stride-2 levels), got %d", cfg->n_feats);
     if (cfg->n_spks < 1 || cfg->spk_emb_dim <= 0) return fail(SBK_ERR_ARG, "sbk_create: bad speaker configuration");
-    if (cfg->precision != SBK_PREC_FP32) return fail(SBK_ERR_UNSUPPORTED, "sbk_create: precision %d not built yet", cfg->precision);
+    if (cfg->precision < SBK_PREC_FP32 || cfg->precision > SBK_PREC_BF16) return fail(SBK_ERR_ARG, "sbk_create: unknown precision %d", cfg->precision);
     sbk_handle* h = new sbk_handle();
     h->cfg = *cfg;
     build_spec(h);
@@ -191,6 +195,7 @@ extern "C" int sbk_create(const sbk_config* cfg, sbk_handle** out) {
 static void free_plan(sbk_handle* h) {
     Plan& p = h->plan;
     for (int i = 0; i < 3; ++i) if (p.gexec[i]) { cudaGraphExecDestroy(p.gexec[i]); p.gexec[i] = nullptr; }
+    for (auto& op : p.ops) if (op.dbg_copy) cudaFree(op.dbg_copy);
     if (p.mem) cudaFree(p.mem);
     p = Plan();
 }
@@ -242,6 +247,40 @@ static int repack(sbk_handle* h, const std::string& src, const std::string& key,
     return SBK_OK;
 }
 
+// Pack a 3x3 conv weight [co][ci][3][3] into the tcgen05 kernel's per-stage shared-memory image
+// [ntile][kstage][tap][16-byte chunk][co % NT][elements]: tf32-rounded fp32 (4 per chunk) or bf16 (8 per chunk).
+static uint32_t f32_to_tf32_rna(float x) {
+    uint32_t u; memcpy(&u, &x, 4);
+    if ((u & 0x7F800000u) != 0x7F800000u) u += 0x1000u;     // round to nearest, ties away (cvt.rna.tf32.f32)
+    return u & 0xFFFFE000u;
+}
+static uint16_t f32_to_bf16_rn(float x) {
+    uint32_t u; memcpy(&u, &x, 4);
+    if ((u & 0x7FFFFFFFu) > 0x7F800000u) return (uint16_t)((u >> 16) | 0x40);
+    u += 0x7FFFu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+static int pack_tc(sbk_handle* h, const std::string& src, const std::string& key, int cout, int cin, bool bf16) {
+    std::vector<float> hs((size_t)cout * cin * 9);
+    CU(cudaMemcpy(hs.data(), h->raw[src], hs.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    const int NT = conv_tc_ntile(cout), CPS = conv_tc_stage_channels(bf16 ? 1 : 0), EPC = bf16 ? 8 : 4, KCHK = CPS / EPC;
+    const int ksteps = cin / CPS;
+    const size_t esz = bf16 ? 2 : 4;
+    std::vector<uint8_t> hd((size_t)cout * cin * 9 * esz);
+    for (int nt = 0; nt < cout / NT; ++nt) for (int ks = 0; ks < ksteps; ++ks) for (int tap = 0; tap < 9; ++tap)
+        for (int k = 0; k < KCHK; ++k) for (int col = 0; col < NT; ++col) for (int e = 0; e < EPC; ++e) {
+            const int co = nt * NT + col, ci = ks * CPS + k * EPC + e;
+            const float w = hs[((size_t)co * cin + ci) * 9 + tap];
+            const size_t idx = (((((size_t)nt * ksteps + ks) * 9 + tap) * KCHK + k) * NT + col) * EPC + e;
+            if (bf16) reinterpret_cast<uint16_t*>(hd.data())[idx] = f32_to_bf16_rn(w);
+            else reinterpret_cast<uint32_t*>(hd.data())[idx] = f32_to_tf32_rna(w);
+        }
+    float*& d = h->packed[key];
+    if (!d) { CU(cudaMalloc(&d, hd.size())); h->owned.push_back(d); }
+    CU(cudaMemcpy(d, hd.data(), hd.size(), cudaMemcpyHostToDevice));
+    return SBK_OK;
+}
+
 #define TRY(x) do { int rc_ = (x); if (rc_ != SBK_OK) return rc_; } while (0)
 
 extern "C" int sbk_pack(sbk_handle* h) {
@@ -281,6 +320,15 @@ extern "C" int sbk_pack(sbk_handle* h) {
         else TRY(repack(h, r.prefix + ".block1.block.0.weight", r.prefix + ".block1.w", (size_t)r.cin * 9 * r.cout, conv_pack));
         TRY(repack(h, r.prefix + ".block2.block.0.weight", r.prefix + ".block2.w", (size_t)r.cout * 9 * r.cout, conv_pack));
         if (r.cin != r.cout) TRY(repack(h, r.prefix + ".res_conv.weight", r.prefix + ".res.w", (size_t)r.cin * r.cout, conv_pack));
+    }
+    if (h->cfg.precision != SBK_PREC_FP32) {
+        const bool bf = h->cfg.precision == SBK_PREC_BF16;
+        const int cps = conv_tc_stage_channels(bf ? 1 : 0);
+        for (auto& r : h->resnets) {
+            if (r.cin % cps == 0) TRY(pack_tc(h, r.prefix + ".block1.block.0.weight", r.prefix + ".block1.wtc", r.cout, r.cin, bf));
+            TRY(pack_tc(h, r.prefix + ".block2.block.0.weight", r.prefix + ".block2.wtc", r.cout, r.cout, bf));
+        }
+        TRY(pack_tc(h, "estimator.final_block.block.0.weight", "estimator.final_block.wtc", h->cfg.dim, h->cfg.dim, bf));
     }
     for (auto& a : h->attns) TRY(repack(h, a.prefix + ".fn.fn.to_qkv.weight", a.prefix + ".kv.w", (size_t)a.c * 256, kv_pack));
     for (int l = 0; l < 2; ++l) {
@@ -396,9 +444,56 @@ static int build_plan(sbk_handle* h, int B, int T, int tb_rows) {
         p.in_lvl = lvl_in; p.out_lvl = lvl_out; p.mask = pl.mask; p.step = pl.step_cur;
         return p;
     };
-    auto push = [&](Op& op, const float* dbg, int64_t numel) { op.dbg_ptr = dbg; op.dbg_numel = numel; pl.ops.push_back(op); };
+    auto push = [&](Op& op, const float* dbg, int64_t numel) {
+        op.dbg_ptr = dbg; op.dbg_numel = numel;
+        if (op.kind == OP_IGEMM) {
+            const IgemmParams& p = op.ig;
+            const double cin = p.c0 + p.c1, opx = (double)B * p.Hout * p.Wout, ipx = (double)B * p.Hin * p.Win;
+            const double taps = p.geom == G_PW ? 1 : (p.geom == G_UP ? 4 : 9);
+            op.flops = 2.0 * opx * p.Cout * cin * taps;
+            op.bytes = 4.0 * (ipx * cin + (p.epi == EPI_KV ? 0.0 : opx * p.Cout) + (p.epi == EPI_RES ? opx * p.Cout : 0.0));
+        } else if (op.kind == OP_FIRST) {
+            op.flops = 2.0 * B * H0 * T * op.fc.C * op.fc.cin * 9;
+            op.bytes = 4.0 * B * H0 * T * (op.fc.cin + op.fc.C);
+        } else if (op.kind == OP_RESFINAL) {
+            op.bytes = 4.0 * B * op.rf.H * op.rf.W * op.rf.C * 3.0;
+        } else if (op.kind == OP_FINAL) {
+            op.flops = 2.0 * B * H0 * T * op.fn.C;
+            op.bytes = 4.0 * B * H0 * T * (op.fn.C + 3.0);
+        }
+        pl.ops.push_back(op);
+    };
     auto npix = [&](int lvl) { return (int64_t)B * Hs[lvl] * Ws[lvl]; };
 
+    const bool use_tc = c.precision != SBK_PREC_FP32;
+    const int tc_cps = conv_tc_stage_channels(c.precision == SBK_PREC_BF16 ? 1 : 0);
+    const int dbg_swap = getenv("SBK_TC_SWAP") ? atoi(getenv("SBK_TC_SWAP")) : 0;
+    // one Block conv (Conv3x3 + bias, GN statistics of the raw output): tcgen05 kernel when the precision
+    // mode allows and the channel count fits a pipeline stage, CUDA-core implicit GEMM otherwise
+    auto block_conv = [&](const std::string& name, const std::string& wkey, const std::string& bkey, int lvl,
+                          const float* in0, int c0, const float* in1, int c1, int cout, float* out, double* st,
+                          int pro, const GnRef* pgn, int tb_k) {
+        Op op; op.name = name;
+        if (use_tc && (c0 + c1) % tc_cps == 0 && c0 % tc_cps == 0 && W(wkey + "tc")) {
+            op.kind = OP_CONVTC;
+            ConvTcParams& p = op.tc; memset(&p, 0, sizeof(p));
+            p.in0 = in0; p.c0 = c0; p.in1 = in1; p.c1 = c1; p.H = Hs[lvl]; p.W = Ws[lvl]; p.B = B;
+            p.wpk = W(wkey + "tc"); p.bias = W(bkey); p.out = out; p.Cout = cout;
+            p.pro = pro; p.mask = pl.mask; p.T = T; p.lvl = lvl; p.step = pl.step_cur;
+            if (pgn) { p.pgn = *pgn; p.tb = pl.tb + h->tb_off[tb_k]; p.tb_stride = pl.tb_stride; }
+            p.ostats = st; p.bf16 = c.precision == SBK_PREC_BF16 ? 1 : 0; p.dbg_swap = dbg_swap;
+            op.flops = 2.0 * B * Hs[lvl] * Ws[lvl] * cout * (c0 + c1) * 9.0;
+            op.bytes = 4.0 * B * Hs[lvl] * Ws[lvl] * (c0 + c1 + cout);
+        } else {
+            op.kind = OP_IGEMM;
+            op.ig = base_ig(G_C3, lvl, lvl);
+            IgemmParams& p = op.ig;
+            p.in0 = in0; p.c0 = c0; p.in1 = in1; p.c1 = c1; p.w = W(wkey); p.bias = W(bkey);
+            p.out = out; p.Cout = cout; p.pro = pro; p.epi = EPI_PLAIN; p.ostats = st;
+            if (pgn) { p.pgn = *pgn; p.tb = pl.tb + h->tb_off[tb_k]; p.tb_stride = pl.tb_stride; }
+        }
+        push(op, out, npix(lvl) * cout);
+    };
     // ResnetBlock (diffusion.py:74-79) at level lvl: in (in0|in1) -> out
     auto resnet = [&](int k, int lvl, const float* in0, int c0, const float* in1, int c1, float* out) {
         const ResnetInfo& r = h->resnets[k];
@@ -412,23 +507,13 @@ static int build_plan(sbk_handle* h, int B, int T, int tb_rows) {
             p.out = A; p.ostats = st1; p.B = B; p.H = H0; p.T = T; p.cin = cin0; p.C = r.cout;
             push(op, A, npix(lvl) * r.cout);
         } else {
-            Op op; op.kind = OP_IGEMM; op.name = r.prefix + ".block1.raw";
-            op.ig = base_ig(G_C3, lvl, lvl);
-            IgemmParams& p = op.ig;
-            p.in0 = in0; p.c0 = c0; p.in1 = in1; p.c1 = c1;
-            p.w = W(r.prefix + ".block1.w"); p.bias = W(r.prefix + ".block1.block.0.bias");
-            p.out = A; p.Cout = r.cout; p.pro = PRO_MASK; p.epi = EPI_PLAIN; p.ostats = st1;
-            push(op, A, npix(lvl) * r.cout);
+            block_conv(r.prefix + ".block1.raw", r.prefix + ".block1.w", r.prefix + ".block1.block.0.bias", lvl,
+                       in0, c0, in1, c1, r.cout, A, st1, PRO_MASK, nullptr, k);
         }
         {
-            Op op; op.kind = OP_IGEMM; op.name = r.prefix + ".block2.raw";
-            op.ig = base_ig(G_C3, lvl, lvl);
-            IgemmParams& p = op.ig;
-            p.in0 = A; p.c0 = r.cout; p.w = W(r.prefix + ".block2.w"); p.bias = W(r.prefix + ".block2.block.0.bias");
-            p.out = Bb; p.Cout = r.cout; p.pro = PRO_GN; p.pgn = gnref(st1, r.prefix + ".block1", r.cout, lvl);
-            p.tb = pl.tb + h->tb_off[k]; p.tb_stride = pl.tb_stride;
-            p.epi = EPI_PLAIN; p.ostats = st2;
-            push(op, Bb, npix(lvl) * r.cout);
+            const GnRef g1 = gnref(st1, r.prefix + ".block1", r.cout, lvl);
+            block_conv(r.prefix + ".block2.raw", r.prefix + ".block2.w", r.prefix + ".block2.block.0.bias", lvl,
+                       A, r.cout, nullptr, 0, r.cout, Bb, st2, PRO_GN, &g1, k);
         }
         if (k == 0 || r.cin == r.cout) {
             Op op; op.kind = OP_RESFINAL; op.name = r.prefix + ".out";
@@ -524,14 +609,8 @@ static int build_plan(sbk_handle* h, int B, int T, int tb_rows) {
     resample(G_UP, "estimator.ups.1.3", 1, 0, bf.X[1], C1, bf.Y[0]);
     // final_block + final_conv + update (:213-216)
     double* stf = stats_slot();
-    {
-        Op op; op.kind = OP_IGEMM; op.name = "estimator.final_block.raw";
-        op.ig = base_ig(G_C3, 0, 0);
-        IgemmParams& p = op.ig;
-        p.in0 = bf.Y[0]; p.c0 = C1; p.w = W("estimator.final_block.w"); p.bias = W("estimator.final_block.block.0.bias");
-        p.out = bf.A[0]; p.Cout = C1; p.pro = PRO_MASK; p.epi = EPI_PLAIN; p.ostats = stf;
-        push(op, bf.A[0], npix(0) * C1);
-    }
+    block_conv("estimator.final_block.raw", "estimator.final_block.w", "estimator.final_block.block.0.bias", 0,
+               bf.Y[0], C1, nullptr, 0, C1, bf.A[0], stf, PRO_MASK, nullptr, 0);
     {
         Op op; op.kind = OP_FINAL; op.name = "estimator.out";
         FinalParams& p = op.fn; memset(&p, 0, sizeof(p));
@@ -558,6 +637,11 @@ static int run_ops(sbk_handle* h, cudaStream_t s) {
             case OP_CTX: n += launch_attn_ctx(op.cx, s); break;
             case OP_MIX: n += launch_attn_mix(op.mx, s); break;
             case OP_FINAL: n += launch_final(op.fn, s); break;
+            case OP_CONVTC: n += launch_conv_tc(op.tc, s); break;
+        }
+        if (h->capture && op.dbg_ptr && op.dbg_numel > 0) {
+            if (!op.dbg_copy) cudaMalloc(&op.dbg_copy, op.dbg_numel * sizeof(float));
+            cudaMemcpyAsync(op.dbg_copy, op.dbg_ptr, op.dbg_numel * sizeof(float), cudaMemcpyDeviceToDevice, s);
         }
     }
     return n;
@@ -602,6 +686,8 @@ static int speaker(sbk_handle* h, const float* spk, int B, cudaStream_t s) {
 static void set_mode(Plan& pl, int mode, bool per_sample_t, float* out) {
     for (auto& op : pl.ops)
         if (op.kind == OP_IGEMM && op.ig.pro == PRO_GN) op.ig.tb_per_sample = per_sample_t ? 1 : 0;
+    for (auto& op : pl.ops)
+        if (op.kind == OP_CONVTC && op.tc.pro == PRO_GN) op.tc.tb_per_sample = per_sample_t ? 1 : 0;
     FinalParams& f = pl.ops[pl.final_op].fn;
     f.mode = mode; f.xt_out = out; f.noise_pp = pl.noise_pp;
 }
@@ -757,8 +843,54 @@ extern "C" int sbk_reverse_diffusion_host(sbk_handle* h, const float* z, const f
     return SBK_OK;
 }
 
+extern "C" int sbk_profile_ops(sbk_handle* h, float* ms, double* flops, double* bytes, int cap, int* n_ops) {
+    if (!h || !ms || !n_ops) return fail(SBK_ERR_ARG, "sbk_profile_ops: null argument");
+    Plan& pl = h->plan;
+    if (!pl.mem) return fail(SBK_ERR_STATE, "sbk_profile_ops: no plan yet (run a sampler call first)");
+    const int n = (int)pl.ops.size();
+    if (cap < n) return fail(SBK_ERR_ARG, "sbk_profile_ops: need room for %d launches", n);
+    CU(cudaSetDevice(h->cfg.device));
+    if (!h->cap_stream) CU(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+    cudaStream_t s = h->cap_stream;
+    CU(cudaDeviceSynchronize());
+    std::vector<cudaEvent_t> ev(n + 1);
+    for (auto& e : ev) CU(cudaEventCreate(&e));
+    StepBeginParams sb{pl.stats, pl.n_stat_doubles, pl.step_cur, pl.step_next};
+    k_set_int<<<1, 1, 0, s>>>(pl.step_next, 0);
+    launch_step_begin(sb, s);
+    for (int i = 0; i < n; ++i) {
+        CU(cudaEventRecord(ev[i], s));
+        Op& op = pl.ops[i];
+        switch (op.kind) {
+            case OP_FIRST: launch_first_conv(op.fc, s); break;
+            case OP_IGEMM: launch_igemm(op.ig, s); break;
+            case OP_RESFINAL: launch_resfinal(op.rf, s); break;
+            case OP_CTX: launch_attn_ctx(op.cx, s); break;
+            case OP_MIX: launch_attn_mix(op.mx, s); break;
+            case OP_FINAL: launch_final(op.fn, s); break;
+            case OP_CONVTC: launch_conv_tc(op.tc, s); break;
+        }
+    }
+    CU(cudaEventRecord(ev[n], s));
+    CU(cudaStreamSynchronize(s));
+    CU(cudaGetLastError());
+    for (int i = 0; i < n; ++i) {
+        CU(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
+        if (flops) flops[i] = pl.ops[i].flops;
+        if (bytes) bytes[i] = pl.ops[i].bytes;
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    *n_ops = n;
+    return SBK_OK;
+}
+
 extern "C" int64_t sbk_last_launch_count(const sbk_handle* h) { return h ? h->last_launches : 0; }
 
+extern "C" int sbk_debug_capture(sbk_handle* h, int on) {
+    if (!h) return fail(SBK_ERR_ARG, "sbk_debug_capture: null handle");
+    h->capture = on != 0;
+    return SBK_OK;
+}
 extern "C" int sbk_debug_num(const sbk_handle* h) { return h ? (int)h->plan.ops.size() : 0; }
 extern "C" const char* sbk_debug_name(const sbk_handle* h, int i) {
     if (!h || i < 0 || i >= (int)h->plan.ops.size()) return nullptr;
@@ -771,7 +903,7 @@ extern "C" int sbk_debug_read(sbk_handle* h, const char* name, float* dst, int64
         if (numel) *numel = op.dbg_numel;
         if (dst && op.dbg_ptr && op.dbg_numel > 0) {
             CU(cudaDeviceSynchronize());
-            CU(cudaMemcpy(dst, op.dbg_ptr, op.dbg_numel * sizeof(float), cudaMemcpyDefault));
+            CU(cudaMemcpy(dst, op.dbg_copy ? op.dbg_copy : op.dbg_ptr, op.dbg_numel * sizeof(float), cudaMemcpyDefault));
         }
         return SBK_OK;
     }

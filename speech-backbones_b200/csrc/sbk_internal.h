@@ -46,6 +46,19 @@ struct IgemmParams {
     float* kv_part;                               // EPI_KV: [B][mtiles][4][kKvPartFloats]
 };
 
+// tcgen05 3x3 convolution (sbk_conv_tc.cu): same prologue/epilogue contract as the G_C3 igemm, EPI_PLAIN only
+struct ConvTcParams {
+    const float* in0; const float* in1; int c0, c1;
+    int H, W, B;
+    const void* wpk;              // [ntile][kstage][tap 9][chunk 2][cout NT][16 B] tf32-rounded fp32 or bf16
+    const float* bias; float* out; int Cout;
+    int pro; const float* mask; int T; int lvl;
+    GnRef pgn; const float* tb; int tb_stride; int tb_per_sample; const int* step;
+    double* ostats;
+    int bf16;                     // 0: kind::tf32, 1: kind::f16 (bf16 operands)
+    int dbg_swap;                 // debug: swap LBO/SBO in the smem descriptors
+};
+
 struct FirstConvParams {        // Block.conv of downs.0.0.block1 on the planar stack([mu, xt(, s)]) * mask
     const float* mu; const float* xt; const float* spk_s;   // [B][H][T], [B][H][T], [B][H] or nullptr
     const float* mask;          // [B][T]
@@ -113,6 +126,9 @@ struct StepBeginParams { double* stats; int n_doubles; int* step_cur; int* step_
 // launchers (all asynchronous on `s`); return the number of kernels launched
 int launch_igemm(const IgemmParams& p, cudaStream_t s);
 int launch_first_conv(const FirstConvParams& p, cudaStream_t s);
+int launch_conv_tc(const ConvTcParams& p, cudaStream_t s);
+int conv_tc_ntile(int Cout);
+int conv_tc_stage_channels(int bf16);
 int launch_resfinal(const ResFinalParams& p, cudaStream_t s);
 int launch_attn_ctx(const AttnCtxParams& p, cudaStream_t s);
 int launch_attn_mix(const AttnMixParams& p, cudaStream_t s);

@@ -19,11 +19,11 @@ def engines(sbk_lib):
     from speech_backbones_b200.binding import Engine
     cache = {}
 
-    def get(n_spks=1, use_graph=True, seed=1234):
-        key = (n_spks, use_graph, seed)
+    def get(n_spks=1, use_graph=True, seed=1234, precision="fp32"):
+        key = (n_spks, use_graph, seed, precision)
         if key not in cache:
             cfg = UNetConfig(n_spks=n_spks)
-            e = Engine(n_spks=n_spks, use_graph=use_graph)
+            e = Engine(n_spks=n_spks, use_graph=use_graph, precision=precision)
             e.load_state_dict(synthetic_state_dict(cfg, seed))
             cache[key] = e
         return cache[key]
@@ -35,8 +35,10 @@ def engines(sbk_lib):
 def stagewise_errors(eng, cfg, sd, xt, mask, mu, t, spk):
     """Run one estimator call on the GPU and compare every named intermediate with the oracle's."""
     dev = "cuda"
+    eng.debug_capture(True)
     y = eng.estimator(xt.to(dev), mask.to(dev), mu.to(dev), t.to(dev), None if spk is None else spk.to(dev))
     torch.cuda.synchronize()
+    eng.debug_capture(False)
     taps = {}
     y_ref = O.estimator(sd, cfg, xt, mask, mu, t, spk, taps=taps)
     rows = []
@@ -188,6 +190,46 @@ def test_config2_shape_properties(engines):
     assert rel_l2(y[b:b + 1], ref) <= EST_TOL
     out = eng.reverse_diffusion(z.cuda(), mask.cuda(), mu.cuda(), 2).cpu()
     assert torch.isfinite(out).all() and (out * (1 - mask)).abs().max().item() == 0.0
+
+
+# ---- tensor-core precision modes (tcgen05 kind::tf32 / kind::f16-bf16 operands, fp32 accumulate in TMEM) ----
+# Tolerances follow the operand rounding (measured by emulation on the reference):
+# tf32 (10-bit mantissa) ~1e-3 per estimator call, bf16 (8-bit) ~9e-3; GN/softmax/Mish/Euler stay fp32.
+TC_TOL = {"tf32": (4e-3, 8e-3), "bf16": (3e-2, 5e-2)}       # (per estimator call / stage, trajectory)
+
+
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+@pytest.mark.parametrize("B,T", [(2, 32), (3, 100), (1, 256)])
+def test_tensor_core_stagewise(engines, precision, B, T):
+    cfg = UNetConfig()
+    sd = synthetic_state_dict(cfg)
+    z, mask, mu, spk, _ = synthetic_inputs(B, T, ragged=True)
+    t = torch.linspace(0.9, 0.2, B)
+    rows = stagewise_errors(engines(1, True, 1234, precision), cfg, sd, z * mask, mask, mu, t, spk)
+    report = "\n".join(f"{n:48s} rel_l2={e:.3e} |ref|max={m:.3g}" for n, e, m in rows)
+    print(report)
+    bad = [r for r in rows if not (r[1] <= TC_TOL[precision][0])]
+    assert not bad, "first divergent stage: %s\n%s" % (bad[0][0], report)
+
+
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+def test_tensor_core_vs_reference_golden(engines, golden, precision):
+    eng = engines(1, True, 1234, precision)
+    for idx, c in _golden_cases("est") + _golden_cases("traj"):
+        if c["n_spks"] != 1:
+            continue
+        cfg, sd, z, mask, mu, spk = case_inputs(golden, c)
+        if c["kind"] == "est":
+            y = eng.estimator((z * mask * c["scale"]).cuda(), mask.cuda(), mu.cuda(), torch.tensor(c["t"]).cuda()).cpu()
+            tol = TC_TOL[precision][0]
+        else:
+            noise = stoc_noise(golden, c).cuda() if c["stoc"] else None
+            y = eng.reverse_diffusion(z.cuda(), mask.cuda(), mu.cuda(), c["N"], c["stoc"], None, noise).cpu()
+            tol = TC_TOL[precision][1]
+        err = rel_l2(y, c["out"])
+        print(precision, case_id(c), "rel_l2", err)
+        assert err <= tol, case_id(c)
+        assert (y * (1 - mask)).abs().max().item() == 0.0
 
 
 def test_error_paths_raise(engines):
