@@ -82,15 +82,50 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def _ncpu():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count()
+
+
+_THREADS = None
+
+
+def pick_cpu_threads(torch, O, cfg, sd):
+    """The reference arm gets all the host threads it can USE: sweep the thread count on a tiny problem and keep
+    the fastest (on many-core boxes PyTorch's CPU convs slow down badly when oversubscribed)."""
+    global _THREADS
+    if _THREADS is not None:
+        torch.set_num_threads(_THREADS)
+        return _THREADS
+    from speech_backbones_b200 import synthetic_inputs
+    z, mask, mu, spk, _ = synthetic_inputs(1, 128, n_spks=cfg.n_spks)
+    n = _ncpu()
+    cands = sorted({c for c in (4, 8, 16, 32, 64, n) if c <= n})
+    best, best_t = cands[0], float("inf")
+    for c in cands:
+        torch.set_num_threads(c)
+        O.reverse_diffusion(sd, cfg, z, mask, mu, 1, False, spk)
+        t0 = time.perf_counter()
+        O.reverse_diffusion(sd, cfg, z, mask, mu, 1, False, spk)
+        dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = c, dt
+    _THREADS = best
+    torch.set_num_threads(best)
+    return best
+
+
 def cpu_reference_sample(wl, torch, n_steps=2, b_sample=2, repeats=1):
     """Time the CPU oracle (port of the reference PyTorch path) on a bounded sample of the workload:
     `b_sample` utterances at the workload's T for `n_steps` Euler steps, after one warm-up step.
     Cost is linear in B and in N (the loop body is step-independent, diffusion.py:258-274)."""
     from oracle import gradtts_oracle as O
     from speech_backbones_b200 import UNetConfig, synthetic_inputs, synthetic_state_dict
-    torch.set_num_threads(os.cpu_count())
     cfg = UNetConfig(n_spks=wl["n_spks"])
     sd = synthetic_state_dict(cfg)
+    threads = pick_cpu_threads(torch, O, cfg, sd)
     z, mask, mu, spk, _ = synthetic_inputs(b_sample, wl["T"], n_spks=cfg.n_spks)
     O.reverse_diffusion(sd, cfg, z, mask, mu, 1, False, spk)                    # warm-up
     best = float("inf")
@@ -100,9 +135,10 @@ def cpu_reference_sample(wl, torch, n_steps=2, b_sample=2, repeats=1):
         best = min(best, time.perf_counter() - t0)
     sec_per_frame_step = best / (b_sample * wl["T"] * n_steps)
     frames_per_sec = 1.0 / (sec_per_frame_step * wl["N"])
-    sample = (f"oracle port, B={b_sample} x T={wl['T']} for {n_steps} of N={wl['N']} Euler steps "
-              f"({best:.2f} s), scaled linearly in B and N")
-    return frames_per_sec, sec_per_frame_step, sample
+    sample = (f"oracle port (PyTorch CPU fp32, {threads} threads = fastest of a sweep up to {_ncpu()} usable cores), "
+              f"B={b_sample} x T={wl['T']} for {n_steps} of N={wl['N']} Euler steps ({best:.2f} s), "
+              f"scaled linearly in B and N")
+    return frames_per_sec, sec_per_frame_step, sample, threads
 
 
 def run_reference(args, wl):
@@ -112,7 +148,7 @@ def run_reference(args, wl):
         return
     vals = []
     for i in range(args.warmup + args.steps):
-        fps, spfs, sample = cpu_reference_sample(wl, torch, n_steps=2, b_sample=2)
+        fps, spfs, sample, threads = cpu_reference_sample(wl, torch, n_steps=2, b_sample=2)
         if i >= args.warmup:
             vals.append((fps, spfs))
     fps = statistics.mean(v[0] for v in vals)
@@ -124,7 +160,7 @@ def run_reference(args, wl):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "batch_per_gpu": wl["B"], "frames": wl["T"], "n_timesteps": wl["N"],
                    "note": "CPU reference arm: each step is a bounded sample, ms_per_step is the extrapolated full step"},
-        "cpu_baseline": {"value": fps, "unit": "mel-frames/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": fps, "unit": "mel-frames/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": fps, "unit": "mel-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -251,7 +287,7 @@ def run_ours(args, wl):
         "whole_step": {"tflops": FLOP_PER_FRAME_STEP * B * T / (ms_step / N * 1e-3) / 1e12,
                        "ideal_hbm_gbs": IDEAL_BYTES_PER_FRAME_STEP * B * T / (ms_step / N * 1e-3) / 1e9},
     }
-    fps_cpu, _, sample = cpu_reference_sample(wl, torch, n_steps=3, b_sample=2) if world == 1 else (None, None, None)
+    fps_cpu, _, sample, threads = cpu_reference_sample(wl, torch, n_steps=3, b_sample=2) if world == 1 else (None,) * 4
     out = {
         "metric": "mel-frames/sec at N=50 reverse-diffusion steps", "value": value, "unit": "mel-frames/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
@@ -269,7 +305,7 @@ def run_ours(args, wl):
         "roofline": roofline,
     }
     if fps_cpu is not None:
-        out["cpu_baseline"] = {"value": fps_cpu, "unit": "mel-frames/s", "cores": os.cpu_count(), "kind": "port",
+        out["cpu_baseline"] = {"value": fps_cpu, "unit": "mel-frames/s", "cores": threads, "kind": "port",
                                "sample": sample}
     print(json.dumps(out), flush=True)
     if world > 1:
