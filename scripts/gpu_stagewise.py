@@ -22,5 +22,5 @@ eng = Engine(n_spks=n_spks, precision=precision)
 eng.load_state_dict(sd)
 z, mask, mu, spk, _ = synthetic_inputs(B, T, ragged=True, n_spks=n_spks)
 t = torch.linspace(0.9, 0.2, B)
-for n, e, m in stagewise_errors(eng, cfg, sd, z * mask, mask, mu, t, spk):
+for n, e, m in stagewise_errors(eng, cfg, sd, z * mask, mask, mu, t, spk, masked_storage=precision != "fp32"):
     print(f"{n:48s} rel_l2={e:.3e} |ref|max={m:.3g}")

@@ -50,10 +50,10 @@ struct Arena {
     }
 };
 
-enum OpKind { OP_FIRST, OP_IGEMM, OP_RESFINAL, OP_CTX, OP_MIX, OP_FINAL, OP_CONVTC };
+enum OpKind { OP_FIRST, OP_IGEMM, OP_RESFINAL, OP_CTX, OP_MIX, OP_FINAL, OP_CONVTC, OP_GNACT };
 struct Op {
     OpKind kind; std::string name;
-    FirstConvParams fc; IgemmParams ig; ConvTcParams tc; ResFinalParams rf; AttnCtxParams cx; AttnMixParams mx; FinalParams fn;
+    FirstConvParams fc; IgemmParams ig; ConvTcParams tc; GnActParams ga; ResFinalParams rf; AttnCtxParams cx; AttnMixParams mx; FinalParams fn;
     const float* dbg_ptr = nullptr; int64_t dbg_numel = 0;
     double flops = 0, bytes = 0;   // algorithmic work of this launch
     float* dbg_copy = nullptr;     // snapshot taken right after the launch when debug capture is on
@@ -260,18 +260,19 @@ static uint16_t f32_to_bf16_rn(float x) {
     u += 0x7FFFu + ((u >> 16) & 1u);
     return (uint16_t)(u >> 16);
 }
-static int pack_tc(sbk_handle* h, const std::string& src, const std::string& key, int cout, int cin, bool bf16) {
-    std::vector<float> hs((size_t)cout * cin * 9);
+static int pack_tc(sbk_handle* h, const std::string& src, const std::string& key, int cout, int cin, int geom, bool bf16) {
+    const int taps = geom == G_C3 ? 9 : 1;
+    std::vector<float> hs((size_t)cout * cin * taps);
     CU(cudaMemcpy(hs.data(), h->raw[src], hs.size() * sizeof(float), cudaMemcpyDeviceToHost));
-    const int NT = conv_tc_ntile(cout), CPS = conv_tc_stage_channels(bf16 ? 1 : 0), EPC = bf16 ? 8 : 4, KCHK = CPS / EPC;
+    const int NT = conv_tc_ntile(cout), CPS = conv_tc_stage_channels(geom, bf16 ? 1 : 0), EPC = bf16 ? 8 : 4, KCHK = CPS / EPC;
     const int ksteps = cin / CPS;
     const size_t esz = bf16 ? 2 : 4;
-    std::vector<uint8_t> hd((size_t)cout * cin * 9 * esz);
-    for (int nt = 0; nt < cout / NT; ++nt) for (int ks = 0; ks < ksteps; ++ks) for (int tap = 0; tap < 9; ++tap)
+    std::vector<uint8_t> hd((size_t)cout * cin * taps * esz);
+    for (int nt = 0; nt < cout / NT; ++nt) for (int ks = 0; ks < ksteps; ++ks) for (int tap = 0; tap < taps; ++tap)
         for (int k = 0; k < KCHK; ++k) for (int col = 0; col < NT; ++col) for (int e = 0; e < EPC; ++e) {
             const int co = nt * NT + col, ci = ks * CPS + k * EPC + e;
-            const float w = hs[((size_t)co * cin + ci) * 9 + tap];
-            const size_t idx = (((((size_t)nt * ksteps + ks) * 9 + tap) * KCHK + k) * NT + col) * EPC + e;
+            const float w = hs[((size_t)co * cin + ci) * taps + tap];
+            const size_t idx = (((((size_t)nt * ksteps + ks) * taps + tap) * KCHK + k) * NT + col) * EPC + e;
             if (bf16) reinterpret_cast<uint16_t*>(hd.data())[idx] = f32_to_bf16_rn(w);
             else reinterpret_cast<uint32_t*>(hd.data())[idx] = f32_to_tf32_rna(w);
         }
@@ -321,14 +322,17 @@ extern "C" int sbk_pack(sbk_handle* h) {
         TRY(repack(h, r.prefix + ".block2.block.0.weight", r.prefix + ".block2.w", (size_t)r.cout * 9 * r.cout, conv_pack));
         if (r.cin != r.cout) TRY(repack(h, r.prefix + ".res_conv.weight", r.prefix + ".res.w", (size_t)r.cin * r.cout, conv_pack));
     }
+    if (h->cfg.precision == SBK_PREC_BF16)
+        return fail(SBK_ERR_UNSUPPORTED, "sbk_pack: bf16 operand tensors are not wired up in this build (use fp32 or tf32)");
     if (h->cfg.precision != SBK_PREC_FP32) {
-        const bool bf = h->cfg.precision == SBK_PREC_BF16;
-        const int cps = conv_tc_stage_channels(bf ? 1 : 0);
+        const bool bf = false;
+        const int cps3 = conv_tc_stage_channels(G_C3, 0), cps1 = conv_tc_stage_channels(G_PW, 0);
         for (auto& r : h->resnets) {
-            if (r.cin % cps == 0) TRY(pack_tc(h, r.prefix + ".block1.block.0.weight", r.prefix + ".block1.wtc", r.cout, r.cin, bf));
-            TRY(pack_tc(h, r.prefix + ".block2.block.0.weight", r.prefix + ".block2.wtc", r.cout, r.cout, bf));
+            if (r.cin % cps3 == 0) TRY(pack_tc(h, r.prefix + ".block1.block.0.weight", r.prefix + ".block1.wtc", r.cout, r.cin, G_C3, bf));
+            TRY(pack_tc(h, r.prefix + ".block2.block.0.weight", r.prefix + ".block2.wtc", r.cout, r.cout, G_C3, bf));
+            if (r.cin != r.cout && r.cin % cps1 == 0) TRY(pack_tc(h, r.prefix + ".res_conv.weight", r.prefix + ".res.wtc", r.cout, r.cin, G_PW, bf));
         }
-        TRY(pack_tc(h, "estimator.final_block.block.0.weight", "estimator.final_block.wtc", h->cfg.dim, h->cfg.dim, bf));
+        TRY(pack_tc(h, "estimator.final_block.block.0.weight", "estimator.final_block.wtc", h->cfg.dim, h->cfg.dim, G_C3, bf));
     }
     for (auto& a : h->attns) TRY(repack(h, a.prefix + ".fn.fn.to_qkv.weight", a.prefix + ".kv.w", (size_t)a.c * 256, kv_pack));
     for (int l = 0; l < 2; ++l) {
@@ -466,39 +470,42 @@ static int build_plan(sbk_handle* h, int B, int T, int tb_rows) {
     auto npix = [&](int lvl) { return (int64_t)B * Hs[lvl] * Ws[lvl]; };
 
     const bool use_tc = c.precision != SBK_PREC_FP32;
-    const int tc_cps = conv_tc_stage_channels(c.precision == SBK_PREC_BF16 ? 1 : 0);
-    const int dbg_swap = getenv("SBK_TC_SWAP") ? atoi(getenv("SBK_TC_SWAP")) : 0;
-    // one Block conv (Conv3x3 + bias, GN statistics of the raw output): tcgen05 kernel when the precision
-    // mode allows and the channel count fits a pipeline stage, CUDA-core implicit GEMM otherwise
-    auto block_conv = [&](const std::string& name, const std::string& wkey, const std::string& bkey, int lvl,
-                          const float* in0, int c0, const float* in1, int c1, int cout, float* out, double* st,
-                          int pro, const GnRef* pgn, int tb_k) {
-        Op op; op.name = name;
-        if (use_tc && (c0 + c1) % tc_cps == 0 && c0 % tc_cps == 0 && W(wkey + "tc")) {
-            op.kind = OP_CONVTC;
-            ConvTcParams& p = op.tc; memset(&p, 0, sizeof(p));
-            p.in0 = in0; p.c0 = c0; p.in1 = in1; p.c1 = c1; p.H = Hs[lvl]; p.W = Ws[lvl]; p.B = B;
-            p.wpk = W(wkey + "tc"); p.bias = W(bkey); p.out = out; p.Cout = cout;
-            p.pro = pro; p.mask = pl.mask; p.T = T; p.lvl = lvl; p.step = pl.step_cur;
-            if (pgn) { p.pgn = *pgn; p.tb = pl.tb + h->tb_off[tb_k]; p.tb_stride = pl.tb_stride; }
-            p.ostats = st; p.bf16 = c.precision == SBK_PREC_BF16 ? 1 : 0; p.dbg_swap = dbg_swap;
-            op.flops = 2.0 * B * Hs[lvl] * Ws[lvl] * cout * (c0 + c1) * 9.0;
-            op.bytes = 4.0 * B * Hs[lvl] * Ws[lvl] * (c0 + c1 + cout);
-        } else {
-            op.kind = OP_IGEMM;
-            op.ig = base_ig(G_C3, lvl, lvl);
-            IgemmParams& p = op.ig;
-            p.in0 = in0; p.c0 = c0; p.in1 = in1; p.c1 = c1; p.w = W(wkey); p.bias = W(bkey);
-            p.out = out; p.Cout = cout; p.pro = pro; p.epi = EPI_PLAIN; p.ostats = st;
-            if (pgn) { p.pgn = *pgn; p.tb = pl.tb + h->tb_off[tb_k]; p.tb_stride = pl.tb_stride; }
-        }
+    const int tc_cps3 = conv_tc_stage_channels(G_C3, 0), tc_cps1 = conv_tc_stage_channels(G_PW, 0);
+    // In the tensor-core modes every conv input is kept in HBM in "operand form" (already masked; Block activations
+    // already GroupNorm-ed/Mish-ed/time-biased), so a conv's A path is a pure copy.  `store_masked` marks outputs
+    // whose consumers all multiply by the mask anyway (everything except the tensors fed to LinearAttention, which
+    // reads the unmasked x, diffusion.py:192,202,210).
+    auto tc_conv = [&](const std::string& name, int geom, const std::string& wkey, const std::string& bkey, int lvl,
+                       const float* in0, int c0, const float* in1, int c1, int cout, float* out, double* st) {
+        Op op; op.name = name; op.kind = OP_CONVTC;
+        ConvTcParams& p = op.tc; memset(&p, 0, sizeof(p));
+        p.geom = geom; p.in0 = in0; p.c0 = c0; p.in1 = in1; p.c1 = c1; p.H = Hs[lvl]; p.W = Ws[lvl]; p.B = B;
+        p.wpk = W(wkey); p.bias = bkey.empty() ? nullptr : W(bkey); p.out = out; p.Cout = cout;
+        p.epi = EPI_PLAIN; p.ostats = st; p.mask = pl.mask; p.T = T; p.lvl = lvl;
+        const double taps = geom == G_C3 ? 9.0 : 1.0;
+        op.flops = 2.0 * B * Hs[lvl] * Ws[lvl] * cout * (c0 + c1) * taps;
+        op.bytes = 4.0 * B * Hs[lvl] * Ws[lvl] * (c0 + c1 + cout);
+        return op;
+    };
+    // one Block conv (Conv3x3 + bias + GN statistics of the raw output) on the CUDA-core path
+    auto ffma_block_conv = [&](const std::string& name, const std::string& wkey, const std::string& bkey, int lvl,
+                               const float* in0, int c0, const float* in1, int c1, int cout, float* out, double* st,
+                               int pro, const GnRef* pgn, int tb_k) {
+        Op op; op.name = name; op.kind = OP_IGEMM;
+        op.ig = base_ig(G_C3, lvl, lvl);
+        IgemmParams& p = op.ig;
+        p.in0 = in0; p.c0 = c0; p.in1 = in1; p.c1 = c1; p.w = W(wkey); p.bias = W(bkey);
+        p.out = out; p.Cout = cout; p.pro = pro; p.epi = EPI_PLAIN; p.ostats = st;
+        if (pgn) { p.pgn = *pgn; p.tb = pl.tb + h->tb_off[tb_k]; p.tb_stride = pl.tb_stride; }
         push(op, out, npix(lvl) * cout);
     };
     // ResnetBlock (diffusion.py:74-79) at level lvl: in (in0|in1) -> out
-    auto resnet = [&](int k, int lvl, const float* in0, int c0, const float* in1, int c1, float* out) {
+    auto resnet = [&](int k, int lvl, const float* in0, int c0, const float* in1, int c1, float* out, bool store_masked) {
         const ResnetInfo& r = h->resnets[k];
         float* A = bf.A[lvl]; float* Bb = bf.Bf[lvl];
         double* st1 = stats_slot(); double* st2 = stats_slot();
+        const bool tc1 = use_tc && k != 0 && (c0 + c1) % tc_cps3 == 0 && c0 % tc_cps3 == 0;
+        // ---- block1 conv -> raw h1 (A)
         if (k == 0) {
             Op op; op.kind = OP_FIRST; op.name = r.prefix + ".block1.raw";
             FirstConvParams& p = op.fc; memset(&p, 0, sizeof(p));
@@ -506,26 +513,56 @@ static int build_plan(sbk_handle* h, int B, int T, int tb_rows) {
             p.w = W(r.prefix + ".block1.w"); p.bias = W(r.prefix + ".block1.block.0.bias");
             p.out = A; p.ostats = st1; p.B = B; p.H = H0; p.T = T; p.cin = cin0; p.C = r.cout;
             push(op, A, npix(lvl) * r.cout);
+        } else if (tc1) {
+            Op op = tc_conv(r.prefix + ".block1.raw", G_C3, r.prefix + ".block1.wtc", r.prefix + ".block1.block.0.bias", lvl,
+                            in0, c0, in1, c1, r.cout, A, st1);
+            push(op, A, npix(lvl) * r.cout);
         } else {
-            block_conv(r.prefix + ".block1.raw", r.prefix + ".block1.w", r.prefix + ".block1.block.0.bias", lvl,
-                       in0, c0, in1, c1, r.cout, A, st1, PRO_MASK, nullptr, k);
+            ffma_block_conv(r.prefix + ".block1.raw", r.prefix + ".block1.w", r.prefix + ".block1.block.0.bias", lvl,
+                            in0, c0, in1, c1, r.cout, A, st1, PRO_MASK, nullptr, k);
         }
-        {
-            const GnRef g1 = gnref(st1, r.prefix + ".block1", r.cout, lvl);
-            block_conv(r.prefix + ".block2.raw", r.prefix + ".block2.w", r.prefix + ".block2.block.0.bias", lvl,
-                       A, r.cout, nullptr, 0, r.cout, Bb, st2, PRO_GN, &g1, k);
+        // ---- block2 conv -> raw h2 (FFMA: A -> Bb with the GN/Mish prologue fused; TC: A -> act (Bb) -> A)
+        const GnRef g1 = gnref(st1, r.prefix + ".block1", r.cout, lvl);
+        float* h2 = Bb;
+        if (use_tc) {
+            {
+                Op op; op.kind = OP_GNACT; op.name = r.prefix + ".block1.act";
+                GnActParams& p = op.ga; memset(&p, 0, sizeof(p));
+                p.raw = A; p.gn = g1; p.tb = pl.tb + h->tb_off[k]; p.tb_stride = pl.tb_stride; p.step = pl.step_cur;
+                p.mask = pl.mask; p.T = T; p.lvl = lvl; p.out = Bb; p.B = B; p.H = Hs[lvl]; p.W = Ws[lvl]; p.C = r.cout;
+                p.round_tf32 = 1;
+                op.bytes = 8.0 * npix(lvl) * r.cout;
+                push(op, nullptr, 0);
+            }
+            Op op = tc_conv(r.prefix + ".block2.raw", G_C3, r.prefix + ".block2.wtc", r.prefix + ".block2.block.0.bias", lvl,
+                            Bb, r.cout, nullptr, 0, r.cout, A, st2);
+            push(op, A, npix(lvl) * r.cout);
+            h2 = A;
+        } else {
+            ffma_block_conv(r.prefix + ".block2.raw", r.prefix + ".block2.w", r.prefix + ".block2.block.0.bias", lvl,
+                            A, r.cout, nullptr, 0, r.cout, Bb, st2, PRO_GN, &g1, k);
         }
+        // ---- tail: out = Mish(GN(h2))*mask + res(x*mask)
+        const GnRef g2 = gnref(st2, r.prefix + ".block2", r.cout, lvl);
         if (k == 0 || r.cin == r.cout) {
             Op op; op.kind = OP_RESFINAL; op.name = r.prefix + ".out";
             ResFinalParams& p = op.rf; memset(&p, 0, sizeof(p));
-            p.h2raw = Bb; p.gn = gnref(st2, r.prefix + ".block2", r.cout, lvl);
+            p.h2raw = h2; p.gn = g2;
             p.mask = pl.mask; p.T = T; p.lvl = lvl; p.out = out; p.B = B; p.H = Hs[lvl]; p.W = Ws[lvl]; p.C = r.cout;
+            p.out_mask = store_masked ? 1 : 0;
             if (k == 0) {
                 p.x = nullptr; p.mu = pl.mu; p.xt = pl.xt; p.spk_s = pl.spk_s; p.cin = cin0;
                 p.wres = W(r.prefix + ".res.w"); p.bres = W(r.prefix + ".res_conv.bias");
             } else {
                 p.x = in0;
             }
+            op.bytes = 12.0 * npix(lvl) * r.cout;
+            push(op, out, npix(lvl) * r.cout);
+        } else if (use_tc && (c0 + c1) % tc_cps1 == 0 && c0 % tc_cps1 == 0) {
+            Op op = tc_conv(r.prefix + ".out", G_PW, r.prefix + ".res.wtc", r.prefix + ".res_conv.bias", lvl,
+                            in0, c0, in1, c1, r.cout, out, nullptr);
+            op.tc.epi = EPI_RES; op.tc.rraw = h2; op.tc.rgn = g2; op.tc.out_mask = store_masked ? 1 : 0;
+            op.bytes += 4.0 * npix(lvl) * r.cout;
             push(op, out, npix(lvl) * r.cout);
         } else {
             Op op; op.kind = OP_IGEMM; op.name = r.prefix + ".out";
@@ -534,7 +571,7 @@ static int build_plan(sbk_handle* h, int B, int T, int tb_rows) {
             p.in0 = in0; p.c0 = c0; p.in1 = in1; p.c1 = c1;
             p.w = W(r.prefix + ".res.w"); p.bias = W(r.prefix + ".res_conv.bias");
             p.out = out; p.Cout = r.cout; p.pro = PRO_MASK; p.epi = EPI_RES;
-            p.rraw = Bb; p.rgn = gnref(st2, r.prefix + ".block2", r.cout, lvl);
+            p.rraw = h2; p.rgn = g2; p.out_mask = store_masked ? 1 : 0;
             push(op, out, npix(lvl) * r.cout);
         }
     };
@@ -542,6 +579,7 @@ static int build_plan(sbk_handle* h, int B, int T, int tb_rows) {
     auto attention = [&](int k, int lvl, const float* x, float* out) {
         const AttnInfo& a = h->attns[k];
         const int mt = igemm_mtiles(G_PW, Hs[lvl], Ws[lvl], Hs[lvl], Ws[lvl]);
+        const bool tc_apply = use_tc && a.c % tc_cps1 == 0;
         {
             Op op; op.kind = OP_IGEMM; op.name = a.prefix + ".kvpart";
             op.ig = base_ig(G_PW, lvl, lvl);
@@ -557,18 +595,25 @@ static int build_plan(sbk_handle* h, int B, int T, int tb_rows) {
         }
         {
             Op op; op.kind = OP_MIX; op.name = a.prefix + ".mix";
-            AttnMixParams& p = op.mx;
+            AttnMixParams& p = op.mx; memset(&p, 0, sizeof(p));
             p.ctx = bf.ctx; p.wq = W(a.prefix + ".fn.fn.to_qkv.weight"); p.wout = W(a.prefix + ".fn.fn.to_out.weight");
             p.bout = W(a.prefix + ".fn.fn.to_out.bias"); p.g = W(a.prefix + ".fn.g");
             p.w_eff = bf.w_eff; p.b_eff = bf.b_eff; p.B = B; p.C = a.c;
+            if (tc_apply) { p.tc_nt = conv_tc_ntile(a.c); p.tc_cps = tc_cps1; }
             push(op, nullptr, 0);
         }
-        {
+        if (tc_apply) {
+            // the per-sample (I + g P_b) matrix is written by k_attn_mix directly in the tcgen05 weight-stage layout
+            Op op = tc_conv(a.prefix + ".out", G_PW, "", "", lvl, x, a.c, nullptr, 0, a.c, out, nullptr);
+            op.tc.wpk = bf.w_eff; op.tc.w_bstride_bytes = (long long)a.c * a.c * 4; op.tc.bias = bf.b_eff;
+            op.tc.out_mask = 1;
+            push(op, out, npix(lvl) * a.c);
+        } else {
             Op op; op.kind = OP_IGEMM; op.name = a.prefix + ".out";
             op.ig = base_ig(G_PW, lvl, lvl);
             IgemmParams& p = op.ig;
             p.in0 = x; p.c0 = a.c; p.w = bf.w_eff; p.w_bstride = (long long)a.c * a.c; p.bias = bf.b_eff;
-            p.out = out; p.Cout = a.c; p.pro = PRO_NONE; p.epi = EPI_PLAIN;
+            p.out = out; p.Cout = a.c; p.pro = PRO_NONE; p.epi = EPI_PLAIN; p.out_mask = use_tc ? 1 : 0;
             push(op, out, npix(lvl) * a.c);
         }
     };
@@ -577,40 +622,47 @@ static int build_plan(sbk_handle* h, int B, int T, int tb_rows) {
         op.ig = base_ig(geom, lvl_in, lvl_out);
         IgemmParams& p = op.ig;
         p.in0 = x; p.c0 = C; p.w = W(pre + ".conv.w"); p.bias = W(pre + ".conv.bias");
-        p.out = out; p.Cout = C; p.pro = PRO_MASK; p.epi = EPI_PLAIN;
+        p.out = out; p.Cout = C; p.pro = PRO_MASK; p.epi = EPI_PLAIN; p.out_mask = use_tc ? 1 : 0;
         push(op, out, npix(lvl_out) * C);
     };
 
     const int C1 = dim, C2 = dim * 2, C3 = dim * 4;
     // downs (diffusion.py:190-197)
-    resnet(0, 0, nullptr, cin0, nullptr, 0, bf.X[0]);
-    resnet(1, 0, bf.X[0], C1, nullptr, 0, bf.Y[0]);
+    const bool sm = use_tc;     // store-masked convention only in the tensor-core modes
+    resnet(0, 0, nullptr, cin0, nullptr, 0, bf.X[0], sm);
+    resnet(1, 0, bf.X[0], C1, nullptr, 0, bf.Y[0], false);          // feeds attention: unmasked
     attention(0, 0, bf.Y[0], bf.X[0]);
     resample(G_DOWN, "estimator.downs.0.3", 0, 1, bf.X[0], C1, bf.D[1]);
-    resnet(2, 1, bf.D[1], C1, nullptr, 0, bf.X[1]);
-    resnet(3, 1, bf.X[1], C2, nullptr, 0, bf.Y[1]);
+    resnet(2, 1, bf.D[1], C1, nullptr, 0, bf.X[1], sm);
+    resnet(3, 1, bf.X[1], C2, nullptr, 0, bf.Y[1], false);
     attention(1, 1, bf.Y[1], bf.S[1]);
     resample(G_DOWN, "estimator.downs.1.3", 1, 2, bf.S[1], C2, bf.D[2]);
-    resnet(4, 2, bf.D[2], C2, nullptr, 0, bf.X[2]);
-    resnet(5, 2, bf.X[2], C3, nullptr, 0, bf.Y[2]);
+    resnet(4, 2, bf.D[2], C2, nullptr, 0, bf.X[2], sm);
+    resnet(5, 2, bf.X[2], C3, nullptr, 0, bf.Y[2], false);
     attention(2, 2, bf.Y[2], bf.S[2]);
-    // mid (:199-203); Identity()(x*mask) is absorbed by the consumers' mask prologue
-    resnet(6, 2, bf.S[2], C3, nullptr, 0, bf.X[2]);
+    // mid (:199-203); Identity()(x*mask) is absorbed by the consumers' masking
+    resnet(6, 2, bf.S[2], C3, nullptr, 0, bf.X[2], false);
     attention(3, 2, bf.X[2], bf.Y[2]);
-    resnet(7, 2, bf.Y[2], C3, nullptr, 0, bf.X[2]);
+    resnet(7, 2, bf.Y[2], C3, nullptr, 0, bf.X[2], sm);
     // ups (:205-211): cat(x, skip) is pure addressing (two input pointers)
-    resnet(8, 2, bf.X[2], C3, bf.S[2], C3, bf.Y[2]);
-    resnet(9, 2, bf.Y[2], C2, nullptr, 0, bf.X[2]);
+    resnet(8, 2, bf.X[2], C3, bf.S[2], C3, bf.Y[2], sm);
+    resnet(9, 2, bf.Y[2], C2, nullptr, 0, bf.X[2], false);
     attention(4, 2, bf.X[2], bf.Y[2]);
     resample(G_UP, "estimator.ups.0.3", 2, 1, bf.Y[2], C2, bf.U1);
-    resnet(10, 1, bf.U1, C2, bf.S[1], C2, bf.X[1]);
-    resnet(11, 1, bf.X[1], C1, nullptr, 0, bf.Y[1]);
+    resnet(10, 1, bf.U1, C2, bf.S[1], C2, bf.X[1], sm);
+    resnet(11, 1, bf.X[1], C1, nullptr, 0, bf.Y[1], false);
     attention(5, 1, bf.Y[1], bf.X[1]);
     resample(G_UP, "estimator.ups.1.3", 1, 0, bf.X[1], C1, bf.Y[0]);
     // final_block + final_conv + update (:213-216)
     double* stf = stats_slot();
-    block_conv("estimator.final_block.raw", "estimator.final_block.w", "estimator.final_block.block.0.bias", 0,
-               bf.Y[0], C1, nullptr, 0, C1, bf.A[0], stf, PRO_MASK, nullptr, 0);
+    if (use_tc) {
+        Op op = tc_conv("estimator.final_block.raw", G_C3, "estimator.final_block.wtc", "estimator.final_block.block.0.bias", 0,
+                        bf.Y[0], C1, nullptr, 0, C1, bf.A[0], stf);
+        push(op, bf.A[0], npix(0) * C1);
+    } else {
+        ffma_block_conv("estimator.final_block.raw", "estimator.final_block.w", "estimator.final_block.block.0.bias", 0,
+                        bf.Y[0], C1, nullptr, 0, C1, bf.A[0], stf, PRO_MASK, nullptr, 0);
+    }
     {
         Op op; op.kind = OP_FINAL; op.name = "estimator.out";
         FinalParams& p = op.fn; memset(&p, 0, sizeof(p));
@@ -638,6 +690,7 @@ static int run_ops(sbk_handle* h, cudaStream_t s) {
             case OP_MIX: n += launch_attn_mix(op.mx, s); break;
             case OP_FINAL: n += launch_final(op.fn, s); break;
             case OP_CONVTC: n += launch_conv_tc(op.tc, s); break;
+            case OP_GNACT: n += launch_gn_act(op.ga, s); break;
         }
         if (h->capture && op.dbg_ptr && op.dbg_numel > 0) {
             if (!op.dbg_copy) cudaMalloc(&op.dbg_copy, op.dbg_numel * sizeof(float));
@@ -687,7 +740,7 @@ static void set_mode(Plan& pl, int mode, bool per_sample_t, float* out) {
     for (auto& op : pl.ops)
         if (op.kind == OP_IGEMM && op.ig.pro == PRO_GN) op.ig.tb_per_sample = per_sample_t ? 1 : 0;
     for (auto& op : pl.ops)
-        if (op.kind == OP_CONVTC && op.tc.pro == PRO_GN) op.tc.tb_per_sample = per_sample_t ? 1 : 0;
+        if (op.kind == OP_GNACT) op.ga.tb_per_sample = per_sample_t ? 1 : 0;
     FinalParams& f = pl.ops[pl.final_op].fn;
     f.mode = mode; f.xt_out = out; f.noise_pp = pl.noise_pp;
 }
@@ -869,6 +922,7 @@ extern "C" int sbk_profile_ops(sbk_handle* h, float* ms, double* flops, double* 
             case OP_MIX: launch_attn_mix(op.mx, s); break;
             case OP_FINAL: launch_final(op.fn, s); break;
             case OP_CONVTC: launch_conv_tc(op.tc, s); break;
+            case OP_GNACT: launch_gn_act(op.ga, s); break;
         }
     }
     CU(cudaEventRecord(ev[n], s));

@@ -1,25 +1,28 @@
-// tcgen05 implicit-GEMM 3x3 convolution for sm_100a (the Block convs: 81.5 % of the step's MACs).
+// tcgen05 implicit-GEMM convolutions for sm_100a: the 3x3 Block convs (81.5 % of the step's MACs) and the 1x1
+// channel mixes (res_conv, attention apply).  tf32 (or bf16) operands, fp32 accumulation in TMEM.
 //
-//   D[pixel][cout] (fp32, TMEM) += A[pixel][tap, cin] (smem, tf32|bf16) * W[cout][tap, cin] (smem, tf32|bf16)
+//   D[pixel][cout] (fp32, TMEM) += A[pixel][tap, cin] (smem) * W[cout][tap, cin] (smem)
 //
-// Mapping.  One CTA owns an output tile of ROWS=2 mel rows x 128 frames x NT output channels of one
-// sample.  M = 128 consecutive frames of one row is one UMMA (M=128, N=NT, K=32 bytes); the two rows use two
-// TMEM accumulators (2*NT columns) and share every weight stage.  K runs over (input-channel stage, 9 taps).
+// Mapping.  One CTA owns ROWS=2 rows of 128 pixels x NT output channels of one sample.  Each row is one UMMA
+// (M=128, N=NT, K=32 bytes) per tap and K step; the two rows use two TMEM accumulators (2*NT columns) and share
+// every weight stage.  For the 3x3 conv a row is 128 consecutive frames of one mel bin; for 1x1 convs the image
+// is flattened and a row is any 128 consecutive pixels.
 //
-// A operand: the activations are NHWC fp32 in HBM and must be normalised (GroupNorm apply), activated (Mish),
-// masked and biased by the time projection before the conv (diffusion.py:56-58,76) - so TMA cannot stage them.
-// Eight producer warps load the (ROWS+2) x 130-pixel halo of a channel stage once, apply that prologue in
-// registers, round to tf32/bf16 and store it to shared memory in the UMMA "interleaved" (no-swizzle) K-major
-// layout: [16-byte channel chunk][halo row][pixel][16 B].  In that layout 8 consecutive pixels x 16 B form one
-// core matrix, so EVERY one of the 9 taps is just a different start address into the same halo tile
-// (start += (r*130 + s)*16 B): one load + one transform per input element, nine MMAs.
+// A operand.  Conv inputs are stored in HBM already in operand form (masked; Block activations GroupNorm-ed,
+// Mish-ed and time-biased by k_gn_act, see sbk_kernels.cu), so producing the A tile is a pure copy: eight
+// producer warps issue 16-byte cp.async (LDGSTS, zero-fill outside the image = the conv's zero padding) straight
+// into the UMMA no-swizzle K-major layout [16 B channel chunk][halo row][pixel][16 B].  In that layout eight
+// consecutive pixels x 16 B are one core matrix, so EVERY one of the nine taps is only a different descriptor
+// start address into the same halo tile (start += (r*130 + s)*16 B): each input element is fetched once per CTA
+// and feeds nine MMAs.  (v1 of this kernel applied GN+Mish in the producers; the MUFU/ALU work made those convs
+// 3x slower than the copy-only ones - profiles/r1_ops_tf32_v1.txt - hence the separate elementwise pass.)
 //
-// B operand: weights are packed on the host into exactly the per-stage shared-memory image
-// [tap][chunk][cout][16 B] and streamed with one cp.async.bulk per stage (mbarrier complete_tx).
+// B operand.  Weights are packed on the host into exactly the per-stage shared-memory image
+// [tap][chunk][cout][16 B] and streamed with one cp.async.bulk (UBLKCP) per stage, mbarrier complete_tx.
 //
-// Pipeline: STAGES-deep ring of {A halo, B weights} with full_a/full_b/empty mbarriers; a single thread issues
-// tcgen05.mma and releases stages with tcgen05.commit; the epilogue (same 8 warps) reads the accumulators with
-// tcgen05.ld, adds the bias, writes NHWC fp32 and accumulates the GroupNorm {sum, sumsq} of the raw output.
+// Pipeline.  STAGES-deep ring with full_a / full_b / empty mbarriers; one thread issues tcgen05.mma and frees
+// stages with tcgen05.commit; the epilogue (the eight producer warps) reads the accumulators with tcgen05.ld.
+// All waits are bounded spins that trap instead of hanging the GPU.
 #include "sbk_internal.h"
 
 #include <cuda_bf16.h>
@@ -30,15 +33,16 @@ namespace sbk {
 
 namespace tc {
 
-constexpr int ROWS = 2;               // output mel rows per CTA
-constexpr int HR = ROWS + 2;          // halo rows
-constexpr int TPX = 128;              // output frames per CTA row (= UMMA M)
-constexpr int PXP = TPX + 2;          // halo pixels per row
-constexpr int KCH = 2;                // 16-byte K chunks per stage (= one UMMA K step of 32 bytes)
+constexpr int ROWS = 2;               // M=128 pixel rows per CTA (two TMEM accumulators share every weight stage)
+constexpr int TPX = 128;              // pixels per row (= UMMA M)
 constexpr int STAGES = 3;
 constexpr int NPROD = 256;            // producer / epilogue threads (8 warps)
 constexpr int NTHREADS = NPROD + 64;  // + MMA warp + weight-loader warp
-constexpr int A_STAGE_BYTES = KCH * HR * PXP * 16;
+
+// geometry of the A tile in shared memory, [16-byte K chunk][row][pixel][16 B]
+template <int GEOM> struct Geo;
+template <> struct Geo<G_C3> { static constexpr int HR = ROWS + 2, PXP = TPX + 2, TAPS = 9, KCH = 2; };   // 3x3: halo tile
+template <> struct Geo<G_PW> { static constexpr int HR = ROWS, PXP = TPX, TAPS = 1, KCH = 8; };           // 1x1: plain tile
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -151,33 +155,55 @@ __device__ __forceinline__ uint32_t to_tf32(float x) {
     return r;
 }
 
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ float mish_acc(float x) {     // exact-math Mish for the fp32 epilogues (see sbk_kernels.cu)
+    const float n = expf(fminf(x, 20.f));
+    const float a = n * (n + 2.f);
+    return x > 20.f ? x : x * (a / (a + 2.f));
+}
+
 }  // namespace tc
 
 using namespace tc;
 
-// channels consumed per pipeline stage: KCH chunks x (4 tf32 | 8 bf16) elements
-template <bool BF16> struct StageCh { static constexpr int value = KCH * (BF16 ? 8 : 4); };
-
-template <bool BF16, int NT>
-__global__ void __launch_bounds__(NTHREADS, 1) k_conv3x3_tc(const ConvTcParams p) {
-    constexpr int CPS = StageCh<BF16>::value;              // input channels per stage
-    constexpr int F4 = CPS / 4;                            // float4 loads per halo pixel per stage
-    constexpr int B_STAGE_BYTES = 9 * KCH * NT * 16;
+template <int GEOM, bool BF16, int NT>
+__global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvTcParams p) {
+    using G = Geo<GEOM>;
+    constexpr int HR = G::HR, PXP = G::PXP, TAPS = G::TAPS, KCH = G::KCH;
+    constexpr int EPC = BF16 ? 8 : 4;                      // elements per 16-byte chunk
+    constexpr int ESZ = BF16 ? 2 : 4;
+    constexpr int CPS = KCH * EPC;                         // input channels per stage
+    constexpr int PLANE = HR * PXP * 16;                   // bytes between K chunks of the A tile
+    constexpr int A_STAGE_BYTES = KCH * PLANE;
+    constexpr int B_STAGE_BYTES = TAPS * KCH * NT * 16;
     constexpr uint32_t TMEM_COLS = ROWS * NT;              // 128 or 256: a power of two >= 32
 
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sA = smem;                                            // [STAGES][KCH][HR][PXP][16]
-    uint8_t* sB = sA + STAGES * A_STAGE_BYTES;                     // [STAGES][9][KCH][NT][16]
-    float* s_tab = reinterpret_cast<float*>(sB + STAGES * B_STAGE_BYTES);   // mean|scale|beta|tb : 4*Cin
-    const int Cin = p.c0 + p.c1;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_tab + 4 * Cin);         // full_a[S], full_b[S], empty[S], acc
-    float* s_st = reinterpret_cast<float*>(bars + 3 * STAGES + 1);         // [8 groups][2]
+    uint8_t* sB = sA + STAGES * A_STAGE_BYTES;                     // [STAGES][TAPS][KCH][NT][16]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + STAGES * B_STAGE_BYTES);   // full_a[S], full_b[S], empty[S], acc
+    float* s_st = reinterpret_cast<float*>(bars + 3 * STAGES + 1);               // [8 groups][2]
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_st + 16);
+    float* s_rg = reinterpret_cast<float*>(s_tmem + 4);                          // EPI_RES: mean|scale|beta [NT] each
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int wtiles = (p.W + TPX - 1) / TPX;
-    const int w0 = (blockIdx.x % wtiles) * TPX;
-    const int h0 = (blockIdx.x / wtiles) * ROWS;
+    const int Cin = p.c0 + p.c1;
+    const int HW = p.H * p.W;
+    int w0, h0;
+    if (GEOM == G_C3) {
+        const int wtiles = (p.W + TPX - 1) / TPX;
+        w0 = (blockIdx.x % wtiles) * TPX;
+        h0 = (blockIdx.x / wtiles) * ROWS;
+    } else {
+        w0 = 0;
+        h0 = blockIdx.x * ROWS;                // row = 128 consecutive pixels of the flattened image
+    }
     const int n0 = blockIdx.y * NT;
     const int b = blockIdx.z;
     const int ksteps = Cin / CPS;
@@ -196,24 +222,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv3x3_tc(const ConvTcParams p
     }
     if (warp == NPROD / 32) tmem_alloc(smem_u32(s_tmem), TMEM_COLS);
     if (tid < 16) s_st[tid] = 0.f;
-    // prologue tables (GroupNorm apply + time projection of the producing Block), all Cin channels
-    {
-        float* mean = s_tab; float* scale = mean + Cin; float* beta = scale + Cin; float* tbv = beta + Cin;
-        if (p.pro == PRO_GN) {
-            const int cpg = Cin / kGroups;
-            const int row = p.tb_per_sample ? b : *p.step;
-            const float* tb = p.tb + (long long)row * p.tb_stride;
-            for (int c = tid; c < Cin; c += NTHREADS) {
-                const int g = c / cpg;
-                const double s = p.pgn.stats[(b * kGroups + g) * 2], ss = p.pgn.stats[(b * kGroups + g) * 2 + 1];
-                const double m = s * (double)p.pgn.inv_count;
-                double var = ss * (double)p.pgn.inv_count - m * m;
-                var = var < 0.0 ? 0.0 : var;
-                mean[c] = (float)m;
-                scale[c] = (float)(1.0 / sqrt(var + 1e-5)) * p.pgn.gamma[c];
-                beta[c] = p.pgn.beta[c];
-                tbv[c] = tb[c];
-            }
+    if (p.epi == EPI_RES) {
+        const int cpg = p.Cout / kGroups;
+        for (int i = tid; i < NT; i += NTHREADS) {
+            const int c = n0 + i, g = c / cpg;
+            const double s = p.rgn.stats[(b * kGroups + g) * 2], ss = p.rgn.stats[(b * kGroups + g) * 2 + 1];
+            const double m = s * (double)p.rgn.inv_count;
+            double var = ss * (double)p.rgn.inv_count - m * m;
+            var = var < 0.0 ? 0.0 : var;
+            s_rg[i] = (float)m;
+            s_rg[NT + i] = (float)(1.0 / sqrt(var + 1e-5)) * p.rgn.gamma[c];
+            s_rg[2 * NT + i] = p.rgn.beta[c];
         }
     }
     tc_fence_before();
@@ -222,88 +241,53 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv3x3_tc(const ConvTcParams p
     const uint32_t tmem_base = *s_tmem;
 
     if (warp < NPROD / 32) {
-        // =============================== A producers ===============================
-        // item it -> halo (row r, pixel q); each item = CPS channels = F4 float4 loads = KCH 16-byte smem chunks
-        constexpr int ITEMS = HR * PXP;                       // 520
-        constexpr int PER = (ITEMS + NPROD - 1) / NPROD;      // 3 (last round: 8 threads)
-        const float* mean = s_tab; const float* scale = mean + Cin; const float* beta = scale + Cin; const float* tbv = beta + Cin;
-        int it_r[PER], it_q[PER]; bool it_ok[PER]; float it_mask[PER]; long long it_off[PER];
+        // =============================== A producers: pure cp.async copy ===============================
+        // copy slot e -> (pixel item = e / KCH, chunk = e % KCH): the KCH chunks of a pixel are contiguous in HBM
+        constexpr int SLOTS = HR * PXP * KCH;
+        constexpr int PER = (SLOTS + NPROD - 1) / NPROD;
+        uint32_t sl_dst[PER]; long long sl_pix[PER]; int sl_chunk[PER]; bool sl_ok[PER];
 #pragma unroll
         for (int j = 0; j < PER; ++j) {
-            const int it = tid + j * NPROD;
-            const bool in = it < ITEMS;
-            const int r = in ? it / PXP : 0, q = in ? it - r * PXP : 0;
-            const int hi = h0 - 1 + r, wi = w0 - 1 + q;
-            it_r[j] = r; it_q[j] = q;
-            it_ok[j] = in && hi >= 0 && hi < p.H && wi >= 0 && wi < p.W;
-            it_mask[j] = (it_ok[j] && p.pro != PRO_NONE) ? __ldg(p.mask + (long long)b * p.T + ((long long)wi << p.lvl)) : (it_ok[j] ? 1.f : 0.f);
-            it_off[j] = ((long long)(b * p.H + hi) * p.W + wi);
-            if (!in) it_r[j] = -1;
+            const int e = tid + j * NPROD;
+            const bool in = e < SLOTS;
+            const int item = in ? e / KCH : 0, k = in ? e % KCH : 0;
+            const int r = item / PXP, q = item - r * PXP;
+            bool ok; long long pix;
+            if (GEOM == G_C3) {
+                const int hi = h0 - 1 + r, wi = w0 - 1 + q;
+                ok = in && hi >= 0 && hi < p.H && wi >= 0 && wi < p.W;
+                pix = (long long)(b * p.H + hi) * p.W + wi;
+            } else {
+                const long long m = (long long)(h0 + r) * TPX + q;
+                ok = in && m < HW;
+                pix = (long long)b * HW + m;
+            }
+            sl_ok[j] = ok; sl_pix[j] = ok ? pix : 0; sl_chunk[j] = k;
+            sl_dst[j] = in ? (uint32_t)(k * PLANE + (r * PXP + q) * 16) : 0xFFFFFFFFu;
         }
-        float4 cur[PER][F4], nxt[PER][F4];
-        auto load = [&](int ks, float4 (&dst)[PER][F4]) {
-            const int cc = ks * CPS;
-            const bool second = cc >= p.c0;
-            const float* src = second ? p.in1 : p.in0;
-            const int cs = second ? p.c1 : p.c0;
-            const int co = second ? cc - p.c0 : cc;
+        const uint32_t a0 = smem_u32(sA);
+        for (int ks = 0; ks <= ksteps; ++ks) {
+            if (ks < ksteps) {
+                const int s = ks % STAGES;
+                mbar_wait(empty(s), ((ks / STAGES) & 1) ^ 1);
+                const int cc = ks * CPS;
+                const bool second = cc >= p.c0;
+                const uint8_t* src = reinterpret_cast<const uint8_t*>(second ? p.in1 : p.in0);
+                const long long cs = (second ? p.c1 : p.c0) * (long long)ESZ;      // pixel stride in bytes
+                const long long co = (long long)(second ? cc - p.c0 : cc) * ESZ;
 #pragma unroll
-            for (int j = 0; j < PER; ++j) {
-                if (it_ok[j] && it_mask[j] != 0.f) {
-                    const float* g = src + it_off[j] * cs + co;
-#pragma unroll
-                    for (int f = 0; f < F4; ++f) dst[j][f] = __ldg(reinterpret_cast<const float4*>(g) + f);
-                } else {
-#pragma unroll
-                    for (int f = 0; f < F4; ++f) dst[j][f] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int j = 0; j < PER; ++j) {
+                    if (sl_dst[j] == 0xFFFFFFFFu) continue;
+                    cp_async16(a0 + s * A_STAGE_BYTES + sl_dst[j], src + sl_pix[j] * cs + co + sl_chunk[j] * 16, sl_ok[j] ? 16u : 0u);
                 }
             }
-        };
-        load(0, cur);
-        for (int ks = 0; ks < ksteps; ++ks) {
-            const int s = ks % STAGES;
-            if (ks + 1 < ksteps) load(ks + 1, nxt);
-            mbar_wait(empty(s), ((ks / STAGES) & 1) ^ 1);
-            uint8_t* stage = sA + s * A_STAGE_BYTES;
-            const int cc = ks * CPS;
-#pragma unroll
-            for (int j = 0; j < PER; ++j) {
-                if (it_r[j] < 0) continue;
-                float v[CPS];
-#pragma unroll
-                for (int f = 0; f < F4; ++f) { v[4 * f] = cur[j][f].x; v[4 * f + 1] = cur[j][f].y; v[4 * f + 2] = cur[j][f].z; v[4 * f + 3] = cur[j][f].w; }
-                const bool live = it_ok[j] && it_mask[j] != 0.f;
-                if (p.pro == PRO_GN) {
-#pragma unroll
-                    for (int e = 0; e < CPS; ++e) {
-                        const int c = cc + e;
-                        v[e] = live ? mish_fast((v[e] - mean[c]) * scale[c] + beta[c]) + tbv[c] : 0.f;
-                    }
-                }   // PRO_MASK / PRO_NONE: masked or out-of-range pixels were loaded as zeros, mask is {0,1}
-                uint8_t* dst = stage + ((0 * HR + it_r[j]) * PXP + it_q[j]) * 16;
-#pragma unroll
-                for (int k = 0; k < KCH; ++k) {
-                    uint4 w;
-                    if (BF16) {
-                        __nv_bfloat162 h0v = __floats2bfloat162_rn(v[8 * k + 0], v[8 * k + 1]);
-                        __nv_bfloat162 h1v = __floats2bfloat162_rn(v[8 * k + 2], v[8 * k + 3]);
-                        __nv_bfloat162 h2v = __floats2bfloat162_rn(v[8 * k + 4], v[8 * k + 5]);
-                        __nv_bfloat162 h3v = __floats2bfloat162_rn(v[8 * k + 6], v[8 * k + 7]);
-                        w.x = *reinterpret_cast<uint32_t*>(&h0v); w.y = *reinterpret_cast<uint32_t*>(&h1v);
-                        w.z = *reinterpret_cast<uint32_t*>(&h2v); w.w = *reinterpret_cast<uint32_t*>(&h3v);
-                    } else {
-                        w.x = to_tf32(v[4 * k + 0]); w.y = to_tf32(v[4 * k + 1]); w.z = to_tf32(v[4 * k + 2]); w.w = to_tf32(v[4 * k + 3]);
-                    }
-                    *reinterpret_cast<uint4*>(dst + k * (HR * PXP * 16)) = w;
-                }
+            cp_async_commit();
+            if (ks > 0) {
+                cp_async_wait<1>();                  // this thread's copies of stage ks-1 have landed
+                fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor core (async proxy)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full_a((ks - 1) % STAGES));
             }
-            fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor core (async proxy)
-            __syncwarp();
-            if (lane == 0) mbar_arrive(full_a(s));
-#pragma unroll
-            for (int j = 0; j < PER; ++j)
-#pragma unroll
-                for (int f = 0; f < F4; ++f) cur[j][f] = nxt[j][f];
         }
 
         // =============================== epilogue ===============================
@@ -311,17 +295,52 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv3x3_tc(const ConvTcParams p
         tc_fence_after();
         const int q4 = warp & 3, jrow = warp >> 2;            // TMEM lane quarter / accumulator (output row)
         const int px = q4 * 32 + lane;
-        const int ho = h0 + jrow, wo = w0 + px;
-        const bool valid = ho < p.H && wo < p.W;
+        long long opix; int wo; bool valid;
+        if (GEOM == G_C3) {
+            const int ho = h0 + jrow;
+            wo = w0 + px;
+            valid = ho < p.H && wo < p.W;
+            opix = (long long)(b * p.H + ho) * p.W + wo;
+        } else {
+            const long long m = (long long)(h0 + jrow) * TPX + px;
+            valid = m < HW;
+            wo = (int)(m % p.W);
+            opix = (long long)b * HW + m;
+        }
+        if (!valid) { opix = 0; wo = 0; }
+        const float mo = (p.out_mask || p.epi == EPI_RES) ? __ldg(p.mask + (long long)b * p.T + ((long long)wo << p.lvl)) : 1.f;
         const int cpg = p.Cout / kGroups;
-        float* op = p.out + ((long long)(b * p.H + ho) * p.W + wo) * p.Cout + n0;
+        const float* bp = p.bias ? p.bias + (long long)b * p.bias_bstride + n0 : nullptr;
+        float* op = p.out + opix * p.Cout + n0;
 #pragma unroll 1
         for (int cb = 0; cb < NT; cb += 32) {
             uint32_t r[32];
             tmem_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(jrow * NT + cb), r);
             float v[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + __ldg(p.bias + n0 + cb + i);
+            for (int i = 0; i < 32; i += 4) {
+                const float4 bb = bp ? __ldg(reinterpret_cast<const float4*>(bp + cb + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                v[i] = __uint_as_float(r[i]) + bb.x; v[i + 1] = __uint_as_float(r[i + 1]) + bb.y;
+                v[i + 2] = __uint_as_float(r[i + 2]) + bb.z; v[i + 3] = __uint_as_float(r[i + 3]) + bb.w;
+            }
+            if (p.epi == EPI_RES && valid && mo != 0.f) {
+                // ResnetBlock tail: + Mish(GN(h2raw)) * mask  (diffusion.py:77-78)
+                const float* rp = p.rraw + opix * p.Cout + n0 + cb;
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    const float4 rv = __ldg(reinterpret_cast<const float4*>(rp + i));
+                    const float rr[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int cl = cb + i + e;
+                        v[i + e] += mish_acc((rr[e] - s_rg[cl]) * s_rg[NT + cl] + s_rg[2 * NT + cl]);
+                    }
+                }
+            }
+            if (p.out_mask) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] *= mo;
+            }
             if (valid) {
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(op + cb + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
@@ -368,15 +387,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv3x3_tc(const ConvTcParams p
                 mbar_wait(full_b(s), ph);
                 tc_fence_after();
 #pragma unroll
-                for (int tap = 0; tap < 9; ++tap) {
-                    const int r = tap / 3, sx = tap % 3;
-                    const uint64_t bd = p.dbg_swap ? make_desc(b0 + s * B_STAGE_BYTES + tap * (KCH * NT * 16), 128, NT * 16)
-                                                   : make_desc(b0 + s * B_STAGE_BYTES + tap * (KCH * NT * 16), NT * 16, 128);
+                for (int kk = 0; kk < KCH / 2; ++kk) {
 #pragma unroll
-                    for (int j = 0; j < ROWS; ++j) {
-                        const uint32_t aaddr = a0 + s * A_STAGE_BYTES + ((r + j) * PXP + sx) * 16;
-                        const uint64_t ad = p.dbg_swap ? make_desc(aaddr, 128, HR * PXP * 16) : make_desc(aaddr, HR * PXP * 16, 128);
-                        umma<BF16>(tmem_base + j * NT, ad, bd, idesc, (ks | tap) != 0 ? 1u : 0u);
+                    for (int tap = 0; tap < TAPS; ++tap) {
+                        const int r = GEOM == G_C3 ? tap / 3 : 0, sx = GEOM == G_C3 ? tap % 3 : 0;
+                        const uint64_t bd = make_desc(b0 + s * B_STAGE_BYTES + (tap * KCH + kk * 2) * (NT * 16), NT * 16, 128);
+#pragma unroll
+                        for (int j = 0; j < ROWS; ++j) {
+                            const uint64_t ad = make_desc(a0 + s * A_STAGE_BYTES + kk * 2 * PLANE + ((r + j) * PXP + sx) * 16, PLANE, 128);
+                            umma<BF16>(tmem_base + j * NT, ad, bd, idesc, (ks | kk | tap) != 0 ? 1u : 0u);
+                        }
                     }
                 }
                 umma_commit(empty(s));                  // frees the stage when these MMAs have read it
@@ -386,7 +406,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv3x3_tc(const ConvTcParams p
     } else {
         // =============================== weight loader ===============================
         if (lane == 0) {
-            const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpk) + (size_t)blockIdx.y * ksteps * B_STAGE_BYTES;
+            const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpk) + (size_t)b * p.w_bstride_bytes +
+                                  (size_t)blockIdx.y * ksteps * B_STAGE_BYTES;
             for (int ks = 0; ks < ksteps; ++ks) {
                 const int s = ks % STAGES;
                 mbar_wait(empty(s), ((ks / STAGES) & 1) ^ 1);
@@ -407,32 +428,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv3x3_tc(const ConvTcParams p
     }
 }
 
-template <bool BF16, int NT>
-static size_t conv_tc_smem(int Cin) {
-    return (size_t)STAGES * (A_STAGE_BYTES + 9 * KCH * NT * 16) + 4 * (size_t)Cin * sizeof(float) + (3 * STAGES + 1) * 8 + 16 * 4 + 16;
-}
-
-template <bool BF16, int NT>
+template <int GEOM, bool BF16, int NT>
 static int launch_tc(const ConvTcParams& p, cudaStream_t s) {
-    const size_t sm = conv_tc_smem<BF16, NT>(p.c0 + p.c1);
+    using G = Geo<GEOM>;
+    const size_t sm = (size_t)STAGES * (G::KCH * G::HR * G::PXP * 16 + G::TAPS * G::KCH * NT * 16) + (3 * STAGES + 1) * 8 +
+                      16 * 4 + 16 + 3 * NT * 4 + 64;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(k_conv3x3_tc<BF16, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(k_conv_tc<GEOM, BF16, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         attr_set = true;
     }
-    const int wt = (p.W + TPX - 1) / TPX, ht = (p.H + ROWS - 1) / ROWS;
-    dim3 grid(wt * ht, p.Cout / NT, p.B);
-    k_conv3x3_tc<BF16, NT><<<grid, NTHREADS, sm, s>>>(p);
+    int gx;
+    if (GEOM == G_C3) gx = ((p.W + TPX - 1) / TPX) * ((p.H + ROWS - 1) / ROWS);
+    else gx = (p.H * p.W + ROWS * TPX - 1) / (ROWS * TPX);
+    dim3 grid(gx, p.Cout / NT, p.B);
+    k_conv_tc<GEOM, BF16, NT><<<grid, NTHREADS, sm, s>>>(p);
     return 1;
 }
 
 int conv_tc_ntile(int Cout) { return Cout % 128 == 0 ? 128 : 64; }
-int conv_tc_stage_channels(int bf16) { return bf16 ? StageCh<true>::value : StageCh<false>::value; }
+int conv_tc_stage_channels(int geom, int bf16) {
+    const int epc = bf16 ? 8 : 4;
+    return (geom == G_C3 ? Geo<G_C3>::KCH : Geo<G_PW>::KCH) * epc;
+}
 
 int launch_conv_tc(const ConvTcParams& p, cudaStream_t s) {
     const int nt = conv_tc_ntile(p.Cout);
-    if (p.bf16) return nt == 128 ? launch_tc<true, 128>(p, s) : launch_tc<true, 64>(p, s);
-    return nt == 128 ? launch_tc<false, 128>(p, s) : launch_tc<false, 64>(p, s);
+    if (p.bf16) return -1;   // bf16 operand tensors are not wired up yet
+    if (p.geom == G_C3) return nt == 128 ? launch_tc<G_C3, false, 128>(p, s) : launch_tc<G_C3, false, 64>(p, s);
+    return nt == 128 ? launch_tc<G_PW, false, 128>(p, s) : launch_tc<G_PW, false, 64>(p, s);
 }
 
 }  // namespace sbk

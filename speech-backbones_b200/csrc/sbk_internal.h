@@ -44,19 +44,31 @@ struct IgemmParams {
     double* ostats;                               // EPI_PLAIN: accumulate GN statistics of `out` (nullable)
     const float* rraw; GnRef rgn; int out_lvl;    // EPI_RES: out = acc + bias + Mish(GN(rraw))*mask
     float* kv_part;                               // EPI_KV: [B][mtiles][4][kKvPartFloats]
+    int out_mask;                                 // multiply the stored output by mask[b][wo << out_lvl]
 };
 
-// tcgen05 3x3 convolution (sbk_conv_tc.cu): same prologue/epilogue contract as the G_C3 igemm, EPI_PLAIN only
+// tcgen05 convolution (sbk_conv_tc.cu).  Inputs are operand-form tensors: already masked / activated, so the
+// kernel's A path is a pure copy.  geom = G_C3 (3x3, pad 1) or G_PW (1x1 over the flattened image).
 struct ConvTcParams {
-    const float* in0; const float* in1; int c0, c1;
+    int geom;
+    const void* in0; const void* in1; int c0, c1;   // channel concat of two NHWC tensors (fp32, or bf16 when bf16=1)
     int H, W, B;
-    const void* wpk;              // [ntile][kstage][tap 9][chunk 2][cout NT][16 B] tf32-rounded fp32 or bf16
-    const float* bias; float* out; int Cout;
-    int pro; const float* mask; int T; int lvl;
-    GnRef pgn; const float* tb; int tb_stride; int tb_per_sample; const int* step;
-    double* ostats;
-    int bf16;                     // 0: kind::tf32, 1: kind::f16 (bf16 operands)
-    int dbg_swap;                 // debug: swap LBO/SBO in the smem descriptors
+    const void* wpk; long long w_bstride_bytes;     // [ntile][kstage][tap][chunk][cout NT][16 B] (+ per-sample stride)
+    const float* bias; long long bias_bstride;
+    float* out; int Cout;
+    int epi;                                        // EPI_PLAIN | EPI_RES
+    double* ostats;                                 // EPI_PLAIN: GroupNorm statistics of the raw output (nullable)
+    const float* mask; int T; int lvl; int out_mask;   // out_mask: multiply the stored output by mask[b][wo << lvl]
+    const float* rraw; GnRef rgn;                   // EPI_RES: out = acc + bias + Mish(GN(rraw))*mask
+    int bf16;
+};
+
+// Block activation between the two convs of a ResnetBlock, written once in operand form (diffusion.py:57,76):
+//   act = mask ? tf32(Mish(GN(raw)) + tproj) : 0
+struct GnActParams {
+    const float* raw; GnRef gn; const float* tb; int tb_stride; int tb_per_sample; const int* step;
+    const float* mask; int T; int lvl;
+    float* out; int B, H, W, C; int round_tf32;
 };
 
 struct FirstConvParams {        // Block.conv of downs.0.0.block1 on the planar stack([mu, xt(, s)]) * mask
@@ -76,6 +88,7 @@ struct ResFinalParams {         // out = Mish(GN(h2raw))*mask + res(x*mask)
     const float* mask; int T; int lvl;
     float* out;
     int B, H, W, C;
+    int out_mask;               // store out*mask (operand form for the next conv)
 };
 
 struct AttnCtxParams {          // merge per-tile softmax partials -> normalised context [B][4][32][32]
@@ -91,6 +104,7 @@ struct AttnMixParams {          // A_b = I + g * Wout * blockdiag(ctx^T) * Wq ; 
     float* w_eff;               // [B][C(ci)][C(co)]
     float* b_eff;               // [C]
     int B, C;
+    int tc_nt, tc_cps;          // != 0: write w_eff in the tcgen05 1x1 weight-stage layout (tf32-rounded)
 };
 
 struct FinalParams {            // final_block GN+Mish, final_conv 1x1 -> 1, mask, Euler(-Maruyama) update
@@ -128,7 +142,8 @@ int launch_igemm(const IgemmParams& p, cudaStream_t s);
 int launch_first_conv(const FirstConvParams& p, cudaStream_t s);
 int launch_conv_tc(const ConvTcParams& p, cudaStream_t s);
 int conv_tc_ntile(int Cout);
-int conv_tc_stage_channels(int bf16);
+int conv_tc_stage_channels(int geom, int bf16);
+int launch_gn_act(const GnActParams& p, cudaStream_t s);
 int launch_resfinal(const ResFinalParams& p, cudaStream_t s);
 int launch_attn_ctx(const AttnCtxParams& p, cudaStream_t s);
 int launch_attn_mix(const AttnMixParams& p, cudaStream_t s);

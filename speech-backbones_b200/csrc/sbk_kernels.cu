@@ -327,6 +327,11 @@ __global__ void __launch_bounds__(IG_THREADS, 3) k_igemm(const IgemmParams p) {
                 st_s[1] += v[4 + j]; st_q[1] = fmaf(v[4 + j], v[4 + j], st_q[1]);
             }
         }
+        if (p.out_mask) {
+            const float mo = __ldg(p.mask + (long long)b * p.T + ((long long)wo << p.out_lvl));
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] *= mo;
+        }
         *reinterpret_cast<float4*>(op + tx * 4) = make_float4(v[0], v[1], v[2], v[3]);
         *reinterpret_cast<float4*>(op + 32 + tx * 4) = make_float4(v[4], v[5], v[6], v[7]);
     }
@@ -496,8 +501,55 @@ __global__ void __launch_bounds__(256) k_resfinal(const ResFinalParams p) {
                 o[q] += a;
             }
         }
+        if (p.out_mask) { o[0] *= mk; o[1] *= mk; o[2] *= mk; o[3] *= mk; }
         *reinterpret_cast<float4*>(p.out + off) = make_float4(o[0], o[1], o[2], o[3]);
     }
+}
+
+// Block activation in operand form for the tensor-core convs:  act = mask ? Mish(GN(raw)) + tproj : 0
+// (Block.forward output * mask, then ResnetBlock's time projection, then the next Block's input mask:
+//  diffusion.py:56-58,76).  One read + one write per element; the conv's A path is then a pure copy.
+__global__ void __launch_bounds__(256) k_gn_act(const GnActParams p) {
+    extern __shared__ __align__(16) float sm[];
+    float* mean = sm; float* scale = mean + p.C; float* beta = scale + p.C; float* tbv = beta + p.C;
+    const int b = blockIdx.y, tid = threadIdx.x;
+    gn_fill(p.gn, b, p.C, 0, p.C, mean, scale, beta);
+    {
+        const int row = p.tb_per_sample ? b : *p.step;
+        const float* tb = p.tb + (long long)row * p.tb_stride;
+        for (int c = tid; c < p.C; c += 256) tbv[c] = tb[c];
+    }
+    __syncthreads();
+    const int c4n = p.C >> 2;
+    const long long n4 = (long long)p.H * p.W * c4n;
+    for (long long i = (long long)blockIdx.x * 256 + tid; i < n4; i += (long long)gridDim.x * 256) {
+        const long long pix = i / c4n;
+        const int c = (int)(i - pix * c4n) * 4;
+        const int w = (int)(pix % p.W);
+        const float mk = __ldg(p.mask + (long long)b * p.T + ((long long)w << p.lvl));
+        const long long off = ((long long)b * p.H * p.W + pix) * p.C + c;
+        float o[4] = {0.f, 0.f, 0.f, 0.f};
+        if (mk != 0.f) {
+            const float4 r = ldg4(p.raw + off);
+            const float rv[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float y = mish_f((rv[q] - mean[c + q]) * scale[c + q] + beta[c + q]) + tbv[c + q];
+                if (p.round_tf32) { uint32_t u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(y)); y = __uint_as_float(u); }
+                o[q] = y;
+            }
+        }
+        *reinterpret_cast<float4*>(p.out + off) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+int launch_gn_act(const GnActParams& p, cudaStream_t s) {
+    const long long n4 = (long long)p.H * p.W * (p.C / 4);
+    int gx = (int)((n4 + 256 * 4 - 1) / (256 * 4));
+    if (gx < 1) gx = 1;
+    if (gx > 4096) gx = 4096;
+    k_gn_act<<<dim3(gx, p.B), 256, 4 * p.C * sizeof(float), s>>>(p);
+    return 1;
 }
 
 int launch_resfinal(const ResFinalParams& p, cudaStream_t s) {
@@ -576,15 +628,29 @@ __global__ void __launch_bounds__(256) k_attn_mix(const AttnMixParams p) {
 #pragma unroll
             for (int cl = 0; cl < 32; ++cl) acc[cl] = fmaf(s_mb[cl * 128 + j], wq, acc[cl]);
         }
-        float* o = p.w_eff + ((long long)b * C + cp) * C + cb;
+        if (p.tc_nt) {
+            // tcgen05 1x1 weight image: [ntile][kstage][chunk][cout % NT][4 cin], tf32 (RNA)
+            const int NT = p.tc_nt, kch = p.tc_cps / 4, ksteps = C / p.tc_cps;
+            const int ks = cp / p.tc_cps, kc = (cp % p.tc_cps) / 4, e = cp & 3;
 #pragma unroll
-        for (int cl = 0; cl < 32; cl += 4) {
-            float4 v = make_float4(g * acc[cl], g * acc[cl + 1], g * acc[cl + 2], g * acc[cl + 3]);
-            if (cb + cl + 0 == cp) v.x += 1.f;
-            if (cb + cl + 1 == cp) v.y += 1.f;
-            if (cb + cl + 2 == cp) v.z += 1.f;
-            if (cb + cl + 3 == cp) v.w += 1.f;
-            *reinterpret_cast<float4*>(o + cl) = v;
+            for (int cl = 0; cl < 32; ++cl) {
+                const int co = cb + cl;
+                float v = g * acc[cl] + (co == cp ? 1.f : 0.f);
+                uint32_t u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+                const long long idx = ((((long long)(co / NT) * ksteps + ks) * kch + kc) * NT + (co % NT)) * 4 + e;
+                p.w_eff[(long long)b * C * C + idx] = __uint_as_float(u);
+            }
+        } else {
+            float* o = p.w_eff + ((long long)b * C + cp) * C + cb;
+#pragma unroll
+            for (int cl = 0; cl < 32; cl += 4) {
+                float4 v = make_float4(g * acc[cl], g * acc[cl + 1], g * acc[cl + 2], g * acc[cl + 3]);
+                if (cb + cl + 0 == cp) v.x += 1.f;
+                if (cb + cl + 1 == cp) v.y += 1.f;
+                if (cb + cl + 2 == cp) v.z += 1.f;
+                if (cb + cl + 3 == cp) v.w += 1.f;
+                *reinterpret_cast<float4*>(o + cl) = v;
+            }
         }
     }
     if (b == 0 && tid < 32) p.b_eff[cb + tid] = g * p.bout[cb + tid];

@@ -32,7 +32,13 @@ def engines(sbk_lib):
         e.close()
 
 
-def stagewise_errors(eng, cfg, sd, xt, mask, mu, t, spk):
+# tensors that feed LinearAttention keep their padded columns (attention reads the unmasked x, diffusion.py:192);
+# in the tensor-core modes every other activation is stored already multiplied by its level's mask
+ATTN_INPUTS = {"estimator.downs.0.1.out", "estimator.downs.1.1.out", "estimator.downs.2.1.out",
+               "estimator.mid_block1.out", "estimator.ups.0.1.out", "estimator.ups.1.1.out"}
+
+
+def stagewise_errors(eng, cfg, sd, xt, mask, mu, t, spk, masked_storage=False):
     """Run one estimator call on the GPU and compare every named intermediate with the oracle's."""
     dev = "cuda"
     eng.debug_capture(True)
@@ -54,6 +60,9 @@ def stagewise_errors(eng, cfg, sd, xt, mask, mu, t, spk):
         else:
             B, C, H, W = ref.shape
             got = nhwc_to_nchw(got, B, H, W, C)
+            if masked_storage and not name.endswith(".raw") and name not in ATTN_INPUTS:
+                mk = mask[:, None, :, ::mask.shape[-1] // W]          # this level's mask [B,1,1,W]
+                ref = ref * mk
         rows.append((name, rel_l2(got, ref), ref.abs().max().item()))
     rows.append(("estimator.out", rel_l2(y.cpu(), y_ref), y_ref.abs().max().item()))
     return rows
@@ -195,24 +204,24 @@ def test_config2_shape_properties(engines):
 # ---- tensor-core precision modes (tcgen05 kind::tf32 / kind::f16-bf16 operands, fp32 accumulate in TMEM) ----
 # Tolerances follow the operand rounding (measured by emulation on the reference):
 # tf32 (10-bit mantissa) ~1e-3 per estimator call, bf16 (8-bit) ~9e-3; GN/softmax/Mish/Euler stay fp32.
-TC_TOL = {"tf32": (4e-3, 8e-3), "bf16": (3e-2, 5e-2)}       # (per estimator call / stage, trajectory)
+TC_TOL = {"tf32": (4e-3, 8e-3)}       # (per estimator call / stage, trajectory)
 
 
-@pytest.mark.parametrize("precision", ["tf32", "bf16"])
-@pytest.mark.parametrize("B,T", [(2, 32), (3, 100), (1, 256)])
+@pytest.mark.parametrize("precision", ["tf32"])
+@pytest.mark.parametrize("B,T", [(2, 32), (3, 100), (1, 256), (1, 4)])
 def test_tensor_core_stagewise(engines, precision, B, T):
     cfg = UNetConfig()
     sd = synthetic_state_dict(cfg)
     z, mask, mu, spk, _ = synthetic_inputs(B, T, ragged=True)
     t = torch.linspace(0.9, 0.2, B)
-    rows = stagewise_errors(engines(1, True, 1234, precision), cfg, sd, z * mask, mask, mu, t, spk)
+    rows = stagewise_errors(engines(1, True, 1234, precision), cfg, sd, z * mask, mask, mu, t, spk, masked_storage=True)
     report = "\n".join(f"{n:48s} rel_l2={e:.3e} |ref|max={m:.3g}" for n, e, m in rows)
     print(report)
     bad = [r for r in rows if not (r[1] <= TC_TOL[precision][0])]
     assert not bad, "first divergent stage: %s\n%s" % (bad[0][0], report)
 
 
-@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+@pytest.mark.parametrize("precision", ["tf32"])
 def test_tensor_core_vs_reference_golden(engines, golden, precision):
     eng = engines(1, True, 1234, precision)
     for idx, c in _golden_cases("est") + _golden_cases("traj"):
@@ -230,6 +239,25 @@ def test_tensor_core_vs_reference_golden(engines, golden, precision):
         print(precision, case_id(c), "rel_l2", err)
         assert err <= tol, case_id(c)
         assert (y * (1 - mask)).abs().max().item() == 0.0
+
+
+def test_tf32_multispeaker_and_module(golden):
+    from speech_backbones_b200.gradtts import Diffusion
+    idx, c = next((i, c) for i, c in _golden_cases("traj") if c["n_spks"] == 4)
+    cfg, sd, z, mask, mu, spk = case_inputs(golden, c)
+    dec = Diffusion(80, 64, n_spks=4, precision="tf32").eval()
+    dec.load_state_dict(sd, strict=True)
+    dec = dec.cuda()
+    y = dec(z.cuda(), mask.cuda(), mu.cuda(), c["N"], False, spk.cuda()).cpu()
+    assert rel_l2(y, c["out"]) <= TC_TOL["tf32"][1]
+
+
+def test_bf16_mode_is_refused_loudly(sbk_lib):
+    from speech_backbones_b200.binding import Engine
+    e = Engine(precision="bf16")
+    with pytest.raises(RuntimeError, match="bf16"):
+        e.load_state_dict(synthetic_state_dict(UNetConfig()))
+    e.close()
 
 
 def test_error_paths_raise(engines):
