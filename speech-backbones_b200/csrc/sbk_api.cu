@@ -260,11 +260,34 @@ static uint16_t f32_to_bf16_rn(float x) {
     u += 0x7FFFu + ((u >> 16) & 1u);
     return (uint16_t)(u >> 16);
 }
+static int pack_tc_host(sbk_handle* h, const std::vector<float>& hs, const std::string& key, int cout, int cin, int geom, bool bf16);
 static int pack_tc(sbk_handle* h, const std::string& src, const std::string& key, int cout, int cin, int geom, bool bf16) {
-    const int taps = geom == G_C3 ? 9 : 1;
+    const int taps = conv_tc_taps(geom);
     std::vector<float> hs((size_t)cout * cin * taps);
     CU(cudaMemcpy(hs.data(), h->raw[src], hs.size() * sizeof(float), cudaMemcpyDeviceToHost));
-    const int NT = conv_tc_ntile(cout), CPS = conv_tc_stage_channels(geom, bf16 ? 1 : 0), EPC = bf16 ? 8 : 4, KCHK = CPS / EPC;
+    return pack_tc_host(h, hs, key, cout, cin, geom, bf16);
+}
+// k|v rows of to_qkv regrouped per head: logical cout index head*64 + {d | 32 + e}
+static int pack_tc_kv(sbk_handle* h, const std::string& src, const std::string& key, int C) {
+    std::vector<float> q((size_t)384 * C), m((size_t)256 * C);
+    CU(cudaMemcpy(q.data(), h->raw[src], q.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    for (int hd = 0; hd < kHeads; ++hd) for (int x = 0; x < 32; ++x) for (int ci = 0; ci < C; ++ci) {
+        m[(size_t)(hd * 64 + x) * C + ci] = q[(size_t)(128 + hd * 32 + x) * C + ci];
+        m[(size_t)(hd * 64 + 32 + x) * C + ci] = q[(size_t)(256 + hd * 32 + x) * C + ci];
+    }
+    return pack_tc_host(h, m, key, 256, C, G_PW, false);
+}
+// ConvTranspose2d weight [ci][co][4][4] -> logical [co][ci][kh*4+kw]
+static int pack_tc_up(sbk_handle* h, const std::string& src, const std::string& key, int C) {
+    std::vector<float> w((size_t)C * C * 16), m((size_t)C * C * 16);
+    CU(cudaMemcpy(w.data(), h->raw[src], w.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    for (int ci = 0; ci < C; ++ci) for (int co = 0; co < C; ++co) for (int t = 0; t < 16; ++t)
+        m[((size_t)co * C + ci) * 16 + t] = w[((size_t)ci * C + co) * 16 + t];
+    return pack_tc_host(h, m, key, C, C, G_UP, false);
+}
+static int pack_tc_host(sbk_handle* h, const std::vector<float>& hs, const std::string& key, int cout, int cin, int geom, bool bf16) {
+    const int taps = conv_tc_taps(geom);
+    const int NT = conv_tc_ntile(geom, cout), CPS = conv_tc_stage_channels(geom, bf16 ? 1 : 0), EPC = bf16 ? 8 : 4, KCHK = CPS / EPC;
     const int ksteps = cin / CPS;
     const size_t esz = bf16 ? 2 : 4;
     std::vector<uint8_t> hd((size_t)cout * cin * taps * esz);
@@ -333,6 +356,16 @@ extern "C" int sbk_pack(sbk_handle* h) {
             if (r.cin != r.cout && r.cin % cps1 == 0) TRY(pack_tc(h, r.prefix + ".res_conv.weight", r.prefix + ".res.wtc", r.cout, r.cin, G_PW, bf));
         }
         TRY(pack_tc(h, "estimator.final_block.block.0.weight", "estimator.final_block.wtc", h->cfg.dim, h->cfg.dim, G_C3, bf));
+        for (auto& a : h->attns)
+            if (a.c % cps1 == 0) TRY(pack_tc_kv(h, a.prefix + ".fn.fn.to_qkv.weight", a.prefix + ".kv.wtc", a.c));
+        for (int l = 0; l < 2; ++l) {
+            const std::string p = "estimator.downs." + std::to_string(l) + ".3.conv";
+            TRY(pack_tc(h, p + ".weight", p + ".wtc", h->cfg.dim << l, h->cfg.dim << l, G_DOWN, bf));
+        }
+        for (int j = 0; j < 2; ++j) {
+            const std::string p = "estimator.ups." + std::to_string(j) + ".3.conv";
+            TRY(pack_tc_up(h, p + ".weight", p + ".wtc", h->cfg.dim << (1 - j)));
+        }
     }
     for (auto& a : h->attns) TRY(repack(h, a.prefix + ".fn.fn.to_qkv.weight", a.prefix + ".kv.w", (size_t)a.c * 256, kv_pack));
     for (int l = 0; l < 2; ++l) {
@@ -480,9 +513,10 @@ static int build_plan(sbk_handle* h, int B, int T, int tb_rows) {
         Op op; op.name = name; op.kind = OP_CONVTC;
         ConvTcParams& p = op.tc; memset(&p, 0, sizeof(p));
         p.geom = geom; p.in0 = in0; p.c0 = c0; p.in1 = in1; p.c1 = c1; p.H = Hs[lvl]; p.W = Ws[lvl]; p.B = B;
+        p.Ho = p.H; p.Wo = p.W;
         p.wpk = W(wkey); p.bias = bkey.empty() ? nullptr : W(bkey); p.out = out; p.Cout = cout;
         p.epi = EPI_PLAIN; p.ostats = st; p.mask = pl.mask; p.T = T; p.lvl = lvl;
-        const double taps = geom == G_C3 ? 9.0 : 1.0;
+        const double taps = geom == G_PW ? 1.0 : (geom == G_UP ? 4.0 : 9.0);
         op.flops = 2.0 * B * Hs[lvl] * Ws[lvl] * cout * (c0 + c1) * taps;
         op.bytes = 4.0 * B * Hs[lvl] * Ws[lvl] * (c0 + c1 + cout);
         return op;
@@ -578,9 +612,17 @@ static int build_plan(sbk_handle* h, int B, int T, int tb_rows) {
     // Residual(Rezero(LinearAttention)) (diffusion.py:39-46,82-110)
     auto attention = [&](int k, int lvl, const float* x, float* out) {
         const AttnInfo& a = h->attns[k];
-        const int mt = igemm_mtiles(G_PW, Hs[lvl], Ws[lvl], Hs[lvl], Ws[lvl]);
+        int mt = igemm_mtiles(G_PW, Hs[lvl], Ws[lvl], Hs[lvl], Ws[lvl]);
         const bool tc_apply = use_tc && a.c % tc_cps1 == 0;
-        {
+        if (tc_apply) {
+            // k/v projection + online-softmax partials on tensor cores: tiles of 256 pixels x 2 heads
+            Op op = tc_conv(a.prefix + ".kvpart", G_PW, a.prefix + ".kv.wtc", "", lvl, x, a.c, nullptr, 0, 256, nullptr, nullptr);
+            op.tc.epi = EPI_KV; op.tc.kv_part = bf.kv_part;
+            op.bytes = 4.0 * npix(lvl) * a.c;
+            op.flops += 2.0 * npix(lvl) * 4096.0;
+            mt = (Hs[lvl] * Ws[lvl] + 255) / 256;
+            push(op, nullptr, 0);
+        } else {
             Op op; op.kind = OP_IGEMM; op.name = a.prefix + ".kvpart";
             op.ig = base_ig(G_PW, lvl, lvl);
             IgemmParams& p = op.ig;
@@ -599,7 +641,7 @@ static int build_plan(sbk_handle* h, int B, int T, int tb_rows) {
             p.ctx = bf.ctx; p.wq = W(a.prefix + ".fn.fn.to_qkv.weight"); p.wout = W(a.prefix + ".fn.fn.to_out.weight");
             p.bout = W(a.prefix + ".fn.fn.to_out.bias"); p.g = W(a.prefix + ".fn.g");
             p.w_eff = bf.w_eff; p.b_eff = bf.b_eff; p.B = B; p.C = a.c;
-            if (tc_apply) { p.tc_nt = conv_tc_ntile(a.c); p.tc_cps = tc_cps1; }
+            if (tc_apply) { p.tc_nt = conv_tc_ntile(G_PW, a.c); p.tc_cps = tc_cps1; }
             push(op, nullptr, 0);
         }
         if (tc_apply) {
@@ -618,6 +660,14 @@ static int build_plan(sbk_handle* h, int B, int T, int tb_rows) {
         }
     };
     auto resample = [&](int geom, const std::string& pre, int lvl_in, int lvl_out, const float* x, int C, float* out) {
+        if (use_tc && C % tc_cps3 == 0 && C % 64 == 0) {
+            Op op = tc_conv(pre + ".out", geom, pre + ".conv.wtc", pre + ".conv.bias", lvl_in, x, C, nullptr, 0, C, out, nullptr);
+            op.tc.Ho = Hs[lvl_out]; op.tc.Wo = Ws[lvl_out]; op.tc.lvl = lvl_out; op.tc.out_mask = 1;
+            op.flops = 2.0 * npix(lvl_out) * C * C * (geom == G_UP ? 4.0 : 9.0);
+            op.bytes = 4.0 * C * (npix(lvl_in) + npix(lvl_out));
+            push(op, out, npix(lvl_out) * C);
+            return;
+        }
         Op op; op.kind = OP_IGEMM; op.name = pre + ".out";
         op.ig = base_ig(geom, lvl_in, lvl_out);
         IgemmParams& p = op.ig;

@@ -41,8 +41,14 @@ constexpr int NTHREADS = NPROD + 64;  // + MMA warp + weight-loader warp
 
 // geometry of the A tile in shared memory, [16-byte K chunk][row][pixel][16 B]
 template <int GEOM> struct Geo;
-template <> struct Geo<G_C3> { static constexpr int HR = ROWS + 2, PXP = TPX + 2, TAPS = 9, KCH = 2; };   // 3x3: halo tile
-template <> struct Geo<G_PW> { static constexpr int HR = ROWS, PXP = TPX, TAPS = 1, KCH = 8; };           // 1x1: plain tile
+template <> struct Geo<G_C3> { static constexpr int HR = ROWS + 2, PXP = TPX + 2, TAPS = 9, KCH = 2, NACC = ROWS; };   // 3x3: halo tile
+template <> struct Geo<G_PW> { static constexpr int HR = ROWS, PXP = TPX, TAPS = 1, KCH = 8, NACC = ROWS; };           // 1x1: plain tile
+// 3x3 stride 2 (Downsample): 5 input rows; input columns de-interleaved into an odd plane (129 px: 2*w0-1+2i) and
+// an even plane (2*w0+2i) so that consecutive OUTPUT pixels read consecutive smem pixels for every tap.
+template <> struct Geo<G_DOWN> { static constexpr int HR = 2 * ROWS + 1, PXP = 2 * (TPX + 1), TAPS = 9, KCH = 2, NACC = ROWS; };
+// ConvTranspose2d(4,2,1) (Upsample): per output parity (ph,pw) a 2x2-tap conv over the same 3x3-style input halo;
+// all four phases are computed from one halo tile into 4*ROWS accumulators; the stage carries all 16 (kh,kw) taps.
+template <> struct Geo<G_UP> { static constexpr int HR = ROWS + 2, PXP = TPX + 2, TAPS = 16, KCH = 2, NACC = 4 * ROWS; };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -182,7 +188,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvTcParams p) {
     constexpr int PLANE = HR * PXP * 16;                   // bytes between K chunks of the A tile
     constexpr int A_STAGE_BYTES = KCH * PLANE;
     constexpr int B_STAGE_BYTES = TAPS * KCH * NT * 16;
-    constexpr uint32_t TMEM_COLS = ROWS * NT;              // 128 or 256: a power of two >= 32
+    constexpr int NACC = G::NACC;
+    constexpr uint32_t TMEM_COLS = NACC * NT;              // 128, 256 or 512: a power of two >= 32
 
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sA = smem;                                            // [STAGES][KCH][HR][PXP][16]
@@ -196,8 +203,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvTcParams p) {
     const int Cin = p.c0 + p.c1;
     const int HW = p.H * p.W;
     int w0, h0;
-    if (GEOM == G_C3) {
-        const int wtiles = (p.W + TPX - 1) / TPX;
+    if (GEOM == G_C3 || GEOM == G_UP || GEOM == G_DOWN) {
+        // C3 / UP tile the input(=output / half-output) grid, DOWN tiles its output grid
+        const int wt = GEOM == G_DOWN ? p.Wo : p.W;
+        const int wtiles = (wt + TPX - 1) / TPX;
         w0 = (blockIdx.x % wtiles) * TPX;
         h0 = (blockIdx.x / wtiles) * ROWS;
     } else {
@@ -253,9 +262,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvTcParams p) {
             const int item = in ? e / KCH : 0, k = in ? e % KCH : 0;
             const int r = item / PXP, q = item - r * PXP;
             bool ok; long long pix;
-            if (GEOM == G_C3) {
+            if (GEOM == G_C3 || GEOM == G_UP) {
                 const int hi = h0 - 1 + r, wi = w0 - 1 + q;
                 ok = in && hi >= 0 && hi < p.H && wi >= 0 && wi < p.W;
+                pix = (long long)(b * p.H + hi) * p.W + wi;
+            } else if (GEOM == G_DOWN) {
+                const int par = q / (TPX + 1), i = q - par * (TPX + 1);      // plane 0: odd columns, plane 1: even
+                const int hi = 2 * h0 - 1 + r, wi = par == 0 ? 2 * w0 - 1 + 2 * i : 2 * w0 + 2 * i;
+                ok = in && hi >= 0 && hi < p.H && wi >= 0 && wi < p.W && !(par == 1 && i == TPX);
                 pix = (long long)(b * p.H + hi) * p.W + wi;
             } else {
                 const long long m = (long long)(h0 + r) * TPX + q;
@@ -295,12 +309,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvTcParams p) {
         tc_fence_after();
         const int q4 = warp & 3, jrow = warp >> 2;            // TMEM lane quarter / accumulator (output row)
         const int px = q4 * 32 + lane;
+        const int Ho = (GEOM == G_DOWN || GEOM == G_UP) ? p.Ho : p.H, Wo = (GEOM == G_DOWN || GEOM == G_UP) ? p.Wo : p.W;
         long long opix; int wo; bool valid;
-        if (GEOM == G_C3) {
+        if (GEOM == G_C3 || GEOM == G_DOWN) {
             const int ho = h0 + jrow;
             wo = w0 + px;
-            valid = ho < p.H && wo < p.W;
-            opix = (long long)(b * p.H + ho) * p.W + wo;
+            valid = ho < Ho && wo < Wo;
+            opix = (long long)(b * Ho + ho) * Wo + wo;
+        } else if (GEOM == G_UP) {
+            valid = (h0 + jrow) < p.H && (w0 + px) < p.W;          // per-phase coordinates are formed below
+            wo = 2 * (w0 + px);
+            opix = (long long)(b * Ho + 2 * (h0 + jrow)) * Wo + wo;
         } else {
             const long long m = (long long)(h0 + jrow) * TPX + px;
             valid = m < HW;
@@ -308,14 +327,96 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvTcParams p) {
             opix = (long long)b * HW + m;
         }
         if (!valid) { opix = 0; wo = 0; }
-        const float mo = (p.out_mask || p.epi == EPI_RES) ? __ldg(p.mask + (long long)b * p.T + ((long long)wo << p.lvl)) : 1.f;
+        if (GEOM == G_PW && p.epi == EPI_KV) {
+            // LinearAttention pass 1 (diffusion.py:93-96).  This N tile holds two heads, columns [k_h(32) | v_h(32)] x 2.
+            // Per tile of 256 pixels: m_d = max_px k, Z_d = sum_px exp(k - m_d), S[d][e] = sum_px exp(k[d,px]-m_d) v[e,px];
+            // k and v never reach HBM.  The accumulators are staged through the (now idle) pipeline smem.
+            constexpr int LDK = NT + 4;                       // padded row: conflict-free 16-byte row-strided stores
+            float* KV = reinterpret_cast<float*>(smem);       // [256 px][LDK]
+            float* s_red = KV + ROWS * TPX * LDK;             // [4][NT/2]
+            float* s_m = s_red + 4 * (NT / 2);                // [NT/2]
+            static_assert((ROWS * TPX * LDK + 5 * (NT / 2)) * 4 <= STAGES * (A_STAGE_BYTES + B_STAGE_BYTES), "KV staging must fit");
+            const int pxl = jrow * TPX + px;
+#pragma unroll 1
+            for (int cb = 0; cb < NT; cb += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(jrow * NT + cb), r);
+#pragma unroll
+                for (int i = 0; i < 32; i += 4)
+                    *reinterpret_cast<float4*>(&KV[pxl * LDK + cb + i]) =
+                        make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+            }
+            tc_fence_before();
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const int nvalid = (int)min((long long)ROWS * TPX, (long long)HW - (long long)h0 * TPX);
+            constexpr int NK = NT / 2;                        // k columns in this tile (32 per head)
+            const int kc = tid % NK, part = tid / NK;         // NK = 64: 4 pixel quarters of 64
+            const int kcol = (kc >> 5) * 64 + (kc & 31);      // column of k[d] of head kc>>5
+            constexpr int PPQ = ROWS * TPX / (NPROD / NK);
+            float mx = -INFINITY;
+#pragma unroll 8
+            for (int q = part * PPQ; q < part * PPQ + PPQ; ++q)
+                if (q < nvalid) mx = fmaxf(mx, KV[q * LDK + kcol]);
+            s_red[part * NK + kc] = mx;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (tid < NK) {
+                float m = s_red[tid];
+                for (int i = 1; i < NPROD / NK; ++i) m = fmaxf(m, s_red[i * NK + tid]);
+                s_m[tid] = m;
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const float md = s_m[kc];
+            float z = 0.f;
+#pragma unroll 8
+            for (int q = part * PPQ; q < part * PPQ + PPQ; ++q) {
+                const float e = q < nvalid ? __expf(KV[q * LDK + kcol] - md) : 0.f;
+                KV[q * LDK + kcol] = e;
+                z += e;
+            }
+            s_red[part * NK + kc] = z;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const int mtiles = gridDim.x;
+            float* part0 = p.kv_part + (((long long)b * mtiles + blockIdx.x) * kHeads + blockIdx.y * (NT / 64)) * kKvPartFloats;
+            if (tid < NK) {
+                float zz = s_red[tid];
+                for (int i = 1; i < NPROD / NK; ++i) zz += s_red[i * NK + tid];
+                float* pt = part0 + (tid >> 5) * kKvPartFloats;
+                pt[tid & 31] = s_m[tid];
+                pt[32 + (tid & 31)] = zz;
+            }
+            // S: thread owns head hh, d = dg*4..+3, e = eg*2..+1
+            constexpr int TPH = NPROD / (NT / 64);            // threads per head (128 for two heads)
+            const int hh = tid / TPH, tl = tid % TPH;
+            const int dg = tl & 7, eg = tl >> 3;              // 8 x 16 = 128 threads cover 32 x 32
+            float sacc[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+#pragma unroll 8
+            for (int q = 0; q < nvalid; ++q) {
+                const float4 pk = *reinterpret_cast<const float4*>(&KV[q * LDK + hh * 64 + dg * 4]);
+                const float2 vv = *reinterpret_cast<const float2*>(&KV[q * LDK + hh * 64 + 32 + eg * 2]);
+                sacc[0][0] = fmaf(pk.x, vv.x, sacc[0][0]); sacc[0][1] = fmaf(pk.x, vv.y, sacc[0][1]);
+                sacc[1][0] = fmaf(pk.y, vv.x, sacc[1][0]); sacc[1][1] = fmaf(pk.y, vv.y, sacc[1][1]);
+                sacc[2][0] = fmaf(pk.z, vv.x, sacc[2][0]); sacc[2][1] = fmaf(pk.z, vv.y, sacc[2][1]);
+                sacc[3][0] = fmaf(pk.w, vv.x, sacc[3][0]); sacc[3][1] = fmaf(pk.w, vv.y, sacc[3][1]);
+            }
+            float* pt = part0 + hh * kKvPartFloats;
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd)
+                *reinterpret_cast<float2*>(&pt[64 + (dg * 4 + qd) * 32 + eg * 2]) = make_float2(sacc[qd][0], sacc[qd][1]);
+        } else {
         const int cpg = p.Cout / kGroups;
         const float* bp = p.bias ? p.bias + (long long)b * p.bias_bstride + n0 : nullptr;
-        float* op = p.out + opix * p.Cout + n0;
+        constexpr int NPH = GEOM == G_UP ? 4 : 1;
+#pragma unroll 1
+        for (int phase = 0; phase < NPH; ++phase) {
+        const long long opix_p = GEOM == G_UP ? opix + (long long)(phase >> 1) * Wo + (phase & 1) : opix;
+        const int wo_p = GEOM == G_UP ? wo + (phase & 1) : wo;
+        const int acc = GEOM == G_UP ? phase * ROWS + jrow : jrow;
+        const float mo = (p.out_mask || p.epi == EPI_RES) ? __ldg(p.mask + (long long)b * p.T + ((long long)wo_p << p.lvl)) : 1.f;
+        float* op = p.out + opix_p * p.Cout + n0;
 #pragma unroll 1
         for (int cb = 0; cb < NT; cb += 32) {
             uint32_t r[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(jrow * NT + cb), r);
+            tmem_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(acc * NT + cb), r);
             float v[32];
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
@@ -325,7 +426,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvTcParams p) {
             }
             if (p.epi == EPI_RES && valid && mo != 0.f) {
                 // ResnetBlock tail: + Mish(GN(h2raw)) * mask  (diffusion.py:77-78)
-                const float* rp = p.rraw + opix * p.Cout + n0 + cb;
+                const float* rp = p.rraw + opix_p * p.Cout + n0 + cb;
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
                     const float4 rv = __ldg(reinterpret_cast<const float4*>(rp + i));
@@ -374,6 +475,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvTcParams p) {
                 }
             }
         }
+        }
+        }
         tc_fence_before();
     } else if (warp == NPROD / 32) {
         // =============================== MMA issuer ===============================
@@ -388,14 +491,39 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvTcParams p) {
                 tc_fence_after();
 #pragma unroll
                 for (int kk = 0; kk < KCH / 2; ++kk) {
+                    const uint32_t a_st = a0 + s * A_STAGE_BYTES + kk * 2 * PLANE;
+                    const uint32_t b_st = b0 + s * B_STAGE_BYTES + kk * 2 * (NT * 16);
+                    if (GEOM == G_UP) {
+                        // ho = 2*hi - 1 + kh: parity ph uses (kh=1,dh=0),(kh=3,dh=-1) if ph=0 and (kh=0,dh=+1),(kh=2,dh=0) if ph=1
 #pragma unroll
-                    for (int tap = 0; tap < TAPS; ++tap) {
-                        const int r = GEOM == G_C3 ? tap / 3 : 0, sx = GEOM == G_C3 ? tap % 3 : 0;
-                        const uint64_t bd = make_desc(b0 + s * B_STAGE_BYTES + (tap * KCH + kk * 2) * (NT * 16), NT * 16, 128);
+                        for (int phase = 0; phase < 4; ++phase) {
+                            const int ph = phase >> 1, pw = phase & 1;
 #pragma unroll
-                        for (int j = 0; j < ROWS; ++j) {
-                            const uint64_t ad = make_desc(a0 + s * A_STAGE_BYTES + kk * 2 * PLANE + ((r + j) * PXP + sx) * 16, PLANE, 128);
-                            umma<BF16>(tmem_base + j * NT, ad, bd, idesc, (ks | kk | tap) != 0 ? 1u : 0u);
+                            for (int t2 = 0; t2 < 4; ++t2) {
+                                const int a = t2 >> 1, bb = t2 & 1;
+                                const int kh = ph ? (a ? 2 : 0) : (a ? 3 : 1), kw = pw ? (bb ? 2 : 0) : (bb ? 3 : 1);
+                                const int dh = ph ? (a ? 0 : 1) : (a ? -1 : 0), dw = pw ? (bb ? 0 : 1) : (bb ? -1 : 0);
+                                const uint64_t bd = make_desc(b_st + (kh * 4 + kw) * KCH * (NT * 16), NT * 16, 128);
+#pragma unroll
+                                for (int j = 0; j < ROWS; ++j) {
+                                    const uint64_t ad = make_desc(a_st + ((1 + j + dh) * PXP + 1 + dw) * 16, PLANE, 128);
+                                    umma<BF16>(tmem_base + (phase * ROWS + j) * NT, ad, bd, idesc, (ks | kk | t2) != 0 ? 1u : 0u);
+                                }
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int tap = 0; tap < TAPS; ++tap) {
+                            const int r = TAPS == 9 ? tap / 3 : 0, sx = TAPS == 9 ? tap % 3 : 0;
+                            const uint64_t bd = make_desc(b_st + tap * KCH * (NT * 16), NT * 16, 128);
+#pragma unroll
+                            for (int j = 0; j < ROWS; ++j) {
+                                // DOWN: input row 2j+r; column tap s reads the odd plane at x (s=0) / x+1 (s=2), the even plane at x (s=1)
+                                const int aoff = GEOM == G_DOWN ? (2 * j + r) * PXP + (sx == 1 ? TPX + 1 : (sx == 2 ? 1 : 0))
+                                                                : (r + j) * PXP + sx;
+                                const uint64_t ad = make_desc(a_st + aoff * 16, PLANE, 128);
+                                umma<BF16>(tmem_base + j * NT, ad, bd, idesc, (ks | kk | tap) != 0 ? 1u : 0u);
+                            }
                         }
                     }
                 }
@@ -439,24 +567,34 @@ static int launch_tc(const ConvTcParams& p, cudaStream_t s) {
         attr_set = true;
     }
     int gx;
-    if (GEOM == G_C3) gx = ((p.W + TPX - 1) / TPX) * ((p.H + ROWS - 1) / ROWS);
+    if (GEOM == G_C3 || GEOM == G_UP) gx = ((p.W + TPX - 1) / TPX) * ((p.H + ROWS - 1) / ROWS);
+    else if (GEOM == G_DOWN) gx = ((p.Wo + TPX - 1) / TPX) * ((p.Ho + ROWS - 1) / ROWS);
     else gx = (p.H * p.W + ROWS * TPX - 1) / (ROWS * TPX);
     dim3 grid(gx, p.Cout / NT, p.B);
     k_conv_tc<GEOM, BF16, NT><<<grid, NTHREADS, sm, s>>>(p);
     return 1;
 }
 
-int conv_tc_ntile(int Cout) { return Cout % 128 == 0 ? 128 : 64; }
+// N tile per geometry: UP needs 8 accumulators (8*64 = all 512 TMEM columns), DOWN's de-interleaved A tile is large
+int conv_tc_ntile(int geom, int Cout) {
+    if (geom == G_UP || geom == G_DOWN) return 64;
+    return Cout % 128 == 0 ? 128 : 64;
+}
+int conv_tc_taps(int geom) { return geom == G_PW ? 1 : (geom == G_UP ? 16 : 9); }
 int conv_tc_stage_channels(int geom, int bf16) {
     const int epc = bf16 ? 8 : 4;
-    return (geom == G_C3 ? Geo<G_C3>::KCH : Geo<G_PW>::KCH) * epc;
+    return (geom == G_PW ? Geo<G_PW>::KCH : Geo<G_C3>::KCH) * epc;
 }
 
 int launch_conv_tc(const ConvTcParams& p, cudaStream_t s) {
-    const int nt = conv_tc_ntile(p.Cout);
+    const int nt = conv_tc_ntile(p.geom, p.Cout);
     if (p.bf16) return -1;   // bf16 operand tensors are not wired up yet
-    if (p.geom == G_C3) return nt == 128 ? launch_tc<G_C3, false, 128>(p, s) : launch_tc<G_C3, false, 64>(p, s);
-    return nt == 128 ? launch_tc<G_PW, false, 128>(p, s) : launch_tc<G_PW, false, 64>(p, s);
+    switch (p.geom) {
+        case G_C3:   return nt == 128 ? launch_tc<G_C3, false, 128>(p, s) : launch_tc<G_C3, false, 64>(p, s);
+        case G_PW:   return nt == 128 ? launch_tc<G_PW, false, 128>(p, s) : launch_tc<G_PW, false, 64>(p, s);
+        case G_DOWN: return launch_tc<G_DOWN, false, 64>(p, s);
+        default:     return launch_tc<G_UP, false, 64>(p, s);
+    }
 }
 
 }  // namespace sbk

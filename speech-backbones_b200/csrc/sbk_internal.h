@@ -52,14 +52,16 @@ struct IgemmParams {
 struct ConvTcParams {
     int geom;
     const void* in0; const void* in1; int c0, c1;   // channel concat of two NHWC tensors (fp32, or bf16 when bf16=1)
-    int H, W, B;
+    int H, W, B;                                    // input grid
+    int Ho, Wo;                                     // output grid (G_DOWN: ~H/2 x W/2, G_UP: 2H x 2W; else = H, W)
     const void* wpk; long long w_bstride_bytes;     // [ntile][kstage][tap][chunk][cout NT][16 B] (+ per-sample stride)
     const float* bias; long long bias_bstride;
     float* out; int Cout;
-    int epi;                                        // EPI_PLAIN | EPI_RES
+    int epi;                                        // EPI_PLAIN | EPI_RES | EPI_KV
     double* ostats;                                 // EPI_PLAIN: GroupNorm statistics of the raw output (nullable)
     const float* mask; int T; int lvl; int out_mask;   // out_mask: multiply the stored output by mask[b][wo << lvl]
     const float* rraw; GnRef rgn;                   // EPI_RES: out = acc + bias + Mish(GN(rraw))*mask
+    float* kv_part;                                 // EPI_KV (1x1, NT=128): [B][gridDim.x][4][kKvPartFloats]
     int bf16;
 };
 
@@ -141,7 +143,8 @@ struct StepBeginParams { double* stats; int n_doubles; int* step_cur; int* step_
 int launch_igemm(const IgemmParams& p, cudaStream_t s);
 int launch_first_conv(const FirstConvParams& p, cudaStream_t s);
 int launch_conv_tc(const ConvTcParams& p, cudaStream_t s);
-int conv_tc_ntile(int Cout);
+int conv_tc_ntile(int geom, int Cout);
+int conv_tc_taps(int geom);
 int conv_tc_stage_channels(int geom, int bf16);
 int launch_gn_act(const GnActParams& p, cudaStream_t s);
 int launch_resfinal(const ResFinalParams& p, cudaStream_t s);
