@@ -35,7 +35,6 @@ namespace tc {
 
 constexpr int ROWS = 2;               // M=128 pixel rows per CTA (two TMEM accumulators share every weight stage)
 constexpr int TPX = 128;              // pixels per row (= UMMA M)
-constexpr int STAGES = 3;
 constexpr int NPROD = 256;            // producer / epilogue threads (8 warps)
 constexpr int NTHREADS = NPROD + 64;  // + MMA warp + weight-loader warp
 
@@ -178,9 +177,25 @@ __device__ __forceinline__ float mish_acc(float x) {     // exact-math Mish for 
 
 using namespace tc;
 
-template <int GEOM, bool BF16, int NT>
-__global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvTcParams p) {
+// Pipeline depth / residency.  Two CTAs per SM (<= ~110 KB smem and <= 256 TMEM columns each) let one CTA's
+// epilogue and setup overlap the other's main loop - this non-persistent kernel has no other overlap - so the
+// bandwidth-heavy, short-K configurations (NT = 64, 1x1) use few stages x 2 CTAs; the long-K NT = 128 3x3 convs
+// keep one CTA with a deeper ring.  The producers keep STAGES-1 stages of cp.async in flight.
+template <int GEOM, int NT, bool KV = false> struct Depth {
+    static constexpr int STAGE_BYTES = Geo<GEOM>::KCH * Geo<GEOM>::HR * Geo<GEOM>::PXP * 16 + Geo<GEOM>::TAPS * Geo<GEOM>::KCH * NT * 16;
+    static constexpr int FIT2 = (108 * 1024) / STAGE_BYTES;             // stages that fit with 2 CTAs / SM
+    static constexpr int FIT1 = (220 * 1024) / STAGE_BYTES;
+    static constexpr bool TWO = !KV && FIT2 >= 2 && Geo<GEOM>::NACC * NT <= 256 && !(GEOM == G_C3 && NT == 128);
+    static constexpr int STAGES = TWO ? FIT2 : (FIT1 > 6 ? 6 : FIT1);
+    static constexpr int MINB = TWO ? 2 : 1;
+};
+
+template <int GEOM, bool BF16, int NT, bool KV = false>
+__global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT, KV>::MINB) k_conv_tc(const ConvTcParams p) {
     using G = Geo<GEOM>;
+    constexpr int STAGES = Depth<GEOM, NT, KV>::STAGES;
+    constexpr int LAG = STAGES >= 3 ? STAGES - 2 : 0;      // cp.async groups allowed in flight behind the newest one
+    static_assert(STAGES >= 2, "need at least 2 stages");
     constexpr int HR = G::HR, PXP = G::PXP, TAPS = G::TAPS, KCH = G::KCH;
     constexpr int EPC = BF16 ? 8 : 4;                      // elements per 16-byte chunk
     constexpr int ESZ = BF16 ? 2 : 4;
@@ -280,7 +295,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvTcParams p) {
             sl_dst[j] = in ? (uint32_t)(k * PLANE + (r * PXP + q) * 16) : 0xFFFFFFFFu;
         }
         const uint32_t a0 = smem_u32(sA);
-        for (int ks = 0; ks <= ksteps; ++ks) {
+        for (int ks = 0; ks < ksteps + LAG; ++ks) {
             if (ks < ksteps) {
                 const int s = ks % STAGES;
                 mbar_wait(empty(s), ((ks / STAGES) & 1) ^ 1);
@@ -295,12 +310,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvTcParams p) {
                     cp_async16(a0 + s * A_STAGE_BYTES + sl_dst[j], src + sl_pix[j] * cs + co + sl_chunk[j] * 16, sl_ok[j] ? 16u : 0u);
                 }
             }
-            cp_async_commit();
-            if (ks > 0) {
-                cp_async_wait<1>();                  // this thread's copies of stage ks-1 have landed
+            cp_async_commit();                       // (empty groups past the last stage keep the accounting uniform)
+            if (ks >= LAG) {
+                cp_async_wait<LAG>();                // this thread's copies of stage ks-LAG have landed
                 fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor core (async proxy)
                 __syncwarp();
-                if (lane == 0) mbar_arrive(full_a((ks - 1) % STAGES));
+                if (lane == 0) mbar_arrive(full_a((ks - LAG) % STAGES));
             }
         }
 
@@ -327,13 +342,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvTcParams p) {
             opix = (long long)b * HW + m;
         }
         if (!valid) { opix = 0; wo = 0; }
-        if (GEOM == G_PW && p.epi == EPI_KV) {
+        if constexpr (KV) {
             // LinearAttention pass 1 (diffusion.py:93-96).  This N tile holds two heads, columns [k_h(32) | v_h(32)] x 2.
             // Per tile of 256 pixels: m_d = max_px k, Z_d = sum_px exp(k - m_d), S[d][e] = sum_px exp(k[d,px]-m_d) v[e,px];
             // k and v never reach HBM.  The accumulators are staged through the (now idle) pipeline smem.
             constexpr int LDK = NT + 4;                       // padded row: conflict-free 16-byte row-strided stores
-            float* KV = reinterpret_cast<float*>(smem);       // [256 px][LDK]
-            float* s_red = KV + ROWS * TPX * LDK;             // [4][NT/2]
+            float* kvs = reinterpret_cast<float*>(smem);       // [256 px][LDK]
+            float* s_red = kvs + ROWS * TPX * LDK;             // [4][NT/2]
             float* s_m = s_red + 4 * (NT / 2);                // [NT/2]
             static_assert((ROWS * TPX * LDK + 5 * (NT / 2)) * 4 <= STAGES * (A_STAGE_BYTES + B_STAGE_BYTES), "KV staging must fit");
             const int pxl = jrow * TPX + px;
@@ -343,7 +358,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvTcParams p) {
                 tmem_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(jrow * NT + cb), r);
 #pragma unroll
                 for (int i = 0; i < 32; i += 4)
-                    *reinterpret_cast<float4*>(&KV[pxl * LDK + cb + i]) =
+                    *reinterpret_cast<float4*>(&kvs[pxl * LDK + cb + i]) =
                         make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
             }
             tc_fence_before();
@@ -356,7 +371,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvTcParams p) {
             float mx = -INFINITY;
 #pragma unroll 8
             for (int q = part * PPQ; q < part * PPQ + PPQ; ++q)
-                if (q < nvalid) mx = fmaxf(mx, KV[q * LDK + kcol]);
+                if (q < nvalid) mx = fmaxf(mx, kvs[q * LDK + kcol]);
             s_red[part * NK + kc] = mx;
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if (tid < NK) {
@@ -369,8 +384,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvTcParams p) {
             float z = 0.f;
 #pragma unroll 8
             for (int q = part * PPQ; q < part * PPQ + PPQ; ++q) {
-                const float e = q < nvalid ? __expf(KV[q * LDK + kcol] - md) : 0.f;
-                KV[q * LDK + kcol] = e;
+                const float e = q < nvalid ? __expf(kvs[q * LDK + kcol] - md) : 0.f;
+                kvs[q * LDK + kcol] = e;
                 z += e;
             }
             s_red[part * NK + kc] = z;
@@ -391,8 +406,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvTcParams p) {
             float sacc[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
 #pragma unroll 8
             for (int q = 0; q < nvalid; ++q) {
-                const float4 pk = *reinterpret_cast<const float4*>(&KV[q * LDK + hh * 64 + dg * 4]);
-                const float2 vv = *reinterpret_cast<const float2*>(&KV[q * LDK + hh * 64 + 32 + eg * 2]);
+                const float4 pk = *reinterpret_cast<const float4*>(&kvs[q * LDK + hh * 64 + dg * 4]);
+                const float2 vv = *reinterpret_cast<const float2*>(&kvs[q * LDK + hh * 64 + 32 + eg * 2]);
                 sacc[0][0] = fmaf(pk.x, vv.x, sacc[0][0]); sacc[0][1] = fmaf(pk.x, vv.y, sacc[0][1]);
                 sacc[1][0] = fmaf(pk.y, vv.x, sacc[1][0]); sacc[1][1] = fmaf(pk.y, vv.y, sacc[1][1]);
                 sacc[2][0] = fmaf(pk.z, vv.x, sacc[2][0]); sacc[2][1] = fmaf(pk.z, vv.y, sacc[2][1]);
@@ -434,7 +449,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvTcParams p) {
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const int cl = cb + i + e;
-                        v[i + e] += mish_acc((rr[e] - s_rg[cl]) * s_rg[NT + cl] + s_rg[2 * NT + cl]);
+                        v[i + e] += mish_fast((rr[e] - s_rg[cl]) * s_rg[NT + cl] + s_rg[2 * NT + cl]);
                     }
                 }
             }
@@ -556,14 +571,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc(const ConvTcParams p) {
     }
 }
 
-template <int GEOM, bool BF16, int NT>
+template <int GEOM, bool BF16, int NT, bool KV = false>
 static int launch_tc(const ConvTcParams& p, cudaStream_t s) {
-    using G = Geo<GEOM>;
-    const size_t sm = (size_t)STAGES * (G::KCH * G::HR * G::PXP * 16 + G::TAPS * G::KCH * NT * 16) + (3 * STAGES + 1) * 8 +
-                      16 * 4 + 16 + 3 * NT * 4 + 64;
+    constexpr int STAGES = Depth<GEOM, NT, KV>::STAGES;
+    const size_t sm = (size_t)STAGES * Depth<GEOM, NT, KV>::STAGE_BYTES + (3 * STAGES + 1) * 8 + 16 * 4 + 16 + 3 * NT * 4 + 64;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(k_conv_tc<GEOM, BF16, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(k_conv_tc<GEOM, BF16, NT, KV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         attr_set = true;
     }
     int gx;
@@ -571,7 +585,7 @@ static int launch_tc(const ConvTcParams& p, cudaStream_t s) {
     else if (GEOM == G_DOWN) gx = ((p.Wo + TPX - 1) / TPX) * ((p.Ho + ROWS - 1) / ROWS);
     else gx = (p.H * p.W + ROWS * TPX - 1) / (ROWS * TPX);
     dim3 grid(gx, p.Cout / NT, p.B);
-    k_conv_tc<GEOM, BF16, NT><<<grid, NTHREADS, sm, s>>>(p);
+    k_conv_tc<GEOM, BF16, NT, KV><<<grid, NTHREADS, sm, s>>>(p);
     return 1;
 }
 
@@ -591,7 +605,9 @@ int launch_conv_tc(const ConvTcParams& p, cudaStream_t s) {
     if (p.bf16) return -1;   // bf16 operand tensors are not wired up yet
     switch (p.geom) {
         case G_C3:   return nt == 128 ? launch_tc<G_C3, false, 128>(p, s) : launch_tc<G_C3, false, 64>(p, s);
-        case G_PW:   return nt == 128 ? launch_tc<G_PW, false, 128>(p, s) : launch_tc<G_PW, false, 64>(p, s);
+        case G_PW:
+            if (p.epi == EPI_KV) return launch_tc<G_PW, false, 128, true>(p, s);
+            return nt == 128 ? launch_tc<G_PW, false, 128>(p, s) : launch_tc<G_PW, false, 64>(p, s);
         case G_DOWN: return launch_tc<G_DOWN, false, 64>(p, s);
         default:     return launch_tc<G_UP, false, 64>(p, s);
     }

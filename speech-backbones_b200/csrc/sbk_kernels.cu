@@ -380,51 +380,57 @@ int launch_igemm(const IgemmParams& p, cudaStream_t s) {
 // (GradLogPEstimator2d.forward, diffusion.py:181-186 feeding downs[0][0].block1, :56-58)
 // ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_first_conv(const FirstConvParams p) {
+    // CTA = 64 consecutive frames of one mel row x 64 output channels.  The 3-row x 66-frame masked input halo and
+    // the 27x64 weights are staged in shared memory; the 16 KB output block is contiguous in NHWC, so it is
+    // transposed through shared memory and written with fully coalesced 16-byte stores.
     __shared__ __align__(16) float s_w[27 * 64];
+    __shared__ __align__(16) float s_out[64 * 68];
+    __shared__ float s_in[3][3][66];
     __shared__ float s_b[64];
     __shared__ float s_st[16];
     const int tid = threadIdx.x, b = blockIdx.z, n0 = blockIdx.y * 64;
+    const int wtiles = (p.T + 63) / 64;
+    const int h = blockIdx.x / wtiles, w0 = (blockIdx.x - h * wtiles) * 64;
     const int K = p.cin * 9;
     for (int i = tid; i < K * 64; i += 256) s_w[i] = p.w[(i >> 6) * p.C + n0 + (i & 63)];
     if (tid < 64) s_b[tid] = p.bias[n0 + tid];
     if (tid < 16) s_st[tid] = 0.f;
+    for (int i = tid; i < p.cin * 3 * 66; i += 256) {
+        const int ci = i / 198, rem = i - ci * 198, r = rem / 66, q = rem - r * 66;
+        const int hi = h + r - 1, wi = w0 + q - 1;
+        float v = 0.f;
+        if (hi >= 0 && hi < p.H && wi >= 0 && wi < p.T) {
+            const float mk = __ldg(p.mask + (long long)b * p.T + wi);
+            const long long idx = ((long long)b * p.H + hi) * p.T + wi;
+            const float x = ci == 0 ? __ldg(p.mu + idx) : (ci == 1 ? __ldg(p.xt + idx) : __ldg(p.spk_s + b * p.H + hi));
+            v = x * mk;
+        }
+        s_in[ci][r][q] = v;
+    }
     __syncthreads();
     const int pxl = tid & 63, cg = tid >> 6;
-    const int HW = p.H * p.T;
-    const int m = blockIdx.x * 64 + pxl;
     float acc[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) acc[j] = s_b[cg * 16 + j];
-    const bool ok = m < HW;
-    if (ok) {
-        const int h = m / p.T, w = m - h * p.T;
-        for (int ci = 0; ci < p.cin; ++ci) {
+    for (int ci = 0; ci < p.cin; ++ci) {
 #pragma unroll
-            for (int t = 0; t < 9; ++t) {
-                const int hi = h + t / 3 - 1, wi = w + t % 3 - 1;
-                float v = 0.f;
-                if (hi >= 0 && hi < p.H && wi >= 0 && wi < p.T) {
-                    const float mk = __ldg(p.mask + (long long)b * p.T + wi);
-                    const long long idx = ((long long)b * p.H + hi) * p.T + wi;
-                    const float x = ci == 0 ? __ldg(p.mu + idx) : (ci == 1 ? __ldg(p.xt + idx) : __ldg(p.spk_s + b * p.H + hi));
-                    v = x * mk;
-                }
-                const float* wr = &s_w[(ci * 9 + t) * 64 + cg * 16];
+        for (int t = 0; t < 9; ++t) {
+            const float v = s_in[ci][t / 3][pxl + t % 3];
+            const float* wr = &s_w[(ci * 9 + t) * 64 + cg * 16];
 #pragma unroll
-                for (int j4 = 0; j4 < 4; ++j4) {
-                    const float4 ww = *reinterpret_cast<const float4*>(wr + j4 * 4);
-                    acc[j4 * 4 + 0] = fmaf(v, ww.x, acc[j4 * 4 + 0]);
-                    acc[j4 * 4 + 1] = fmaf(v, ww.y, acc[j4 * 4 + 1]);
-                    acc[j4 * 4 + 2] = fmaf(v, ww.z, acc[j4 * 4 + 2]);
-                    acc[j4 * 4 + 3] = fmaf(v, ww.w, acc[j4 * 4 + 3]);
-                }
+            for (int j4 = 0; j4 < 4; ++j4) {
+                const float4 ww = *reinterpret_cast<const float4*>(wr + j4 * 4);
+                acc[j4 * 4 + 0] = fmaf(v, ww.x, acc[j4 * 4 + 0]);
+                acc[j4 * 4 + 1] = fmaf(v, ww.y, acc[j4 * 4 + 1]);
+                acc[j4 * 4 + 2] = fmaf(v, ww.z, acc[j4 * 4 + 2]);
+                acc[j4 * 4 + 3] = fmaf(v, ww.w, acc[j4 * 4 + 3]);
             }
         }
-        float* op = p.out + ((long long)b * HW + m) * p.C + n0 + cg * 16;
-#pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4)
-            *reinterpret_cast<float4*>(op + j4 * 4) = make_float4(acc[j4 * 4], acc[j4 * 4 + 1], acc[j4 * 4 + 2], acc[j4 * 4 + 3]);
     }
+    const bool ok = w0 + pxl < p.T;
+#pragma unroll
+    for (int j4 = 0; j4 < 4; ++j4)
+        *reinterpret_cast<float4*>(&s_out[pxl * 68 + cg * 16 + j4 * 4]) = make_float4(acc[j4 * 4], acc[j4 * 4 + 1], acc[j4 * 4 + 2], acc[j4 * 4 + 3]);
     // GN statistics: each half of the thread's 16 channels lies in one group (8 | C/8)
     const int cpg = p.C / kGroups, gb = n0 / cpg;
 #pragma unroll
@@ -434,7 +440,6 @@ __global__ void __launch_bounds__(256) k_first_conv(const FirstConvParams p) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) { const float v = acc[hf * 8 + j]; s += v; q = fmaf(v, v, q); }
         }
-        // warp-level pre-reduction: all lanes of a warp share cg
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
         if ((tid & 31) == 0) {
@@ -444,12 +449,17 @@ __global__ void __launch_bounds__(256) k_first_conv(const FirstConvParams p) {
         }
     }
     __syncthreads();
+    float* obase = p.out + (((long long)b * p.H + h) * p.T + w0) * p.C + n0;
+    for (int i = tid; i < 64 * 16; i += 256) {
+        const int q = i >> 4, c4 = (i & 15) * 4;
+        if (w0 + q < p.T) *reinterpret_cast<float4*>(obase + (long long)q * p.C + c4) = *reinterpret_cast<const float4*>(&s_out[q * 68 + c4]);
+    }
     const int ng = (64 + cpg - 1) / cpg;
     if (tid < ng * 2) atomicAdd(&p.ostats[((long long)b * kGroups + gb + (tid >> 1)) * 2 + (tid & 1)], (double)s_st[tid]);
 }
 
 int launch_first_conv(const FirstConvParams& p, cudaStream_t s) {
-    dim3 grid((p.H * p.T + 63) / 64, p.C / 64, p.B);
+    dim3 grid(((p.T + 63) / 64) * p.H, p.C / 64, p.B);
     k_first_conv<<<grid, 256, 0, s>>>(p);
     return 1;
 }
