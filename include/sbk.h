@@ -106,6 +106,9 @@ int sbk_debug_read(sbk_handle* h, const char* name, float* dst, int64_t* numel);
 /* test hook: when on, sbk_estimator snapshots every launch's output right after the launch (workspace buffers
  * are reused across stages, so later stages would otherwise overwrite earlier intermediates) */
 int sbk_debug_capture(sbk_handle* h, int on);
+/* test hook: layout of the intermediates sbk_debug_read returns: 0 = NHWC [B][H][W][C] (fp32 mode),
+ * 1 = channel-chunk planar [B][H][C/4][W][4] (tensor-core modes) */
+int sbk_debug_layout(const sbk_handle* h);
 /* test hook: enumerate intermediate names */
 int sbk_debug_num(const sbk_handle* h);
 const char* sbk_debug_name(const sbk_handle* h, int i);

@@ -17,7 +17,7 @@ EXPORTS = [
     "sbk_create", "sbk_destroy", "sbk_set_weight", "sbk_pack", "sbk_num_weights", "sbk_weight_name",
     "sbk_workspace_bytes", "sbk_estimator", "sbk_reverse_diffusion", "sbk_reverse_steps",
     "sbk_reverse_diffusion_host", "sbk_last_launch_count", "sbk_debug_read", "sbk_debug_num",
-    "sbk_debug_name", "sbk_last_error", "sbk_version", "sbk_profile_ops", "sbk_debug_capture",
+    "sbk_debug_name", "sbk_last_error", "sbk_version", "sbk_profile_ops", "sbk_debug_capture", "sbk_debug_layout",
 ]
 
 
@@ -59,6 +59,7 @@ def load_library() -> C.CDLL:
     lib.sbk_debug_read.argtypes = [P, C.c_char_p, F, C.POINTER(C.c_int64)]
     lib.sbk_debug_num.argtypes = [P]
     lib.sbk_debug_capture.argtypes = [P, I]
+    lib.sbk_debug_layout.argtypes = [P]
     lib.sbk_debug_name.argtypes = [P, I]
     lib.sbk_debug_name.restype = C.c_char_p
     lib.sbk_profile_ops.argtypes = [P, F, F, F, I, C.POINTER(C.c_int)]
@@ -207,6 +208,9 @@ class Engine:
     # ---- test hooks
     def debug_capture(self, on=True):
         _check(self.lib.sbk_debug_capture(self.h, 1 if on else 0), "sbk_debug_capture")
+
+    def debug_layout(self):
+        return int(self.lib.sbk_debug_layout(self.h))
 
     def debug_names(self):
         return [self.lib.sbk_debug_name(self.h, i).decode() for i in range(self.lib.sbk_debug_num(self.h))]

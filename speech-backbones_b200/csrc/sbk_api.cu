@@ -545,7 +545,7 @@ static int build_plan(sbk_handle* h, int B, int T, int tb_rows) {
             FirstConvParams& p = op.fc; memset(&p, 0, sizeof(p));
             p.mu = pl.mu; p.xt = pl.xt; p.spk_s = pl.spk_s; p.mask = pl.mask;
             p.w = W(r.prefix + ".block1.w"); p.bias = W(r.prefix + ".block1.block.0.bias");
-            p.out = A; p.ostats = st1; p.B = B; p.H = H0; p.T = T; p.cin = cin0; p.C = r.cout;
+            p.out = A; p.ostats = st1; p.B = B; p.H = H0; p.T = T; p.cin = cin0; p.C = r.cout; p.chw4 = use_tc ? 1 : 0;
             push(op, A, npix(lvl) * r.cout);
         } else if (tc1) {
             Op op = tc_conv(r.prefix + ".block1.raw", G_C3, r.prefix + ".block1.wtc", r.prefix + ".block1.block.0.bias", lvl,
@@ -564,7 +564,7 @@ static int build_plan(sbk_handle* h, int B, int T, int tb_rows) {
                 GnActParams& p = op.ga; memset(&p, 0, sizeof(p));
                 p.raw = A; p.gn = g1; p.tb = pl.tb + h->tb_off[k]; p.tb_stride = pl.tb_stride; p.step = pl.step_cur;
                 p.mask = pl.mask; p.T = T; p.lvl = lvl; p.out = Bb; p.B = B; p.H = Hs[lvl]; p.W = Ws[lvl]; p.C = r.cout;
-                p.round_tf32 = 1;
+                p.round_tf32 = 1; p.chw4 = 1;
                 op.bytes = 8.0 * npix(lvl) * r.cout;
                 push(op, nullptr, 0);
             }
@@ -583,7 +583,7 @@ static int build_plan(sbk_handle* h, int B, int T, int tb_rows) {
             ResFinalParams& p = op.rf; memset(&p, 0, sizeof(p));
             p.h2raw = h2; p.gn = g2;
             p.mask = pl.mask; p.T = T; p.lvl = lvl; p.out = out; p.B = B; p.H = Hs[lvl]; p.W = Ws[lvl]; p.C = r.cout;
-            p.out_mask = store_masked ? 1 : 0;
+            p.out_mask = store_masked ? 1 : 0; p.chw4 = use_tc ? 1 : 0;
             if (k == 0) {
                 p.x = nullptr; p.mu = pl.mu; p.xt = pl.xt; p.spk_s = pl.spk_s; p.cin = cin0;
                 p.wres = W(r.prefix + ".res.w"); p.bres = W(r.prefix + ".res_conv.bias");
@@ -719,7 +719,7 @@ static int build_plan(sbk_handle* h, int B, int T, int tb_rows) {
         p.raw = bf.A[0]; p.gn = gnref(stf, "estimator.final_block", C1, 0);
         p.wfin = W("estimator.final_conv.weight"); p.bfin = W("estimator.final_conv.bias");
         p.mask = pl.mask; p.mu = pl.mu; p.xt_in = pl.xt; p.xt_out = pl.xt;
-        p.coef = pl.coef; p.step = pl.step_cur; p.B = B; p.H = H0; p.T = T; p.C = C1;
+        p.coef = pl.coef; p.step = pl.step_cur; p.B = B; p.H = H0; p.T = T; p.C = C1; p.chw4 = use_tc ? 1 : 0;
         pl.final_op = (int)pl.ops.size();
         push(op, nullptr, 0);
     }
@@ -995,6 +995,7 @@ extern "C" int sbk_debug_capture(sbk_handle* h, int on) {
     h->capture = on != 0;
     return SBK_OK;
 }
+extern "C" int sbk_debug_layout(const sbk_handle* h) { return (h && h->cfg.precision != SBK_PREC_FP32) ? 1 : 0; }
 extern "C" int sbk_debug_num(const sbk_handle* h) { return h ? (int)h->plan.ops.size() : 0; }
 extern "C" const char* sbk_debug_name(const sbk_handle* h, int i) {
     if (!h || i < 0 || i >= (int)h->plan.ops.size()) return nullptr;

@@ -194,17 +194,17 @@ template <int GEOM, bool BF16, int NT, bool KV = false>
 __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT, KV>::MINB) k_conv_tc(const ConvTcParams p) {
     using G = Geo<GEOM>;
     constexpr int STAGES = Depth<GEOM, NT, KV>::STAGES;
-    constexpr int LAG = STAGES >= 3 ? STAGES - 2 : 0;      // cp.async groups allowed in flight behind the newest one
+    constexpr int LAG = STAGES >= 3 ? STAGES - 2 : 0;      // G_DOWN only: cp.async groups in flight behind the newest
     static_assert(STAGES >= 2, "need at least 2 stages");
+    static_assert(!BF16, "bf16 operand tensors are not wired up");
     constexpr int HR = G::HR, PXP = G::PXP, TAPS = G::TAPS, KCH = G::KCH;
-    constexpr int EPC = BF16 ? 8 : 4;                      // elements per 16-byte chunk
-    constexpr int ESZ = BF16 ? 2 : 4;
-    constexpr int CPS = KCH * EPC;                         // input channels per stage
+    constexpr int CPS = KCH * 4;                           // input channels per stage
     constexpr int PLANE = HR * PXP * 16;                   // bytes between K chunks of the A tile
     constexpr int A_STAGE_BYTES = KCH * PLANE;
     constexpr int B_STAGE_BYTES = TAPS * KCH * NT * 16;
     constexpr int NACC = G::NACC;
     constexpr uint32_t TMEM_COLS = NACC * NT;              // 128, 256 or 512: a power of two >= 32
+    constexpr bool BULK = GEOM != G_DOWN;                  // A tile = contiguous runs -> cp.async.bulk (no LSU work)
 
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sA = smem;                                            // [STAGES][KCH][HR][PXP][16]
@@ -259,63 +259,68 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT, KV>::MINB) k_conv_tc
             s_rg[2 * NT + i] = p.rgn.beta[c];
         }
     }
+    if (BULK) {
+        // Bulk copies only write the in-image part of the tile; everything else (zero padding, ragged last tile)
+        // must read as zero and is identical for every K stage, so it is cleared once - only for border tiles.
+        bool border;
+        if (GEOM == G_PW) border = (long long)(h0 + ROWS) * TPX > HW;
+        else border = h0 == 0 || h0 + ROWS + 1 > p.H || w0 == 0 || w0 + TPX + 1 > p.W;
+        if (border) {
+            uint4* z = reinterpret_cast<uint4*>(sA);
+            for (int i = tid; i < STAGES * A_STAGE_BYTES / 16; i += NTHREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+            fence_proxy_async();
+        }
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
 
     if (warp < NPROD / 32) {
-        // =============================== A producers: pure cp.async copy ===============================
-        // copy slot e -> (pixel item = e / KCH, chunk = e % KCH): the KCH chunks of a pixel are contiguous in HBM
-        constexpr int SLOTS = HR * PXP * KCH;
-        constexpr int PER = (SLOTS + NPROD - 1) / NPROD;
-        uint32_t sl_dst[PER]; long long sl_pix[PER]; int sl_chunk[PER]; bool sl_ok[PER];
+        if (!BULK) {
+            // ============ A producers (Downsample only): 16-byte cp.async gathers that de-interleave even/odd columns ============
+            constexpr int SLOTS = HR * PXP * KCH;
+            constexpr int PER = (SLOTS + NPROD - 1) / NPROD;
+            uint32_t sl_dst[PER]; long long sl_off[PER]; int sl_chunk[PER]; bool sl_ok[PER];
 #pragma unroll
-        for (int j = 0; j < PER; ++j) {
-            const int e = tid + j * NPROD;
-            const bool in = e < SLOTS;
-            const int item = in ? e / KCH : 0, k = in ? e % KCH : 0;
-            const int r = item / PXP, q = item - r * PXP;
-            bool ok; long long pix;
-            if (GEOM == G_C3 || GEOM == G_UP) {
-                const int hi = h0 - 1 + r, wi = w0 - 1 + q;
-                ok = in && hi >= 0 && hi < p.H && wi >= 0 && wi < p.W;
-                pix = (long long)(b * p.H + hi) * p.W + wi;
-            } else if (GEOM == G_DOWN) {
+            for (int j = 0; j < PER; ++j) {
+                const int e = tid + j * NPROD;
+                const bool in = e < SLOTS;
+                const int k = in ? e / (HR * PXP) : 0, item = in ? e - k * (HR * PXP) : 0;     // pixel fastest: coalesced 16 B pieces
+                const int r = item / PXP, q = item - r * PXP;
                 const int par = q / (TPX + 1), i = q - par * (TPX + 1);      // plane 0: odd columns, plane 1: even
                 const int hi = 2 * h0 - 1 + r, wi = par == 0 ? 2 * w0 - 1 + 2 * i : 2 * w0 + 2 * i;
-                ok = in && hi >= 0 && hi < p.H && wi >= 0 && wi < p.W && !(par == 1 && i == TPX);
-                pix = (long long)(b * p.H + hi) * p.W + wi;
-            } else {
-                const long long m = (long long)(h0 + r) * TPX + q;
-                ok = in && m < HW;
-                pix = (long long)b * HW + m;
+                const bool ok = in && hi >= 0 && hi < p.H && wi >= 0 && wi < p.W && !(par == 1 && i == TPX);
+                sl_ok[j] = ok; sl_chunk[j] = k;
+                sl_off[j] = ok ? ((long long)(b * p.H + hi)) : 0;             // row index; chunk/w folded in below
+                sl_off[j] = sl_off[j] * 1048576 + (ok ? wi : 0);              // pack (row, w): w < 2^20
+                sl_dst[j] = in ? (uint32_t)(k * PLANE + (r * PXP + q) * 16) : 0xFFFFFFFFu;
             }
-            sl_ok[j] = ok; sl_pix[j] = ok ? pix : 0; sl_chunk[j] = k;
-            sl_dst[j] = in ? (uint32_t)(k * PLANE + (r * PXP + q) * 16) : 0xFFFFFFFFu;
-        }
-        const uint32_t a0 = smem_u32(sA);
-        for (int ks = 0; ks < ksteps + LAG; ++ks) {
-            if (ks < ksteps) {
-                const int s = ks % STAGES;
-                mbar_wait(empty(s), ((ks / STAGES) & 1) ^ 1);
-                const int cc = ks * CPS;
-                const bool second = cc >= p.c0;
-                const uint8_t* src = reinterpret_cast<const uint8_t*>(second ? p.in1 : p.in0);
-                const long long cs = (second ? p.c1 : p.c0) * (long long)ESZ;      // pixel stride in bytes
-                const long long co = (long long)(second ? cc - p.c0 : cc) * ESZ;
+            const uint32_t a0 = smem_u32(sA);
+            for (int ks = 0; ks < ksteps + LAG; ++ks) {
+                if (ks < ksteps) {
+                    const int s = ks % STAGES;
+                    mbar_wait(empty(s), ((ks / STAGES) & 1) ^ 1);
+                    const int ck = ks * KCH;                                   // first 16-byte channel chunk of this stage
+                    const bool second = ck * 4 >= p.c0;
+                    const float* src = reinterpret_cast<const float*>(second ? p.in1 : p.in0);
+                    const int chs = (second ? p.c1 : p.c0) / 4;
+                    const int c0k = second ? ck - p.c0 / 4 : ck;
 #pragma unroll
-                for (int j = 0; j < PER; ++j) {
-                    if (sl_dst[j] == 0xFFFFFFFFu) continue;
-                    cp_async16(a0 + s * A_STAGE_BYTES + sl_dst[j], src + sl_pix[j] * cs + co + sl_chunk[j] * 16, sl_ok[j] ? 16u : 0u);
+                    for (int j = 0; j < PER; ++j) {
+                        if (sl_dst[j] == 0xFFFFFFFFu) continue;
+                        const long long row = sl_off[j] / 1048576, wi = sl_off[j] % 1048576;
+                        const float* g = src + ((row * chs + c0k + sl_chunk[j]) * p.W + wi) * 4;
+                        cp_async16(a0 + s * A_STAGE_BYTES + sl_dst[j], g, sl_ok[j] ? 16u : 0u);
+                    }
                 }
-            }
-            cp_async_commit();                       // (empty groups past the last stage keep the accounting uniform)
-            if (ks >= LAG) {
-                cp_async_wait<LAG>();                // this thread's copies of stage ks-LAG have landed
-                fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor core (async proxy)
-                __syncwarp();
-                if (lane == 0) mbar_arrive(full_a((ks - LAG) % STAGES));
+                cp_async_commit();                       // (empty groups past the last stage keep the accounting uniform)
+                if (ks >= LAG) {
+                    cp_async_wait<LAG>();                // this thread's copies of stage ks-LAG have landed
+                    fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor core (async proxy)
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(full_a((ks - LAG) % STAGES));
+                }
             }
         }
 
@@ -325,23 +330,21 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT, KV>::MINB) k_conv_tc
         const int q4 = warp & 3, jrow = warp >> 2;            // TMEM lane quarter / accumulator (output row)
         const int px = q4 * 32 + lane;
         const int Ho = (GEOM == G_DOWN || GEOM == G_UP) ? p.Ho : p.H, Wo = (GEOM == G_DOWN || GEOM == G_UP) ? p.Wo : p.W;
-        long long opix; int wo; bool valid;
+        const int CHo = p.Cout / 4;                            // 16-byte channel chunks of the output tensor
+        int ho, wo; bool valid;
         if (GEOM == G_C3 || GEOM == G_DOWN) {
-            const int ho = h0 + jrow;
-            wo = w0 + px;
+            ho = h0 + jrow; wo = w0 + px;
             valid = ho < Ho && wo < Wo;
-            opix = (long long)(b * Ho + ho) * Wo + wo;
         } else if (GEOM == G_UP) {
             valid = (h0 + jrow) < p.H && (w0 + px) < p.W;          // per-phase coordinates are formed below
-            wo = 2 * (w0 + px);
-            opix = (long long)(b * Ho + 2 * (h0 + jrow)) * Wo + wo;
+            ho = 2 * (h0 + jrow); wo = 2 * (w0 + px);
         } else {
             const long long m = (long long)(h0 + jrow) * TPX + px;
             valid = m < HW;
-            wo = (int)(m % p.W);
-            opix = (long long)b * HW + m;
+            ho = valid ? (int)(m / p.W) : 0;
+            wo = valid ? (int)(m - (long long)ho * p.W) : 0;
         }
-        if (!valid) { opix = 0; wo = 0; }
+        if (!valid) { ho = 0; wo = 0; }
         if constexpr (KV) {
             // LinearAttention pass 1 (diffusion.py:93-96).  This N tile holds two heads, columns [k_h(32) | v_h(32)] x 2.
             // Per tile of 256 pixels: m_d = max_px k, Z_d = sum_px exp(k - m_d), S[d][e] = sum_px exp(k[d,px]-m_d) v[e,px];
@@ -423,11 +426,13 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT, KV>::MINB) k_conv_tc
         constexpr int NPH = GEOM == G_UP ? 4 : 1;
 #pragma unroll 1
         for (int phase = 0; phase < NPH; ++phase) {
-        const long long opix_p = GEOM == G_UP ? opix + (long long)(phase >> 1) * Wo + (phase & 1) : opix;
+        const int ho_p = GEOM == G_UP ? ho + (phase >> 1) : ho;
         const int wo_p = GEOM == G_UP ? wo + (phase & 1) : wo;
         const int acc = GEOM == G_UP ? phase * ROWS + jrow : jrow;
         const float mo = (p.out_mask || p.epi == EPI_RES) ? __ldg(p.mask + (long long)b * p.T + ((long long)wo_p << p.lvl)) : 1.f;
-        float* op = p.out + opix_p * p.Cout + n0;
+        // element (b, ho, chunk, wo) of a [B][H][C/4][W][4] tensor; consecutive lanes = consecutive pixels = 16 B apart
+        const long long obase = (((long long)(b * Ho + ho_p) * CHo + n0 / 4) * Wo + wo_p) * 4;
+        const long long cstride = (long long)Wo * 4;           // floats between consecutive channel chunks
 #pragma unroll 1
         for (int cb = 0; cb < NT; cb += 32) {
             uint32_t r[32];
@@ -441,10 +446,10 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT, KV>::MINB) k_conv_tc
             }
             if (p.epi == EPI_RES && valid && mo != 0.f) {
                 // ResnetBlock tail: + Mish(GN(h2raw)) * mask  (diffusion.py:77-78)
-                const float* rp = p.rraw + opix_p * p.Cout + n0 + cb;
+                const float* rp = p.rraw + obase + (cb / 4) * cstride;
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
-                    const float4 rv = __ldg(reinterpret_cast<const float4*>(rp + i));
+                    const float4 rv = __ldg(reinterpret_cast<const float4*>(rp + (i / 4) * cstride));
                     const float rr[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
@@ -458,8 +463,9 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT, KV>::MINB) k_conv_tc
                 for (int i = 0; i < 32; ++i) v[i] *= mo;
             }
             if (valid) {
+                float* op = p.out + obase + (cb / 4) * cstride;
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(op + cb + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(op + (i / 4) * cstride) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
             }
             if (p.ostats) {
                 // GroupNorm partials of this 32-column chunk: 8-channel sub-sums first (static register indexing),
@@ -501,8 +507,8 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT, KV>::MINB) k_conv_tc
             for (int ks = 0; ks < ksteps; ++ks) {
                 const int s = ks % STAGES;
                 const uint32_t ph = (ks / STAGES) & 1;
-                mbar_wait(full_a(s), ph);
-                mbar_wait(full_b(s), ph);
+                if (!BULK) mbar_wait(full_a(s), ph);
+                mbar_wait(full_b(s), ph);               // weights (+ the A runs when they are bulk copies)
                 tc_fence_after();
 #pragma unroll
                 for (int kk = 0; kk < KCH / 2; ++kk) {
@@ -512,12 +518,12 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT, KV>::MINB) k_conv_tc
                         // ho = 2*hi - 1 + kh: parity ph uses (kh=1,dh=0),(kh=3,dh=-1) if ph=0 and (kh=0,dh=+1),(kh=2,dh=0) if ph=1
 #pragma unroll
                         for (int phase = 0; phase < 4; ++phase) {
-                            const int ph = phase >> 1, pw = phase & 1;
+                            const int pph = phase >> 1, pw = phase & 1;
 #pragma unroll
                             for (int t2 = 0; t2 < 4; ++t2) {
                                 const int a = t2 >> 1, bb = t2 & 1;
-                                const int kh = ph ? (a ? 2 : 0) : (a ? 3 : 1), kw = pw ? (bb ? 2 : 0) : (bb ? 3 : 1);
-                                const int dh = ph ? (a ? 0 : 1) : (a ? -1 : 0), dw = pw ? (bb ? 0 : 1) : (bb ? -1 : 0);
+                                const int kh = pph ? (a ? 2 : 0) : (a ? 3 : 1), kw = pw ? (bb ? 2 : 0) : (bb ? 3 : 1);
+                                const int dh = pph ? (a ? 0 : 1) : (a ? -1 : 0), dw = pw ? (bb ? 0 : 1) : (bb ? -1 : 0);
                                 const uint64_t bd = make_desc(b_st + (kh * 4 + kw) * KCH * (NT * 16), NT * 16, 128);
 #pragma unroll
                                 for (int j = 0; j < ROWS; ++j) {
@@ -547,15 +553,66 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT, KV>::MINB) k_conv_tc
             umma_commit(acc_bar);                       // accumulators complete
         }
     } else {
-        // =============================== weight loader ===============================
+        // =============================== loader: weights (+ A runs) by cp.async.bulk ===============================
         if (lane == 0) {
             const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpk) + (size_t)b * p.w_bstride_bytes +
                                   (size_t)blockIdx.y * ksteps * B_STAGE_BYTES;
+            // bytes of A the bulk runs deliver per stage (identical for every stage)
+            uint32_t a_bytes = 0;
+            if (BULK) {
+                if (GEOM == G_PW) {
+                    for (int r = 0; r < HR; ++r) {
+                        const long long m_lo = (long long)(h0 + r) * TPX;
+                        const long long n = m_lo >= HW ? 0 : (HW - m_lo < TPX ? HW - m_lo : TPX);
+                        a_bytes += (uint32_t)n * 16u;
+                    }
+                } else {
+                    const int wlo = w0 - 1 < 0 ? 0 : w0 - 1, whi = w0 + TPX + 1 > p.W ? p.W : w0 + TPX + 1;
+                    for (int r = 0; r < HR; ++r) {
+                        const int hi = h0 - 1 + r;
+                        if (hi >= 0 && hi < p.H) a_bytes += (uint32_t)(whi - wlo) * 16u;
+                    }
+                }
+                a_bytes *= KCH;
+            }
             for (int ks = 0; ks < ksteps; ++ks) {
                 const int s = ks % STAGES;
                 mbar_wait(empty(s), ((ks / STAGES) & 1) ^ 1);
-                mbar_arrive_expect_tx(full_b(s), B_STAGE_BYTES);
+                mbar_arrive_expect_tx(full_b(s), B_STAGE_BYTES + a_bytes);
                 bulk_g2s(smem_u32(sB + s * B_STAGE_BYTES), wsrc + (size_t)ks * B_STAGE_BYTES, B_STAGE_BYTES, full_b(s));
+                if (BULK) {
+                    const uint32_t a_s = smem_u32(sA) + s * A_STAGE_BYTES;
+#pragma unroll 1
+                    for (int k = 0; k < KCH; ++k) {
+                        const int ck = ks * KCH + k;                     // 16-byte channel chunk index over the concat
+                        const bool second = ck * 4 >= p.c0;
+                        const float* src = reinterpret_cast<const float*>(second ? p.in1 : p.in0);
+                        const int chs = (second ? p.c1 : p.c0) / 4;
+                        const int cl = second ? ck - p.c0 / 4 : ck;
+                        if (GEOM == G_PW) {
+                            for (int r = 0; r < HR; ++r) {
+                                long long m = (long long)(h0 + r) * TPX;
+                                const long long m_hi = m + TPX < HW ? m + TPX : HW;
+                                int q = 0;
+                                while (m < m_hi) {                     // split the flattened run at image-row boundaries
+                                    const int hh = (int)(m / p.W), ww = (int)(m - (long long)hh * p.W);
+                                    const int n = (int)((p.W - ww) < (m_hi - m) ? (p.W - ww) : (m_hi - m));
+                                    bulk_g2s(a_s + k * PLANE + (r * PXP + q) * 16,
+                                             src + (((long long)(b * p.H + hh) * chs + cl) * p.W + ww) * 4, (uint32_t)n * 16u, full_b(s));
+                                    m += n; q += n;
+                                }
+                            }
+                        } else {
+                            const int wlo = w0 - 1 < 0 ? 0 : w0 - 1, whi = w0 + TPX + 1 > p.W ? p.W : w0 + TPX + 1;
+                            for (int r = 0; r < HR; ++r) {
+                                const int hi = h0 - 1 + r;
+                                if (hi < 0 || hi >= p.H) continue;
+                                bulk_g2s(a_s + k * PLANE + (r * PXP + (wlo - (w0 - 1))) * 16,
+                                         src + (((long long)(b * p.H + hi) * chs + cl) * p.W + wlo) * 4, (uint32_t)(whi - wlo) * 16u, full_b(s));
+                            }
+                        }
+                    }
+                }
             }
         }
     }

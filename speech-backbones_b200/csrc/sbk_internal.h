@@ -71,6 +71,7 @@ struct GnActParams {
     const float* raw; GnRef gn; const float* tb; int tb_stride; int tb_per_sample; const int* step;
     const float* mask; int T; int lvl;
     float* out; int B, H, W, C; int round_tf32;
+    int chw4;
 };
 
 struct FirstConvParams {        // Block.conv of downs.0.0.block1 on the planar stack([mu, xt(, s)]) * mask
@@ -78,8 +79,9 @@ struct FirstConvParams {        // Block.conv of downs.0.0.block1 on the planar 
     const float* mask;          // [B][T]
     const float* w;             // packed [cin*9 + r*3 + s][64]
     const float* bias;
-    float* out; double* ostats; // [B][H][T][C], [B][8][2]
+    float* out; double* ostats; // [B][H][T][C] (or [B][H][C/4][T][4] when chw4), [B][8][2]
     int B, H, T, cin, C;
+    int chw4;
 };
 
 struct ResFinalParams {         // out = Mish(GN(h2raw))*mask + res(x*mask)
@@ -91,6 +93,7 @@ struct ResFinalParams {         // out = Mish(GN(h2raw))*mask + res(x*mask)
     float* out;
     int B, H, W, C;
     int out_mask;               // store out*mask (operand form for the next conv)
+    int chw4;                   // activations are [B][H][C/4][W][4] (tensor-core modes) instead of NHWC
 };
 
 struct AttnCtxParams {          // merge per-tile softmax partials -> normalised context [B][4][32][32]
@@ -119,6 +122,7 @@ struct FinalParams {            // final_block GN+Mish, final_conv 1x1 -> 1, mas
     const int* step;
     int mode;                   // 0: estimator output, 1: deterministic Euler, 2: Euler-Maruyama
     int B, H, T, C;
+    int chw4;
 };
 
 struct TimeTableParams {        // SinusoidalPosEmb + mlp + the 12 per-ResnetBlock projections

@@ -449,10 +449,19 @@ __global__ void __launch_bounds__(256) k_first_conv(const FirstConvParams p) {
         }
     }
     __syncthreads();
-    float* obase = p.out + (((long long)b * p.H + h) * p.T + w0) * p.C + n0;
-    for (int i = tid; i < 64 * 16; i += 256) {
-        const int q = i >> 4, c4 = (i & 15) * 4;
-        if (w0 + q < p.T) *reinterpret_cast<float4*>(obase + (long long)q * p.C + c4) = *reinterpret_cast<const float4*>(&s_out[q * 68 + c4]);
+    if (p.chw4) {
+        // [B][H][C/4][T][4]: per channel chunk the 64 frames are one contiguous 1 KB run
+        float* obase = p.out + ((((long long)b * p.H + h) * (p.C / 4) + n0 / 4) * p.T + w0) * 4;
+        for (int i = tid; i < 64 * 16; i += 256) {
+            const int ch = i >> 6, q = i & 63;
+            if (w0 + q < p.T) *reinterpret_cast<float4*>(obase + ((long long)ch * p.T + q) * 4) = *reinterpret_cast<const float4*>(&s_out[q * 68 + ch * 4]);
+        }
+    } else {
+        float* obase = p.out + (((long long)b * p.H + h) * p.T + w0) * p.C + n0;
+        for (int i = tid; i < 64 * 16; i += 256) {
+            const int q = i >> 4, c4 = (i & 15) * 4;
+            if (w0 + q < p.T) *reinterpret_cast<float4*>(obase + (long long)q * p.C + c4) = *reinterpret_cast<const float4*>(&s_out[q * 68 + c4]);
+        }
     }
     const int ng = (64 + cpg - 1) / cpg;
     if (tid < ng * 2) atomicAdd(&p.ostats[((long long)b * kGroups + gb + (tid >> 1)) * 2 + (tid & 1)], (double)s_st[tid]);
@@ -480,11 +489,21 @@ __global__ void __launch_bounds__(256) k_resfinal(const ResFinalParams p) {
     const int c4n = p.C >> 2;
     const long long n4 = (long long)p.H * p.W * c4n;
     for (long long i = (long long)blockIdx.x * 256 + tid; i < n4; i += (long long)gridDim.x * 256) {
-        const long long pix = i / c4n;
-        const int c = (int)(i - pix * c4n) * 4;
-        const int w = (int)(pix % p.W);
+        // float4 unit i of this sample -> (pixel, channel quad); in both layouts the unit index IS the memory order
+        long long pix; int c, w;
+        if (p.chw4) {
+            const long long hc = i / p.W;                    // (h, chunk)
+            w = (int)(i - hc * p.W);
+            const int h = (int)(hc / c4n);
+            c = (int)(hc - (long long)h * c4n) * 4;
+            pix = (long long)h * p.W + w;
+        } else {
+            pix = i / c4n;
+            c = (int)(i - pix * c4n) * 4;
+            w = (int)(pix % p.W);
+        }
         const float mk = __ldg(p.mask + (long long)b * p.T + ((long long)w << p.lvl));
-        const long long off = ((long long)b * p.H * p.W + pix) * p.C + c;
+        const long long off = ((long long)b * n4 + i) * 4;
         float o[4] = {0.f, 0.f, 0.f, 0.f};
         if (mk != 0.f) {
             const float4 r = ldg4(p.h2raw + off);
@@ -533,11 +552,18 @@ __global__ void __launch_bounds__(256) k_gn_act(const GnActParams p) {
     const int c4n = p.C >> 2;
     const long long n4 = (long long)p.H * p.W * c4n;
     for (long long i = (long long)blockIdx.x * 256 + tid; i < n4; i += (long long)gridDim.x * 256) {
-        const long long pix = i / c4n;
-        const int c = (int)(i - pix * c4n) * 4;
-        const int w = (int)(pix % p.W);
+        int c, w;
+        if (p.chw4) {
+            const long long hc = i / p.W;
+            w = (int)(i - hc * p.W);
+            c = (int)(hc % c4n) * 4;
+        } else {
+            const long long pix = i / c4n;
+            c = (int)(i - pix * c4n) * 4;
+            w = (int)(pix % p.W);
+        }
         const float mk = __ldg(p.mask + (long long)b * p.T + ((long long)w << p.lvl));
-        const long long off = ((long long)b * p.H * p.W + pix) * p.C + c;
+        const long long off = ((long long)b * n4 + i) * 4;
         float o[4] = {0.f, 0.f, 0.f, 0.f};
         if (mk != 0.f) {
             const float4 r = ldg4(p.raw + off);
@@ -690,6 +716,45 @@ __global__ void __launch_bounds__(256) k_final(const FinalParams p) {
     float4 cf = make_float4(0.f, 0.f, 0.f, 0.f);
     int srow = 0;
     if (p.mode != 0) { srow = *p.step; cf = p.coef[srow]; }
+    auto update = [&](long long idx, float mk, float dot) {
+        const float est = mk != 0.f ? dot + bf : 0.f;
+        if (p.mode == 0) {
+            p.xt_out[idx] = est;
+        } else {
+            const float xt = p.xt_in[idx], mu = __ldg(p.mu + idx);
+            float dxt;
+            if (p.mode == 1) {
+                dxt = ((0.5f * ((mu - xt) - est)) * cf.x) * cf.y;
+            } else {
+                const float eps = __ldg(*p.noise_pp + (long long)srow * p.B * HW + idx);
+                dxt = ((0.5f * (mu - xt) - est) * cf.x) * cf.y + eps * cf.z;
+            }
+            p.xt_out[idx] = (xt - dxt) * mk;
+        }
+    };
+    if (p.chw4) {
+        // [B][H][C/4][T][4]: one thread per frame; per channel chunk a warp reads 32 frames x 16 B = 512 contiguous bytes
+        const int c4n = p.C / 4;
+        for (int m = blockIdx.x * 256 + tid; m < HW; m += gridDim.x * 256) {
+            const int h = m / p.T, w = m - h * p.T;
+            const float mk = __ldg(p.mask + (long long)b * p.T + w);
+            float dot = 0.f;
+            if (mk != 0.f) {
+                const float* rp = p.raw + ((((long long)b * p.H + h) * c4n) * p.T + w) * 4;
+#pragma unroll 4
+                for (int ch = 0; ch < c4n; ++ch) {
+                    const float4 r = ldg4(rp + (long long)ch * p.T * 4);
+                    const int c = ch * 4;
+                    dot = fmaf(wf[c + 0], mish_f((r.x - mean[c + 0]) * scale[c + 0] + beta[c + 0]), dot);
+                    dot = fmaf(wf[c + 1], mish_f((r.y - mean[c + 1]) * scale[c + 1] + beta[c + 1]), dot);
+                    dot = fmaf(wf[c + 2], mish_f((r.z - mean[c + 2]) * scale[c + 2] + beta[c + 2]), dot);
+                    dot = fmaf(wf[c + 3], mish_f((r.w - mean[c + 3]) * scale[c + 3] + beta[c + 3]), dot);
+                }
+            }
+            update((long long)b * HW + m, mk, dot);
+        }
+        return;
+    }
     for (int base = blockIdx.x * 128; base < HW; base += gridDim.x * 128) {
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
@@ -710,29 +775,13 @@ __global__ void __launch_bounds__(256) k_final(const FinalParams p) {
             }
 #pragma unroll
             for (int o = 8; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o, 16);
-            if (lane16 == 0 && inb) {
-                const long long idx = (long long)b * HW + m;
-                const float est = mk != 0.f ? dot + bf : 0.f;
-                if (p.mode == 0) {
-                    p.xt_out[idx] = est;
-                } else {
-                    const float xt = p.xt_in[idx], mu = __ldg(p.mu + idx);
-                    float dxt;
-                    if (p.mode == 1) {
-                        dxt = ((0.5f * ((mu - xt) - est)) * cf.x) * cf.y;
-                    } else {
-                        const float eps = __ldg(*p.noise_pp + (long long)srow * p.B * HW + idx);
-                        dxt = ((0.5f * (mu - xt) - est) * cf.x) * cf.y + eps * cf.z;
-                    }
-                    p.xt_out[idx] = (xt - dxt) * mk;
-                }
-            }
+            if (lane16 == 0 && inb) update((long long)b * HW + m, mk, dot);
         }
     }
 }
 
 int launch_final(const FinalParams& p, cudaStream_t s) {
-    int gx = (p.H * p.T + 127) / 128;
+    int gx = p.chw4 ? (p.H * p.T + 255) / 256 : (p.H * p.T + 127) / 128;
     if (gx > 2048) gx = 2048;
     k_final<<<dim3(gx, p.B), 256, 4 * p.C * sizeof(float), s>>>(p);
     return 1;

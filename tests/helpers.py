@@ -27,5 +27,8 @@ def rel_l2(a, b):
     return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
 
 
-def nhwc_to_nchw(flat, B, H, W, C):
+def nhwc_to_nchw(flat, B, H, W, C, layout=0):
+    """layout 0: [B][H][W][C]; layout 1: [B][H][C/4][W][4] (tensor-core modes)."""
+    if layout == 1:
+        return flat.view(B, H, C // 4, W, 4).permute(0, 2, 4, 1, 3).reshape(B, C, H, W).contiguous()
     return flat.view(B, H, W, C).permute(0, 3, 1, 2).contiguous()

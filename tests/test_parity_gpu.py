@@ -59,7 +59,7 @@ def stagewise_errors(eng, cfg, sd, xt, mask, mu, t, spk, masked_storage=False):
             got = got.view(ref.shape)
         else:
             B, C, H, W = ref.shape
-            got = nhwc_to_nchw(got, B, H, W, C)
+            got = nhwc_to_nchw(got, B, H, W, C, eng.debug_layout())
             if masked_storage and not name.endswith(".raw") and name not in ATTN_INPUTS:
                 mk = mask[:, None, :, ::mask.shape[-1] // W]          # this level's mask [B,1,1,W]
                 ref = ref * mk
