@@ -146,6 +146,26 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+           "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+           "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+           "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand is read from tensor memory (lanes = M rows, one 32-bit column per K element)
+__device__ __forceinline__ void umma_ts_tf32(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
 __device__ __forceinline__ float mish_fast(float x) {
     // same closed form as mish_f (sbk_kernels.cu); exp via ex2.approx and an approximate reciprocal:
     // relative error ~1e-6, far below the tf32/bf16 operand rounding this path already applies.
@@ -203,14 +223,14 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT, KV>::MINB) k_conv_tc
     constexpr int A_STAGE_BYTES = KCH * PLANE;
     constexpr int B_STAGE_BYTES = TAPS * KCH * NT * 16;
     constexpr int NACC = G::NACC;
-    constexpr uint32_t TMEM_COLS = NACC * NT;              // 128, 256 or 512: a power of two >= 32
+    constexpr uint32_t TMEM_COLS = KV ? 512 : NACC * NT;   // 128, 256 or 512: a power of two >= 32 (KV: 256 + 64 used)
     constexpr bool BULK = GEOM != G_DOWN;                  // A tile = contiguous runs -> cp.async.bulk (no LSU work)
 
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sA = smem;                                            // [STAGES][KCH][HR][PXP][16]
     uint8_t* sB = sA + STAGES * A_STAGE_BYTES;                     // [STAGES][TAPS][KCH][NT][16]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sB + STAGES * B_STAGE_BYTES);   // full_a[S], full_b[S], empty[S], acc
-    float* s_st = reinterpret_cast<float*>(bars + 3 * STAGES + 1);               // [8 groups][2]
+    float* s_st = reinterpret_cast<float*>(bars + 3 * STAGES + 2);               // [8 groups][2]
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_st + 16);
     float* s_rg = reinterpret_cast<float*>(s_tmem + 4);                          // EPI_RES: mean|scale|beta [NT] each
 
@@ -237,11 +257,13 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT, KV>::MINB) k_conv_tc
     auto full_b = [&](int s) { return bar0 + 8u * (STAGES + s); };
     auto empty = [&](int s) { return bar0 + 8u * (2 * STAGES + s); };
     const uint32_t acc_bar = bar0 + 8u * (3 * STAGES);
+    const uint32_t kv_bar = bar0 + 8u * (3 * STAGES + 1);   // KV: S = P V^T complete
 
     // ---- one-time setup
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_a(s), NPROD / 32); mbar_init(full_b(s), 1); mbar_init(empty(s), 1); }
         mbar_init(acc_bar, 1);
+        mbar_init(kv_bar, 1);
         fence_barrier_init();
     }
     if (warp == NPROD / 32) tmem_alloc(smem_u32(s_tmem), TMEM_COLS);
@@ -346,80 +368,92 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT, KV>::MINB) k_conv_tc
         }
         if (!valid) { ho = 0; wo = 0; }
         if constexpr (KV) {
-            // LinearAttention pass 1 (diffusion.py:93-96).  This N tile holds two heads, columns [k_h(32) | v_h(32)] x 2.
-            // Per tile of 256 pixels: m_d = max_px k, Z_d = sum_px exp(k - m_d), S[d][e] = sum_px exp(k[d,px]-m_d) v[e,px];
-            // k and v never reach HBM.  The accumulators are staged through the (now idle) pipeline smem.
-            constexpr int LDK = NT + 4;                       // padded row: conflict-free 16-byte row-strided stores
-            float* kvs = reinterpret_cast<float*>(smem);       // [256 px][LDK]
-            float* s_red = kvs + ROWS * TPX * LDK;             // [4][NT/2]
-            float* s_m = s_red + 4 * (NT / 2);                // [NT/2]
-            static_assert((ROWS * TPX * LDK + 5 * (NT / 2)) * 4 <= STAGES * (A_STAGE_BYTES + B_STAGE_BYTES), "KV staging must fit");
-            const int pxl = jrow * TPX + px;
+            // LinearAttention pass 1 (diffusion.py:93-96) with the GEMM roles swapped: the main loop computed
+            //   D1[kv channel (TMEM lane)][pixel (column)] = W_kv[128 x C] * X^T        (M = 128, N = 256 pixels)
+            // with lanes 0-31 = k of head h0, 32-63 = v of h0, 64-95 = k of h1, 96-127 = v of h1.  So one thread owns one
+            // channel across all 256 pixels: the softmax max / sum are private reductions over its TMEM columns (no
+            // shuffles, no smem).  P = exp(k - max) is written back to TMEM in place, V^T goes to shared memory as a
+            // K-major operand, and S[d][e] = sum_px P[d,px] V[e,px] is a second UMMA with A = P read from TMEM.
+            // k and v never reach HBM; per 256-pixel tile only (max, sum, S) partials are written.
+            constexpr int NPX = ROWS * TPX;                        // 256 pixels = columns of D1
+            const int q = warp & 3, half = warp >> 2;              // lane quarter (channel block) / pixel half
+            const bool is_k = (q & 1) == 0;
+            const int hh = q >> 1;                                 // head within this N tile
+            const int nvalid = (int)min((long long)NPX, (long long)HW - (long long)h0 * TPX);
+            const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16);
+            float* s_m2 = reinterpret_cast<float*>(smem + 64 * 1024);       // [2 halves][128 lanes] max, then sum
+            uint8_t* vt = smem;                                    // V^T operand: [64 px chunks][64 rows][16 B]
+            const int col0 = half * (NPX / 2);
+            float mx = -INFINITY;
+            if (is_k) {
 #pragma unroll 1
-            for (int cb = 0; cb < NT; cb += 32) {
-                uint32_t r[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(jrow * NT + cb), r);
+                for (int c = 0; c < NPX / 2; c += 32) {
+                    uint32_t r[32];
+                    tmem_ld32(tq + col0 + c, r);
 #pragma unroll
-                for (int i = 0; i < 32; i += 4)
-                    *reinterpret_cast<float4*>(&kvs[pxl * LDK + cb + i]) =
-                        make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+                    for (int i = 0; i < 32; ++i) if (col0 + c + i < nvalid) mx = fmaxf(mx, __uint_as_float(r[i]));
+                }
+                s_m2[half * 128 + q * 32 + lane] = mx;
+            } else {
+                // V^T: row = hh*32 + lane, 4 consecutive pixels per 16-byte chunk
+                const int row = hh * 32 + lane;
+#pragma unroll 1
+                for (int c = 0; c < NPX / 2; c += 32) {
+                    uint32_t r[32];
+                    tmem_ld32(tq + col0 + c, r);
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4)
+                        *reinterpret_cast<uint4*>(vt + ((size_t)((col0 + c + i) / 4) * 64 + row) * 16) = make_uint4(r[i], r[i + 1], r[i + 2], r[i + 3]);
+                }
             }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            float zsum = 0.f, md = 0.f;
+            if (is_k) {
+                md = fmaxf(s_m2[q * 32 + lane], s_m2[128 + q * 32 + lane]);
+#pragma unroll 1
+                for (int c = 0; c < NPX / 2; c += 32) {
+                    uint32_t r[32];
+                    tmem_ld32(tq + col0 + c, r);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float e = (col0 + c + i < nvalid) ? __expf(__uint_as_float(r[i]) - md) : 0.f;
+                        zsum += e;
+                        r[i] = __float_as_uint(e);
+                    }
+                    tmem_st32(tq + col0 + c, r);
+                }
+                tmem_wait_st();
+            }
+            fence_proxy_async();                                   // V^T smem writes -> visible to the tensor core
             tc_fence_before();
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            const int nvalid = (int)min((long long)ROWS * TPX, (long long)HW - (long long)h0 * TPX);
-            constexpr int NK = NT / 2;                        // k columns in this tile (32 per head)
-            const int kc = tid % NK, part = tid / NK;         // NK = 64: 4 pixel quarters of 64
-            const int kcol = (kc >> 5) * 64 + (kc & 31);      // column of k[d] of head kc>>5
-            constexpr int PPQ = ROWS * TPX / (NPROD / NK);
-            float mx = -INFINITY;
-#pragma unroll 8
-            for (int q = part * PPQ; q < part * PPQ + PPQ; ++q)
-                if (q < nvalid) mx = fmaxf(mx, kvs[q * LDK + kcol]);
-            s_red[part * NK + kc] = mx;
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (tid < NK) {
-                float m = s_red[tid];
-                for (int i = 1; i < NPROD / NK; ++i) m = fmaxf(m, s_red[i * NK + tid]);
-                s_m[tid] = m;
+            if (is_k) s_m2[half * 128 + q * 32 + lane] = zsum;     // (max values were consumed before the barrier)
+            if (tid == 0) {
+                tc_fence_after();
+                const uint32_t idesc2 = make_idesc<false>(TPX, 64);
+                const uint32_t vt0 = smem_u32(vt);
+#pragma unroll 1
+                for (int kk = 0; kk < NPX / 8; ++kk) {             // K = 8 pixels (32 bytes) per MMA
+                    const uint64_t bd = make_desc(vt0 + kk * 2 * (64 * 16), 64 * 16, 128);
+                    umma_ts_tf32(tmem_base + NPX, tmem_base + kk * 8, bd, idesc2, kk != 0 ? 1u : 0u);
+                }
+                umma_commit(kv_bar);
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            const float md = s_m[kc];
-            float z = 0.f;
-#pragma unroll 8
-            for (int q = part * PPQ; q < part * PPQ + PPQ; ++q) {
-                const float e = q < nvalid ? __expf(kvs[q * LDK + kcol] - md) : 0.f;
-                kvs[q * LDK + kcol] = e;
-                z += e;
-            }
-            s_red[part * NK + kc] = z;
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            const int mtiles = gridDim.x;
-            float* part0 = p.kv_part + (((long long)b * mtiles + blockIdx.x) * kHeads + blockIdx.y * (NT / 64)) * kKvPartFloats;
-            if (tid < NK) {
-                float zz = s_red[tid];
-                for (int i = 1; i < NPROD / NK; ++i) zz += s_red[i * NK + tid];
-                float* pt = part0 + (tid >> 5) * kKvPartFloats;
-                pt[tid & 31] = s_m[tid];
-                pt[32 + (tid & 31)] = zz;
-            }
-            // S: thread owns head hh, d = dg*4..+3, e = eg*2..+1
-            constexpr int TPH = NPROD / (NT / 64);            // threads per head (128 for two heads)
-            const int hh = tid / TPH, tl = tid % TPH;
-            const int dg = tl & 7, eg = tl >> 3;              // 8 x 16 = 128 threads cover 32 x 32
-            float sacc[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
-#pragma unroll 8
-            for (int q = 0; q < nvalid; ++q) {
-                const float4 pk = *reinterpret_cast<const float4*>(&kvs[q * LDK + hh * 64 + dg * 4]);
-                const float2 vv = *reinterpret_cast<const float2*>(&kvs[q * LDK + hh * 64 + 32 + eg * 2]);
-                sacc[0][0] = fmaf(pk.x, vv.x, sacc[0][0]); sacc[0][1] = fmaf(pk.x, vv.y, sacc[0][1]);
-                sacc[1][0] = fmaf(pk.y, vv.x, sacc[1][0]); sacc[1][1] = fmaf(pk.y, vv.y, sacc[1][1]);
-                sacc[2][0] = fmaf(pk.z, vv.x, sacc[2][0]); sacc[2][1] = fmaf(pk.z, vv.y, sacc[2][1]);
-                sacc[3][0] = fmaf(pk.w, vv.x, sacc[3][0]); sacc[3][1] = fmaf(pk.w, vv.y, sacc[3][1]);
-            }
-            float* pt = part0 + hh * kKvPartFloats;
+            if (is_k && half == 0) {
+                mbar_wait(kv_bar, 0);
+                tc_fence_after();
+                uint32_t r[32];
+                tmem_ld32(tq + NPX + hh * 32, r);                  // S[d = lane][e = 0..31] of head hh
+                const int mtiles = gridDim.x;
+                float* pt = p.kv_part + (((long long)b * mtiles + blockIdx.x) * kHeads + blockIdx.y * 2 + hh) * kKvPartFloats;
+                pt[lane] = md;
+                pt[32 + lane] = s_m2[q * 32 + lane] + s_m2[128 + q * 32 + lane];
 #pragma unroll
-            for (int qd = 0; qd < 4; ++qd)
-                *reinterpret_cast<float2*>(&pt[64 + (dg * 4 + qd) * 32 + eg * 2]) = make_float2(sacc[qd][0], sacc[qd][1]);
+                for (int i = 0; i < 32; i += 4)
+                    *reinterpret_cast<float4*>(&pt[64 + lane * 32 + i]) =
+                        make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+            }
         } else {
         const int cpg = p.Cout / kGroups;
         const float* bp = p.bias ? p.bias + (long long)b * p.bias_bstride + n0 : nullptr;
@@ -514,7 +548,12 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT, KV>::MINB) k_conv_tc
                 for (int kk = 0; kk < KCH / 2; ++kk) {
                     const uint32_t a_st = a0 + s * A_STAGE_BYTES + kk * 2 * PLANE;
                     const uint32_t b_st = b0 + s * B_STAGE_BYTES + kk * 2 * (NT * 16);
-                    if (GEOM == G_UP) {
+                    if (KV) {
+                        // swapped roles: A = weight tile (128 kv channels), B = the 256-pixel activation tile
+                        const uint64_t wd = make_desc(b_st, NT * 16, 128);
+                        const uint64_t xd = make_desc(a_st, PLANE, 128);
+                        umma<BF16>(tmem_base, wd, xd, make_idesc<BF16>(TPX, ROWS * TPX), (ks | kk) != 0 ? 1u : 0u);
+                    } else if (GEOM == G_UP) {
                         // ho = 2*hi - 1 + kh: parity ph uses (kh=1,dh=0),(kh=3,dh=-1) if ph=0 and (kh=0,dh=+1),(kh=2,dh=0) if ph=1
 #pragma unroll
                         for (int phase = 0; phase < 4; ++phase) {
@@ -631,7 +670,7 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT, KV>::MINB) k_conv_tc
 template <int GEOM, bool BF16, int NT, bool KV = false>
 static int launch_tc(const ConvTcParams& p, cudaStream_t s) {
     constexpr int STAGES = Depth<GEOM, NT, KV>::STAGES;
-    const size_t sm = (size_t)STAGES * Depth<GEOM, NT, KV>::STAGE_BYTES + (3 * STAGES + 1) * 8 + 16 * 4 + 16 + 3 * NT * 4 + 64;
+    const size_t sm = (size_t)STAGES * Depth<GEOM, NT, KV>::STAGE_BYTES + (3 * STAGES + 2) * 8 + 16 * 4 + 16 + 3 * NT * 4 + 64;
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(k_conv_tc<GEOM, BF16, NT, KV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
