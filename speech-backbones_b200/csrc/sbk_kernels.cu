@@ -638,19 +638,26 @@ int launch_attn_ctx(const AttnCtxParams& p, cudaStream_t s) {
 // This kernel builds (I + g P_b) in the implicit-GEMM weight layout [ci][co].
 __global__ void __launch_bounds__(256) k_attn_mix(const AttnMixParams p) {
     __shared__ float s_ctx[kHeads * 32 * 33];
-    __shared__ float s_mb[32 * 128];
+    __shared__ __align__(16) float s_mb[128 * 32];     // Mb transposed: [j = h*32+d][cl]
     const int cb = blockIdx.x * 32, b = blockIdx.y, tid = threadIdx.x, C = p.C;
     for (int i = tid; i < kHeads * 32 * 32; i += 256)
         s_ctx[(i >> 5) * 33 + (i & 31)] = p.ctx[(long long)b * kHeads * 1024 + i];
     __syncthreads();
-    {   // Mb[cl][h*32+d] = sum_e wout[c][h*32+e] * ctx[h][d][e]
+    {   // Mb[cl][h*32+d] = sum_e wout[c][h*32+e] * ctx[h][d][e]; stored j-major so the next phase reads float4 rows
         const int j = tid & 127, hh = j >> 5, cl0 = (tid >> 7) * 16;
+        float cr[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) cr[e] = s_ctx[j * 33 + e];
         for (int cl = cl0; cl < cl0 + 16; ++cl) {
-            const float* wo = p.wout + (long long)(cb + cl) * kAttnHidden + hh * 32;
-            float a = 0.f;
-#pragma unroll 8
-            for (int e = 0; e < 32; ++e) a = fmaf(__ldg(wo + e), s_ctx[j * 33 + e], a);
-            s_mb[cl * 128 + j] = a;
+            const float4* wo4 = reinterpret_cast<const float4*>(p.wout + (long long)(cb + cl) * kAttnHidden + hh * 32);
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+            for (int e4 = 0; e4 < 8; ++e4) {
+                const float4 w = __ldg(wo4 + e4);
+                a0 = fmaf(w.x, cr[4 * e4 + 0], a0); a1 = fmaf(w.y, cr[4 * e4 + 1], a1);
+                a2 = fmaf(w.z, cr[4 * e4 + 2], a2); a3 = fmaf(w.w, cr[4 * e4 + 3], a3);
+            }
+            s_mb[j * 32 + cl] = (a0 + a1) + (a2 + a3);
         }
     }
     __syncthreads();
@@ -659,10 +666,16 @@ __global__ void __launch_bounds__(256) k_attn_mix(const AttnMixParams p) {
         float acc[32];
 #pragma unroll
         for (int cl = 0; cl < 32; ++cl) acc[cl] = 0.f;
+#pragma unroll 2
         for (int j = 0; j < kAttnHidden; ++j) {
             const float wq = __ldg(p.wq + (long long)j * C + cp);
+            const float4* m4 = reinterpret_cast<const float4*>(&s_mb[j * 32]);
 #pragma unroll
-            for (int cl = 0; cl < 32; ++cl) acc[cl] = fmaf(s_mb[cl * 128 + j], wq, acc[cl]);
+            for (int q = 0; q < 8; ++q) {
+                const float4 m = m4[q];
+                acc[4 * q + 0] = fmaf(m.x, wq, acc[4 * q + 0]); acc[4 * q + 1] = fmaf(m.y, wq, acc[4 * q + 1]);
+                acc[4 * q + 2] = fmaf(m.z, wq, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(m.w, wq, acc[4 * q + 3]);
+            }
         }
         if (p.tc_nt) {
             // tcgen05 1x1 weight image: [ntile][kstage][chunk][cout % NT][4 cin], tf32 (RNA)
