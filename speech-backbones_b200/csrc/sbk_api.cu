@@ -86,6 +86,7 @@ struct sbk_handle {
     std::map<std::string, float*> packed;     // kernel layouts
     std::vector<void*> owned;
     float* d_freqs = nullptr;
+    float* d_zero = nullptr;                  // zero page for the tensor-core kernels' border copies
     bool is_packed = false;
     Plan plan;
     cudaStream_t cap_stream = nullptr;
@@ -388,6 +389,11 @@ extern "C" int sbk_pack(sbk_handle* h) {
         if (!h->d_freqs) { CU(cudaMalloc(&h->d_freqs, half * sizeof(float))); h->owned.push_back(h->d_freqs); }
         CU(cudaMemcpy(h->d_freqs, f.data(), half * sizeof(float), cudaMemcpyHostToDevice));
     }
+    if (!h->d_zero) {
+        CU(cudaMalloc(&h->d_zero, 8192));
+        h->owned.push_back(h->d_zero);
+        CU(cudaMemset(h->d_zero, 0, 8192));
+    }
     free_plan(h);   // packed pointers may have changed
     h->is_packed = true;
     return SBK_OK;
@@ -515,7 +521,7 @@ static int build_plan(sbk_handle* h, int B, int T, int tb_rows) {
         p.geom = geom; p.in0 = in0; p.c0 = c0; p.in1 = in1; p.c1 = c1; p.H = Hs[lvl]; p.W = Ws[lvl]; p.B = B;
         p.Ho = p.H; p.Wo = p.W;
         p.wpk = W(wkey); p.bias = bkey.empty() ? nullptr : W(bkey); p.out = out; p.Cout = cout;
-        p.epi = EPI_PLAIN; p.ostats = st; p.mask = pl.mask; p.T = T; p.lvl = lvl;
+        p.epi = EPI_PLAIN; p.ostats = st; p.mask = pl.mask; p.T = T; p.lvl = lvl; p.zero_page = h->d_zero;
         const double taps = geom == G_PW ? 1.0 : (geom == G_UP ? 4.0 : 9.0);
         op.flops = 2.0 * B * Hs[lvl] * Ws[lvl] * cout * (c0 + c1) * taps;
         op.bytes = 4.0 * B * Hs[lvl] * Ws[lvl] * (c0 + c1 + cout);

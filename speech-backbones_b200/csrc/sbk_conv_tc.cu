@@ -197,23 +197,30 @@ __device__ __forceinline__ float mish_acc(float x) {     // exact-math Mish for 
 
 using namespace tc;
 
-// Pipeline depth / residency.  Two CTAs per SM (<= ~110 KB smem and <= 256 TMEM columns each) let one CTA's
-// epilogue and setup overlap the other's main loop - this non-persistent kernel has no other overlap - so the
-// bandwidth-heavy, short-K configurations (NT = 64, 1x1) use few stages x 2 CTAs; the long-K NT = 128 3x3 convs
-// keep one CTA with a deeper ring.  The producers keep STAGES-1 stages of cp.async in flight.
+// Residency / pipeline / accumulator configuration.
+//   * persistent CTAs: each CTA loops over output tiles (round-robin), every role keeps its own ring / slot counters;
+//   * NSLOT TMEM accumulator slots: with two slots the epilogue of tile i overlaps the loads + MMAs of tile i+1;
+//   * two CTAs per SM when smem (<= ~108 KB) and TMEM (<= 256 columns) allow, else one CTA with a deeper ring.
+constexpr int pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
 template <int GEOM, int NT, bool KV = false> struct Depth {
     static constexpr int STAGE_BYTES = Geo<GEOM>::KCH * Geo<GEOM>::HR * Geo<GEOM>::PXP * 16 + Geo<GEOM>::TAPS * Geo<GEOM>::KCH * NT * 16;
-    static constexpr int FIT2 = (108 * 1024) / STAGE_BYTES;             // stages that fit with 2 CTAs / SM
-    static constexpr int FIT1 = (220 * 1024) / STAGE_BYTES;
-    static constexpr bool TWO = !KV && FIT2 >= 2 && Geo<GEOM>::NACC * NT <= 256 && !(GEOM == G_C3 && NT == 128);
-    static constexpr int STAGES = TWO ? FIT2 : (FIT1 > 6 ? 6 : FIT1);
+    static constexpr int SLOT_COLS = KV ? 320 : Geo<GEOM>::NACC * NT;        // KV: D1 (256 px columns) + S (64)
+    static constexpr int NSLOT = (!KV && 2 * SLOT_COLS <= 512) ? 2 : 1;
+    static constexpr int TMEM_COLS = pow2_cols(NSLOT * SLOT_COLS);
+    static constexpr int EXTRA = KV ? 66 * 1024 : 0;                          // KV: V^T operand tile + reduction scratch
+    static constexpr int FIT2 = (108 * 1024) / STAGE_BYTES;
+    static constexpr int FIT1 = (220 * 1024 - EXTRA) / STAGE_BYTES;
+    static constexpr bool TWO = !KV && FIT2 >= 2 && TMEM_COLS <= 256;
+    static constexpr int STAGES = TWO ? (FIT2 > 4 ? 4 : FIT2) : (FIT1 > 6 ? 6 : FIT1);
     static constexpr int MINB = TWO ? 2 : 1;
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + EXTRA + (2 * STAGES + 2 * NSLOT + 2) * 8 + 16 * 4 + 16 + 3 * NT * 4 + 64;
 };
 
 template <int GEOM, bool BF16, int NT, bool KV = false>
 __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT, KV>::MINB) k_conv_tc(const ConvTcParams p) {
     using G = Geo<GEOM>;
-    constexpr int STAGES = Depth<GEOM, NT, KV>::STAGES;
+    using D = Depth<GEOM, NT, KV>;
+    constexpr int STAGES = D::STAGES, NSLOT = D::NSLOT, SLOT_COLS = D::SLOT_COLS;
     constexpr int LAG = STAGES >= 3 ? STAGES - 2 : 0;      // G_DOWN only: cp.async groups in flight behind the newest
     static_assert(STAGES >= 2, "need at least 2 stages");
     static_assert(!BF16, "bf16 operand tensors are not wired up");
@@ -222,151 +229,151 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT, KV>::MINB) k_conv_tc
     constexpr int PLANE = HR * PXP * 16;                   // bytes between K chunks of the A tile
     constexpr int A_STAGE_BYTES = KCH * PLANE;
     constexpr int B_STAGE_BYTES = TAPS * KCH * NT * 16;
-    constexpr int NACC = G::NACC;
-    constexpr uint32_t TMEM_COLS = KV ? 512 : NACC * NT;   // 128, 256 or 512: a power of two >= 32 (KV: 256 + 64 used)
     constexpr bool BULK = GEOM != G_DOWN;                  // A tile = contiguous runs -> cp.async.bulk (no LSU work)
 
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sA = smem;                                            // [STAGES][KCH][HR][PXP][16]
     uint8_t* sB = sA + STAGES * A_STAGE_BYTES;                     // [STAGES][TAPS][KCH][NT][16]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + STAGES * B_STAGE_BYTES);   // full_a[S], full_b[S], empty[S], acc
-    float* s_st = reinterpret_cast<float*>(bars + 3 * STAGES + 2);               // [8 groups][2]
+    uint8_t* sX = sB + STAGES * B_STAGE_BYTES;                     // KV scratch (V^T operand + reductions)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sX + D::EXTRA);   // full[S], empty[S], tfull[NSLOT], tempty[NSLOT], fa[S]*, kv
+    float* s_st = reinterpret_cast<float*>(bars + 3 * STAGES + 2 * NSLOT + 2);   // [8 groups][2]
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_st + 16);
     float* s_rg = reinterpret_cast<float*>(s_tmem + 4);                          // EPI_RES: mean|scale|beta [NT] each
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int Cin = p.c0 + p.c1;
     const int HW = p.H * p.W;
-    int w0, h0;
-    if (GEOM == G_C3 || GEOM == G_UP || GEOM == G_DOWN) {
-        // C3 / UP tile the input(=output / half-output) grid, DOWN tiles its output grid
-        const int wt = GEOM == G_DOWN ? p.Wo : p.W;
-        const int wtiles = (wt + TPX - 1) / TPX;
-        w0 = (blockIdx.x % wtiles) * TPX;
-        h0 = (blockIdx.x / wtiles) * ROWS;
-    } else {
-        w0 = 0;
-        h0 = blockIdx.x * ROWS;                // row = 128 consecutive pixels of the flattened image
-    }
-    const int n0 = blockIdx.y * NT;
-    const int b = blockIdx.z;
     const int ksteps = Cin / CPS;
+    // ---- tile space: (sample, pixel tile, N tile), N tile fastest so neighbours in time share the A tile in L2
+    const int wt_w = (GEOM == G_DOWN ? p.Wo : p.W), wt_h = (GEOM == G_DOWN ? p.Ho : p.H);
+    const int wtiles = (wt_w + TPX - 1) / TPX;
+    const int mtiles = GEOM == G_PW ? (HW + ROWS * TPX - 1) / (ROWS * TPX) : wtiles * ((wt_h + ROWS - 1) / ROWS);
+    const int ntn = p.Cout / NT;
+    const int total_tiles = p.B * mtiles * ntn;
+    auto decode = [&](int t, int& b, int& h0, int& w0, int& n0, int& mt) {
+        const int nt = t % ntn; const int r = t / ntn;
+        mt = r % mtiles; b = r / mtiles; n0 = nt * NT;
+        if (GEOM == G_PW) { w0 = 0; h0 = mt * ROWS; }
+        else { w0 = (mt % wtiles) * TPX; h0 = (mt / wtiles) * ROWS; }
+    };
 
     const uint32_t bar0 = smem_u32(bars);
-    auto full_a = [&](int s) { return bar0 + 8u * s; };
-    auto full_b = [&](int s) { return bar0 + 8u * (STAGES + s); };
-    auto empty = [&](int s) { return bar0 + 8u * (2 * STAGES + s); };
-    const uint32_t acc_bar = bar0 + 8u * (3 * STAGES);
-    const uint32_t kv_bar = bar0 + 8u * (3 * STAGES + 1);   // KV: S = P V^T complete
+    auto full_b = [&](int s) { return bar0 + 8u * s; };                       // weights (+ bulk A runs): tx-count
+    auto empty = [&](int s) { return bar0 + 8u * (STAGES + s); };
+    auto tfull = [&](int a) { return bar0 + 8u * (2 * STAGES + a); };         // accumulator slot complete
+    auto tempty = [&](int a) { return bar0 + 8u * (2 * STAGES + NSLOT + a); };// accumulator slot drained
+    auto full_a = [&](int s) { return bar0 + 8u * (2 * STAGES + 2 * NSLOT + s); };   // G_DOWN cp.async producers
+    const uint32_t kv_bar = bar0 + 8u * (3 * STAGES + 2 * NSLOT);
 
     // ---- one-time setup
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_a(s), NPROD / 32); mbar_init(full_b(s), 1); mbar_init(empty(s), 1); }
-        mbar_init(acc_bar, 1);
+        for (int a = 0; a < NSLOT; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), NPROD / 32); }
         mbar_init(kv_bar, 1);
         fence_barrier_init();
     }
-    if (warp == NPROD / 32) tmem_alloc(smem_u32(s_tmem), TMEM_COLS);
+    if (warp == NPROD / 32) tmem_alloc(smem_u32(s_tmem), D::TMEM_COLS);
     if (tid < 16) s_st[tid] = 0.f;
-    if (p.epi == EPI_RES) {
-        const int cpg = p.Cout / kGroups;
-        for (int i = tid; i < NT; i += NTHREADS) {
-            const int c = n0 + i, g = c / cpg;
-            const double s = p.rgn.stats[(b * kGroups + g) * 2], ss = p.rgn.stats[(b * kGroups + g) * 2 + 1];
-            const double m = s * (double)p.rgn.inv_count;
-            double var = ss * (double)p.rgn.inv_count - m * m;
-            var = var < 0.0 ? 0.0 : var;
-            s_rg[i] = (float)m;
-            s_rg[NT + i] = (float)(1.0 / sqrt(var + 1e-5)) * p.rgn.gamma[c];
-            s_rg[2 * NT + i] = p.rgn.beta[c];
-        }
-    }
-    if (BULK) {
-        // Bulk copies only write the in-image part of the tile; everything else (zero padding, ragged last tile)
-        // must read as zero and is identical for every K stage, so it is cleared once - only for border tiles.
-        bool border;
-        if (GEOM == G_PW) border = (long long)(h0 + ROWS) * TPX > HW;
-        else border = h0 == 0 || h0 + ROWS + 1 > p.H || w0 == 0 || w0 + TPX + 1 > p.W;
-        if (border) {
-            uint4* z = reinterpret_cast<uint4*>(sA);
-            for (int i = tid; i < STAGES * A_STAGE_BYTES / 16; i += NTHREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
-            fence_proxy_async();
-        }
-    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
 
     if (warp < NPROD / 32) {
-        if (!BULK) {
-            // ============ A producers (Downsample only): 16-byte cp.async gathers that de-interleave even/odd columns ============
-            constexpr int SLOTS = HR * PXP * KCH;
-            constexpr int PER = (SLOTS + NPROD - 1) / NPROD;
-            uint32_t sl_dst[PER]; long long sl_off[PER]; int sl_chunk[PER]; bool sl_ok[PER];
+        // =========================================================================================================
+        // warps 0-7: (G_DOWN: cp.async A producers, then) epilogue of every tile
+        // =========================================================================================================
+        uint32_t it = 0;      // G_DOWN producer ring counter
+        int tl = 0;           // tile counter (accumulator slot / phase)
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
+            int b, h0, w0, n0, mt;
+            decode(t, b, h0, w0, n0, mt);
+            if (!BULK) {
+                // ---- A producers (Downsample only): 16-byte cp.async gathers that de-interleave even/odd columns
+                constexpr int SLOTS = HR * PXP * KCH;
+                constexpr int PER = (SLOTS + NPROD - 1) / NPROD;
+                uint32_t sl_dst[PER]; long long sl_off[PER]; int sl_chunk[PER]; bool sl_ok[PER];
 #pragma unroll
-            for (int j = 0; j < PER; ++j) {
-                const int e = tid + j * NPROD;
-                const bool in = e < SLOTS;
-                const int k = in ? e / (HR * PXP) : 0, item = in ? e - k * (HR * PXP) : 0;     // pixel fastest: coalesced 16 B pieces
-                const int r = item / PXP, q = item - r * PXP;
-                const int par = q / (TPX + 1), i = q - par * (TPX + 1);      // plane 0: odd columns, plane 1: even
-                const int hi = 2 * h0 - 1 + r, wi = par == 0 ? 2 * w0 - 1 + 2 * i : 2 * w0 + 2 * i;
-                const bool ok = in && hi >= 0 && hi < p.H && wi >= 0 && wi < p.W && !(par == 1 && i == TPX);
-                sl_ok[j] = ok; sl_chunk[j] = k;
-                sl_off[j] = ok ? ((long long)(b * p.H + hi)) : 0;             // row index; chunk/w folded in below
-                sl_off[j] = sl_off[j] * 1048576 + (ok ? wi : 0);              // pack (row, w): w < 2^20
-                sl_dst[j] = in ? (uint32_t)(k * PLANE + (r * PXP + q) * 16) : 0xFFFFFFFFu;
-            }
-            const uint32_t a0 = smem_u32(sA);
-            for (int ks = 0; ks < ksteps + LAG; ++ks) {
-                if (ks < ksteps) {
-                    const int s = ks % STAGES;
-                    mbar_wait(empty(s), ((ks / STAGES) & 1) ^ 1);
-                    const int ck = ks * KCH;                                   // first 16-byte channel chunk of this stage
-                    const bool second = ck * 4 >= p.c0;
-                    const float* src = reinterpret_cast<const float*>(second ? p.in1 : p.in0);
-                    const int chs = (second ? p.c1 : p.c0) / 4;
-                    const int c0k = second ? ck - p.c0 / 4 : ck;
+                for (int j = 0; j < PER; ++j) {
+                    const int e = tid + j * NPROD;
+                    const bool in = e < SLOTS;
+                    const int k = in ? e / (HR * PXP) : 0, item = in ? e - k * (HR * PXP) : 0;     // pixel fastest
+                    const int r = item / PXP, q = item - r * PXP;
+                    const int par = q / (TPX + 1), i = q - par * (TPX + 1);      // plane 0: odd columns, plane 1: even
+                    const int hi = 2 * h0 - 1 + r, wi = par == 0 ? 2 * w0 - 1 + 2 * i : 2 * w0 + 2 * i;
+                    const bool ok = in && hi >= 0 && hi < p.H && wi >= 0 && wi < p.W && !(par == 1 && i == TPX);
+                    sl_ok[j] = ok; sl_chunk[j] = k;
+                    sl_off[j] = (ok ? (long long)(b * p.H + hi) : 0) * 1048576 + (ok ? wi : 0);   // pack (row, w)
+                    sl_dst[j] = in ? (uint32_t)(k * PLANE + (r * PXP + q) * 16) : 0xFFFFFFFFu;
+                }
+                const uint32_t a0 = smem_u32(sA);
+                for (int ks = 0; ks < ksteps + LAG; ++ks) {
+                    if (ks < ksteps) {
+                        const uint32_t g = it + ks;
+                        const int s = g % STAGES;
+                        mbar_wait(empty(s), ((g / STAGES) & 1) ^ 1);
+                        const int ck = ks * KCH;
+                        const bool second = ck * 4 >= p.c0;
+                        const float* src = reinterpret_cast<const float*>(second ? p.in1 : p.in0);
+                        const int chs = (second ? p.c1 : p.c0) / 4;
+                        const int c0k = second ? ck - p.c0 / 4 : ck;
 #pragma unroll
-                    for (int j = 0; j < PER; ++j) {
-                        if (sl_dst[j] == 0xFFFFFFFFu) continue;
-                        const long long row = sl_off[j] / 1048576, wi = sl_off[j] % 1048576;
-                        const float* g = src + ((row * chs + c0k + sl_chunk[j]) * p.W + wi) * 4;
-                        cp_async16(a0 + s * A_STAGE_BYTES + sl_dst[j], g, sl_ok[j] ? 16u : 0u);
+                        for (int j = 0; j < PER; ++j) {
+                            if (sl_dst[j] == 0xFFFFFFFFu) continue;
+                            const long long row = sl_off[j] / 1048576, wi = sl_off[j] % 1048576;
+                            const float* gp = src + ((row * chs + c0k + sl_chunk[j]) * p.W + wi) * 4;
+                            cp_async16(a0 + s * A_STAGE_BYTES + sl_dst[j], gp, sl_ok[j] ? 16u : 0u);
+                        }
+                    }
+                    cp_async_commit();                       // (empty groups past the last stage keep the accounting uniform)
+                    if (ks >= LAG) {
+                        cp_async_wait<LAG>();                // this thread's copies of stage ks-LAG have landed
+                        fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor core
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(full_a((it + ks - LAG) % STAGES));
                     }
                 }
-                cp_async_commit();                       // (empty groups past the last stage keep the accounting uniform)
-                if (ks >= LAG) {
-                    cp_async_wait<LAG>();                // this thread's copies of stage ks-LAG have landed
-                    fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor core (async proxy)
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(full_a((ks - LAG) % STAGES));
-                }
+                it += ksteps;
             }
-        }
 
-        // =============================== epilogue ===============================
-        mbar_wait(acc_bar, 0);
-        tc_fence_after();
-        const int q4 = warp & 3, jrow = warp >> 2;            // TMEM lane quarter / accumulator (output row)
-        const int px = q4 * 32 + lane;
-        const int Ho = (GEOM == G_DOWN || GEOM == G_UP) ? p.Ho : p.H, Wo = (GEOM == G_DOWN || GEOM == G_UP) ? p.Wo : p.W;
-        const int CHo = p.Cout / 4;                            // 16-byte channel chunks of the output tensor
-        int ho, wo; bool valid;
-        if (GEOM == G_C3 || GEOM == G_DOWN) {
-            ho = h0 + jrow; wo = w0 + px;
-            valid = ho < Ho && wo < Wo;
-        } else if (GEOM == G_UP) {
-            valid = (h0 + jrow) < p.H && (w0 + px) < p.W;          // per-phase coordinates are formed below
-            ho = 2 * (h0 + jrow); wo = 2 * (w0 + px);
-        } else {
-            const long long m = (long long)(h0 + jrow) * TPX + px;
-            valid = m < HW;
-            ho = valid ? (int)(m / p.W) : 0;
-            wo = valid ? (int)(m - (long long)ho * p.W) : 0;
-        }
-        if (!valid) { ho = 0; wo = 0; }
+            // ---- epilogue of tile t
+            const int slot = tl % NSLOT;
+            const uint32_t tslot = tmem_base + slot * SLOT_COLS;
+            if (p.epi == EPI_RES) {
+                asm volatile("bar.sync 1, 256;" ::: "memory");        // previous tile's readers of s_rg are done
+                const int cpg = p.Cout / kGroups;
+                for (int i = tid; i < NT; i += NPROD) {
+                    const int c = n0 + i, g = c / cpg;
+                    const double sm_ = p.rgn.stats[(b * kGroups + g) * 2], ss = p.rgn.stats[(b * kGroups + g) * 2 + 1];
+                    const double m = sm_ * (double)p.rgn.inv_count;
+                    double var = ss * (double)p.rgn.inv_count - m * m;
+                    var = var < 0.0 ? 0.0 : var;
+                    s_rg[i] = (float)m;
+                    s_rg[NT + i] = (float)(1.0 / sqrt(var + 1e-5)) * p.rgn.gamma[c];
+                    s_rg[2 * NT + i] = p.rgn.beta[c];
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
+            mbar_wait(tfull(slot), (tl / NSLOT) & 1);
+            tc_fence_after();
+            const int q4 = warp & 3, jrow = warp >> 2;            // TMEM lane quarter / accumulator (output row)
+            const int px = q4 * 32 + lane;
+            const int Ho = (GEOM == G_DOWN || GEOM == G_UP) ? p.Ho : p.H, Wo = (GEOM == G_DOWN || GEOM == G_UP) ? p.Wo : p.W;
+            const int CHo = p.Cout / 4;                            // 16-byte channel chunks of the output tensor
+            int ho, wo; bool valid;
+            if (GEOM == G_C3 || GEOM == G_DOWN) {
+                ho = h0 + jrow; wo = w0 + px;
+                valid = ho < Ho && wo < Wo;
+            } else if (GEOM == G_UP) {
+                valid = (h0 + jrow) < p.H && (w0 + px) < p.W;          // per-phase coordinates are formed below
+                ho = 2 * (h0 + jrow); wo = 2 * (w0 + px);
+            } else {
+                const long long m = (long long)(h0 + jrow) * TPX + px;
+                valid = m < HW;
+                ho = valid ? (int)(m / p.W) : 0;
+                wo = valid ? (int)(m - (long long)ho * p.W) : 0;
+            }
+            if (!valid) { ho = 0; wo = 0; }
         if constexpr (KV) {
             // LinearAttention pass 1 (diffusion.py:93-96) with the GEMM roles swapped: the main loop computed
             //   D1[kv channel (TMEM lane)][pixel (column)] = W_kv[128 x C] * X^T        (M = 128, N = 256 pixels)
@@ -380,9 +387,9 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT, KV>::MINB) k_conv_tc
             const bool is_k = (q & 1) == 0;
             const int hh = q >> 1;                                 // head within this N tile
             const int nvalid = (int)min((long long)NPX, (long long)HW - (long long)h0 * TPX);
-            const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16);
-            float* s_m2 = reinterpret_cast<float*>(smem + 64 * 1024);       // [2 halves][128 lanes] max, then sum
-            uint8_t* vt = smem;                                    // V^T operand: [64 px chunks][64 rows][16 B]
+            const uint32_t tq = tslot + ((uint32_t)(q * 32) << 16);
+            float* s_m2 = reinterpret_cast<float*>(sX + 64 * 1024);       // [2 halves][128 lanes] max, then sum
+            uint8_t* vt = sX;                                    // V^T operand: [64 px chunks][64 rows][16 B]
             const int col0 = half * (NPX / 2);
             float mx = -INFINITY;
             if (is_k) {
@@ -435,18 +442,17 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT, KV>::MINB) k_conv_tc
 #pragma unroll 1
                 for (int kk = 0; kk < NPX / 8; ++kk) {             // K = 8 pixels (32 bytes) per MMA
                     const uint64_t bd = make_desc(vt0 + kk * 2 * (64 * 16), 64 * 16, 128);
-                    umma_ts_tf32(tmem_base + NPX, tmem_base + kk * 8, bd, idesc2, kk != 0 ? 1u : 0u);
+                    umma_ts_tf32(tslot + NPX, tslot + kk * 8, bd, idesc2, kk != 0 ? 1u : 0u);
                 }
                 umma_commit(kv_bar);
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if (is_k && half == 0) {
-                mbar_wait(kv_bar, 0);
+                mbar_wait(kv_bar, tl & 1);
                 tc_fence_after();
                 uint32_t r[32];
                 tmem_ld32(tq + NPX + hh * 32, r);                  // S[d = lane][e = 0..31] of head hh
-                const int mtiles = gridDim.x;
-                float* pt = p.kv_part + (((long long)b * mtiles + blockIdx.x) * kHeads + blockIdx.y * 2 + hh) * kKvPartFloats;
+                float* pt = p.kv_part + (((long long)b * mtiles + mt) * kHeads + (n0 / 64) + hh) * kKvPartFloats;
                 pt[lane] = md;
                 pt[32 + lane] = s_m2[q * 32 + lane] + s_m2[128 + q * 32 + lane];
 #pragma unroll
@@ -470,7 +476,7 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT, KV>::MINB) k_conv_tc
 #pragma unroll 1
         for (int cb = 0; cb < NT; cb += 32) {
             uint32_t r[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(acc * NT + cb), r);
+            tmem_ld32(tslot + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(acc * NT + cb), r);
             float v[32];
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
@@ -532,122 +538,141 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT, KV>::MINB) k_conv_tc
         }
         }
         }
-        tc_fence_before();
+            // accumulator slot drained: hand it back to the MMA issuer
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty(slot));
+            if (p.ostats) {
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                const int cpg = p.Cout / kGroups, gb = n0 / cpg, ng = (NT + cpg - 1) / cpg;
+                if (tid < ng * 2) {
+                    atomicAdd(&p.ostats[((long long)b * kGroups + gb + (tid >> 1)) * 2 + (tid & 1)], (double)s_st[tid]);
+                    s_st[tid] = 0.f;
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
+        }
     } else if (warp == NPROD / 32) {
-        // =============================== MMA issuer ===============================
+        // =========================================================================================================
+        // MMA issuer (one thread)
+        // =========================================================================================================
         if (lane == 0) {
             const uint32_t idesc = make_idesc<BF16>(TPX, NT);
             const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
-            for (int ks = 0; ks < ksteps; ++ks) {
-                const int s = ks % STAGES;
-                const uint32_t ph = (ks / STAGES) & 1;
-                if (!BULK) mbar_wait(full_a(s), ph);
-                mbar_wait(full_b(s), ph);               // weights (+ the A runs when they are bulk copies)
+            uint32_t it = 0;
+            int tl = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
+                const int slot = tl % NSLOT;
+                const uint32_t tslot = tmem_base + slot * SLOT_COLS;
+                mbar_wait(tempty(slot), ((tl / NSLOT) & 1) ^ 1);        // epilogue has drained this slot
                 tc_fence_after();
+                for (int ks = 0; ks < ksteps; ++ks, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    if (!BULK) mbar_wait(full_a(s), ph);
+                    mbar_wait(full_b(s), ph);               // weights (+ the A runs when they are bulk copies)
+                    tc_fence_after();
 #pragma unroll
-                for (int kk = 0; kk < KCH / 2; ++kk) {
-                    const uint32_t a_st = a0 + s * A_STAGE_BYTES + kk * 2 * PLANE;
-                    const uint32_t b_st = b0 + s * B_STAGE_BYTES + kk * 2 * (NT * 16);
-                    if (KV) {
-                        // swapped roles: A = weight tile (128 kv channels), B = the 256-pixel activation tile
-                        const uint64_t wd = make_desc(b_st, NT * 16, 128);
-                        const uint64_t xd = make_desc(a_st, PLANE, 128);
-                        umma<BF16>(tmem_base, wd, xd, make_idesc<BF16>(TPX, ROWS * TPX), (ks | kk) != 0 ? 1u : 0u);
-                    } else if (GEOM == G_UP) {
-                        // ho = 2*hi - 1 + kh: parity ph uses (kh=1,dh=0),(kh=3,dh=-1) if ph=0 and (kh=0,dh=+1),(kh=2,dh=0) if ph=1
+                    for (int kk = 0; kk < KCH / 2; ++kk) {
+                        const uint32_t a_st = a0 + s * A_STAGE_BYTES + kk * 2 * PLANE;
+                        const uint32_t b_st = b0 + s * B_STAGE_BYTES + kk * 2 * (NT * 16);
+                        if (KV) {
+                            // swapped roles: A = weight tile (128 kv channels), B = the 256-pixel activation tile
+                            const uint64_t wd = make_desc(b_st, NT * 16, 128);
+                            const uint64_t xd = make_desc(a_st, PLANE, 128);
+                            umma<BF16>(tslot, wd, xd, make_idesc<BF16>(TPX, ROWS * TPX), (ks | kk) != 0 ? 1u : 0u);
+                        } else if (GEOM == G_UP) {
+                            // ho = 2*hi - 1 + kh: parity ph uses (kh=1,dh=0),(kh=3,dh=-1) if ph=0 and (kh=0,dh=+1),(kh=2,dh=0) if ph=1
 #pragma unroll
-                        for (int phase = 0; phase < 4; ++phase) {
-                            const int pph = phase >> 1, pw = phase & 1;
+                            for (int phase = 0; phase < 4; ++phase) {
+                                const int pph = phase >> 1, pw = phase & 1;
 #pragma unroll
-                            for (int t2 = 0; t2 < 4; ++t2) {
-                                const int a = t2 >> 1, bb = t2 & 1;
-                                const int kh = pph ? (a ? 2 : 0) : (a ? 3 : 1), kw = pw ? (bb ? 2 : 0) : (bb ? 3 : 1);
-                                const int dh = pph ? (a ? 0 : 1) : (a ? -1 : 0), dw = pw ? (bb ? 0 : 1) : (bb ? -1 : 0);
-                                const uint64_t bd = make_desc(b_st + (kh * 4 + kw) * KCH * (NT * 16), NT * 16, 128);
+                                for (int t2 = 0; t2 < 4; ++t2) {
+                                    const int a = t2 >> 1, bb = t2 & 1;
+                                    const int kh = pph ? (a ? 2 : 0) : (a ? 3 : 1), kw = pw ? (bb ? 2 : 0) : (bb ? 3 : 1);
+                                    const int dh = pph ? (a ? 0 : 1) : (a ? -1 : 0), dw = pw ? (bb ? 0 : 1) : (bb ? -1 : 0);
+                                    const uint64_t bd = make_desc(b_st + (kh * 4 + kw) * KCH * (NT * 16), NT * 16, 128);
 #pragma unroll
-                                for (int j = 0; j < ROWS; ++j) {
-                                    const uint64_t ad = make_desc(a_st + ((1 + j + dh) * PXP + 1 + dw) * 16, PLANE, 128);
-                                    umma<BF16>(tmem_base + (phase * ROWS + j) * NT, ad, bd, idesc, (ks | kk | t2) != 0 ? 1u : 0u);
-                                }
-                            }
-                        }
-                    } else {
-#pragma unroll
-                        for (int tap = 0; tap < TAPS; ++tap) {
-                            const int r = TAPS == 9 ? tap / 3 : 0, sx = TAPS == 9 ? tap % 3 : 0;
-                            const uint64_t bd = make_desc(b_st + tap * KCH * (NT * 16), NT * 16, 128);
-#pragma unroll
-                            for (int j = 0; j < ROWS; ++j) {
-                                // DOWN: input row 2j+r; column tap s reads the odd plane at x (s=0) / x+1 (s=2), the even plane at x (s=1)
-                                const int aoff = GEOM == G_DOWN ? (2 * j + r) * PXP + (sx == 1 ? TPX + 1 : (sx == 2 ? 1 : 0))
-                                                                : (r + j) * PXP + sx;
-                                const uint64_t ad = make_desc(a_st + aoff * 16, PLANE, 128);
-                                umma<BF16>(tmem_base + j * NT, ad, bd, idesc, (ks | kk | tap) != 0 ? 1u : 0u);
-                            }
-                        }
-                    }
-                }
-                umma_commit(empty(s));                  // frees the stage when these MMAs have read it
-            }
-            umma_commit(acc_bar);                       // accumulators complete
-        }
-    } else {
-        // =============================== loader: weights (+ A runs) by cp.async.bulk ===============================
-        if (lane == 0) {
-            const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpk) + (size_t)b * p.w_bstride_bytes +
-                                  (size_t)blockIdx.y * ksteps * B_STAGE_BYTES;
-            // bytes of A the bulk runs deliver per stage (identical for every stage)
-            uint32_t a_bytes = 0;
-            if (BULK) {
-                if (GEOM == G_PW) {
-                    for (int r = 0; r < HR; ++r) {
-                        const long long m_lo = (long long)(h0 + r) * TPX;
-                        const long long n = m_lo >= HW ? 0 : (HW - m_lo < TPX ? HW - m_lo : TPX);
-                        a_bytes += (uint32_t)n * 16u;
-                    }
-                } else {
-                    const int wlo = w0 - 1 < 0 ? 0 : w0 - 1, whi = w0 + TPX + 1 > p.W ? p.W : w0 + TPX + 1;
-                    for (int r = 0; r < HR; ++r) {
-                        const int hi = h0 - 1 + r;
-                        if (hi >= 0 && hi < p.H) a_bytes += (uint32_t)(whi - wlo) * 16u;
-                    }
-                }
-                a_bytes *= KCH;
-            }
-            for (int ks = 0; ks < ksteps; ++ks) {
-                const int s = ks % STAGES;
-                mbar_wait(empty(s), ((ks / STAGES) & 1) ^ 1);
-                mbar_arrive_expect_tx(full_b(s), B_STAGE_BYTES + a_bytes);
-                bulk_g2s(smem_u32(sB + s * B_STAGE_BYTES), wsrc + (size_t)ks * B_STAGE_BYTES, B_STAGE_BYTES, full_b(s));
-                if (BULK) {
-                    const uint32_t a_s = smem_u32(sA) + s * A_STAGE_BYTES;
-#pragma unroll 1
-                    for (int k = 0; k < KCH; ++k) {
-                        const int ck = ks * KCH + k;                     // 16-byte channel chunk index over the concat
-                        const bool second = ck * 4 >= p.c0;
-                        const float* src = reinterpret_cast<const float*>(second ? p.in1 : p.in0);
-                        const int chs = (second ? p.c1 : p.c0) / 4;
-                        const int cl = second ? ck - p.c0 / 4 : ck;
-                        if (GEOM == G_PW) {
-                            for (int r = 0; r < HR; ++r) {
-                                long long m = (long long)(h0 + r) * TPX;
-                                const long long m_hi = m + TPX < HW ? m + TPX : HW;
-                                int q = 0;
-                                while (m < m_hi) {                     // split the flattened run at image-row boundaries
-                                    const int hh = (int)(m / p.W), ww = (int)(m - (long long)hh * p.W);
-                                    const int n = (int)((p.W - ww) < (m_hi - m) ? (p.W - ww) : (m_hi - m));
-                                    bulk_g2s(a_s + k * PLANE + (r * PXP + q) * 16,
-                                             src + (((long long)(b * p.H + hh) * chs + cl) * p.W + ww) * 4, (uint32_t)n * 16u, full_b(s));
-                                    m += n; q += n;
+                                    for (int j = 0; j < ROWS; ++j) {
+                                        const uint64_t ad = make_desc(a_st + ((1 + j + dh) * PXP + 1 + dw) * 16, PLANE, 128);
+                                        umma<BF16>(tslot + (phase * ROWS + j) * NT, ad, bd, idesc, (ks | kk | t2) != 0 ? 1u : 0u);
+                                    }
                                 }
                             }
                         } else {
-                            const int wlo = w0 - 1 < 0 ? 0 : w0 - 1, whi = w0 + TPX + 1 > p.W ? p.W : w0 + TPX + 1;
-                            for (int r = 0; r < HR; ++r) {
-                                const int hi = h0 - 1 + r;
-                                if (hi < 0 || hi >= p.H) continue;
-                                bulk_g2s(a_s + k * PLANE + (r * PXP + (wlo - (w0 - 1))) * 16,
-                                         src + (((long long)(b * p.H + hi) * chs + cl) * p.W + wlo) * 4, (uint32_t)(whi - wlo) * 16u, full_b(s));
+#pragma unroll
+                            for (int tap = 0; tap < TAPS; ++tap) {
+                                const int r = TAPS == 9 ? tap / 3 : 0, sx = TAPS == 9 ? tap % 3 : 0;
+                                const uint64_t bd = make_desc(b_st + tap * KCH * (NT * 16), NT * 16, 128);
+#pragma unroll
+                                for (int j = 0; j < ROWS; ++j) {
+                                    // DOWN: input row 2j+r; column tap s reads the odd plane at x (s=0) / x+1 (s=2), the even plane at x (s=1)
+                                    const int aoff = GEOM == G_DOWN ? (2 * j + r) * PXP + (sx == 1 ? TPX + 1 : (sx == 2 ? 1 : 0))
+                                                                    : (r + j) * PXP + sx;
+                                    const uint64_t ad = make_desc(a_st + aoff * 16, PLANE, 128);
+                                    umma<BF16>(tslot + j * NT, ad, bd, idesc, (ks | kk | tap) != 0 ? 1u : 0u);
+                                }
+                            }
+                        }
+                    }
+                    umma_commit(empty(s));                  // frees the stage when these MMAs have read it
+                }
+                umma_commit(tfull(slot));                   // this tile's accumulators are complete
+            }
+        }
+    } else {
+        // =========================================================================================================
+        // loader (one thread): weights + A runs by cp.async.bulk.  Every byte of the A tile is written every stage:
+        // out-of-image rows / columns (the conv's zero padding, the ragged last 1x1 tile) come from a zero page.
+        // =========================================================================================================
+        if (lane == 0) {
+            uint32_t it = 0;
+            const float* zero = p.zero_page;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                int b, h0, w0, n0, mt;
+                decode(t, b, h0, w0, n0, mt);
+                const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpk) + (size_t)b * p.w_bstride_bytes +
+                                      (size_t)(n0 / NT) * ksteps * B_STAGE_BYTES;
+                for (int ks = 0; ks < ksteps; ++ks, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(empty(s), ((it / STAGES) & 1) ^ 1);
+                    mbar_arrive_expect_tx(full_b(s), B_STAGE_BYTES + (BULK ? A_STAGE_BYTES : 0));
+                    bulk_g2s(smem_u32(sB + s * B_STAGE_BYTES), wsrc + (size_t)ks * B_STAGE_BYTES, B_STAGE_BYTES, full_b(s));
+                    if (BULK) {
+                        const uint32_t a_s = smem_u32(sA) + s * A_STAGE_BYTES;
+#pragma unroll 1
+                        for (int k = 0; k < KCH; ++k) {
+                            const int ck = ks * KCH + k;                     // 16-byte channel chunk index over the concat
+                            const bool second = ck * 4 >= p.c0;
+                            const float* src = reinterpret_cast<const float*>(second ? p.in1 : p.in0);
+                            const int chs = (second ? p.c1 : p.c0) / 4;
+                            const int cl = second ? ck - p.c0 / 4 : ck;
+                            if (GEOM == G_PW) {
+                                for (int r = 0; r < HR; ++r) {
+                                    long long m = (long long)(h0 + r) * TPX;
+                                    const long long m_hi = m >= HW ? m : (m + TPX < HW ? m + TPX : HW);
+                                    int q = 0;
+                                    while (m < m_hi) {                     // split the flattened run at image-row boundaries
+                                        const int hh = (int)(m / p.W), ww = (int)(m - (long long)hh * p.W);
+                                        const int n = (int)((p.W - ww) < (m_hi - m) ? (p.W - ww) : (m_hi - m));
+                                        bulk_g2s(a_s + k * PLANE + (r * PXP + q) * 16,
+                                                 src + (((long long)(b * p.H + hh) * chs + cl) * p.W + ww) * 4, (uint32_t)n * 16u, full_b(s));
+                                        m += n; q += n;
+                                    }
+                                    if (q < PXP) bulk_g2s(a_s + k * PLANE + (r * PXP + q) * 16, zero, (uint32_t)(PXP - q) * 16u, full_b(s));
+                                }
+                            } else {
+                                const int wlo = w0 - 1 < 0 ? 0 : w0 - 1, whi = w0 + TPX + 1 > p.W ? p.W : w0 + TPX + 1;
+                                const int qlo = wlo - (w0 - 1), qhi = qlo + (whi - wlo);
+                                for (int r = 0; r < HR; ++r) {
+                                    const int hi = h0 - 1 + r;
+                                    const uint32_t row_s = a_s + k * PLANE + (r * PXP) * 16;
+                                    if (hi < 0 || hi >= p.H) { bulk_g2s(row_s, zero, PXP * 16u, full_b(s)); continue; }
+                                    if (qlo > 0) bulk_g2s(row_s, zero, (uint32_t)qlo * 16u, full_b(s));
+                                    bulk_g2s(row_s + qlo * 16, src + (((long long)(b * p.H + hi) * chs + cl) * p.W + wlo) * 4,
+                                             (uint32_t)(whi - wlo) * 16u, full_b(s));
+                                    if (qhi < PXP) bulk_g2s(row_s + qhi * 16, zero, (uint32_t)(PXP - qhi) * 16u, full_b(s));
+                                }
                             }
                         }
                     }
@@ -657,31 +682,32 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT, KV>::MINB) k_conv_tc
     }
 
     __syncthreads();
-    if (p.ostats) {
-        const int cpg = p.Cout / kGroups, gb = n0 / cpg, ng = (NT + cpg - 1) / cpg;
-        if (tid < ng * 2) atomicAdd(&p.ostats[((long long)b * kGroups + gb + (tid >> 1)) * 2 + (tid & 1)], (double)s_st[tid]);
-    }
     if (warp == NPROD / 32) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS);
+        tmem_dealloc(tmem_base, D::TMEM_COLS);
     }
 }
 
 template <int GEOM, bool BF16, int NT, bool KV = false>
 static int launch_tc(const ConvTcParams& p, cudaStream_t s) {
-    constexpr int STAGES = Depth<GEOM, NT, KV>::STAGES;
-    const size_t sm = (size_t)STAGES * Depth<GEOM, NT, KV>::STAGE_BYTES + (3 * STAGES + 2) * 8 + 16 * 4 + 16 + 3 * NT * 4 + 64;
+    using D = Depth<GEOM, NT, KV>;
     static bool attr_set = false;
+    static int num_sms = 0;
     if (!attr_set) {
         cudaFuncSetAttribute(k_conv_tc<GEOM, BF16, NT, KV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
         attr_set = true;
     }
-    int gx;
-    if (GEOM == G_C3 || GEOM == G_UP) gx = ((p.W + TPX - 1) / TPX) * ((p.H + ROWS - 1) / ROWS);
-    else if (GEOM == G_DOWN) gx = ((p.Wo + TPX - 1) / TPX) * ((p.Ho + ROWS - 1) / ROWS);
-    else gx = (p.H * p.W + ROWS * TPX - 1) / (ROWS * TPX);
-    dim3 grid(gx, p.Cout / NT, p.B);
-    k_conv_tc<GEOM, BF16, NT, KV><<<grid, NTHREADS, sm, s>>>(p);
+    int mt;
+    if (GEOM == G_C3 || GEOM == G_UP) mt = ((p.W + TPX - 1) / TPX) * ((p.H + ROWS - 1) / ROWS);
+    else if (GEOM == G_DOWN) mt = ((p.Wo + TPX - 1) / TPX) * ((p.Ho + ROWS - 1) / ROWS);
+    else mt = (p.H * p.W + ROWS * TPX - 1) / (ROWS * TPX);
+    const long long total = (long long)mt * (p.Cout / NT) * p.B;
+    const long long cap = (long long)num_sms * D::MINB;             // persistent: one wave of resident CTAs
+    const int grid = (int)(total < cap ? total : cap);
+    k_conv_tc<GEOM, BF16, NT, KV><<<grid, NTHREADS, D::SMEM, s>>>(p);
     return 1;
 }
 

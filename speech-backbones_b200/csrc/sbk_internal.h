@@ -61,7 +61,8 @@ struct ConvTcParams {
     double* ostats;                                 // EPI_PLAIN: GroupNorm statistics of the raw output (nullable)
     const float* mask; int T; int lvl; int out_mask;   // out_mask: multiply the stored output by mask[b][wo << lvl]
     const float* rraw; GnRef rgn;                   // EPI_RES: out = acc + bias + Mish(GN(rraw))*mask
-    float* kv_part;                                 // EPI_KV (1x1, NT=128): [B][gridDim.x][4][kKvPartFloats]
+    float* kv_part;                                 // EPI_KV (1x1, NT=128): [B][ceil(HW/256)][4][kKvPartFloats]
+    const float* zero_page;                         // >= 4 KB of zeros in global memory (out-of-image parts of A tiles)
     int bf16;
 };
 
