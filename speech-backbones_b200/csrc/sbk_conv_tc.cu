@@ -205,12 +205,14 @@ constexpr int pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ?
 template <int GEOM, int NT, bool KV = false> struct Depth {
     static constexpr int STAGE_BYTES = Geo<GEOM>::KCH * Geo<GEOM>::HR * Geo<GEOM>::PXP * 16 + Geo<GEOM>::TAPS * Geo<GEOM>::KCH * NT * 16;
     static constexpr int SLOT_COLS = KV ? 320 : Geo<GEOM>::NACC * NT;        // KV: D1 (256 px columns) + S (64)
-    static constexpr int NSLOT = (!KV && 2 * SLOT_COLS <= 512) ? 2 : 1;
-    static constexpr int TMEM_COLS = pow2_cols(NSLOT * SLOT_COLS);
     static constexpr int EXTRA = KV ? 66 * 1024 : 0;                          // KV: V^T operand tile + reduction scratch
     static constexpr int FIT2 = (108 * 1024) / STAGE_BYTES;
     static constexpr int FIT1 = (220 * 1024 - EXTRA) / STAGE_BYTES;
-    static constexpr bool TWO = !KV && FIT2 >= 2 && TMEM_COLS <= 256;
+    // long-K 3x3 convs (NT = 128) are MMA-bound: one CTA, deep ring, two accumulator slots.  Everything else is
+    // epilogue/latency-bound: two CTAs per SM double the epilogue warps; slots as TMEM (256 columns per CTA) allows.
+    static constexpr bool TWO = !KV && FIT2 >= 2 && SLOT_COLS <= 256 && !(GEOM == G_C3 && NT == 128);
+    static constexpr int NSLOT = KV ? 1 : (TWO ? (2 * SLOT_COLS <= 256 ? 2 : 1) : (2 * SLOT_COLS <= 512 ? 2 : 1));
+    static constexpr int TMEM_COLS = pow2_cols(NSLOT * SLOT_COLS);
     static constexpr int STAGES = TWO ? (FIT2 > 4 ? 4 : FIT2) : (FIT1 > 6 ? 6 : FIT1);
     static constexpr int MINB = TWO ? 2 : 1;
     static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + EXTRA + (2 * STAGES + 2 * NSLOT + 2) * 8 + 16 * 4 + 16 + 3 * NT * 4 + 64;
@@ -628,6 +630,9 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT, KV>::MINB) k_conv_tc
         if (lane == 0) {
             uint32_t it = 0;
             const float* zero = p.zero_page;
+            uint32_t stage_pat[STAGES];
+#pragma unroll
+            for (int i = 0; i < STAGES; ++i) stage_pat[i] = 0xFFFFFFFFu;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 int b, h0, w0, n0, mt;
                 decode(t, b, h0, w0, n0, mt);
@@ -636,7 +641,33 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT, KV>::MINB) k_conv_tc
                 for (int ks = 0; ks < ksteps; ++ks, ++it) {
                     const int s = it % STAGES;
                     mbar_wait(empty(s), ((it / STAGES) & 1) ^ 1);
-                    mbar_arrive_expect_tx(full_b(s), B_STAGE_BYTES + (BULK ? A_STAGE_BYTES : 0));
+                    uint32_t a_tx = BULK ? A_STAGE_BYTES : 0;
+                    if (BULK && GEOM != G_PW) {
+                        // Image-border columns (the conv's zero padding) are never written by the row copies, so they only
+                        // need zeroing when this stage buffer last served a tile with a different border pattern.  With
+                        // the round-robin tile order a CTA normally keeps one pattern, so this (and its proxy fence,
+                        // which would otherwise serialise against the bulk copies in flight) runs a handful of times.
+                        const int wlo = w0 - 1 < 0 ? 0 : w0 - 1, whi = w0 + TPX + 1 > p.W ? p.W : w0 + TPX + 1;
+                        const int qlo = wlo - (w0 - 1), qhi = qlo + (whi - wlo);
+                        const uint32_t pat = (uint32_t)qlo | ((uint32_t)qhi << 8);
+                        if (stage_pat[s] != pat) {
+                            stage_pat[s] = pat;
+                            if (qlo > 0 || qhi < PXP) {
+                                uint8_t* st = sA + s * A_STAGE_BYTES;
+                                for (int k = 0; k < KCH; ++k)
+                                    for (int r = 0; r < HR; ++r) {
+                                        uint4* rowp = reinterpret_cast<uint4*>(st + k * PLANE + (r * PXP) * 16);
+                                        for (int q = 0; q < qlo; ++q) rowp[q] = make_uint4(0u, 0u, 0u, 0u);
+                                        for (int q = qhi; q < PXP; ++q) rowp[q] = make_uint4(0u, 0u, 0u, 0u);
+                                    }
+                                fence_proxy_async();
+                            }
+                        }
+                        int vrows = 0;
+                        for (int r = 0; r < HR; ++r) { const int hi = h0 - 1 + r; vrows += (hi >= 0 && hi < p.H) ? 1 : 0; }
+                        a_tx -= (uint32_t)(KCH * vrows * (PXP - (qhi - qlo))) * 16u;
+                    }
+                    mbar_arrive_expect_tx(full_b(s), B_STAGE_BYTES + a_tx);
                     bulk_g2s(smem_u32(sB + s * B_STAGE_BYTES), wsrc + (size_t)ks * B_STAGE_BYTES, B_STAGE_BYTES, full_b(s));
                     if (BULK) {
                         const uint32_t a_s = smem_u32(sA) + s * A_STAGE_BYTES;
@@ -668,10 +699,8 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT, KV>::MINB) k_conv_tc
                                     const int hi = h0 - 1 + r;
                                     const uint32_t row_s = a_s + k * PLANE + (r * PXP) * 16;
                                     if (hi < 0 || hi >= p.H) { bulk_g2s(row_s, zero, PXP * 16u, full_b(s)); continue; }
-                                    if (qlo > 0) bulk_g2s(row_s, zero, (uint32_t)qlo * 16u, full_b(s));
                                     bulk_g2s(row_s + qlo * 16, src + (((long long)(b * p.H + hi) * chs + cl) * p.W + wlo) * 4,
                                              (uint32_t)(whi - wlo) * 16u, full_b(s));
-                                    if (qhi < PXP) bulk_g2s(row_s + qhi * 16, zero, (uint32_t)(PXP - qhi) * 16u, full_b(s));
                                 }
                             }
                         }
