@@ -654,7 +654,8 @@ static int build_plan(sbk_handle* h, int B, int T, int tb_rows) {
             // the per-sample (I + g P_b) matrix is written by k_attn_mix directly in the tcgen05 weight-stage layout
             Op op = tc_conv(a.prefix + ".out", G_PW, "", "", lvl, x, a.c, nullptr, 0, a.c, out, nullptr);
             op.tc.wpk = bf.w_eff; op.tc.w_bstride_bytes = (long long)a.c * a.c * 4; op.tc.bias = bf.b_eff;
-            op.tc.out_mask = 1;
+            op.tc.out_mask = 1; op.tc.addin = x;
+            op.bytes += 4.0 * npix(lvl) * a.c;
             push(op, out, npix(lvl) * a.c);
         } else {
             Op op; op.kind = OP_IGEMM; op.name = a.prefix + ".out";

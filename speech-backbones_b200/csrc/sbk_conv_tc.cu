@@ -500,6 +500,15 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT, KV>::MINB) k_conv_tc
                     }
                 }
             }
+            if (p.addin && valid) {
+                // fp32-exact residual (attention: x + g*P x): the tensor core only carries the small g*P x term
+                const float* ap = p.addin + obase + (cb / 4) * cstride;
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    const float4 av = __ldg(reinterpret_cast<const float4*>(ap + (i / 4) * cstride));
+                    v[i] += av.x; v[i + 1] += av.y; v[i + 2] += av.z; v[i + 3] += av.w;
+                }
+            }
             if (p.out_mask) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] *= mo;

@@ -62,6 +62,7 @@ struct ConvTcParams {
     const float* mask; int T; int lvl; int out_mask;   // out_mask: multiply the stored output by mask[b][wo << lvl]
     const float* rraw; GnRef rgn;                   // EPI_RES: out = acc + bias + Mish(GN(rraw))*mask
     float* kv_part;                                 // EPI_KV (1x1, NT=128): [B][ceil(HW/256)][4][kKvPartFloats]
+    const float* addin;                             // EPI_PLAIN: out += addin (same shape/layout as out): fp32-exact residual
     const float* zero_page;                         // >= 4 KB of zeros in global memory (out-of-image parts of A tiles)
     int bf16;
 };
@@ -110,7 +111,8 @@ struct AttnMixParams {          // A_b = I + g * Wout * blockdiag(ctx^T) * Wq ; 
     float* w_eff;               // [B][C(ci)][C(co)]
     float* b_eff;               // [C]
     int B, C;
-    int tc_nt, tc_cps;          // != 0: write w_eff in the tcgen05 1x1 weight-stage layout (tf32-rounded)
+    int tc_nt, tc_cps;          // != 0: write g*P only (the identity/residual is added in fp32 by the conv epilogue),
+                                // in the tcgen05 1x1 weight-stage layout, tf32-rounded
 };
 
 struct FinalParams {            // final_block GN+Mish, final_conv 1x1 -> 1, mask, Euler(-Maruyama) update

@@ -29,6 +29,13 @@ __device__ __forceinline__ float mish_f(float x) {
     return x > 20.f ? x : x * r;
 }
 
+// tensor-core modes: operands are rounded to tf32 anyway, so the activation may use the fast intrinsics
+__device__ __forceinline__ float mish_fast_f(float x) {
+    const float n = __expf(fminf(x, 20.f));
+    const float a = n * (n + 2.f);
+    return x > 20.f ? x : x * __fdividef(a, a + 2.f);
+}
+
 __device__ __forceinline__ void gn_mean_rstd(const GnRef& g, int b, int grp, float& mean, float& rstd) {
     const double s = g.stats[(b * kGroups + grp) * 2 + 0];
     const double ss = g.stats[(b * kGroups + grp) * 2 + 1];
@@ -488,6 +495,53 @@ __global__ void __launch_bounds__(256) k_resfinal(const ResFinalParams p) {
     __syncthreads();
     const int c4n = p.C >> 2;
     const long long n4 = (long long)p.H * p.W * c4n;
+    if (p.x) {
+        // identity residual: pure streaming (2 reads + 1 write per element); 4 independent units per thread
+        constexpr int U = 4;
+        for (long long i0 = (long long)blockIdx.x * (256 * U) + tid; i0 < n4; i0 += (long long)gridDim.x * (256 * U)) {
+            float4 r[U], xv[U]; float mk[U]; int cc[U]; bool in[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const long long i = i0 + u * 256;
+                in[u] = i < n4;
+                int c = 0, w = 0;
+                if (in[u]) {
+                    if (p.chw4) {
+                        const long long hc = i / p.W;
+                        w = (int)(i - hc * p.W);
+                        c = (int)(hc % c4n) * 4;
+                    } else {
+                        const long long pix = i / c4n;
+                        c = (int)(i - pix * c4n) * 4;
+                        w = (int)(pix % p.W);
+                    }
+                }
+                cc[u] = c;
+                mk[u] = in[u] ? __ldg(p.mask + (long long)b * p.T + ((long long)w << p.lvl)) : 0.f;
+                const bool live = in[u] && mk[u] != 0.f;
+                const long long off = ((long long)b * n4 + i) * 4;
+                r[u] = live ? ldg4(p.h2raw + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+                xv[u] = live ? ldg4(p.x + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (!in[u]) continue;
+                const int c = cc[u];
+                float o[4] = {0.f, 0.f, 0.f, 0.f};
+                if (mk[u] != 0.f) {
+                    const float rv[4] = {r[u].x, r[u].y, r[u].z, r[u].w};
+                    const float xx[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float xn = (rv[q] - mean[c + q]) * scale[c + q] + beta[c + q];
+                        o[q] = (p.chw4 ? mish_fast_f(xn) : mish_f(xn)) + xx[q];
+                    }
+                }
+                *reinterpret_cast<float4*>(p.out + ((long long)b * n4 + i0 + u * 256) * 4) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+        }
+        return;
+    }
     for (long long i = (long long)blockIdx.x * 256 + tid; i < n4; i += (long long)gridDim.x * 256) {
         // float4 unit i of this sample -> (pixel, channel quad); in both layouts the unit index IS the memory order
         long long pix; int c, w;
@@ -551,37 +605,52 @@ __global__ void __launch_bounds__(256) k_gn_act(const GnActParams p) {
     __syncthreads();
     const int c4n = p.C >> 2;
     const long long n4 = (long long)p.H * p.W * c4n;
-    for (long long i = (long long)blockIdx.x * 256 + tid; i < n4; i += (long long)gridDim.x * 256) {
-        int c, w;
-        if (p.chw4) {
-            const long long hc = i / p.W;
-            w = (int)(i - hc * p.W);
-            c = (int)(hc % c4n) * 4;
-        } else {
-            const long long pix = i / c4n;
-            c = (int)(i - pix * c4n) * 4;
-            w = (int)(pix % p.W);
-        }
-        const float mk = __ldg(p.mask + (long long)b * p.T + ((long long)w << p.lvl));
-        const long long off = ((long long)b * n4 + i) * 4;
-        float o[4] = {0.f, 0.f, 0.f, 0.f};
-        if (mk != 0.f) {
-            const float4 r = ldg4(p.raw + off);
-            const float rv[4] = {r.x, r.y, r.z, r.w};
+    constexpr int U = 4;                         // independent 16-byte loads in flight per thread
+    for (long long i0 = (long long)blockIdx.x * (256 * U) + tid; i0 < n4; i0 += (long long)gridDim.x * (256 * U)) {
+        float4 r[U]; float mk[U]; int cc[U]; bool in[U];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                float y = mish_f((rv[q] - mean[c + q]) * scale[c + q] + beta[c + q]) + tbv[c + q];
-                if (p.round_tf32) { uint32_t u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(y)); y = __uint_as_float(u); }
-                o[q] = y;
+        for (int u = 0; u < U; ++u) {
+            const long long i = i0 + u * 256;
+            in[u] = i < n4;
+            int c = 0, w = 0;
+            if (in[u]) {
+                if (p.chw4) {
+                    const long long hc = i / p.W;
+                    w = (int)(i - hc * p.W);
+                    c = (int)(hc % c4n) * 4;
+                } else {
+                    const long long pix = i / c4n;
+                    c = (int)(i - pix * c4n) * 4;
+                    w = (int)(pix % p.W);
+                }
             }
+            cc[u] = c;
+            mk[u] = in[u] ? __ldg(p.mask + (long long)b * p.T + ((long long)w << p.lvl)) : 0.f;
+            r[u] = (in[u] && mk[u] != 0.f) ? ldg4(p.raw + ((long long)b * n4 + i) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        *reinterpret_cast<float4*>(p.out + off) = make_float4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (!in[u]) continue;
+            const int c = cc[u];
+            float o[4] = {0.f, 0.f, 0.f, 0.f};
+            if (mk[u] != 0.f) {
+                const float rv[4] = {r[u].x, r[u].y, r[u].z, r[u].w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float xn = (rv[q] - mean[c + q]) * scale[c + q] + beta[c + q];
+                    float y = (p.chw4 ? mish_fast_f(xn) : mish_f(xn)) + tbv[c + q];
+                    if (p.round_tf32) { uint32_t t; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(y)); y = __uint_as_float(t); }
+                    o[q] = y;
+                }
+            }
+            *reinterpret_cast<float4*>(p.out + ((long long)b * n4 + i0 + u * 256) * 4) = make_float4(o[0], o[1], o[2], o[3]);
+        }
     }
 }
 
 int launch_gn_act(const GnActParams& p, cudaStream_t s) {
     const long long n4 = (long long)p.H * p.W * (p.C / 4);
-    int gx = (int)((n4 + 256 * 4 - 1) / (256 * 4));
+    int gx = (int)((n4 + 256 * 4 * 8 - 1) / (256 * 4 * 8));   // ~8 passes of the 4-way unrolled loop per CTA (amortises the GN table set-up)
     if (gx < 1) gx = 1;
     if (gx > 4096) gx = 4096;
     k_gn_act<<<dim3(gx, p.B), 256, 4 * p.C * sizeof(float), s>>>(p);
@@ -590,7 +659,7 @@ int launch_gn_act(const GnActParams& p, cudaStream_t s) {
 
 int launch_resfinal(const ResFinalParams& p, cudaStream_t s) {
     const long long n4 = (long long)p.H * p.W * (p.C / 4);
-    int gx = (int)((n4 + 256 * 4 - 1) / (256 * 4));
+    int gx = p.x ? (int)((n4 + 256 * 4 * 8 - 1) / (256 * 4 * 8)) : (int)((n4 + 256 * 4 - 1) / (256 * 4));
     if (gx < 1) gx = 1;
     if (gx > 4096) gx = 4096;
     const size_t sm = (3 * p.C + (p.x ? 0 : (p.cin + 1) * p.C)) * sizeof(float);
@@ -684,7 +753,7 @@ __global__ void __launch_bounds__(256) k_attn_mix(const AttnMixParams p) {
 #pragma unroll
             for (int cl = 0; cl < 32; ++cl) {
                 const int co = cb + cl;
-                float v = g * acc[cl] + (co == cp ? 1.f : 0.f);
+                float v = g * acc[cl];
                 uint32_t u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
                 const long long idx = ((((long long)(co / NT) * ksteps + ks) * kch + kc) * NT + (co % NT)) * 4 + e;
                 p.w_eff[(long long)b * C * C + idx] = __uint_as_float(u);
@@ -758,10 +827,10 @@ __global__ void __launch_bounds__(256) k_final(const FinalParams p) {
                 for (int ch = 0; ch < c4n; ++ch) {
                     const float4 r = ldg4(rp + (long long)ch * p.T * 4);
                     const int c = ch * 4;
-                    dot = fmaf(wf[c + 0], mish_f((r.x - mean[c + 0]) * scale[c + 0] + beta[c + 0]), dot);
-                    dot = fmaf(wf[c + 1], mish_f((r.y - mean[c + 1]) * scale[c + 1] + beta[c + 1]), dot);
-                    dot = fmaf(wf[c + 2], mish_f((r.z - mean[c + 2]) * scale[c + 2] + beta[c + 2]), dot);
-                    dot = fmaf(wf[c + 3], mish_f((r.w - mean[c + 3]) * scale[c + 3] + beta[c + 3]), dot);
+                    dot = fmaf(wf[c + 0], mish_fast_f((r.x - mean[c + 0]) * scale[c + 0] + beta[c + 0]), dot);
+                    dot = fmaf(wf[c + 1], mish_fast_f((r.y - mean[c + 1]) * scale[c + 1] + beta[c + 1]), dot);
+                    dot = fmaf(wf[c + 2], mish_fast_f((r.z - mean[c + 2]) * scale[c + 2] + beta[c + 2]), dot);
+                    dot = fmaf(wf[c + 3], mish_fast_f((r.w - mean[c + 3]) * scale[c + 3] + beta[c + 3]), dot);
                 }
             }
             update((long long)b * HW + m, mk, dot);

@@ -205,6 +205,10 @@ def test_config2_shape_properties(engines):
 # Tolerances follow the operand rounding (measured by emulation on the reference):
 # tf32 (10-bit mantissa) ~1e-3 per estimator call, bf16 (8-bit) ~9e-3; GN/softmax/Mish/Euler stay fp32.
 TC_TOL = {"tf32": (4e-3, 8e-3)}       # (per estimator call / stage, trajectory)
+# The |xt| x100 stress case drives the attention logits k to O(100): softmax turns the tf32 operand rounding of the
+# k projection (|k| * 2^-11 absolute) into a relative error of the same size in p = exp(k - max), so this one case
+# gets a wider bound (measured 4.7e-3; the reference's own TF32 GPU path has the same sensitivity).
+TC_TOL_STRESS = {"tf32": 1e-2}
 
 
 @pytest.mark.parametrize("precision", ["tf32"])
@@ -230,7 +234,7 @@ def test_tensor_core_vs_reference_golden(engines, golden, precision):
         cfg, sd, z, mask, mu, spk = case_inputs(golden, c)
         if c["kind"] == "est":
             y = eng.estimator((z * mask * c["scale"]).cuda(), mask.cuda(), mu.cuda(), torch.tensor(c["t"]).cuda()).cpu()
-            tol = TC_TOL[precision][0]
+            tol = TC_TOL[precision][0] if c["scale"] == 1.0 else TC_TOL_STRESS[precision]
         else:
             noise = stoc_noise(golden, c).cuda() if c["stoc"] else None
             y = eng.reverse_diffusion(z.cuda(), mask.cuda(), mu.cuda(), c["N"], c["stoc"], None, noise).cpu()
