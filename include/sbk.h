@@ -31,7 +31,7 @@ enum { SBK_OK = 0, SBK_ERR_ARG = 1, SBK_ERR_CUDA = 2, SBK_ERR_STATE = 3, SBK_ERR
 /* arithmetic of the dense contractions (3x3/1x1 convs); GN / softmax / Mish / Euler are always fp32 */
 enum { SBK_PREC_FP32 = 0,   /* CUDA-core FFMA, fp32 operands (bit-faithful class of the CPU reference)   */
        SBK_PREC_TF32 = 1,   /* tcgen05 kind::tf32, fp32 accumulate in TMEM (PyTorch's default GPU class) */
-       SBK_PREC_BF16 = 2 }; /* tcgen05 kind::f16 bf16 operands, fp32 accumulate                          */
+       SBK_PREC_BF16 = 2 }; /* reserved: bf16 operand tensors are not built yet; sbk_pack() refuses it        */
 
 enum { SBK_MODEL_GRADTTS = 0, SBK_MODEL_DIFFVC = 1 };
 

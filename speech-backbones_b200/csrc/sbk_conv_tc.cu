@@ -174,11 +174,6 @@ __device__ __forceinline__ float mish_fast(float x) {
     return x > 20.f ? x : x * __fdividef(a, a + 2.f);
 }
 
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
-}
 
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
@@ -187,11 +182,6 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__device__ __forceinline__ float mish_acc(float x) {     // exact-math Mish for the fp32 epilogues (see sbk_kernels.cu)
-    const float n = expf(fminf(x, 20.f));
-    const float a = n * (n + 2.f);
-    return x > 20.f ? x : x * (a / (a + 2.f));
-}
 
 }  // namespace tc
 
@@ -703,7 +693,7 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT, KV>::MINB) k_conv_tc
                                 }
                             } else {
                                 const int wlo = w0 - 1 < 0 ? 0 : w0 - 1, whi = w0 + TPX + 1 > p.W ? p.W : w0 + TPX + 1;
-                                const int qlo = wlo - (w0 - 1), qhi = qlo + (whi - wlo);
+                                const int qlo = wlo - (w0 - 1);
                                 for (int r = 0; r < HR; ++r) {
                                     const int hi = h0 - 1 + r;
                                     const uint32_t row_s = a_s + k * PLANE + (r * PXP) * 16;
