@@ -163,7 +163,7 @@ def synthetic_state_dict(cfg: UNetConfig, seed: int = 1234, rezero_g: float = 0.
     for name, shape in (spec or estimator_param_spec(cfg)).items():
         if name.endswith(".fn.g") or name.endswith(".g") and len(shape) == 1 and shape[0] == 1:
             sd[name] = torch.full(shape, float(rezero_g), dtype=torch.float32)
-        elif ".block.1." in name or ".norm." in name:   # GroupNorm / InstanceNorm affine
+        elif ".block.1." in name or ".norm." in name or (".ref_block.block" in name and ".1." in name):   # GroupNorm / InstanceNorm affine
             base = 1.0 if name.endswith("weight") else 0.0
             sd[name] = base + 0.1 * synthetic_tensor(seed, name, shape)
         elif name.endswith("bias"):
@@ -201,3 +201,118 @@ def synthetic_inputs(B: int, T: int, n_feats: int = 80, seed: int = 1234, ragged
 def synthetic_noise(N: int, B: int, T: int, n_feats: int = 80, seed: int = 1234) -> torch.Tensor:
     """Pre-drawn per-step noise [N,B,n_feats,T] for the stochastic sampler (diffusion.py:267)."""
     return synthetic_tensor(seed, f"noise:{N}x{B}x{T}", (N, B, n_feats, T))
+
+
+# ---------------------------------------------------------------------------------------------
+# DiffVC decoder (DiffVC/model/diffusion.py:17-59, DiffVC/model/modules.py:128-154)
+# ---------------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class DiffVCConfig:
+    """Constructor arguments of DiffVC's Diffusion (DiffVC/model/diffusion.py:110; params.py:26-28)."""
+    n_feats: int = 80
+    dim_unet: int = 256
+    dim_spk: int = 128
+    use_ref_t: bool = True
+    beta_min: float = 0.05
+    beta_max: float = 20.0
+
+    @property
+    def level_dims(self):
+        return [2 + self.dim_spk, self.dim_unet, self.dim_unet * 2, self.dim_unet * 4]
+
+
+def diffvc_param_spec(cfg: DiffVCConfig):
+    """Ordered {name: shape} of the 206 tensors under `estimator.` of DiffVC's decoder."""
+    dim, dc = cfg.dim_unet, cfg.dim_spk
+    spec: dict[str, tuple] = {}
+    spec["estimator.mlp.0.weight"] = (dim * 4, dim)
+    spec["estimator.mlp.0.bias"] = (dim * 4,)
+    spec["estimator.mlp.2.weight"] = (dim, dim * 4)
+    spec["estimator.mlp.2.bias"] = (dim,)
+    cond_total = dim + 256
+    if cfg.use_ref_t:
+        base = dc // 4
+        spec["estimator.ref_block.mlp1.1.weight"] = (base, dim)
+        spec["estimator.ref_block.mlp1.1.bias"] = (base,)
+        spec["estimator.ref_block.mlp2.1.weight"] = (2 * base, dim)
+        spec["estimator.ref_block.mlp2.1.bias"] = (2 * base,)
+        for name, ci, co in (("block11", 1, 2 * base), ("block12", base, 2 * base), ("block21", base, 4 * base),
+                             ("block22", 2 * base, 4 * base), ("block31", 2 * base, 8 * base),
+                             ("block32", 4 * base, 8 * base)):
+            spec[f"estimator.ref_block.{name}.0.weight"] = (co, ci, 3, 3)
+            spec[f"estimator.ref_block.{name}.0.bias"] = (co,)
+            spec[f"estimator.ref_block.{name}.1.weight"] = (co,)
+            spec[f"estimator.ref_block.{name}.1.bias"] = (co,)
+        spec["estimator.ref_block.final_conv.weight"] = (dc, 4 * base, 1, 1)
+        spec["estimator.ref_block.final_conv.bias"] = (dc,)
+        cond_total += dc
+    spec["estimator.cond_block.0.weight"] = (4 * dc, cond_total)
+    spec["estimator.cond_block.0.bias"] = (4 * dc,)
+    spec["estimator.cond_block.2.weight"] = (dc, 4 * dc)
+    spec["estimator.cond_block.2.bias"] = (dc,)
+    d = cfg.level_dims
+
+    def resnet(prefix, cin, cout):
+        spec[f"{prefix}.mlp.1.weight"] = (cout, dim)
+        spec[f"{prefix}.mlp.1.bias"] = (cout,)
+        for blk, ci in (("block1", cin), ("block2", cout)):
+            spec[f"{prefix}.{blk}.block.0.weight"] = (cout, ci, 3, 3)
+            spec[f"{prefix}.{blk}.block.0.bias"] = (cout,)
+            spec[f"{prefix}.{blk}.block.1.weight"] = (cout,)
+            spec[f"{prefix}.{blk}.block.1.bias"] = (cout,)
+        if cin != cout:
+            spec[f"{prefix}.res_conv.weight"] = (cout, cin, 1, 1)
+            spec[f"{prefix}.res_conv.bias"] = (cout,)
+
+    def attn(prefix, c):
+        spec[f"{prefix}.fn.g"] = (1,)
+        spec[f"{prefix}.fn.fn.to_qkv.weight"] = (ATTN_HIDDEN * 3, c, 1, 1)
+        spec[f"{prefix}.fn.fn.to_out.weight"] = (c, ATTN_HIDDEN, 1, 1)
+        spec[f"{prefix}.fn.fn.to_out.bias"] = (c,)
+
+    for l in range(3):
+        resnet(f"estimator.downs.{l}.0", d[l], d[l + 1])
+        resnet(f"estimator.downs.{l}.1", d[l + 1], d[l + 1])
+        attn(f"estimator.downs.{l}.2", d[l + 1])
+        if l < 2:
+            spec[f"estimator.downs.{l}.3.conv.weight"] = (d[l + 1], d[l + 1], 3, 3)
+            spec[f"estimator.downs.{l}.3.conv.bias"] = (d[l + 1],)
+    resnet("estimator.mid_block1", d[3], d[3])
+    attn("estimator.mid_attn", d[3])
+    resnet("estimator.mid_block2", d[3], d[3])
+    for j, (cin, cout) in enumerate([(d[2], d[3]), (d[1], d[2])]):
+        resnet(f"estimator.ups.{j}.0", cout * 2, cin)
+        resnet(f"estimator.ups.{j}.1", cin, cin)
+        attn(f"estimator.ups.{j}.2", cin)
+        spec[f"estimator.ups.{j}.3.conv.weight"] = (cin, cin, 4, 4)
+        spec[f"estimator.ups.{j}.3.conv.bias"] = (cin,)
+    spec["estimator.final_block.block.0.weight"] = (dim, dim, 3, 3)
+    spec["estimator.final_block.block.0.bias"] = (dim,)
+    spec["estimator.final_block.block.1.weight"] = (dim,)
+    spec["estimator.final_block.block.1.bias"] = (dim,)
+    spec["estimator.final_conv.weight"] = (1, dim, 1, 1)
+    spec["estimator.final_conv.bias"] = (1,)
+    return spec
+
+
+def synthetic_diffvc_inputs(B: int, T: int, T_ref: int, n_feats: int = 80, seed: int = 1234, ragged: bool = False):
+    """(z, mask, mean, ref, ref_mask, mean_ref, c) as DiffVC.forward builds them (DiffVC/model/vc.py:104-125):
+    z = mean + N(0,1); c = L2-normalised 256-d speaker embedding."""
+    mean = synthetic_tensor(seed, f"vc_mean:{B}x{T}", (B, n_feats, T))
+    z = mean + synthetic_tensor(seed, f"vc_eps:{B}x{T}", (B, n_feats, T))
+    ref = synthetic_tensor(seed, f"vc_ref:{B}x{T_ref}", (B, n_feats, T_ref))
+    mean_ref = synthetic_tensor(seed, f"vc_mean_ref:{B}x{T_ref}", (B, n_feats, T_ref))
+    c = synthetic_tensor(seed, f"vc_c:{B}", (B, 256))
+    c = c / c.norm(dim=1, keepdim=True)
+
+    def lens(tag, n):
+        if not ragged:
+            return torch.full((B,), n, dtype=torch.long)
+        g = torch.Generator(device="cpu")
+        g.manual_seed(_key_seed(seed, f"{tag}:{B}x{n}"))
+        l = torch.randint(max(1, n // 2), n + 1, (B,), generator=g)
+        l[0] = n
+        return l
+    mask = (torch.arange(T)[None, :] < lens("vc_len", T)[:, None]).to(torch.float32)[:, None, :]
+    ref_mask = (torch.arange(T_ref)[None, :] < lens("vc_reflen", T_ref)[:, None]).to(torch.float32)[:, None, :]
+    return z, mask, mean, ref, ref_mask, mean_ref, c
