@@ -48,6 +48,9 @@ typedef struct sbk_config {
     int32_t device;       /* CUDA device ordinal                                            */
     int32_t precision;    /* SBK_PREC_*                                                     */
     int32_t use_graph;    /* 1: capture one reverse step as a CUDA graph and replay it      */
+    /* SBK_MODEL_DIFFVC only (DiffVC/model/diffusion.py:110, DiffVC/params.py:26-28); `dim` is dim_unet (256) */
+    int32_t dim_cond;     /* dim_spk = 128: width of the conditioning vector                */
+    int32_t use_ref_t;    /* 1: the state_dict carries ref_block.* (strict loading)         */
 } sbk_config;
 
 /* Diffusion.__init__ / GradLogPEstimator2d.__init__ (diffusion.py:128-172,228-242). */
@@ -78,6 +81,20 @@ int sbk_estimator(sbk_handle* h, const float* x, const float* mask, const float*
  * out may alias z.  Device pointers. */
 int sbk_reverse_diffusion(sbk_handle* h, const float* z, const float* mask, const float* mu, const float* spk,
                           const float* noise, float* out, int B, int T, int n_timesteps, int stoc, void* stream);
+
+/* ---- DiffVC (SBK_MODEL_DIFFVC) ------------------------------------------------------------------------------
+ * GradLogPEstimator.forward (DiffVC/model/diffusion.py:61-106) with the xt-independent conditioning vector
+ * (time sinusoid | RefBlock | speaker embedding -> cond_block, :62-71) supplied by the caller: cond [B][dim_cond].
+ * x, mean, out: [B,n_feats,T]; mask [B,1,T]; t [B].  Device pointers. */
+int sbk_vc_estimator(sbk_handle* h, const float* x, const float* mask, const float* mean, const float* cond,
+                     const float* t, float* out, int B, int T, void* stream);
+
+/* Diffusion.reverse_diffusion (DiffVC/model/diffusion.py:164-196), mode 0 = 'pf', 1 = 'em', 2 = 'ml';
+ * t_i = 1 - i/N.  cond: [N][B][dim_cond], the conditioning vector of every step (it depends on t, ref and c only,
+ * never on xt, so the binding evaluates it for all N steps before the loop).  noise: [N][B][n_feats][T] for
+ * 'em'/'ml' (the reference draws randn_like(z) per step, :194), NULL for 'pf'.  out may alias z. */
+int sbk_vc_reverse_diffusion(sbk_handle* h, const float* z, const float* mask, const float* mean, const float* cond,
+                             const float* noise, float* out, int B, int T, int n_timesteps, int mode, void* stream);
 
 /* The same loop in slices: runs steps [step_begin, step_end) of an n_timesteps-step trajectory in place
  * on xt (which must already hold z*mask at step 0, or the previous slice's result).  noise, when stoc,

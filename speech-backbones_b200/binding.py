@@ -17,7 +17,7 @@ EXPORTS = [
     "sbk_create", "sbk_destroy", "sbk_set_weight", "sbk_pack", "sbk_num_weights", "sbk_weight_name",
     "sbk_workspace_bytes", "sbk_estimator", "sbk_reverse_diffusion", "sbk_reverse_steps",
     "sbk_reverse_diffusion_host", "sbk_last_launch_count", "sbk_debug_read", "sbk_debug_num",
-    "sbk_debug_name", "sbk_last_error", "sbk_version", "sbk_profile_ops", "sbk_debug_capture", "sbk_debug_layout",
+    "sbk_debug_name", "sbk_last_error", "sbk_version", "sbk_profile_ops", "sbk_debug_capture", "sbk_debug_layout", "sbk_vc_estimator", "sbk_vc_reverse_diffusion",
 ]
 
 
@@ -25,7 +25,7 @@ class SbkConfig(C.Structure):
     _fields_ = [("model", C.c_int32), ("n_feats", C.c_int32), ("dim", C.c_int32), ("n_spks", C.c_int32),
                 ("spk_emb_dim", C.c_int32), ("beta_min", C.c_float), ("beta_max", C.c_float),
                 ("pe_scale", C.c_float), ("device", C.c_int32), ("precision", C.c_int32),
-                ("use_graph", C.c_int32)]
+                ("use_graph", C.c_int32), ("dim_cond", C.c_int32), ("use_ref_t", C.c_int32)]
 
 
 _lib = None
@@ -52,6 +52,8 @@ def load_library() -> C.CDLL:
     lib.sbk_workspace_bytes.restype = C.c_size_t
     lib.sbk_estimator.argtypes = [P, F, F, F, F, F, F, I, I, P]
     lib.sbk_reverse_diffusion.argtypes = [P, F, F, F, F, F, F, I, I, I, I, P]
+    lib.sbk_vc_estimator.argtypes = [P, F, F, F, F, F, F, I, I, P]
+    lib.sbk_vc_reverse_diffusion.argtypes = [P, F, F, F, F, F, F, I, I, I, I, P]
     lib.sbk_reverse_steps.argtypes = [P, F, F, F, F, F, I, I, I, I, I, I, P]
     lib.sbk_reverse_diffusion_host.argtypes = [P, F, F, F, F, F, F, I, I, I, I]
     lib.sbk_last_launch_count.argtypes = [P]
@@ -88,10 +90,13 @@ class Engine:
     """One sbk_handle: a (device, configuration) pair owning packed weights, workspace and graphs."""
 
     def __init__(self, n_feats=80, dim=64, n_spks=1, spk_emb_dim=64, beta_min=0.05, beta_max=20.0,
-                 pe_scale=1000.0, device=0, precision="fp32", use_graph=True, model="gradtts"):
+                 pe_scale=1000.0, device=0, precision="fp32", use_graph=True, model="gradtts", dim_cond=0,
+                 use_ref_t=True):
         self.lib = load_library()
         self.cfg = SbkConfig(MODEL[model], n_feats, dim, n_spks, spk_emb_dim, beta_min, beta_max, pe_scale,
-                             device, PREC[precision], 1 if use_graph else 0)
+                             device, PREC[precision], 1 if use_graph else 0, dim_cond, 1 if use_ref_t else 0)
+        self.model = model
+        self.dim_cond = dim_cond
         self.h = C.c_void_p()
         _check(self.lib.sbk_create(C.byref(self.cfg), C.byref(self.h)), "sbk_create")
         self.device = device
@@ -177,6 +182,34 @@ class Engine:
                                           int(n_timesteps), int(step_begin), int(step_end), 1 if stoc else 0,
                                           self._stream()), "sbk_reverse_steps")
         return xt
+
+    # ---- DiffVC (model="diffvc")
+    VC_MODES = {"pf": 0, "em": 1, "ml": 2}
+
+    def vc_estimator(self, x, mask, mean, cond, t):
+        B, T = self._check_inputs(x, mask, mean, None)
+        x, mask, mean, cond, t = (_f32c(v, n) for v, n in ((x, "x"), (mask, "mask"), (mean, "mean"), (cond, "cond"), (t, "t")))
+        if tuple(cond.shape) != (B, self.dim_cond):
+            raise RuntimeError(f"cond shape {tuple(cond.shape)} != {(B, self.dim_cond)}")
+        out = torch.empty_like(x)
+        _check(self.lib.sbk_vc_estimator(self.h, _ptr(x), _ptr(mask), _ptr(mean), _ptr(cond), _ptr(t), _ptr(out), B, T,
+                                         self._stream()), "sbk_vc_estimator")
+        return out
+
+    def vc_reverse_diffusion(self, z, mask, mean, cond, n_timesteps, mode, noise=None):
+        B, T = self._check_inputs(z, mask, mean, None)
+        z, mask, mean, cond = _f32c(z, "z"), _f32c(mask, "mask"), _f32c(mean, "mean"), _f32c(cond, "cond")
+        if tuple(cond.shape) != (n_timesteps, B, self.dim_cond):
+            raise RuntimeError(f"cond shape {tuple(cond.shape)} != {(n_timesteps, B, self.dim_cond)}")
+        if mode != "pf":
+            if noise is None:
+                raise RuntimeError("modes 'em'/'ml' need pre-drawn noise [N,B,n_feats,T]")
+            noise = _f32c(noise, "noise")
+        out = torch.empty_like(z)
+        _check(self.lib.sbk_vc_reverse_diffusion(self.h, _ptr(z), _ptr(mask), _ptr(mean), _ptr(cond),
+                                                 _ptr(noise) if mode != "pf" else None, _ptr(out), B, T, int(n_timesteps),
+                                                 self.VC_MODES[mode], self._stream()), "sbk_vc_reverse_diffusion")
+        return out
 
     def reverse_diffusion_host(self, z, mask, mu, n_timesteps, stoc=False, spk=None, noise=None, out=None):
         """Host-buffer entry point: CPU (ideally pinned) tensors in, CPU tensor out; copies are inside the call."""

@@ -70,8 +70,10 @@ struct Plan {
     float *tb = nullptr, *t_rows = nullptr; float4* coef = nullptr;
     int* step_cur = nullptr; int* step_next = nullptr;
     const float** noise_pp = nullptr;
+    float *vc_cond = nullptr, *vc_wextra = nullptr, *vc_rextra = nullptr;   // DiffVC conditioning tables [rows][B][...]
+    int first_op = -1, first_res_op = -1;
     int tb_stride = 0;
-    cudaGraphExec_t gexec[3] = {nullptr, nullptr, nullptr};   // per FinalParams.mode
+    cudaGraphExec_t gexec[4] = {nullptr, nullptr, nullptr, nullptr};   // per FinalParams.mode
     int launches_per_step = 0;
 };
 
@@ -102,7 +104,8 @@ struct sbk_handle {
 static void build_spec(sbk_handle* h) {
     const sbk_config& c = h->cfg;
     const int dim = c.dim;
-    const int d[4] = {2 + (c.n_spks > 1 ? 1 : 0), dim, dim * 2, dim * 4};
+    const bool vc = c.model == SBK_MODEL_DIFFVC;
+    const int d[4] = {vc ? 2 + c.dim_cond : 2 + (c.n_spks > 1 ? 1 : 0), dim, dim * 2, dim * 4};
     auto add = [&](const std::string& n, std::vector<int64_t> s) { h->spec.push_back({n, s}); };
     auto resnet = [&](const std::string& p, int cin, int cout) {
         add(p + ".mlp.1.weight", {cout, dim});
@@ -138,6 +141,28 @@ static void build_spec(sbk_handle* h) {
     add("estimator.mlp.0.bias", {dim * 4});
     add("estimator.mlp.2.weight", {dim, dim * 4});
     add("estimator.mlp.2.bias", {dim});
+    if (vc) {
+        // RefBlock + cond_block (DiffVC/model/modules.py:128-154, diffusion.py:28-33): accepted by the strict loader;
+        // this round the binding evaluates them (they are xt-independent and hoisted out of the loop)
+        const int dc = c.dim_cond, base = dc / 4;
+        int cond_total = dim + 256;
+        if (c.use_ref_t) {
+            add("estimator.ref_block.mlp1.1.weight", {base, dim}); add("estimator.ref_block.mlp1.1.bias", {base});
+            add("estimator.ref_block.mlp2.1.weight", {2 * base, dim}); add("estimator.ref_block.mlp2.1.bias", {2 * base});
+            const char* nm[6] = {"block11", "block12", "block21", "block22", "block31", "block32"};
+            const int ci[6] = {1, base, base, 2 * base, 2 * base, 4 * base}, co[6] = {2 * base, 2 * base, 4 * base, 4 * base, 8 * base, 8 * base};
+            for (int k = 0; k < 6; ++k) {
+                const std::string q = std::string("estimator.ref_block.") + nm[k];
+                add(q + ".0.weight", {co[k], ci[k], 3, 3}); add(q + ".0.bias", {co[k]});
+                add(q + ".1.weight", {co[k]}); add(q + ".1.bias", {co[k]});
+            }
+            add("estimator.ref_block.final_conv.weight", {dc, 4 * base, 1, 1});
+            add("estimator.ref_block.final_conv.bias", {dc});
+            cond_total += dc;
+        }
+        add("estimator.cond_block.0.weight", {4 * dc, cond_total}); add("estimator.cond_block.0.bias", {4 * dc});
+        add("estimator.cond_block.2.weight", {dc, 4 * dc}); add("estimator.cond_block.2.bias", {dc});
+    }
     for (int l = 0; l < 3; ++l) {
         const std::string p = "estimator.downs." + std::to_string(l);
         resnet(p + ".0", d[l], d[l + 1]);
@@ -181,7 +206,8 @@ extern "C" const char* sbk_version(void) { return "sbk 0.1 (sm_100a)"; }
 
 extern "C" int sbk_create(const sbk_config* cfg, sbk_handle** out) {
     if (!cfg || !out) return fail(SBK_ERR_ARG, "sbk_create: null argument");
-    if (cfg->model != SBK_MODEL_GRADTTS) return fail(SBK_ERR_UNSUPPORTED, "sbk_create: model %d not supported", cfg->model);
+    if (cfg->model != SBK_MODEL_GRADTTS && cfg->model != SBK_MODEL_DIFFVC) return fail(SBK_ERR_UNSUPPORTED, "sbk_create: model %d not supported", cfg->model);
+    if (cfg->model == SBK_MODEL_DIFFVC && (cfg->dim_cond <= 0 || cfg->dim_cond % 4 != 0)) return fail(SBK_ERR_ARG, "sbk_create: DiffVC needs dim_cond > 0 (multiple of 4), got %d", cfg->dim_cond);
     if (cfg->dim <= 0 || cfg->dim % 64 != 0) return fail(SBK_ERR_ARG, "sbk_create: dim must be a positive multiple of 64 (got %d)", cfg->dim);
     if (cfg->n_feats <= 0 || cfg->n_feats % 4 != 0) return fail(SBK_ERR_ARG, "sbk_create: n_feats must be a multiple of 4 (two stride-2 levels), got %d", cfg->n_feats);
     if (cfg->n_spks < 1 || cfg->spk_emb_dim <= 0) return fail(SBK_ERR_ARG, "sbk_create: bad speaker configuration");
@@ -195,7 +221,7 @@ extern "C" int sbk_create(const sbk_config* cfg, sbk_handle** out) {
 
 static void free_plan(sbk_handle* h) {
     Plan& p = h->plan;
-    for (int i = 0; i < 3; ++i) if (p.gexec[i]) { cudaGraphExecDestroy(p.gexec[i]); p.gexec[i] = nullptr; }
+    for (int i = 0; i < 4; ++i) if (p.gexec[i]) { cudaGraphExecDestroy(p.gexec[i]); p.gexec[i] = nullptr; }
     for (auto& op : p.ops) if (op.dbg_copy) cudaFree(op.dbg_copy);
     if (p.mem) cudaFree(p.mem);
     p = Plan();
@@ -442,6 +468,11 @@ static size_t layout(const sbk_handle* h, int B, int T, int tb_rows, Arena& ar, 
     p.step_cur = (int*)ar.take(sizeof(int));
     p.step_next = (int*)ar.take(sizeof(int));
     p.noise_pp = (const float**)ar.take(sizeof(float*));
+    if (c.model == SBK_MODEL_DIFFVC) {
+        p.vc_cond = f((size_t)tb_rows * B * c.dim_cond);
+        p.vc_wextra = f((size_t)tb_rows * B * 9 * dim);
+        p.vc_rextra = f((size_t)tb_rows * B * dim);
+    }
     return ar.off + 256;
 }
 
@@ -466,7 +497,8 @@ static int build_plan(sbk_handle* h, int B, int T, int tb_rows) {
 
     const int dim = c.dim, H0 = c.n_feats;
     const int Hs[3] = {H0, H0 / 2, H0 / 4}, Ws[3] = {T, T / 2, T / 4};
-    const int cin0 = 2 + (c.n_spks > 1 ? 1 : 0);
+    const bool vc = c.model == SBK_MODEL_DIFFVC;
+    const int cin0 = vc ? 3 : 2 + (c.n_spks > 1 ? 1 : 0);     // DiffVC: {mean, xt, folded conditioning channel}
     int gn_slot = 0;
     auto stats_slot = [&]() { return pl.stats + (size_t)(gn_slot++) * B * kGroups * 2; };
     auto W = [&](const std::string& k) -> const float* {
@@ -552,6 +584,8 @@ static int build_plan(sbk_handle* h, int B, int T, int tb_rows) {
             p.mu = pl.mu; p.xt = pl.xt; p.spk_s = pl.spk_s; p.mask = pl.mask;
             p.w = W(r.prefix + ".block1.w"); p.bias = W(r.prefix + ".block1.block.0.bias");
             p.out = A; p.ostats = st1; p.B = B; p.H = H0; p.T = T; p.cin = cin0; p.C = r.cout; p.chw4 = use_tc ? 1 : 0;
+            if (vc) { p.w_extra = pl.vc_wextra; p.step = pl.step_cur; }
+            pl.first_op = (int)pl.ops.size();
             push(op, A, npix(lvl) * r.cout);
         } else if (tc1) {
             Op op = tc_conv(r.prefix + ".block1.raw", G_C3, r.prefix + ".block1.wtc", r.prefix + ".block1.block.0.bias", lvl,
@@ -593,6 +627,8 @@ static int build_plan(sbk_handle* h, int B, int T, int tb_rows) {
             if (k == 0) {
                 p.x = nullptr; p.mu = pl.mu; p.xt = pl.xt; p.spk_s = pl.spk_s; p.cin = cin0;
                 p.wres = W(r.prefix + ".res.w"); p.bres = W(r.prefix + ".res_conv.bias");
+                if (vc) { p.r_extra = pl.vc_rextra; p.step = pl.step_cur; }
+                pl.first_res_op = (int)pl.ops.size();
             } else {
                 p.x = in0;
             }
@@ -798,6 +834,8 @@ static void set_mode(Plan& pl, int mode, bool per_sample_t, float* out) {
         if (op.kind == OP_IGEMM && op.ig.pro == PRO_GN) op.ig.tb_per_sample = per_sample_t ? 1 : 0;
     for (auto& op : pl.ops)
         if (op.kind == OP_GNACT) op.ga.tb_per_sample = per_sample_t ? 1 : 0;
+    if (pl.first_op >= 0) pl.ops[pl.first_op].fc.extra_per_sample_row = per_sample_t ? 1 : 0;
+    if (pl.first_res_op >= 0) pl.ops[pl.first_res_op].rf.extra_per_sample_row = per_sample_t ? 1 : 0;
     FinalParams& f = pl.ops[pl.final_op].fn;
     f.mode = mode; f.xt_out = out; f.noise_pp = pl.noise_pp;
 }
@@ -805,6 +843,7 @@ static void set_mode(Plan& pl, int mode, bool per_sample_t, float* out) {
 extern "C" int sbk_estimator(sbk_handle* h, const float* x, const float* mask, const float* mu, const float* t,
                              const float* spk, float* out, int B, int T, void* stream) {
     if (!h || !x || !mask || !mu || !t || !out) return fail(SBK_ERR_ARG, "sbk_estimator: null argument");
+    if (h->cfg.model != SBK_MODEL_GRADTTS) return fail(SBK_ERR_ARG, "sbk_estimator: this handle is a DiffVC model, use sbk_vc_*");
     if (h->cfg.n_spks > 1 && !spk) return fail(SBK_ERR_ARG, "sbk_estimator: spk is required when n_spks > 1");
     TRY(ensure_plan(h, B, T, B));
     cudaStream_t s = (cudaStream_t)stream;
@@ -837,7 +876,7 @@ static void step_coefs(const sbk_config& c, int n_timesteps, int i, float* t_out
 
 static int run_steps(sbk_handle* h, const float* noise, int B, int T, int N, int s0, int s1, int stoc, cudaStream_t s, int64_t* launches) {
     Plan& pl = h->plan;
-    const int mode = stoc ? 2 : 1;
+    const int mode = h->cfg.model == SBK_MODEL_DIFFVC ? 3 : (stoc ? 2 : 1);
     set_mode(pl, mode, false, pl.xt);
     // the kernel indexes noise by absolute step: bias the base so slab s0 is the first one supplied
     const float* nbase = noise ? noise - (long long)s0 * B * h->cfg.n_feats * T : nullptr;
@@ -887,6 +926,7 @@ extern "C" int sbk_reverse_steps(sbk_handle* h, float* xt, const float* mask, co
     if (n_timesteps < 1 || step_begin < 0 || step_end > n_timesteps || step_begin > step_end)
         return fail(SBK_ERR_ARG, "sbk_reverse_steps: bad step range [%d,%d) of %d", step_begin, step_end, n_timesteps);
     if (stoc && !noise) return fail(SBK_ERR_ARG, "sbk_reverse_steps: stoc=1 needs a noise buffer");
+    if (h->cfg.model != SBK_MODEL_GRADTTS) return fail(SBK_ERR_ARG, "sbk_reverse_steps: this handle is a DiffVC model, use sbk_vc_*");
     if (h->cfg.n_spks > 1 && !spk) return fail(SBK_ERR_ARG, "sbk_reverse_steps: spk is required when n_spks > 1");
     TRY(ensure_plan(h, B, T, n_timesteps));
     cudaStream_t s = (cudaStream_t)stream;
@@ -906,6 +946,7 @@ extern "C" int sbk_reverse_diffusion(sbk_handle* h, const float* z, const float*
     if (!h || !z || !mask || !mu || !out) return fail(SBK_ERR_ARG, "sbk_reverse_diffusion: null argument");
     if (n_timesteps < 1) return fail(SBK_ERR_ARG, "sbk_reverse_diffusion: n_timesteps must be >= 1");
     if (stoc && !noise) return fail(SBK_ERR_ARG, "sbk_reverse_diffusion: stoc=1 needs a noise buffer");
+    if (h->cfg.model != SBK_MODEL_GRADTTS) return fail(SBK_ERR_ARG, "sbk_reverse_diffusion: this handle is a DiffVC model, use sbk_vc_*");
     if (h->cfg.n_spks > 1 && !spk) return fail(SBK_ERR_ARG, "sbk_reverse_diffusion: spk is required when n_spks > 1");
     TRY(ensure_plan(h, B, T, n_timesteps));
     cudaStream_t s = (cudaStream_t)stream;
@@ -925,6 +966,7 @@ extern "C" int sbk_reverse_diffusion_host(sbk_handle* h, const float* z, const f
     if (!h || !z || !mask || !mu || !out) return fail(SBK_ERR_ARG, "sbk_reverse_diffusion_host: null argument");
     if (n_timesteps < 1) return fail(SBK_ERR_ARG, "sbk_reverse_diffusion_host: n_timesteps must be >= 1");
     if (stoc && !noise) return fail(SBK_ERR_ARG, "sbk_reverse_diffusion_host: stoc=1 needs a noise buffer");
+    if (h->cfg.model != SBK_MODEL_GRADTTS) return fail(SBK_ERR_ARG, "sbk_reverse_diffusion_host: this handle is a DiffVC model, use sbk_vc_*");
     if (h->cfg.n_spks > 1 && !spk) return fail(SBK_ERR_ARG, "sbk_reverse_diffusion_host: spk is required when n_spks > 1");
     TRY(ensure_plan(h, B, T, n_timesteps));
     if (!h->cap_stream) CU(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
@@ -992,6 +1034,101 @@ extern "C" int sbk_profile_ops(sbk_handle* h, float* ms, double* flops, double* 
     }
     for (auto& e : ev) cudaEventDestroy(e);
     *n_ops = n;
+    return SBK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// DiffVC entry points (DiffVC/model/diffusion.py:61-106, 164-196)
+// ------------------------------------------------------------------------------------------------
+// host scalars of step i with the reference's double-precision scalar math (get_gamma / get_mu / get_nu / get_sigma,
+// diffusion.py:124-149, 169-193): dxt = (mean - xt)*A - est*Bc + eps*sigma
+static void vc_step_coefs(const sbk_config& c, int N, int i, int mode, float* t_out, float4* cf) {
+    const double h = 1.0 / N, t = 1.0 - i * h;
+    const double bmin = c.beta_min, bmax = c.beta_max;
+    auto gamma = [&](double s, double tt, double p) {
+        double bi = bmin + 0.5 * (bmax - bmin) * (tt + s);
+        bi *= (tt - s);
+        return exp(-0.5 * p * bi);
+    };
+    const double beta_t = bmin + (bmax - bmin) * t;
+    double A, Bc, sigma;
+    if (mode == 0) { A = 0.5 * beta_t * h; Bc = 0.5 * beta_t * h; sigma = 0.0; }
+    else if (mode == 2) {
+        double kappa = gamma(0, t - h, 1.0) * (1.0 - gamma(t - h, t, 2.0));
+        kappa /= (gamma(0, t, 1.0) * beta_t * h);
+        kappa -= 1.0;
+        const double ct = 1.0 - gamma(0, t, 2.0);
+        const double nu = gamma(0, t - h, 1.0) * (1.0 - gamma(t - h, t, 2.0)) / ct;
+        const double mu = gamma(t - h, t, 1.0) * (1.0 - gamma(0, t - h, 2.0)) / ct;
+        double omega = nu / gamma(0, t, 1.0);
+        omega += mu;
+        omega -= (0.5 * beta_t * h + 1.0);
+        sigma = sqrt((1.0 - gamma(0, t - h, 2.0)) * (1.0 - gamma(t - h, t, 2.0)) / ct);
+        A = 0.5 * beta_t * h + omega; Bc = (1.0 + kappa) * (beta_t * h);
+    } else { A = 0.5 * beta_t * h; Bc = beta_t * h; sigma = sqrt(beta_t * h); }
+    *t_out = (float)t;
+    *cf = make_float4((float)A, (float)Bc, (float)sigma, 0.f);
+}
+
+static int vc_fold(sbk_handle* h, const float* cond, int rows, int B, cudaStream_t s) {
+    Plan& pl = h->plan;
+    const sbk_config& c = h->cfg;
+    CU(cudaMemcpyAsync(pl.vc_cond, cond, (size_t)rows * B * c.dim_cond * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    CondFoldParams p;
+    p.cond = pl.vc_cond; p.w1 = h->raw["estimator.downs.0.0.block1.block.0.weight"];
+    p.wres = h->raw["estimator.downs.0.0.res_conv.weight"];
+    p.w_extra = pl.vc_wextra; p.r_extra = pl.vc_rextra; p.rows = rows; p.B = B; p.dc = c.dim_cond; p.C = c.dim;
+    return launch_cond_fold(p, s);
+}
+
+extern "C" int sbk_vc_estimator(sbk_handle* h, const float* x, const float* mask, const float* mean, const float* cond,
+                                const float* t, float* out, int B, int T, void* stream) {
+    if (!h || !x || !mask || !mean || !cond || !t || !out) return fail(SBK_ERR_ARG, "sbk_vc_estimator: null argument");
+    if (h->cfg.model != SBK_MODEL_DIFFVC) return fail(SBK_ERR_ARG, "sbk_vc_estimator: this handle is not a DiffVC model");
+    TRY(ensure_plan(h, B, T, B));
+    cudaStream_t s = (cudaStream_t)stream;
+    Plan& pl = h->plan;
+    const size_t nb = (size_t)B * h->cfg.n_feats * T * sizeof(float);
+    CU(cudaMemcpyAsync(pl.xt, x, nb, cudaMemcpyDeviceToDevice, s));
+    CU(cudaMemcpyAsync(pl.mu, mean, nb, cudaMemcpyDeviceToDevice, s));
+    CU(cudaMemcpyAsync(pl.mask, mask, (size_t)B * T * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    CU(cudaMemcpyAsync(pl.t_rows, t, (size_t)B * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    int64_t n = 0;
+    n += vc_fold(h, cond, 1, B, s);               // one row: the per-sample conditioning vectors
+    n += time_table(h, B, s);
+    set_mode(pl, 0, true, out);
+    k_set_int<<<1, 1, 0, s>>>(pl.step_next, 0); ++n;
+    n += run_ops(h, s);
+    CU(cudaGetLastError());
+    h->last_launches = n;
+    return SBK_OK;
+}
+
+extern "C" int sbk_vc_reverse_diffusion(sbk_handle* h, const float* z, const float* mask, const float* mean, const float* cond,
+                                        const float* noise, float* out, int B, int T, int n_timesteps, int mode, void* stream) {
+    if (!h || !z || !mask || !mean || !cond || !out) return fail(SBK_ERR_ARG, "sbk_vc_reverse_diffusion: null argument");
+    if (h->cfg.model != SBK_MODEL_DIFFVC) return fail(SBK_ERR_ARG, "sbk_vc_reverse_diffusion: this handle is not a DiffVC model");
+    if (mode < 0 || mode > 2) return fail(SBK_ERR_ARG, "sbk_vc_reverse_diffusion: mode must be 0 (pf), 1 (em) or 2 (ml)");
+    if (n_timesteps < 1) return fail(SBK_ERR_ARG, "sbk_vc_reverse_diffusion: n_timesteps must be >= 1");
+    if (mode != 0 && !noise) return fail(SBK_ERR_ARG, "sbk_vc_reverse_diffusion: modes em/ml need a noise buffer");
+    TRY(ensure_plan(h, B, T, n_timesteps));
+    cudaStream_t s = (cudaStream_t)stream;
+    Plan& pl = h->plan;
+    const int N = n_timesteps;
+    const size_t nb = (size_t)B * h->cfg.n_feats * T * sizeof(float);
+    int64_t n = 0;
+    CU(cudaMemcpyAsync(pl.mu, mean, nb, cudaMemcpyDeviceToDevice, s));
+    CU(cudaMemcpyAsync(pl.mask, mask, (size_t)B * T * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    std::vector<float> tr(N); std::vector<float4> cf(N);
+    for (int i = 0; i < N; ++i) vc_step_coefs(h->cfg, N, i, mode, &tr[i], &cf[i]);
+    CU(cudaMemcpyAsync(pl.t_rows, tr.data(), N * sizeof(float), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(pl.coef, cf.data(), N * sizeof(float4), cudaMemcpyHostToDevice, s));
+    n += vc_fold(h, cond, N, B, s);
+    n += time_table(h, N, s);
+    n += launch_scale_mask(z, pl.mask, pl.xt, 0, B, h->cfg.n_feats, T, s);
+    TRY(run_steps(h, noise, B, T, N, 0, N, mode != 0, s, &n));
+    CU(cudaMemcpyAsync(out, pl.xt, nb, cudaMemcpyDeviceToDevice, s));
+    h->last_launches = n;
     return SBK_OK;
 }
 

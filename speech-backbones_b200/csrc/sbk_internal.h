@@ -84,6 +84,9 @@ struct FirstConvParams {        // Block.conv of downs.0.0.block1 on the planar 
     float* out; double* ostats; // [B][H][T][C] (or [B][H][C/4][T][4] when chw4), [B][8][2]
     int B, H, T, cin, C;
     int chw4;
+    // DiffVC: the 128 conditioning channels are spatially constant, so they act as ONE extra input channel whose
+    // value is the mask and whose weights are per (row, sample): w_extra[(row*B + b)][9][C] (row = *step or 0)
+    const float* w_extra; const int* step; int extra_per_sample_row;
 };
 
 struct ResFinalParams {         // out = Mish(GN(h2raw))*mask + res(x*mask)
@@ -91,6 +94,7 @@ struct ResFinalParams {         // out = Mish(GN(h2raw))*mask + res(x*mask)
     const float* x;             // identity residual source (NHWC, same C) or nullptr for the planar first block
     const float* mu; const float* xt; const float* spk_s;   // planar inputs for downs.0.0.res_conv
     const float* wres; const float* bres; int cin;          // [cin][C], [C]
+    const float* r_extra; const int* step; int extra_per_sample_row;   // DiffVC: + mask * r_extra[(row*B + b)][C]
     const float* mask; int T; int lvl;
     float* out;
     int B, H, W, C;
@@ -123,7 +127,8 @@ struct FinalParams {            // final_block GN+Mish, final_conv 1x1 -> 1, mas
     const float* const* noise_pp;   // stoc: device cell holding a base such that step i's slab is base + i*B*H*T
     const float4* coef;         // per step {beta, h, sqrt(beta*h), 0}
     const int* step;
-    int mode;                   // 0: estimator output, 1: deterministic Euler, 2: Euler-Maruyama
+    int mode;                   // 0: estimator output, 1: deterministic Euler, 2: Euler-Maruyama (Grad-TTS),
+                                // 3: DiffVC  xt' = (xt - ((mean-xt)*A - est*Bc + eps*sigma))*mask, coef = {A, Bc, sigma}
     int B, H, T, C;
     int chw4;
 };
@@ -143,6 +148,19 @@ struct SpkParams {              // spk_mlp: Linear(E,4E) -> Mish -> Linear(4E, n
     const float* spk; const float* w0; const float* b0; const float* w2; const float* b2;
     float* out; int B, E, n_feats;
 };
+
+// DiffVC: fold the conditioning vector into the first ResnetBlock (diffusion.py:73-76 of DiffVC: condition is
+// broadcast over the grid and concatenated as 128 extra channels): per (row, sample)
+//   w_extra[tap][co] = sum_ci cond[ci] * W1[co][2+ci][tap],   r_extra[co] = sum_ci cond[ci] * Wres[co][2+ci]
+struct CondFoldParams {
+    const float* cond;      // [rows][B][dc]
+    const float* w1;        // raw block1 conv weight [C][2+dc][3][3]
+    const float* wres;      // raw res_conv weight [C][2+dc]
+    float* w_extra;         // [rows*B][9][C]
+    float* r_extra;         // [rows*B][C]
+    int rows, B, dc, C;
+};
+int launch_cond_fold(const CondFoldParams& p, cudaStream_t s);
 
 struct StepBeginParams { double* stats; int n_doubles; int* step_cur; int* step_next; };
 

@@ -399,7 +399,13 @@ __global__ void __launch_bounds__(256) k_first_conv(const FirstConvParams p) {
     const int wtiles = (p.T + 63) / 64;
     const int h = blockIdx.x / wtiles, w0 = (blockIdx.x - h * wtiles) * 64;
     const int K = p.cin * 9;
-    for (int i = tid; i < K * 64; i += 256) s_w[i] = p.w[(i >> 6) * p.C + n0 + (i & 63)];
+    const int kreal = p.w_extra ? (p.cin - 1) * 9 : K;       // rows of s_w that come from the shared weight
+    for (int i = tid; i < kreal * 64; i += 256) s_w[i] = p.w[(i >> 6) * p.C + n0 + (i & 63)];
+    if (p.w_extra) {
+        const int row = p.extra_per_sample_row ? 0 : *p.step;
+        const float* we = p.w_extra + ((long long)row * p.B + b) * 9 * p.C;
+        for (int i = tid; i < 9 * 64; i += 256) s_w[kreal * 64 + i] = we[(i >> 6) * p.C + n0 + (i & 63)];
+    }
     if (tid < 64) s_b[tid] = p.bias[n0 + tid];
     if (tid < 16) s_st[tid] = 0.f;
     for (int i = tid; i < p.cin * 3 * 66; i += 256) {
@@ -409,7 +415,7 @@ __global__ void __launch_bounds__(256) k_first_conv(const FirstConvParams p) {
         if (hi >= 0 && hi < p.H && wi >= 0 && wi < p.T) {
             const float mk = __ldg(p.mask + (long long)b * p.T + wi);
             const long long idx = ((long long)b * p.H + hi) * p.T + wi;
-            const float x = ci == 0 ? __ldg(p.mu + idx) : (ci == 1 ? __ldg(p.xt + idx) : __ldg(p.spk_s + b * p.H + hi));
+            const float x = ci == 0 ? __ldg(p.mu + idx) : (ci == 1 ? __ldg(p.xt + idx) : (p.w_extra ? 1.f : __ldg(p.spk_s + b * p.H + hi)));
             v = x * mk;
         }
         s_in[ci][r][q] = v;
@@ -491,7 +497,12 @@ __global__ void __launch_bounds__(256) k_resfinal(const ResFinalParams p) {
     float* wres = beta + p.C;            // [cin][C] + [C] bias when planar
     const int b = blockIdx.y, tid = threadIdx.x;
     gn_fill(p.gn, b, p.C, 0, p.C, mean, scale, beta);
-    if (!p.x) for (int i = tid; i < (p.cin + 1) * p.C; i += 256) wres[i] = i < p.cin * p.C ? p.wres[i] : p.bres[i - p.cin * p.C];
+    if (!p.x) {
+        // rows [0, nreal) = shared res_conv weights of the planar channels, row cin = bias (rows in between unused)
+        const int nreal = p.r_extra ? p.cin - 1 : p.cin;
+        for (int i = tid; i < (p.cin + 1) * p.C; i += 256)
+            wres[i] = i < nreal * p.C ? p.wres[i] : (i >= p.cin * p.C ? p.bres[i - p.cin * p.C] : 0.f);
+    }
     __syncthreads();
     const int c4n = p.C >> 2;
     const long long n4 = (long long)p.H * p.W * c4n;
@@ -576,11 +587,15 @@ __global__ void __launch_bounds__(256) k_resfinal(const ResFinalParams p) {
             float in[3];
             in[0] = __ldg(p.mu + idx) * mk;
             in[1] = __ldg(p.xt + idx) * mk;
-            in[2] = p.cin > 2 ? __ldg(p.spk_s + b * p.H + h) * mk : 0.f;
+            in[2] = (p.cin > 2 && !p.r_extra) ? __ldg(p.spk_s + b * p.H + h) * mk : 0.f;
+            const int nreal = p.r_extra ? p.cin - 1 : p.cin;
+            const float* re = nullptr;
+            if (p.r_extra) re = p.r_extra + ((long long)(p.extra_per_sample_row ? 0 : *p.step) * p.B + b) * p.C;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 float a = wres[p.cin * p.C + c + q];
-                for (int ci = 0; ci < p.cin; ++ci) a = fmaf(in[ci], wres[ci * p.C + c + q], a);
+                for (int ci = 0; ci < nreal; ++ci) a = fmaf(in[ci], wres[ci * p.C + c + q], a);
+                if (re) a = fmaf(mk, __ldg(re + c + q), a);
                 o[q] += a;
             }
         }
@@ -807,6 +822,10 @@ __global__ void __launch_bounds__(256) k_final(const FinalParams p) {
             float dxt;
             if (p.mode == 1) {
                 dxt = ((0.5f * ((mu - xt) - est)) * cf.x) * cf.y;
+            } else if (p.mode == 3) {
+                // DiffVC pf / em / ml (DiffVC/model/diffusion.py:177-194): coef = {A, Bc, sigma}
+                dxt = (mu - xt) * cf.x - est * cf.y;
+                if (cf.z != 0.f) dxt += __ldg(*p.noise_pp + (long long)srow * p.B * HW + idx) * cf.z;
             } else {
                 const float eps = __ldg(*p.noise_pp + (long long)srow * p.B * HW + idx);
                 dxt = ((0.5f * (mu - xt) - est) * cf.x) * cf.y + eps * cf.z;
@@ -932,6 +951,33 @@ __global__ void __launch_bounds__(256) k_spk(const SpkParams p) {
 
 int launch_spk(const SpkParams& p, cudaStream_t s) {
     k_spk<<<p.B, 256, 5 * p.E * sizeof(float), s>>>(p);
+    return 1;
+}
+
+// DiffVC conditioning fold (see CondFoldParams): grid (rows*B), 256 threads
+__global__ void __launch_bounds__(256) k_cond_fold(const CondFoldParams p) {
+    extern __shared__ float s_c[];                      // cond vector [dc]
+    const int rb = blockIdx.x, tid = threadIdx.x;
+    for (int i = tid; i < p.dc; i += 256) s_c[i] = p.cond[(long long)rb * p.dc + i];
+    __syncthreads();
+    const int cin = 2 + p.dc;
+    for (int o = tid; o < 10 * p.C; o += 256) {
+        const int t = o / p.C, co = o - t * p.C;        // t < 9: conv tap, t == 9: res_conv
+        float a = 0.f;
+        if (t < 9) {
+            const float* w = p.w1 + ((long long)co * cin + 2) * 9 + t;
+            for (int ci = 0; ci < p.dc; ++ci) a = fmaf(s_c[ci], __ldg(w + (long long)ci * 9), a);
+            p.w_extra[((long long)rb * 9 + t) * p.C + co] = a;
+        } else {
+            const float* w = p.wres + (long long)co * cin + 2;
+            for (int ci = 0; ci < p.dc; ++ci) a = fmaf(s_c[ci], __ldg(w + ci), a);
+            p.r_extra[(long long)rb * p.C + co] = a;
+        }
+    }
+}
+
+int launch_cond_fold(const CondFoldParams& p, cudaStream_t s) {
+    k_cond_fold<<<p.rows * p.B, 256, p.dc * sizeof(float), s>>>(p);
     return 1;
 }
 

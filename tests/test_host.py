@@ -114,3 +114,22 @@ def test_sinusoid_frequency_table_matches_torch():
     assert ulp.max() <= 1
     assert np.array_equal(mine[:8], ref[:8])
     assert (1000.0 * np.abs(mine.astype(np.float64) - ref.astype(np.float64))).max() < 1e-6
+
+
+def test_diffvc_module_and_c_abi_inventory():
+    """DiffVC drop-in: 206 reference names/shapes, 117,794,599 parameters, same inventory through the C ABI."""
+    from speech_backbones_b200.binding import Engine
+    from speech_backbones_b200.diffvc import Diffusion
+    from speech_backbones_b200.spec import DiffVCConfig, diffvc_param_spec, synthetic_diffvc_inputs
+    cfg = DiffVCConfig()
+    spec = diffvc_param_spec(cfg)
+    m = Diffusion(80, 256, 128, True, 0.05, 20.0)
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == {k: tuple(v) for k, v in spec.items()}
+    assert m.nparams == 117_794_599
+    e = Engine(80, 256, model="diffvc", dim_cond=128)
+    assert e.weight_names() == list(spec)
+    e.close()
+    args = synthetic_diffvc_inputs(1, 8, 8)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(*args, n_timesteps=2, mode="pf")
+    assert m(*args, n_timesteps=2, mode="nope") is args[0]
