@@ -276,9 +276,16 @@ def run_ours(args, wl):
              "attention" if (".2." in n or "mid_attn" in n) else "resample" if ".3." in n else
              "final_euler" if n == "estimator.out" else "resblock_tail")
         by_kind[k] = by_kind.get(k, 0.0) + ms
+    # DRAM bytes per launch of the same kernel class from the committed ncu capture (scripts/ncu_traffic.py), if present
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic_conv3x3.json")
+    if os.path.exists(tpath) and args.precision == "tf32" and (B, T) == (32, 512):
+        tj = json.load(open(tpath))
+        traffic, traffic_src = tj["dram_bytes_per_launch"], "profiles/r1_traffic_conv3x3.json (ncu dram__bytes_read+write, %d launches)" % tj["launches"]
     roofline = {
         "kernel": "conv3x3 implicit GEMM (25 launches/step)", "bound": "tensor", "achieved": achieved, "peak": tensor_peak,
-        "unit": "TFLOP/s", "frac": achieved / tensor_peak, "traffic": None,
+        "unit": "TFLOP/s", "frac": achieved / tensor_peak, "traffic": traffic, "traffic_source": traffic_src,
+        "algorithmic_bytes_per_launch": conv_by / max(1, len(conv)),
         "peak_note": f"{peaks['src']} cuBLAS bf16 sustained x0.5 (tf32 / fp32-operand tensor rate)",
         "launches": len(conv), "avg_launch_ms": conv_ms / max(1, len(conv)),
         "flop_per_launch_avg": conv_fl / max(1, len(conv)), "share_of_step": conv_ms / all_ms,
