@@ -96,6 +96,14 @@ int sbk_vc_estimator(sbk_handle* h, const float* x, const float* mask, const flo
 int sbk_vc_reverse_diffusion(sbk_handle* h, const float* z, const float* mask, const float* mean, const float* cond,
                              const float* noise, float* out, int B, int T, int n_timesteps, int mode, void* stream);
 
+/* The hoisted conditioning branch natively (tensor-core precision modes only): for every step i (t_i = 1 - i/N)
+ * xt_ref = compute_diffused_mean(ref, ref_mask, mean_ref, t_i) (:151-155) -> RefBlock (modules.py:156-166: six
+ * Conv3x3 + InstanceNorm2d + GLU on tcgen05, two time biases, 1x1 conv, masked mean) -> cond_block over
+ * [sinusoid(t_i) | RefBlock | c] (:62-71).  ref, mean_ref: [B,n_feats,Tr]; ref_mask: [B,1,Tr]; c: [B,256];
+ * cond_out: [N][B][dim_cond], ready for sbk_vc_reverse_diffusion.  Returns SBK_ERR_UNSUPPORTED in fp32 mode. */
+int sbk_vc_conditioning(sbk_handle* h, const float* ref, const float* ref_mask, const float* mean_ref, const float* c,
+                        float* cond_out, int B, int Tr, int n_timesteps, void* stream);
+
 /* The same loop in slices: runs steps [step_begin, step_end) of an n_timesteps-step trajectory in place
  * on xt (which must already hold z*mask at step 0, or the previous slice's result).  noise, when stoc,
  * holds (step_end-step_begin) slabs of [B,n_feats,T].  Lets a caller stream noise for large N. */

@@ -17,7 +17,7 @@ EXPORTS = [
     "sbk_create", "sbk_destroy", "sbk_set_weight", "sbk_pack", "sbk_num_weights", "sbk_weight_name",
     "sbk_workspace_bytes", "sbk_estimator", "sbk_reverse_diffusion", "sbk_reverse_steps",
     "sbk_reverse_diffusion_host", "sbk_last_launch_count", "sbk_debug_read", "sbk_debug_num",
-    "sbk_debug_name", "sbk_last_error", "sbk_version", "sbk_profile_ops", "sbk_debug_capture", "sbk_debug_layout", "sbk_vc_estimator", "sbk_vc_reverse_diffusion",
+    "sbk_debug_name", "sbk_last_error", "sbk_version", "sbk_profile_ops", "sbk_debug_capture", "sbk_debug_layout", "sbk_vc_estimator", "sbk_vc_reverse_diffusion", "sbk_vc_conditioning",
 ]
 
 
@@ -54,6 +54,7 @@ def load_library() -> C.CDLL:
     lib.sbk_reverse_diffusion.argtypes = [P, F, F, F, F, F, F, I, I, I, I, P]
     lib.sbk_vc_estimator.argtypes = [P, F, F, F, F, F, F, I, I, P]
     lib.sbk_vc_reverse_diffusion.argtypes = [P, F, F, F, F, F, F, I, I, I, I, P]
+    lib.sbk_vc_conditioning.argtypes = [P, F, F, F, F, F, I, I, I, P]
     lib.sbk_reverse_steps.argtypes = [P, F, F, F, F, F, I, I, I, I, I, I, P]
     lib.sbk_reverse_diffusion_host.argtypes = [P, F, F, F, F, F, F, I, I, I, I]
     lib.sbk_last_launch_count.argtypes = [P]
@@ -156,8 +157,28 @@ class Engine:
                                       self._stream()), "sbk_estimator")
         return out
 
+    # ---- oversize batches: utterances are independent, so a batch whose workspace would not fit is run in slices
+    max_workspace_bytes = None      # default: 60 % of the device memory
+
+    def batch_slices(self, B, T):
+        limit = self.max_workspace_bytes
+        if limit is None:
+            limit = 0.6 * torch.cuda.get_device_properties(self.device).total_memory
+        need = self.workspace_bytes(B, T)
+        if need <= limit or B == 1:
+            return [(0, B)]
+        per = need / B
+        chunk = max(1, int(limit // per))
+        return [(lo, min(B, lo + chunk)) for lo in range(0, B, chunk)]
+
     def reverse_diffusion(self, z, mask, mu, n_timesteps, stoc=False, spk=None, noise=None):
         B, T = self._check_inputs(z, mask, mu, spk)
+        sl = self.batch_slices(B, T)
+        if len(sl) > 1:
+            outs = [self.reverse_diffusion(z[a:b], mask[a:b], mu[a:b], n_timesteps, stoc,
+                                           None if spk is None else spk[a:b],
+                                           None if noise is None else noise[:, a:b].contiguous()) for a, b in sl]
+            return torch.cat(outs, 0)
         z, mask, mu = _f32c(z, "z"), _f32c(mask, "mask"), _f32c(mu, "mu")
         spk = _f32c(spk, "spk") if (spk is not None and self.n_spks > 1) else None
         if stoc:
@@ -196,8 +217,27 @@ class Engine:
                                          self._stream()), "sbk_vc_estimator")
         return out
 
+    def vc_conditioning(self, ref, ref_mask, mean_ref, c, n_timesteps):
+        """Native hoisted conditioning branch (tensor-core modes): cond [N, B, dim_cond] for t_i = 1 - i/N."""
+        for n, t in (("ref", ref), ("ref_mask", ref_mask), ("mean_ref", mean_ref), ("c", c)):
+            if not t.is_cuda:
+                raise RuntimeError(f"{n} must be a CUDA tensor: the sampler has no CPU path")
+        B, Fm, Tr = ref.shape
+        ref, ref_mask, mean_ref, c = _f32c(ref, "ref"), _f32c(ref_mask, "ref_mask"), _f32c(mean_ref, "mean_ref"), _f32c(c, "c")
+        if Fm != self.n_feats or mean_ref.shape != ref.shape or ref_mask.shape != (B, 1, Tr) or tuple(c.shape) != (B, 256):
+            raise RuntimeError("shape mismatch in vc_conditioning inputs")
+        out = torch.empty((n_timesteps, B, self.dim_cond), dtype=torch.float32, device=ref.device)
+        _check(self.lib.sbk_vc_conditioning(self.h, _ptr(ref), _ptr(ref_mask), _ptr(mean_ref), _ptr(c), _ptr(out), B, Tr,
+                                            int(n_timesteps), self._stream()), "sbk_vc_conditioning")
+        return out
+
     def vc_reverse_diffusion(self, z, mask, mean, cond, n_timesteps, mode, noise=None):
         B, T = self._check_inputs(z, mask, mean, None)
+        sl = self.batch_slices(B, T)
+        if len(sl) > 1:
+            outs = [self.vc_reverse_diffusion(z[a:b], mask[a:b], mean[a:b], cond[:, a:b].contiguous(), n_timesteps, mode,
+                                              None if noise is None else noise[:, a:b].contiguous()) for a, b in sl]
+            return torch.cat(outs, 0)
         z, mask, mean, cond = _f32c(z, "z"), _f32c(mask, "mask"), _f32c(mean, "mean"), _f32c(cond, "cond")
         if tuple(cond.shape) != (n_timesteps, B, self.dim_cond):
             raise RuntimeError(f"cond shape {tuple(cond.shape)} != {(n_timesteps, B, self.dim_cond)}")

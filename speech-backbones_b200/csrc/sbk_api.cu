@@ -89,6 +89,7 @@ struct sbk_handle {
     std::vector<void*> owned;
     float* d_freqs = nullptr;
     float* d_zero = nullptr;                  // zero page for the tensor-core kernels' border copies
+    void* ref_mem = nullptr; size_t ref_bytes = 0;   // DiffVC RefBlock workspace (grown on demand)
     bool is_packed = false;
     Plan plan;
     cudaStream_t cap_stream = nullptr;
@@ -232,6 +233,7 @@ extern "C" void sbk_destroy(sbk_handle* h) {
     free_plan(h);
     for (auto& kv : h->raw) cudaFree(kv.second);
     for (void* p : h->owned) cudaFree(p);
+    if (h->ref_mem) cudaFree(h->ref_mem);
     if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
     delete h;
 }
@@ -392,6 +394,16 @@ extern "C" int sbk_pack(sbk_handle* h) {
         for (int j = 0; j < 2; ++j) {
             const std::string p = "estimator.ups." + std::to_string(j) + ".3.conv";
             TRY(pack_tc_up(h, p + ".weight", p + ".wtc", h->cfg.dim << (1 - j)));
+        }
+        if (h->cfg.model == SBK_MODEL_DIFFVC && h->cfg.use_ref_t) {
+            const int base = h->cfg.dim_cond / 4;
+            const char* nm[5] = {"block12", "block21", "block22", "block31", "block32"};
+            const int ci[5] = {base, base, 2 * base, 2 * base, 4 * base}, co[5] = {2 * base, 4 * base, 4 * base, 8 * base, 8 * base};
+            for (int k = 0; k < 5; ++k) {
+                const std::string q = std::string("estimator.ref_block.") + nm[k];
+                TRY(pack_tc(h, q + ".0.weight", q + ".wtc", co[k], ci[k], G_C3, bf));
+            }
+            TRY(repack(h, "estimator.ref_block.block11.0.weight", "estimator.ref_block.block11.w", (size_t)9 * 2 * base, first_pack));
         }
     }
     for (auto& a : h->attns) TRY(repack(h, a.prefix + ".fn.fn.to_qkv.weight", a.prefix + ".kv.w", (size_t)a.c * 256, kv_pack));
@@ -1128,6 +1140,123 @@ extern "C" int sbk_vc_reverse_diffusion(sbk_handle* h, const float* z, const flo
     n += launch_scale_mask(z, pl.mask, pl.xt, 0, B, h->cfg.n_feats, T, s);
     TRY(run_steps(h, noise, B, T, N, 0, N, mode != 0, s, &n));
     CU(cudaMemcpyAsync(out, pl.xt, nb, cudaMemcpyDeviceToDevice, s));
+    h->last_launches = n;
+    return SBK_OK;
+}
+
+extern "C" int sbk_vc_conditioning(sbk_handle* h, const float* ref, const float* ref_mask, const float* mean_ref, const float* c,
+                                   float* cond_out, int B, int Tr, int n_timesteps, void* stream) {
+    if (!h || !ref || !ref_mask || !mean_ref || !c || !cond_out) return fail(SBK_ERR_ARG, "sbk_vc_conditioning: null argument");
+    if (h->cfg.model != SBK_MODEL_DIFFVC) return fail(SBK_ERR_ARG, "sbk_vc_conditioning: this handle is not a DiffVC model");
+    if (!h->is_packed) return fail(SBK_ERR_STATE, "sbk_vc_conditioning: weights not packed");
+    if (h->cfg.precision == SBK_PREC_FP32)
+        return fail(SBK_ERR_UNSUPPORTED, "sbk_vc_conditioning: the native RefBlock runs on the tensor-core path only (precision tf32); "
+                                         "in fp32 mode the binding evaluates the hoisted conditioning branch itself");
+    if (B <= 0 || Tr <= 0 || n_timesteps < 1) return fail(SBK_ERR_ARG, "sbk_vc_conditioning: bad sizes");
+    CU(cudaSetDevice(h->cfg.device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const sbk_config& cf = h->cfg;
+    const int H = cf.n_feats, dc = cf.dim_cond, base = dc / 4, N = n_timesteps, dim = cf.dim;
+    const size_t px = (size_t)B * H * Tr;
+    // ---- workspace
+    Arena probe;
+    auto carve = [&](Arena& ar, float*& xt_ref, float*& raw, float*& act, double*& st, double*& ys, float*& tb, float*& trows) {
+        xt_ref = (float*)ar.take(px * sizeof(float));
+        raw = (float*)ar.take(px * 8 * base * sizeof(float));
+        act = (float*)ar.take(px * 4 * base * sizeof(float));
+        st = (double*)ar.take((size_t)B * 8 * base * 2 * sizeof(double));
+        ys = (double*)ar.take((size_t)B * dc * 2 * sizeof(double));
+        tb = (float*)ar.take((size_t)N * 3 * base * sizeof(float));
+        trows = (float*)ar.take((size_t)N * sizeof(float));
+    };
+    float *xt_ref, *raw, *act, *tb, *trows; double *st, *ys;
+    carve(probe, xt_ref, raw, act, st, ys, tb, trows);
+    const size_t need = probe.off + 256;
+    if (need > h->ref_bytes) {
+        if (h->ref_mem) CU(cudaFree(h->ref_mem));
+        h->ref_mem = nullptr; h->ref_bytes = 0;
+        CU(cudaMalloc(&h->ref_mem, need));
+        h->ref_bytes = need;
+    }
+    Arena ar; ar.base = (char*)h->ref_mem; ar.cap = h->ref_bytes;
+    carve(ar, xt_ref, raw, act, st, ys, tb, trows);
+    // ---- time values + the two RefBlock time biases (mlp1, mlp2: Mish -> Linear on the time-MLP output) for all steps
+    std::vector<float> tr(N);
+    for (int i = 0; i < N; ++i) tr[i] = (float)(1.0 - i * (1.0 / N));
+    CU(cudaMemcpyAsync(trows, tr.data(), N * sizeof(float), cudaMemcpyHostToDevice, s));
+    int64_t n = 0;
+    if (cf.use_ref_t) {
+        TimeTableParams tp; memset(&tp, 0, sizeof(tp));
+        tp.t_rows = trows; tp.rows = N; tp.freqs = h->d_freqs; tp.pe_scale = 1000.0f; tp.dim = dim;
+        tp.w0 = h->raw["estimator.mlp.0.weight"]; tp.b0 = h->raw["estimator.mlp.0.bias"];
+        tp.w2 = h->raw["estimator.mlp.2.weight"]; tp.b2 = h->raw["estimator.mlp.2.bias"];
+        tp.nproj = 2;
+        tp.pw[0] = h->raw["estimator.ref_block.mlp1.1.weight"]; tp.pb[0] = h->raw["estimator.ref_block.mlp1.1.bias"]; tp.pc[0] = base; tp.poff[0] = 0;
+        tp.pw[1] = h->raw["estimator.ref_block.mlp2.1.weight"]; tp.pb[1] = h->raw["estimator.ref_block.mlp2.1.bias"]; tp.pc[1] = 2 * base; tp.poff[1] = base;
+        tp.tb = tb; tp.tb_stride = 3 * base;
+        n += launch_time_table(tp, s);
+    }
+    auto W = [&](const std::string& k) -> const float* {
+        auto it = h->packed.find(k);
+        if (it != h->packed.end()) return it->second;
+        auto it2 = h->raw.find(k);
+        return it2 != h->raw.end() ? it2->second : nullptr;
+    };
+    auto gamma0 = [&](double t) {       // get_gamma(0, t), diffusion.py:124-131
+        double bi = cf.beta_min + 0.5 * ((double)cf.beta_max - cf.beta_min) * t;
+        bi *= t;
+        return exp(-0.5 * bi);
+    };
+    auto conv = [&](const char* name, int cin, int cout) {
+        ConvTcParams p; memset(&p, 0, sizeof(p));
+        const std::string q = std::string("estimator.ref_block.") + name;
+        p.geom = G_C3; p.in0 = act; p.c0 = cin; p.H = H; p.W = Tr; p.B = B; p.Ho = H; p.Wo = Tr;
+        p.wpk = W(q + ".wtc"); p.bias = W(q + ".0.bias"); p.out = raw; p.Cout = cout; p.epi = EPI_PLAIN;
+        p.mask = ref_mask; p.T = Tr; p.zero_page = h->d_zero;
+        return launch_conv_tc(p, s);
+    };
+    auto norm_glu = [&](const char* name, int C, const float* tbias) {
+        const std::string q = std::string("estimator.ref_block.") + name;
+        ChanStatsParams cs{raw, st, B, H, Tr, C};
+        int k = launch_chan_stats(cs, s);
+        InGluParams g; memset(&g, 0, sizeof(g));
+        g.raw = raw; g.stats = st; g.gamma = W(q + ".1.weight"); g.beta = W(q + ".1.bias"); g.tb = tbias;
+        g.mask = ref_mask; g.T = Tr; g.out = act; g.B = B; g.H = H; g.W = Tr; g.C = C;
+        return k + launch_in_glu(g, s);
+    };
+    for (int i = 0; i < N; ++i) {
+        if (cf.use_ref_t) {
+            DiffMeanParams dm{ref, mean_ref, ref_mask, xt_ref, (float)gamma0(1.0 - i * (1.0 / N)), B, H, Tr};
+            n += launch_diff_mean(dm, s);
+            FirstConvParams fc; memset(&fc, 0, sizeof(fc));
+            fc.mu = xt_ref; fc.xt = xt_ref; fc.mask = ref_mask; fc.w = W("estimator.ref_block.block11.w");
+            fc.bias = W("estimator.ref_block.block11.0.bias"); fc.out = raw; fc.ostats = nullptr;
+            fc.B = B; fc.H = H; fc.T = Tr; fc.cin = 1; fc.C = 2 * base; fc.chw4 = 1;
+            n += launch_first_conv(fc, s);
+            n += norm_glu("block11", 2 * base, nullptr);
+            n += conv("block12", base, 2 * base);
+            n += norm_glu("block12", 2 * base, tb + (size_t)i * 3 * base);
+            n += conv("block21", base, 4 * base);
+            n += norm_glu("block21", 4 * base, nullptr);
+            n += conv("block22", 2 * base, 4 * base);
+            n += norm_glu("block22", 4 * base, tb + (size_t)i * 3 * base + base);
+            n += conv("block31", 2 * base, 8 * base);
+            n += norm_glu("block31", 8 * base, nullptr);
+            n += conv("block32", 4 * base, 8 * base);
+            n += norm_glu("block32", 8 * base, nullptr);
+            ChanStatsParams ysm{act, ys, B, H, Tr, 4 * base};
+            n += launch_chan_stats(ysm, s);
+        }
+        VcCondParams vp; memset(&vp, 0, sizeof(vp));
+        vp.ysum = ys; vp.mask = ref_mask; vp.Tr = Tr; vp.H = H;
+        vp.wf = W("estimator.ref_block.final_conv.weight"); vp.bf = W("estimator.ref_block.final_conv.bias");
+        vp.c = c; vp.freqs = h->d_freqs; vp.t = tr[i]; vp.dim = dim;
+        vp.w0 = W("estimator.cond_block.0.weight"); vp.b0 = W("estimator.cond_block.0.bias");
+        vp.w2 = W("estimator.cond_block.2.weight"); vp.b2 = W("estimator.cond_block.2.bias");
+        vp.out = cond_out + (size_t)i * B * dc; vp.B = B; vp.dc = dc; vp.use_ref = cf.use_ref_t ? 1 : 0;
+        n += launch_vc_cond(vp, s);
+    }
+    CU(cudaGetLastError());
     h->last_launches = n;
     return SBK_OK;
 }

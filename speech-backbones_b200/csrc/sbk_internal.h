@@ -162,6 +162,34 @@ struct CondFoldParams {
 };
 int launch_cond_fold(const CondFoldParams& p, cudaStream_t s);
 
+// ---- DiffVC RefBlock / conditioning branch (DiffVC/model/modules.py:128-166, diffusion.py:62-71), tensor-core modes ----
+struct DiffMeanParams {          // xt_ref = (ref*g + mean_ref*(1-g)) * ref_mask  (compute_diffused_mean, diffusion.py:151-155)
+    const float* ref; const float* mean_ref; const float* mask; float* out; float g; int B, H, T;
+};
+struct ChanStatsParams {         // per (sample, channel) {sum, sum of squares} over H*W of a [B][H][C/4][W][4] tensor (InstanceNorm2d)
+    const float* x; double* stats; int B, H, W, C;
+};
+struct InGluParams {             // y = mask ? tf32( IN(raw[c]) * sigmoid(IN(raw[c + C/2])) + tb[c] ) : 0   -> C/2 channels
+    const float* raw; const double* stats; const float* gamma; const float* beta;   // InstanceNorm2d affine, eps 1e-5
+    const float* tb;             // [C/2] time bias (mlp1 / mlp2 row of this step) or nullptr
+    const float* mask; int T;    // ref_mask [B][T]
+    float* out; int B, H, W, C;  // C = raw channels
+};
+struct VcCondParams {            // cond_block( [sinusoid(t) | final_conv(mean-pooled RefBlock) | c] )  (diffusion.py:62-71)
+    const double* ysum;          // [B][dc][2] channel sums of the masked RefBlock output (before final_conv)
+    const float* mask; int Tr; int H;
+    const float* wf; const float* bf;         // ref_block.final_conv [dc][dc], [dc]
+    const float* c;              // [B][256] speaker embedding
+    const float* freqs; float t; int dim;     // sinusoid
+    const float* w0; const float* b0; const float* w2; const float* b2;   // cond_block
+    float* out;                  // [B][dc] (row of this step)
+    int B, dc, use_ref;
+};
+int launch_diff_mean(const DiffMeanParams& p, cudaStream_t s);
+int launch_chan_stats(const ChanStatsParams& p, cudaStream_t s);
+int launch_in_glu(const InGluParams& p, cudaStream_t s);
+int launch_vc_cond(const VcCondParams& p, cudaStream_t s);
+
 struct StepBeginParams { double* stats; int n_doubles; int* step_cur; int* step_next; };
 
 // launchers (all asynchronous on `s`); return the number of kernels launched

@@ -396,8 +396,8 @@ __global__ void __launch_bounds__(256) k_first_conv(const FirstConvParams p) {
     __shared__ float s_b[64];
     __shared__ float s_st[16];
     const int tid = threadIdx.x, b = blockIdx.z, n0 = blockIdx.y * 64;
-    const int wtiles = (p.T + 63) / 64;
-    const int h = blockIdx.x / wtiles, w0 = (blockIdx.x - h * wtiles) * 64;
+    const int wtiles = (p.T + 255) / 256;          // a CTA walks 4 strips of 64 frames, re-using the staged weights
+    const int h = blockIdx.x / wtiles, wbase = (blockIdx.x - h * wtiles) * 256;
     const int K = p.cin * 9;
     const int kreal = p.w_extra ? (p.cin - 1) * 9 : K;       // rows of s_w that come from the shared weight
     for (int i = tid; i < kreal * 64; i += 256) s_w[i] = p.w[(i >> 6) * p.C + n0 + (i & 63)];
@@ -408,6 +408,8 @@ __global__ void __launch_bounds__(256) k_first_conv(const FirstConvParams p) {
     }
     if (tid < 64) s_b[tid] = p.bias[n0 + tid];
     if (tid < 16) s_st[tid] = 0.f;
+    for (int w0 = wbase; w0 < wbase + 256 && w0 < p.T; w0 += 64) {
+    __syncthreads();                                   // previous strip's s_in / s_out readers are done
     for (int i = tid; i < p.cin * 3 * 66; i += 256) {
         const int ci = i / 198, rem = i - ci * 198, r = rem / 66, q = rem - r * 66;
         const int hi = h + r - 1, wi = w0 + q - 1;
@@ -445,7 +447,7 @@ __global__ void __launch_bounds__(256) k_first_conv(const FirstConvParams p) {
     for (int j4 = 0; j4 < 4; ++j4)
         *reinterpret_cast<float4*>(&s_out[pxl * 68 + cg * 16 + j4 * 4]) = make_float4(acc[j4 * 4], acc[j4 * 4 + 1], acc[j4 * 4 + 2], acc[j4 * 4 + 3]);
     // GN statistics: each half of the thread's 16 channels lies in one group (8 | C/8)
-    const int cpg = p.C / kGroups, gb = n0 / cpg;
+    const int cpg_ = p.C / kGroups, gb_ = n0 / cpg_;
 #pragma unroll
     for (int hf = 0; hf < 2; ++hf) {
         float s = 0.f, q = 0.f;
@@ -456,7 +458,7 @@ __global__ void __launch_bounds__(256) k_first_conv(const FirstConvParams p) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
         if ((tid & 31) == 0) {
-            const int g = (n0 + cg * 16 + hf * 8) / cpg - gb;
+            const int g = (n0 + cg * 16 + hf * 8) / cpg_ - gb_;
             atomicAdd(&s_st[g * 2], s);
             atomicAdd(&s_st[g * 2 + 1], q);
         }
@@ -476,12 +478,15 @@ __global__ void __launch_bounds__(256) k_first_conv(const FirstConvParams p) {
             if (w0 + q < p.T) *reinterpret_cast<float4*>(obase + (long long)q * p.C + c4) = *reinterpret_cast<const float4*>(&s_out[q * 68 + c4]);
         }
     }
+    }   // strips
+    __syncthreads();
+    const int cpg = p.C / kGroups, gb = n0 / cpg;
     const int ng = (64 + cpg - 1) / cpg;
-    if (tid < ng * 2) atomicAdd(&p.ostats[((long long)b * kGroups + gb + (tid >> 1)) * 2 + (tid & 1)], (double)s_st[tid]);
+    if (p.ostats && tid < ng * 2) atomicAdd(&p.ostats[((long long)b * kGroups + gb + (tid >> 1)) * 2 + (tid & 1)], (double)s_st[tid]);
 }
 
 int launch_first_conv(const FirstConvParams& p, cudaStream_t s) {
-    dim3 grid(((p.T + 63) / 64) * p.H, p.C / 64, p.B);
+    dim3 grid(((p.T + 255) / 256) * p.H, p.C / 64, p.B);
     k_first_conv<<<grid, 256, 0, s>>>(p);
     return 1;
 }
@@ -746,43 +751,42 @@ __global__ void __launch_bounds__(256) k_attn_mix(const AttnMixParams p) {
     }
     __syncthreads();
     const float g = __ldg(p.g);
-    for (int cp = tid; cp < C; cp += 256) {   // cp = input channel c'
-        float acc[32];
+    // P[cl][c'] = sum_j Mb[cl][j] * Wq[j][c']: thread = (input channel c' within a block of 64, group of 8 output rows)
+    const int cq = tid >> 6, cl0 = cq * 8;
+    for (int cp = tid & 63; cp < C; cp += 64) {
+        float acc[8];
 #pragma unroll
-        for (int cl = 0; cl < 32; ++cl) acc[cl] = 0.f;
-#pragma unroll 2
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll 4
         for (int j = 0; j < kAttnHidden; ++j) {
             const float wq = __ldg(p.wq + (long long)j * C + cp);
-            const float4* m4 = reinterpret_cast<const float4*>(&s_mb[j * 32]);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const float4 m = m4[q];
-                acc[4 * q + 0] = fmaf(m.x, wq, acc[4 * q + 0]); acc[4 * q + 1] = fmaf(m.y, wq, acc[4 * q + 1]);
-                acc[4 * q + 2] = fmaf(m.z, wq, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(m.w, wq, acc[4 * q + 3]);
-            }
+            const float4 m0 = *reinterpret_cast<const float4*>(&s_mb[j * 32 + cl0]);
+            const float4 m1 = *reinterpret_cast<const float4*>(&s_mb[j * 32 + cl0 + 4]);
+            acc[0] = fmaf(m0.x, wq, acc[0]); acc[1] = fmaf(m0.y, wq, acc[1]); acc[2] = fmaf(m0.z, wq, acc[2]); acc[3] = fmaf(m0.w, wq, acc[3]);
+            acc[4] = fmaf(m1.x, wq, acc[4]); acc[5] = fmaf(m1.y, wq, acc[5]); acc[6] = fmaf(m1.z, wq, acc[6]); acc[7] = fmaf(m1.w, wq, acc[7]);
         }
         if (p.tc_nt) {
-            // tcgen05 1x1 weight image: [ntile][kstage][chunk][cout % NT][4 cin], tf32 (RNA)
+            // tcgen05 1x1 weight image: [ntile][kstage][chunk][cout % NT][4 cin], tf32 (RNA); g*P only (see AttnMixParams)
             const int NT = p.tc_nt, kch = p.tc_cps / 4, ksteps = C / p.tc_cps;
             const int ks = cp / p.tc_cps, kc = (cp % p.tc_cps) / 4, e = cp & 3;
 #pragma unroll
-            for (int cl = 0; cl < 32; ++cl) {
-                const int co = cb + cl;
-                float v = g * acc[cl];
+            for (int i = 0; i < 8; ++i) {
+                const int co = cb + cl0 + i;
+                float v = g * acc[i];
                 uint32_t u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
                 const long long idx = ((((long long)(co / NT) * ksteps + ks) * kch + kc) * NT + (co % NT)) * 4 + e;
                 p.w_eff[(long long)b * C * C + idx] = __uint_as_float(u);
             }
         } else {
-            float* o = p.w_eff + ((long long)b * C + cp) * C + cb;
+            float* o = p.w_eff + ((long long)b * C + cp) * C + cb + cl0;
 #pragma unroll
-            for (int cl = 0; cl < 32; cl += 4) {
-                float4 v = make_float4(g * acc[cl], g * acc[cl + 1], g * acc[cl + 2], g * acc[cl + 3]);
-                if (cb + cl + 0 == cp) v.x += 1.f;
-                if (cb + cl + 1 == cp) v.y += 1.f;
-                if (cb + cl + 2 == cp) v.z += 1.f;
-                if (cb + cl + 3 == cp) v.w += 1.f;
-                *reinterpret_cast<float4*>(o + cl) = v;
+            for (int i = 0; i < 8; i += 4) {
+                float4 v = make_float4(g * acc[i], g * acc[i + 1], g * acc[i + 2], g * acc[i + 3]);
+                if (cb + cl0 + i + 0 == cp) v.x += 1.f;
+                if (cb + cl0 + i + 1 == cp) v.y += 1.f;
+                if (cb + cl0 + i + 2 == cp) v.z += 1.f;
+                if (cb + cl0 + i + 3 == cp) v.w += 1.f;
+                *reinterpret_cast<float4*>(o + i) = v;
             }
         }
     }
@@ -978,6 +982,162 @@ __global__ void __launch_bounds__(256) k_cond_fold(const CondFoldParams p) {
 
 int launch_cond_fold(const CondFoldParams& p, cudaStream_t s) {
     k_cond_fold<<<p.rows * p.B, 256, p.dc * sizeof(float), s>>>(p);
+    return 1;
+}
+
+// ----------------------------------------------------------------------------------------------
+// DiffVC RefBlock glue (tensor-core modes; the six 3x3 convs themselves run on k_conv_tc<G_C3>)
+// ----------------------------------------------------------------------------------------------
+__global__ void k_diff_mean(const DiffMeanParams p) {
+    const long long n = (long long)p.B * p.H * p.T;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int w = (int)(i % p.T);
+    const long long b = i / ((long long)p.H * p.T);
+    p.out[i] = (p.ref[i] * p.g + p.mean_ref[i] * (1.0f - p.g)) * p.mask[b * p.T + w];
+}
+int launch_diff_mean(const DiffMeanParams& p, cudaStream_t s) {
+    const long long n = (long long)p.B * p.H * p.T;
+    k_diff_mean<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p);
+    return 1;
+}
+
+// InstanceNorm2d statistics: one CTA per (16-byte channel chunk, sample); the chunk's rows are contiguous float4 runs
+__global__ void __launch_bounds__(256) k_chan_stats(const ChanStatsParams p) {
+    __shared__ double s_s[8][8];
+    const int ch = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, c4n = p.C / 4;
+    float sx[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
+    double ds[4] = {0, 0, 0, 0}, dq[4] = {0, 0, 0, 0};
+    for (int h = 0; h < p.H; ++h) {
+        const float* row = p.x + ((((long long)b * p.H + h) * c4n + ch) * p.W) * 4;
+        for (int w = tid; w < p.W; w += 256) {
+            const float4 v = ldg4(row + (long long)w * 4);
+            sx[0] += v.x; sx[1] += v.y; sx[2] += v.z; sx[3] += v.w;
+            sq[0] = fmaf(v.x, v.x, sq[0]); sq[1] = fmaf(v.y, v.y, sq[1]); sq[2] = fmaf(v.z, v.z, sq[2]); sq[3] = fmaf(v.w, v.w, sq[3]);
+        }
+        if ((h & 7) == 7 || h == p.H - 1) {      // flush the fp32 partials into fp64 every 8 rows
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { ds[q] += sx[q]; dq[q] += sq[q]; sx[q] = 0.f; sq[q] = 0.f; }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { ds[q] += __shfl_xor_sync(0xffffffffu, ds[q], o); dq[q] += __shfl_xor_sync(0xffffffffu, dq[q], o); }
+    }
+    if ((tid & 31) == 0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { s_s[tid >> 5][q] = ds[q]; s_s[tid >> 5][4 + q] = dq[q]; }
+    }
+    __syncthreads();
+    if (tid < 8) {
+        double a = 0;
+        for (int wv = 0; wv < 8; ++wv) a += s_s[wv][tid];
+        const int q = tid & 3, which = tid >> 2;
+        p.stats[((long long)b * p.C + ch * 4 + q) * 2 + which] = a;
+    }
+}
+int launch_chan_stats(const ChanStatsParams& p, cudaStream_t s) {
+    k_chan_stats<<<dim3(p.C / 4, p.B), 256, 0, s>>>(p);
+    return 1;
+}
+
+// InstanceNorm2d(affine) + GLU(dim=1) (+ time bias) * mask, written in operand form (tf32-rounded)
+__global__ void __launch_bounds__(256) k_in_glu(const InGluParams p) {
+    extern __shared__ float sm[];
+    float* mean = sm; float* scale = mean + p.C; float* beta = scale + p.C; float* tbv = beta + p.C;   // tbv: [C/2]
+    const int b = blockIdx.y, tid = threadIdx.x, Ch = p.C / 2;
+    const double inv = 1.0 / ((double)p.H * p.W);
+    for (int c = tid; c < p.C; c += 256) {
+        const double s = p.stats[((long long)b * p.C + c) * 2], ss = p.stats[((long long)b * p.C + c) * 2 + 1];
+        const double m = s * inv;
+        double var = ss * inv - m * m;
+        var = var < 0.0 ? 0.0 : var;
+        mean[c] = (float)m;
+        scale[c] = (float)(1.0 / sqrt(var + 1e-5)) * p.gamma[c];
+        beta[c] = p.beta[c];
+    }
+    for (int c = tid; c < Ch; c += 256) tbv[c] = p.tb ? p.tb[c] : 0.f;
+    __syncthreads();
+    const int o4n = Ch / 4, i4n = p.C / 4;            // output / input channel chunks
+    const long long n4 = (long long)p.H * p.W * o4n;
+    for (long long i = (long long)blockIdx.x * 256 + tid; i < n4; i += (long long)gridDim.x * 256) {
+        const long long hc = i / p.W;
+        const int w = (int)(i - hc * p.W);
+        const int h = (int)(hc / o4n), ch = (int)(hc - (long long)h * o4n);
+        const float mk = __ldg(p.mask + (long long)b * p.T + w);
+        float o[4] = {0.f, 0.f, 0.f, 0.f};
+        if (mk != 0.f) {
+            const float* rowa = p.raw + ((((long long)b * p.H + h) * i4n + ch) * p.W + w) * 4;
+            const float4 a = ldg4(rowa), g = ldg4(rowa + (long long)o4n * p.W * 4);      // gate half: channel c + C/2
+            const float av[4] = {a.x, a.y, a.z, a.w}, gv[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int c = ch * 4 + q;
+                const float xa = (av[q] - mean[c]) * scale[c] + beta[c];
+                const float xg = (gv[q] - mean[Ch + c]) * scale[Ch + c] + beta[Ch + c];
+                float y = xa * __fdividef(1.f, 1.f + __expf(-xg)) + tbv[c];
+                uint32_t t; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(y));
+                o[q] = __uint_as_float(t);
+            }
+        }
+        *reinterpret_cast<float4*>(p.out + ((long long)b * n4 + i) * 4) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+int launch_in_glu(const InGluParams& p, cudaStream_t s) {
+    const long long n4 = (long long)p.H * p.W * (p.C / 8);
+    int gx = (int)((n4 + 256 * 8 - 1) / (256 * 8));
+    if (gx < 1) gx = 1;
+    if (gx > 4096) gx = 4096;
+    k_in_glu<<<dim3(gx, p.B), 256, (3 * p.C + p.C / 2) * sizeof(float), s>>>(p);
+    return 1;
+}
+
+// conditioning vector of one step: [sinusoid(1000 t) | ref_block.final_conv(mean-pooled y) | c] -> cond_block
+__global__ void __launch_bounds__(256) k_vc_cond(const VcCondParams p) {
+    extern __shared__ float sm[];
+    const int b = blockIdx.x, tid = threadIdx.x, dim = p.dim, dc = p.dc, half = dim / 2;
+    const int n_in = dim + (p.use_ref ? dc : 0) + 256;
+    float* in = sm;                 // [n_in]
+    float* ybar = in + n_in;        // [dc]
+    float* hid = ybar + dc;         // [4*dc]
+    const float a = 1000.0f * p.t;  // SinusoidalPosEmb hard-codes the scale (modules.py:123)
+    for (int j = tid; j < half; j += 256) {
+        const float arg = a * p.freqs[j];
+        in[j] = sinf(arg);
+        in[half + j] = cosf(arg);
+    }
+    if (p.use_ref) {
+        float msum = 0.f;
+        for (int w = 0; w < p.Tr; ++w) msum += p.mask[(long long)b * p.Tr + w];
+        const double den = (double)msum * p.H;
+        for (int c = tid; c < dc; c += 256) ybar[c] = (float)(p.ysum[((long long)b * dc + c) * 2] / den);
+    }
+    for (int j = tid; j < 256; j += 256) in[dim + (p.use_ref ? dc : 0) + j] = p.c[(long long)b * 256 + j];
+    __syncthreads();
+    if (p.use_ref) {
+        for (int o = tid; o < dc; o += 256) {
+            float acc = p.bf[o];
+            for (int k = 0; k < dc; ++k) acc = fmaf(p.wf[o * dc + k], ybar[k], acc);
+            in[dim + o] = acc;
+        }
+        __syncthreads();
+    }
+    for (int o = tid; o < 4 * dc; o += 256) {
+        float acc = p.b0[o];
+        for (int k = 0; k < n_in; ++k) acc = fmaf(p.w0[(long long)o * n_in + k], in[k], acc);
+        hid[o] = mish_f(acc);
+    }
+    __syncthreads();
+    for (int o = tid; o < dc; o += 256) {
+        float acc = p.b2[o];
+        for (int k = 0; k < 4 * dc; ++k) acc = fmaf(p.w2[o * 4 * dc + k], hid[k], acc);
+        p.out[(long long)b * dc + o] = acc;
+    }
+}
+int launch_vc_cond(const VcCondParams& p, cudaStream_t s) {
+    const int n_in = p.dim + (p.use_ref ? p.dc : 0) + 256;
+    k_vc_cond<<<p.B, 256, (n_in + p.dc + 4 * p.dc) * sizeof(float), s>>>(p);
     return 1;
 }
 

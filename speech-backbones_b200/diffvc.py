@@ -7,10 +7,10 @@ names/shapes under `estimator.*` (so `DiffVC.load_state_dict` / `vc_*.pt` checkp
 
 Split of the work.  Everything in the conditioning branch of `GradLogPEstimator.forward` (:62-71: time sinusoid,
 RefBlock on the diffused reference, speaker embedding, cond_block) depends on t, ref and c only - never on xt - so it
-is hoisted out of the loop and evaluated once for all N steps.  This round that hoisted branch (RefBlock + cond_block,
-0.6 M of the 117.8 M parameters) runs as plain PyTorch on the GPU; the U-Net (downs/mid/ups/final, the three samplers
-pf / em / ml and the fold of the conditioning vector into the first ResnetBlock) runs in libsbk.so.  There is no CPU
-path: CPU tensors raise.
+is hoisted out of the loop and evaluated once for all N steps (`conditioning_table`): natively in libsbk.so in the
+tensor-core mode, with PyTorch ops in the exact-fp32 mode.  The U-Net (downs/mid/ups/final), the three samplers
+pf / em / ml and the fold of the conditioning vector into the first ResnetBlock always run in libsbk.so.  There is no
+CPU path: CPU tensors raise.
 """
 from __future__ import annotations
 
@@ -159,7 +159,13 @@ class Diffusion(BaseModule):
     # ---- sampling (diffusion.py:164-205) ------------------------------------------------------
     @torch.no_grad()
     def conditioning_table(self, ref, ref_mask, mean_ref, c, n_timesteps):
-        """cond[i] for every step i (t_i = 1 - i/N): the hoisted conditioning branch, batched over steps."""
+        """cond[i] for every step i (t_i = 1 - i/N): the hoisted conditioning branch.
+        precision="tf32": native (libsbk: RefBlock convs on tcgen05, InstanceNorm/GLU/cond_block kernels);
+        precision="fp32": the CUDA-core mode has no InstanceNorm/GLU conv path, so this 0.6 M-parameter branch is
+        evaluated with PyTorch ops on the GPU."""
+        if self.precision != "fp32":
+            with torch.cuda.device(ref.device):
+                return self.engine().vc_conditioning(ref, ref_mask, mean_ref, c, n_timesteps)
         h = 1.0 / n_timesteps
         rows = []
         for i in range(n_timesteps):

@@ -82,6 +82,42 @@ def test_vc_samplers_vs_reference_golden(vc_engines, vc_golden, precision):
         assert (y * (1 - mask)).abs().max().item() == 0.0
 
 
+def test_vc_native_conditioning_vs_oracle(vc_engines, vc_golden):
+    """RefBlock + cond_block natively: sbk_vc_conditioning vs the CPU oracle, every step."""
+    eng, cfg, sd = vc_engines("tf32")
+    c = next(c for c in vc_golden["cases"] if c["kind"] == "traj" and c["mode"] == "ml" and c["B"] == 2)
+    z, mask, mean, r, rmask, mean_ref, spk = _inputs(vc_golden, c)
+    N = c["N"]
+    got = eng.vc_conditioning(r.cuda(), rmask.cuda(), mean_ref.cuda(), spk.cuda(), N).cpu()
+    for i in range(N):
+        t, _, _, _, g0t = O.step_coefficients(cfg, N, i, "ml")
+        xt_ref = ((r * g0t + mean_ref * (1.0 - g0t)) * rmask)[:, None]
+        ref = O.conditioning(sd, cfg, xt_ref, rmask, spk, t * torch.ones(c["B"]))[1]
+        err = rel_l2(got[i], ref)
+        print("step", i, "cond rel_l2", err)
+        assert err <= 4e-3
+    # and the sampler fed by the native table
+    torch.manual_seed(vc_golden["noise_seed"])
+    noise = torch.stack([torch.randn_like(z) for _ in range(N)]).cuda()
+    y = eng.vc_reverse_diffusion(z.cuda(), mask.cuda(), mean.cuda(), got.cuda(), N, "ml", noise).cpu()
+    assert rel_l2(y, c["out"]) <= TOL["tf32"][1]
+    with pytest.raises(RuntimeError, match="tensor-core"):
+        vc_engines("fp32")[0].vc_conditioning(r.cuda(), rmask.cuda(), mean_ref.cuda(), spk.cuda(), N)
+
+
+def test_vc_dropin_module_tf32_native_conditioning(vc_golden):
+    from speech_backbones_b200.diffvc import Diffusion
+    cfg = DiffVCConfig()
+    sd = synthetic_state_dict(cfg, vc_golden["seed"], spec=diffvc_param_spec(cfg))
+    dec = Diffusion(80, 256, 128, True, 0.05, 20.0, precision="tf32").eval()
+    dec.load_state_dict(sd, strict=True)
+    dec = dec.cuda()
+    c = next(c for c in vc_golden["cases"] if c["kind"] == "traj" and c["mode"] == "pf")
+    args = [v.cuda() for v in _inputs(vc_golden, c)]
+    y = dec(*args, n_timesteps=c["N"], mode="pf")
+    assert rel_l2(y.cpu(), c["out"]) <= TOL["tf32"][1]
+
+
 def test_vc_dropin_module(vc_golden):
     """Diffusion(...).load_state_dict(strict) -> .cuda() -> forward(...): the call DiffVC/model/vc.py:125 makes."""
     from speech_backbones_b200.diffvc import Diffusion

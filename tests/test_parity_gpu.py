@@ -264,6 +264,20 @@ def test_bf16_mode_is_refused_loudly(sbk_lib):
     e.close()
 
 
+def test_oversize_batch_is_sliced(engines):
+    """A batch whose workspace exceeds the limit is processed in independent slices with identical results."""
+    eng = engines(1, True)
+    z, mask, mu, _, _ = synthetic_inputs(5, 32, ragged=True)
+    full = eng.reverse_diffusion(z.cuda(), mask.cuda(), mu.cuda(), 3).cpu()
+    eng.max_workspace_bytes = eng.workspace_bytes(2, 32)
+    try:
+        assert len(eng.batch_slices(5, 32)) == 3
+        sliced = eng.reverse_diffusion(z.cuda(), mask.cuda(), mu.cuda(), 3).cpu()
+    finally:
+        eng.max_workspace_bytes = None
+    assert rel_l2(sliced, full) < 1e-5
+
+
 def test_error_paths_raise(engines):
     eng = engines(1, True)
     z, mask, mu, _, _ = synthetic_inputs(1, 8)
