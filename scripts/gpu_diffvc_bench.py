@@ -36,7 +36,7 @@ for N in (6, 30):
     torch.cuda.synchronize()
     t_cond, t_loop = e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])
     print(json.dumps({"case": f"DiffVC ml N={N}", "precision": precision, "B": B, "T": T, "T_ref": Tr,
-                      "ms_conditioning_pytorch": t_cond, "ms_loop_libsbk": t_loop, "ms_per_step": t_loop / N,
+                      "ms_conditioning": t_cond, "ms_loop_libsbk": t_loop, "ms_per_step": t_loop / N,
                       "mel_frames_per_s": B * T / ((t_cond + t_loop) * 1e-3), "mel_frames_per_s_loop_only": B * T / (t_loop * 1e-3),
                       "tflops_loop": 2013.7e6 * B * T * N / (t_loop * 1e-3) / 1e12, "finite": bool(torch.isfinite(y).all())}), flush=True)
 rows = eng.profile_ops()
