@@ -511,6 +511,44 @@ __global__ void __launch_bounds__(256) k_resfinal(const ResFinalParams p) {
     __syncthreads();
     const int c4n = p.C >> 2;
     const long long n4 = (long long)p.H * p.W * c4n;
+    if (p.x && p.chw4) {
+        // planar layout, identity residual: one channel chunk per CTA, walking mel bins (see k_gn_act)
+        constexpr int U = 4;
+        const int ch = blockIdx.x % c4n, hg = blockIdx.x / c4n, nhg = gridDim.x / c4n;
+        const int tw = p.W >= 256 ? 256 : p.W, nsub = 256 / tw, sub = tid / tw, wl = tid - sub * tw;
+        if (sub >= nsub) return;
+        const float4 pm = reinterpret_cast<const float4*>(mean)[ch], ps = reinterpret_cast<const float4*>(scale)[ch];
+        const float4 pb = reinterpret_cast<const float4*>(beta)[ch];
+        const long long base = ((long long)b * n4 + (long long)ch * p.W) * 4;
+        const float* hb = p.h2raw + base; const float* xb = p.x + base; float* outb = p.out + base;
+        const int hstride = c4n * p.W * 4;
+        for (int w = wl; w < p.W; w += tw) {
+            const float mk = __ldg(p.mask + (long long)b * p.T + ((long long)w << p.lvl));
+            for (int h0 = (hg * nsub + sub) * U; h0 < p.H; h0 += nhg * nsub * U) {
+                float4 r[U], xv[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const bool live = mk != 0.f && h0 + u < p.H;
+                    const long long off = (long long)(h0 + u) * hstride + w * 4;
+                    r[u] = live ? ldg4(hb + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    xv[u] = live ? ldg4(xb + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (h0 + u >= p.H) continue;
+                    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (mk != 0.f) {
+                        o.x = mish_fast_f((r[u].x - pm.x) * ps.x + pb.x) + xv[u].x;
+                        o.y = mish_fast_f((r[u].y - pm.y) * ps.y + pb.y) + xv[u].y;
+                        o.z = mish_fast_f((r[u].z - pm.z) * ps.z + pb.z) + xv[u].z;
+                        o.w = mish_fast_f((r[u].w - pm.w) * ps.w + pb.w) + xv[u].w;
+                    }
+                    *reinterpret_cast<float4*>(outb + (long long)(h0 + u) * hstride + w * 4) = o;
+                }
+            }
+        }
+        return;
+    }
     if (p.x) {
         // identity residual: pure streaming (2 reads + 1 write per element); 4 independent units per thread
         constexpr int U = 4;
@@ -554,6 +592,60 @@ __global__ void __launch_bounds__(256) k_resfinal(const ResFinalParams p) {
                     }
                 }
                 *reinterpret_cast<float4*>(p.out + ((long long)b * n4 + i0 + u * 256) * 4) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+        }
+        return;
+    }
+    if (p.chw4) {
+        // planar layout, res_conv over the 2-3 network inputs (first ResnetBlock): one channel chunk per CTA (see k_gn_act)
+        constexpr int U = 4;
+        const int ch = blockIdx.x % c4n, hg = blockIdx.x / c4n, nhg = gridDim.x / c4n;
+        const int tw = p.W >= 256 ? 256 : p.W, nsub = 256 / tw, sub = tid / tw, wl = tid - sub * tw;
+        if (sub >= nsub) return;
+        const int nreal = p.r_extra ? p.cin - 1 : p.cin;
+        const float* re = p.r_extra ? p.r_extra + ((long long)(p.extra_per_sample_row ? 0 : *p.step) * p.B + b) * p.C : nullptr;
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 pm = reinterpret_cast<const float4*>(mean)[ch], ps = reinterpret_cast<const float4*>(scale)[ch];
+        const float4 pb = reinterpret_cast<const float4*>(beta)[ch];
+        const float4 wb = reinterpret_cast<const float4*>(wres + p.cin * p.C)[ch];
+        const float4 w0 = reinterpret_cast<const float4*>(wres)[ch];
+        const float4 w1 = nreal > 1 ? reinterpret_cast<const float4*>(wres + p.C)[ch] : z4;
+        const float4 w2 = nreal > 2 ? reinterpret_cast<const float4*>(wres + 2 * p.C)[ch] : z4;
+        const float4 rx = re ? ldg4(re + ch * 4) : z4;
+        const bool has_spk = p.cin > 2 && !p.r_extra;
+        const long long base = ((long long)b * n4 + (long long)ch * p.W) * 4;
+        const float* hb = p.h2raw + base; float* outb = p.out + base;
+        const int hstride = c4n * p.W * 4;
+        for (int w = wl; w < p.W; w += tw) {
+            const float mk = __ldg(p.mask + (long long)b * p.T + ((long long)w << p.lvl));
+            for (int h0 = (hg * nsub + sub) * U; h0 < p.H; h0 += nhg * nsub * U) {
+                float4 r[U]; float i0[U], i1[U], i2[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const bool live = mk != 0.f && h0 + u < p.H;
+                    const long long idx = ((long long)b * p.H + h0 + u) * p.T + w;
+                    r[u] = live ? ldg4(hb + (long long)(h0 + u) * hstride + w * 4) : z4;
+                    i0[u] = live ? __ldg(p.mu + idx) * mk : 0.f;
+                    i1[u] = live ? __ldg(p.xt + idx) * mk : 0.f;
+                    i2[u] = (live && has_spk) ? __ldg(p.spk_s + b * p.H + h0 + u) * mk : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (h0 + u >= p.H) continue;
+                    float4 o;
+                    o.x = fmaf(mk, rx.x, fmaf(i2[u], w2.x, fmaf(i1[u], w1.x, fmaf(i0[u], w0.x, wb.x))));
+                    o.y = fmaf(mk, rx.y, fmaf(i2[u], w2.y, fmaf(i1[u], w1.y, fmaf(i0[u], w0.y, wb.y))));
+                    o.z = fmaf(mk, rx.z, fmaf(i2[u], w2.z, fmaf(i1[u], w1.z, fmaf(i0[u], w0.z, wb.z))));
+                    o.w = fmaf(mk, rx.w, fmaf(i2[u], w2.w, fmaf(i1[u], w1.w, fmaf(i0[u], w0.w, wb.w))));
+                    if (mk != 0.f) {
+                        o.x += mish_fast_f((r[u].x - pm.x) * ps.x + pb.x);
+                        o.y += mish_fast_f((r[u].y - pm.y) * ps.y + pb.y);
+                        o.z += mish_fast_f((r[u].z - pm.z) * ps.z + pb.z);
+                        o.w += mish_fast_f((r[u].w - pm.w) * ps.w + pb.w);
+                    }
+                    if (p.out_mask) { o.x *= mk; o.y *= mk; o.z *= mk; o.w *= mk; }
+                    *reinterpret_cast<float4*>(outb + (long long)(h0 + u) * hstride + w * 4) = o;
+                }
             }
         }
         return;
@@ -626,6 +718,47 @@ __global__ void __launch_bounds__(256) k_gn_act(const GnActParams p) {
     const int c4n = p.C >> 2;
     const long long n4 = (long long)p.H * p.W * c4n;
     constexpr int U = 4;                         // independent 16-byte loads in flight per thread
+    if (p.chw4) {
+        // planar layout: a CTA owns ONE channel chunk (4 channels: their GN / time parameters live in registers for the
+        // whole kernel) and walks mel bins, 4 at a time; a thread owns frame(s) w, so the mask is read once and every
+        // index is 32-bit and division-free (the generic loop below was issue-bound on 64-bit divisions).
+        const int ch = blockIdx.x % c4n, hg = blockIdx.x / c4n, nhg = gridDim.x / c4n;
+        const int tw = p.W >= 256 ? 256 : p.W, nsub = 256 / tw, sub = tid / tw, wl = tid - sub * tw;
+        if (sub >= nsub) return;
+        const float4 pm = reinterpret_cast<const float4*>(mean)[ch], ps = reinterpret_cast<const float4*>(scale)[ch];
+        const float4 pb = reinterpret_cast<const float4*>(beta)[ch], pt = reinterpret_cast<const float4*>(tbv)[ch];
+        const float* rawb = p.raw + ((long long)b * n4 + (long long)ch * p.W) * 4;
+        float* outb = p.out + ((long long)b * n4 + (long long)ch * p.W) * 4;
+        const int hstride = c4n * p.W * 4;                               // floats between consecutive mel bins of one chunk
+        for (int w = wl; w < p.W; w += tw) {
+            const float mk = __ldg(p.mask + (long long)b * p.T + ((long long)w << p.lvl));
+            for (int h0 = (hg * nsub + sub) * U; h0 < p.H; h0 += nhg * nsub * U) {
+                float4 r[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    r[u] = (mk != 0.f && h0 + u < p.H) ? ldg4(rawb + (long long)(h0 + u) * hstride + w * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (h0 + u >= p.H) continue;
+                    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (mk != 0.f) {
+                        o.x = mish_fast_f((r[u].x - pm.x) * ps.x + pb.x) + pt.x;
+                        o.y = mish_fast_f((r[u].y - pm.y) * ps.y + pb.y) + pt.y;
+                        o.z = mish_fast_f((r[u].z - pm.z) * ps.z + pb.z) + pt.z;
+                        o.w = mish_fast_f((r[u].w - pm.w) * ps.w + pb.w) + pt.w;
+                        if (p.round_tf32) {
+                            uint32_t t0, t1, t2, t3;
+                            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t0) : "f"(o.x)); asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t1) : "f"(o.y));
+                            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t2) : "f"(o.z)); asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t3) : "f"(o.w));
+                            o = make_float4(__uint_as_float(t0), __uint_as_float(t1), __uint_as_float(t2), __uint_as_float(t3));
+                        }
+                    }
+                    *reinterpret_cast<float4*>(outb + (long long)(h0 + u) * hstride + w * 4) = o;
+                }
+            }
+        }
+        return;
+    }
     for (long long i0 = (long long)blockIdx.x * (256 * U) + tid; i0 < n4; i0 += (long long)gridDim.x * (256 * U)) {
         float4 r[U]; float mk[U]; int cc[U]; bool in[U];
 #pragma unroll
@@ -668,11 +801,21 @@ __global__ void __launch_bounds__(256) k_gn_act(const GnActParams p) {
     }
 }
 
+// planar elementwise kernels: grid.x = (channel chunks) x (mel-bin groups); a 256-thread CTA covers min(W,256) frames x
+// 256/min(W,256) bin sub-groups, each walking 4 bins per pass, ~2 passes per thread.
+static int planar_ew_grid(int H, int W, int C) {
+    const int nsub = W >= 256 ? 1 : 256 / W;
+    int nhg = (H + 8 * nsub - 1) / (8 * nsub);
+    if (nhg < 1) nhg = 1;
+    return (C / 4) * nhg;
+}
+
 int launch_gn_act(const GnActParams& p, cudaStream_t s) {
     const long long n4 = (long long)p.H * p.W * (p.C / 4);
     int gx = (int)((n4 + 256 * 4 * 8 - 1) / (256 * 4 * 8));   // ~8 passes of the 4-way unrolled loop per CTA (amortises the GN table set-up)
     if (gx < 1) gx = 1;
     if (gx > 4096) gx = 4096;
+    if (p.chw4) gx = planar_ew_grid(p.H, p.W, p.C);           // must stay a multiple of C/4 (chunk = blockIdx.x % (C/4))
     k_gn_act<<<dim3(gx, p.B), 256, 4 * p.C * sizeof(float), s>>>(p);
     return 1;
 }
@@ -682,6 +825,7 @@ int launch_resfinal(const ResFinalParams& p, cudaStream_t s) {
     int gx = p.x ? (int)((n4 + 256 * 4 * 8 - 1) / (256 * 4 * 8)) : (int)((n4 + 256 * 4 - 1) / (256 * 4));
     if (gx < 1) gx = 1;
     if (gx > 4096) gx = 4096;
+    if (p.chw4) gx = planar_ew_grid(p.H, p.W, p.C);           // must stay a multiple of C/4 (chunk = blockIdx.x % (C/4))
     const size_t sm = (3 * p.C + (p.x ? 0 : (p.cin + 1) * p.C)) * sizeof(float);
     k_resfinal<<<dim3(gx, p.B), 256, sm, s>>>(p);
     return 1;
