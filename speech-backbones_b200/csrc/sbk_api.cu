@@ -296,15 +296,20 @@ static int pack_tc(sbk_handle* h, const std::string& src, const std::string& key
     CU(cudaMemcpy(hs.data(), h->raw[src], hs.size() * sizeof(float), cudaMemcpyDeviceToHost));
     return pack_tc_host(h, hs, key, cout, cin, geom, bf16);
 }
-// k|v rows of to_qkv regrouped per head: logical cout index head*64 + {d | 32 + e}
+// k and v rows of to_qkv ('(qkv heads c)': k = rows 128.., v = rows 256..) in k_attn_kv's per-stage shared-memory image
+// [32-channel stage][k|v][16-byte chunk][row = head*32 + c][4], tf32-rounded
 static int pack_tc_kv(sbk_handle* h, const std::string& src, const std::string& key, int C) {
-    std::vector<float> q((size_t)384 * C), m((size_t)256 * C);
+    std::vector<float> q((size_t)384 * C);
+    std::vector<uint32_t> m((size_t)256 * C);
     CU(cudaMemcpy(q.data(), h->raw[src], q.size() * sizeof(float), cudaMemcpyDeviceToHost));
-    for (int hd = 0; hd < kHeads; ++hd) for (int x = 0; x < 32; ++x) for (int ci = 0; ci < C; ++ci) {
-        m[(size_t)(hd * 64 + x) * C + ci] = q[(size_t)(128 + hd * 32 + x) * C + ci];
-        m[(size_t)(hd * 64 + 32 + x) * C + ci] = q[(size_t)(256 + hd * 32 + x) * C + ci];
-    }
-    return pack_tc_host(h, m, key, 256, C, G_PW, false);
+    for (int ks = 0; ks < C / 32; ++ks) for (int kv = 0; kv < 2; ++kv) for (int k = 0; k < 8; ++k)
+        for (int row = 0; row < 128; ++row) for (int e = 0; e < 4; ++e)
+            m[((((size_t)ks * 2 + kv) * 8 + k) * 128 + row) * 4 + e] =
+                f32_to_tf32_rna(q[(size_t)(128 + kv * 128 + row) * C + ks * 32 + k * 4 + e]);
+    float*& d = h->packed[key];
+    if (!d) { CU(cudaMalloc(&d, m.size() * 4)); h->owned.push_back(d); }
+    CU(cudaMemcpy(d, m.data(), m.size() * 4, cudaMemcpyHostToDevice));
+    return SBK_OK;
 }
 // ConvTranspose2d weight [ci][co][4][4] -> logical [co][ci][kh*4+kw]
 static int pack_tc_up(sbk_handle* h, const std::string& src, const std::string& key, int C) {
@@ -669,12 +674,12 @@ static int build_plan(sbk_handle* h, int B, int T, int tb_rows) {
         int mt = igemm_mtiles(G_PW, Hs[lvl], Ws[lvl], Hs[lvl], Ws[lvl]);
         const bool tc_apply = use_tc && a.c % tc_cps1 == 0;
         if (tc_apply) {
-            // k/v projection + online-softmax partials on tensor cores: tiles of 256 pixels x 2 heads
+            // k/v projection + softmax partials on tensor cores (k_attn_kv): items of 128 pixels x 4 heads
             Op op = tc_conv(a.prefix + ".kvpart", G_PW, a.prefix + ".kv.wtc", "", lvl, x, a.c, nullptr, 0, 256, nullptr, nullptr);
             op.tc.epi = EPI_KV; op.tc.kv_part = bf.kv_part;
             op.bytes = 4.0 * npix(lvl) * a.c;
             op.flops += 2.0 * npix(lvl) * 4096.0;
-            mt = (Hs[lvl] * Ws[lvl] + 255) / 256;
+            mt = (Hs[lvl] * Ws[lvl] + attn_kv_tile_pixels() - 1) / attn_kv_tile_pixels();
             push(op, nullptr, 0);
         } else {
             Op op; op.kind = OP_IGEMM; op.name = a.prefix + ".kvpart";

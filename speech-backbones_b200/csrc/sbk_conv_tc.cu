@@ -739,6 +739,242 @@ static int launch_tc(const ConvTcParams& p, cudaStream_t s) {
     return 1;
 }
 
+// =================================================================================================================
+// LinearAttention pass 1 (diffusion.py:93-96): k/v projection + softmax-over-pixels partials, one 128-pixel item at a
+// time, all four heads per item.  Roles are swapped relative to the convs: the weights are the M operand, so a TMEM
+// lane is a k (or v) channel and a column is a pixel:
+//     D1K[k channel 32*head+d][px] = Wk * X^T ,   D1V[v channel 32*head+e][px] = Wv * X^T      (two UMMAs per K step)
+// One thread therefore owns one k row AND one v row over 64 pixels: the softmax max / sum are private reductions
+// over its own TMEM columns (held in registers between the max and the exp pass), P = exp(k - max) goes back to TMEM
+// in place, V^T goes to shared memory as a K-major operand, and S[d][e] = sum_px P[d,px] V[e,px] is a second UMMA
+// with A = P read from TMEM, accumulated into the (already drained) D1V columns.  k and v never reach HBM; per item
+// only (max, sum, S) partials of the four 32x32 diagonal blocks are written, merged by k_attn_ctx.
+// Pipeline: two 256-column TMEM slots, so the projection of item i+1 runs under the softmax of item i; the context
+// UMMA of item i runs under the first half of item i+1 (its read-out is deferred until just before V^T is rewritten).
+// =================================================================================================================
+namespace kvk {
+constexpr int PX = 128;                        // pixels per item: N of the projection, K extent of the context UMMA
+constexpr int KCH = 8;                         // 16-byte channel chunks per stage (32 channels)
+constexpr int XS = KCH * PX * 16;              // activation stage  [chunk][pixel][16 B]
+constexpr int WS = 2 * KCH * 128 * 16;         // weight stage      [k|v][chunk][row][16 B]
+constexpr int STAGE = XS + WS;
+constexpr int STAGES = 3;
+constexpr int VT = (PX / 4) * 128 * 16;        // V^T operand       [pixel chunk][v row][16 B]
+constexpr int RED = 2 * 2 * 2 * 128 * 4;       // max | sum exchange between the two pixel halves, double-buffered
+constexpr int NSLOT = 2, SLOT_COLS = 256;
+constexpr int NBARS = 2 * STAGES + 3 * NSLOT;
+constexpr size_t SMEM = (size_t)STAGES * STAGE + VT + RED + NBARS * 8 + 16;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) k_attn_kv(const ConvTcParams p) {
+    using namespace kvk;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sS = smem;                                            // [STAGES][X | Wk | Wv]
+    uint8_t* vt = sS + STAGES * STAGE;
+    float* s_mx = reinterpret_cast<float*>(vt + VT);               // [2 parity][2 halves][128]
+    float* s_z = s_mx + 2 * 2 * 128;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_z + 2 * 2 * 128);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + NBARS);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int HW = p.H * p.W;
+    const int ksteps = p.c0 / (KCH * 4);
+    const int mtiles = (HW + PX - 1) / PX;
+    const int total = p.B * mtiles;
+    const uint32_t bar0 = smem_u32(bars);
+    auto full = [&](int s) { return bar0 + 8u * s; };
+    auto empty = [&](int s) { return bar0 + 8u * (STAGES + s); };
+    auto tfull = [&](int a) { return bar0 + 8u * (2 * STAGES + a); };
+    auto tempty = [&](int a) { return bar0 + 8u * (2 * STAGES + NSLOT + a); };
+    auto kvdone = [&](int a) { return bar0 + 8u * (2 * STAGES + 2 * NSLOT + a); };
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+        for (int a = 0; a < NSLOT; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), NPROD / 32); mbar_init(kvdone(a), 1); }
+        fence_barrier_init();
+    }
+    if (warp == NPROD / 32) tmem_alloc(smem_u32(s_tmem), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    if (warp < NPROD / 32) {
+        // ---------------------------------------------------------------- softmax / context warps
+        const int q = warp & 3, half = warp >> 2;                  // TMEM lane quarter = head, pixel half
+        const int row = q * 32 + lane;
+        const int col0 = half * (PX / 2);
+        const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+        const uint32_t idesc2 = make_idesc<false>(128, 128);
+        const uint32_t vt0 = smem_u32(vt);
+        int tl = 0;
+        int pb = 0, pmt = 0; float pmd = 0.f, pz = 0.f;            // previous item (deferred read-out)
+        auto finish = [&](int ptl) {
+            const int pslot = ptl & 1;
+            mbar_wait(kvdone(pslot), (ptl >> 1) & 1);
+            tc_fence_after();
+            if (half == 0) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + pslot * SLOT_COLS + lane_sel + 128 + q * 32, r);     // S[d = lane][e] of head q
+                float* pt = p.kv_part + (((long long)pb * mtiles + pmt) * kHeads + q) * kKvPartFloats;
+                pt[lane] = pmd;
+                pt[32 + lane] = pz;
+#pragma unroll
+                for (int i = 0; i < 32; i += 4)
+                    *reinterpret_cast<float4*>(&pt[64 + lane * 32 + i]) =
+                        make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty(pslot));
+        };
+        for (int t = blockIdx.x; t < total; t += gridDim.x, ++tl) {
+            const int b = t / mtiles, mt = t - b * mtiles;
+            const int slot = tl & 1, par = tl & 1;
+            const uint32_t tq = tmem_base + slot * SLOT_COLS + lane_sel;
+            const int nvalid = min(PX, HW - mt * PX) - col0;       // valid columns of this thread's half (may be <= 0)
+            mbar_wait(tfull(slot), (tl >> 1) & 1);
+            tc_fence_after();
+            uint32_t k0[32], k1[32];
+            tmem_ld32(tq + col0, k0);
+            tmem_ld32(tq + col0 + 32, k1);
+            float mx = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                if (i < nvalid) mx = fmaxf(mx, __uint_as_float(k0[i]));
+                if (32 + i < nvalid) mx = fmaxf(mx, __uint_as_float(k1[i]));
+            }
+            s_mx[(par * 2 + half) * 128 + row] = mx;
+            if (tl > 0) finish(tl - 1);                            // context UMMA of the previous item has read V^T
+#pragma unroll
+            for (int c = 0; c < PX / 2; c += 32) {
+                uint32_t r[32];
+                tmem_ld32(tq + 128 + col0 + c, r);
+#pragma unroll
+                for (int i = 0; i < 32; i += 4)
+                    *reinterpret_cast<uint4*>(vt + ((size_t)((col0 + c + i) / 4) * 128 + row) * 16) = make_uint4(r[i], r[i + 1], r[i + 2], r[i + 3]);
+            }
+            fence_proxy_async();                                   // V^T smem writes -> visible to the tensor core
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const float md = fmaxf(s_mx[(par * 2) * 128 + row], s_mx[(par * 2 + 1) * 128 + row]);
+            float z0 = 0.f, z1 = 0.f, z2 = 0.f, z3 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+                const float e0 = i < nvalid ? __expf(__uint_as_float(k0[i]) - md) : 0.f;
+                const float e1 = i + 1 < nvalid ? __expf(__uint_as_float(k0[i + 1]) - md) : 0.f;
+                const float e2 = 32 + i < nvalid ? __expf(__uint_as_float(k1[i]) - md) : 0.f;
+                const float e3 = 33 + i < nvalid ? __expf(__uint_as_float(k1[i + 1]) - md) : 0.f;
+                z0 += e0; z1 += e1; z2 += e2; z3 += e3;
+                k0[i] = __float_as_uint(e0); k0[i + 1] = __float_as_uint(e1);
+                k1[i] = __float_as_uint(e2); k1[i + 1] = __float_as_uint(e3);
+            }
+            tmem_st32(tq + col0, k0);
+            tmem_st32(tq + col0 + 32, k1);
+            tmem_wait_st();
+            s_z[(par * 2 + half) * 128 + row] = (z0 + z1) + (z2 + z3);
+            tc_fence_before();
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (tid == 0) {
+                tc_fence_after();
+#pragma unroll 1
+                for (int kk = 0; kk < PX / 8; ++kk) {              // K = 8 pixels (32 bytes) per UMMA
+                    const uint64_t bd = make_desc(vt0 + kk * 2 * (128 * 16), 128 * 16, 128);
+                    umma_ts_tf32(tmem_base + slot * SLOT_COLS + 128, tmem_base + slot * SLOT_COLS + kk * 8, bd, idesc2, kk != 0 ? 1u : 0u);
+                }
+                umma_commit(kvdone(slot));
+            }
+            __syncwarp();
+            pb = b; pmt = mt; pmd = md;
+            pz = s_z[(par * 2) * 128 + row] + s_z[(par * 2 + 1) * 128 + row];
+        }
+        if (tl > 0) finish(tl - 1);
+    } else if (warp == NPROD / 32) {
+        // ---------------------------------------------------------------- projection UMMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc<false>(128, PX);
+            const uint32_t s0 = smem_u32(sS);
+            uint32_t it = 0;
+            int tl = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x, ++tl) {
+                const int slot = tl & 1;
+                const uint32_t tslot = tmem_base + slot * SLOT_COLS;
+                mbar_wait(tempty(slot), ((tl >> 1) & 1) ^ 1);
+                tc_fence_after();
+                for (int ks = 0; ks < ksteps; ++ks, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(full(s), (it / STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t xs = s0 + s * STAGE, wk = xs + XS, wv = wk + KCH * 128 * 16;
+#pragma unroll
+                    for (int kk = 0; kk < KCH / 2; ++kk) {
+                        const uint64_t xd = make_desc(xs + kk * 2 * (PX * 16), PX * 16, 128);
+                        const uint64_t kd = make_desc(wk + kk * 2 * (128 * 16), 128 * 16, 128);
+                        const uint64_t vd = make_desc(wv + kk * 2 * (128 * 16), 128 * 16, 128);
+                        umma<false>(tslot, kd, xd, idesc, (ks | kk) != 0 ? 1u : 0u);
+                        umma<false>(tslot + 128, vd, xd, idesc, (ks | kk) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(empty(s));
+                }
+                umma_commit(tfull(slot));
+            }
+        }
+    } else {
+        // ---------------------------------------------------------------- loader: weights + activation runs (cp.async.bulk)
+        if (lane == 0) {
+            uint32_t it = 0;
+            const int chs = p.c0 / 4;
+            const float* src = reinterpret_cast<const float*>(p.in0);
+            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+                const int b = t / mtiles, mt = t - b * mtiles;
+                for (int ks = 0; ks < ksteps; ++ks, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(empty(s), ((it / STAGES) & 1) ^ 1);
+                    mbar_arrive_expect_tx(full(s), STAGE);
+                    const uint32_t xs = smem_u32(sS) + s * STAGE;
+                    bulk_g2s(xs + XS, reinterpret_cast<const uint8_t*>(p.wpk) + (size_t)ks * WS, WS, full(s));
+#pragma unroll 1
+                    for (int k = 0; k < KCH; ++k) {
+                        const int cl = ks * KCH + k;
+                        long long m = (long long)mt * PX;
+                        const long long m_hi = m + PX < HW ? m + PX : HW;
+                        int qx = 0;
+                        while (m < m_hi) {                         // split the flattened run at image-row boundaries
+                            const int hh = (int)(m / p.W), ww = (int)(m - (long long)hh * p.W);
+                            const int n = (int)((p.W - ww) < (m_hi - m) ? (p.W - ww) : (m_hi - m));
+                            bulk_g2s(xs + (k * PX + qx) * 16, src + (((long long)(b * p.H + hh) * chs + cl) * p.W + ww) * 4,
+                                     (uint32_t)n * 16u, full(s));
+                            m += n; qx += n;
+                        }
+                        if (qx < PX) bulk_g2s(xs + (k * PX + qx) * 16, p.zero_page, (uint32_t)(PX - qx) * 16u, full(s));
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == NPROD / 32) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+static int launch_attn_kv(const ConvTcParams& p, cudaStream_t s) {
+    static bool attr_set = false;
+    static int num_sms = 0;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_attn_kv, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        attr_set = true;
+    }
+    const long long total = (long long)p.B * ((p.H * p.W + kvk::PX - 1) / kvk::PX);
+    const int grid = (int)(total < num_sms ? total : num_sms);
+    k_attn_kv<<<grid, NTHREADS, kvk::SMEM, s>>>(p);
+    return 1;
+}
+int attn_kv_tile_pixels() { return kvk::PX; }
+
 // N tile per geometry: UP needs 8 accumulators (8*64 = all 512 TMEM columns), DOWN's de-interleaved A tile is large
 int conv_tc_ntile(int geom, int Cout) {
     if (geom == G_UP || geom == G_DOWN) return 64;
@@ -756,7 +992,7 @@ int launch_conv_tc(const ConvTcParams& p, cudaStream_t s) {
     switch (p.geom) {
         case G_C3:   return nt == 128 ? launch_tc<G_C3, false, 128>(p, s) : launch_tc<G_C3, false, 64>(p, s);
         case G_PW:
-            if (p.epi == EPI_KV) return launch_tc<G_PW, false, 128, true>(p, s);
+            if (p.epi == EPI_KV) return launch_attn_kv(p, s);
             return nt == 128 ? launch_tc<G_PW, false, 128>(p, s) : launch_tc<G_PW, false, 64>(p, s);
         case G_DOWN: return launch_tc<G_DOWN, false, 64>(p, s);
         default:     return launch_tc<G_UP, false, 64>(p, s);

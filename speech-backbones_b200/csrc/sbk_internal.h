@@ -202,6 +202,7 @@ int conv_tc_stage_channels(int geom, int bf16);
 int launch_gn_act(const GnActParams& p, cudaStream_t s);
 int launch_resfinal(const ResFinalParams& p, cudaStream_t s);
 int launch_attn_ctx(const AttnCtxParams& p, cudaStream_t s);
+int attn_kv_tile_pixels();
 int launch_attn_mix(const AttnMixParams& p, cudaStream_t s);
 int launch_final(const FinalParams& p, cudaStream_t s);
 int launch_time_table(const TimeTableParams& p, cudaStream_t s);
