@@ -750,7 +750,8 @@ static int launch_tc(const ConvTcParams& p, cudaStream_t s) {
 // with A = P read from TMEM, accumulated into the (already drained) D1V columns.  k and v never reach HBM; per item
 // only (max, sum, S) partials of the four 32x32 diagonal blocks are written, merged by k_attn_ctx.
 // Pipeline: two 256-column TMEM slots, so the projection of item i+1 runs under the softmax of item i; the context
-// UMMA of item i runs under the first half of item i+1 (its read-out is deferred until just before V^T is rewritten).
+// UMMA of item i (issued by its own warp) runs under the max/exp pass of item i+1: its read-out is deferred until just
+// before V^T is rewritten.  One named barrier per item; everything else is mbarrier hand-offs.
 // =================================================================================================================
 namespace kvk {
 constexpr int PX = 128;                        // pixels per item: N of the projection, K extent of the context UMMA
@@ -760,20 +761,25 @@ constexpr int WS = 2 * KCH * 128 * 16;         // weight stage      [k|v][chunk]
 constexpr int STAGE = XS + WS;
 constexpr int STAGES = 3;
 constexpr int VT = (PX / 4) * 128 * 16;        // V^T operand       [pixel chunk][v row][16 B]
-constexpr int RED = 2 * 2 * 2 * 128 * 4;       // max | sum exchange between the two pixel halves, double-buffered
+constexpr int NPART = 4;                       // pixel parts: 4 lane quarters x NPART = softmax warps
+constexpr int PCOLS = PX / NPART;              // columns (pixels) per thread
+constexpr int EPW = 4 * NPART;                 // softmax warps
+constexpr int THREADS = (EPW + 3) * 32;        // + projection-UMMA warp, loader warp, context-UMMA warp
+constexpr int RED = 2 * 2 * NPART * 128 * 4;   // max | sum exchange between the pixel parts, double-buffered
 constexpr int NSLOT = 2, SLOT_COLS = 256;
-constexpr int NBARS = 2 * STAGES + 3 * NSLOT;
+constexpr int NBARS = 2 * STAGES + 4 * NSLOT;
 constexpr size_t SMEM = (size_t)STAGES * STAGE + VT + RED + NBARS * 8 + 16;
+static_assert(PCOLS == 32 || PCOLS == 64, "one or two 32-column TMEM loads per thread");
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1) k_attn_kv(const ConvTcParams p) {
+__global__ void __launch_bounds__(kvk::THREADS, 1) k_attn_kv(const ConvTcParams p) {
     using namespace kvk;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sS = smem;                                            // [STAGES][X | Wk | Wv]
     uint8_t* vt = sS + STAGES * STAGE;
-    float* s_mx = reinterpret_cast<float*>(vt + VT);               // [2 parity][2 halves][128]
-    float* s_z = s_mx + 2 * 2 * 128;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_z + 2 * 2 * 128);
+    float* s_mx = reinterpret_cast<float*>(vt + VT);               // [2 parity][NPART][128]
+    float* s_z = s_mx + 2 * NPART * 128;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_z + 2 * NPART * 128);
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + NBARS);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -784,41 +790,45 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_attn_kv(const ConvTcParams p) {
     const uint32_t bar0 = smem_u32(bars);
     auto full = [&](int s) { return bar0 + 8u * s; };
     auto empty = [&](int s) { return bar0 + 8u * (STAGES + s); };
-    auto tfull = [&](int a) { return bar0 + 8u * (2 * STAGES + a); };
-    auto tempty = [&](int a) { return bar0 + 8u * (2 * STAGES + NSLOT + a); };
-    auto kvdone = [&](int a) { return bar0 + 8u * (2 * STAGES + 2 * NSLOT + a); };
+    auto tfull = [&](int a) { return bar0 + 8u * (2 * STAGES + a); };              // projection of the slot complete
+    auto tempty = [&](int a) { return bar0 + 8u * (2 * STAGES + NSLOT + a); };     // slot drained
+    auto pready = [&](int a) { return bar0 + 8u * (2 * STAGES + 2 * NSLOT + a); }; // P in TMEM + V^T in smem written
+    auto kvdone = [&](int a) { return bar0 + 8u * (2 * STAGES + 3 * NSLOT + a); }; // context UMMA complete
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
-        for (int a = 0; a < NSLOT; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), NPROD / 32); mbar_init(kvdone(a), 1); }
+        for (int a = 0; a < NSLOT; ++a) {
+            mbar_init(tfull(a), 1); mbar_init(tempty(a), EPW); mbar_init(pready(a), EPW); mbar_init(kvdone(a), 1);
+        }
         fence_barrier_init();
     }
-    if (warp == NPROD / 32) tmem_alloc(smem_u32(s_tmem), 512);
+    if (warp == EPW) tmem_alloc(smem_u32(s_tmem), 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
 
-    if (warp < NPROD / 32) {
-        // ---------------------------------------------------------------- softmax / context warps
-        const int q = warp & 3, half = warp >> 2;                  // TMEM lane quarter = head, pixel half
+    if (warp < EPW) {
+        // ---------------------------------------------------------------- softmax warps
+        const int q = warp & 3, part = warp >> 2;                  // TMEM lane quarter = head, pixel part
         const int row = q * 32 + lane;
-        const int col0 = half * (PX / 2);
+        const int col0 = part * PCOLS;
         const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
-        const uint32_t idesc2 = make_idesc<false>(128, 128);
-        const uint32_t vt0 = smem_u32(vt);
         int tl = 0;
-        int pb = 0, pmt = 0; float pmd = 0.f, pz = 0.f;            // previous item (deferred read-out)
+        int pb = 0, pmt = 0; float pmd = 0.f;                      // previous item (deferred read-out)
         auto finish = [&](int ptl) {
             const int pslot = ptl & 1;
             mbar_wait(kvdone(pslot), (ptl >> 1) & 1);
             tc_fence_after();
-            if (half == 0) {
+            if (part == 0) {
                 uint32_t r[32];
                 tmem_ld32(tmem_base + pslot * SLOT_COLS + lane_sel + 128 + q * 32, r);     // S[d = lane][e] of head q
                 float* pt = p.kv_part + (((long long)pb * mtiles + pmt) * kHeads + q) * kKvPartFloats;
+                float z = 0.f;
+#pragma unroll
+                for (int j = 0; j < NPART; ++j) z += s_z[(pslot * NPART + j) * 128 + row];
                 pt[lane] = pmd;
-                pt[32 + lane] = pz;
+                pt[32 + lane] = z;
 #pragma unroll
                 for (int i = 0; i < 32; i += 4)
                     *reinterpret_cast<float4*>(&pt[64 + lane * 32 + i]) =
@@ -830,65 +840,60 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_attn_kv(const ConvTcParams p) {
         };
         for (int t = blockIdx.x; t < total; t += gridDim.x, ++tl) {
             const int b = t / mtiles, mt = t - b * mtiles;
-            const int slot = tl & 1, par = tl & 1;
+            const int slot = tl & 1;
             const uint32_t tq = tmem_base + slot * SLOT_COLS + lane_sel;
-            const int nvalid = min(PX, HW - mt * PX) - col0;       // valid columns of this thread's half (may be <= 0)
+            const int nvalid = min(PX, HW - mt * PX) - col0;       // valid columns of this thread's part (may be <= 0)
             mbar_wait(tfull(slot), (tl >> 1) & 1);
             tc_fence_after();
-            uint32_t k0[32], k1[32];
-            tmem_ld32(tq + col0, k0);
-            tmem_ld32(tq + col0 + 32, k1);
+            uint32_t kr[PCOLS / 32][32];
             float mx = -INFINITY;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                if (i < nvalid) mx = fmaxf(mx, __uint_as_float(k0[i]));
-                if (32 + i < nvalid) mx = fmaxf(mx, __uint_as_float(k1[i]));
-            }
-            s_mx[(par * 2 + half) * 128 + row] = mx;
-            if (tl > 0) finish(tl - 1);                            // context UMMA of the previous item has read V^T
+            for (int c = 0; c < PCOLS / 32; ++c) {
+                tmem_ld32(tq + col0 + c * 32, kr[c]);
 #pragma unroll
-            for (int c = 0; c < PX / 2; c += 32) {
+                for (int i = 0; i < 32; ++i) if (c * 32 + i < nvalid) mx = fmaxf(mx, __uint_as_float(kr[c][i]));
+            }
+            s_mx[(slot * NPART + part) * 128 + row] = mx;
+            asm volatile("bar.sync 1, %0;" ::"n"(EPW * 32) : "memory");
+            float md = s_mx[(slot * NPART) * 128 + row];
+#pragma unroll
+            for (int j = 1; j < NPART; ++j) md = fmaxf(md, s_mx[(slot * NPART + j) * 128 + row]);
+            float z0 = 0.f, z1 = 0.f, z2 = 0.f, z3 = 0.f;
+#pragma unroll
+            for (int c = 0; c < PCOLS / 32; ++c) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    const float e0 = c * 32 + i < nvalid ? __expf(__uint_as_float(kr[c][i]) - md) : 0.f;
+                    const float e1 = c * 32 + i + 1 < nvalid ? __expf(__uint_as_float(kr[c][i + 1]) - md) : 0.f;
+                    const float e2 = c * 32 + i + 2 < nvalid ? __expf(__uint_as_float(kr[c][i + 2]) - md) : 0.f;
+                    const float e3 = c * 32 + i + 3 < nvalid ? __expf(__uint_as_float(kr[c][i + 3]) - md) : 0.f;
+                    z0 += e0; z1 += e1; z2 += e2; z3 += e3;
+                    kr[c][i] = __float_as_uint(e0); kr[c][i + 1] = __float_as_uint(e1);
+                    kr[c][i + 2] = __float_as_uint(e2); kr[c][i + 3] = __float_as_uint(e3);
+                }
+                tmem_st32(tq + col0 + c * 32, kr[c]);
+            }
+            s_z[(slot * NPART + part) * 128 + row] = (z0 + z1) + (z2 + z3);
+            // The context UMMA of the previous item has had the whole max/exp pass to finish; it must be complete before
+            // V^T is overwritten.  Its S block is read out (and its slot released) here.
+            if (tl > 0) finish(tl - 1);
+#pragma unroll
+            for (int c = 0; c < PCOLS; c += 32) {
                 uint32_t r[32];
                 tmem_ld32(tq + 128 + col0 + c, r);
 #pragma unroll
                 for (int i = 0; i < 32; i += 4)
                     *reinterpret_cast<uint4*>(vt + ((size_t)((col0 + c + i) / 4) * 128 + row) * 16) = make_uint4(r[i], r[i + 1], r[i + 2], r[i + 3]);
             }
-            fence_proxy_async();                                   // V^T smem writes -> visible to the tensor core
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            const float md = fmaxf(s_mx[(par * 2) * 128 + row], s_mx[(par * 2 + 1) * 128 + row]);
-            float z0 = 0.f, z1 = 0.f, z2 = 0.f, z3 = 0.f;
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-                const float e0 = i < nvalid ? __expf(__uint_as_float(k0[i]) - md) : 0.f;
-                const float e1 = i + 1 < nvalid ? __expf(__uint_as_float(k0[i + 1]) - md) : 0.f;
-                const float e2 = 32 + i < nvalid ? __expf(__uint_as_float(k1[i]) - md) : 0.f;
-                const float e3 = 33 + i < nvalid ? __expf(__uint_as_float(k1[i + 1]) - md) : 0.f;
-                z0 += e0; z1 += e1; z2 += e2; z3 += e3;
-                k0[i] = __float_as_uint(e0); k0[i + 1] = __float_as_uint(e1);
-                k1[i] = __float_as_uint(e2); k1[i + 1] = __float_as_uint(e3);
-            }
-            tmem_st32(tq + col0, k0);
-            tmem_st32(tq + col0 + 32, k1);
             tmem_wait_st();
-            s_z[(par * 2 + half) * 128 + row] = (z0 + z1) + (z2 + z3);
+            fence_proxy_async();                                   // V^T smem writes -> visible to the tensor core
             tc_fence_before();
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (tid == 0) {
-                tc_fence_after();
-#pragma unroll 1
-                for (int kk = 0; kk < PX / 8; ++kk) {              // K = 8 pixels (32 bytes) per UMMA
-                    const uint64_t bd = make_desc(vt0 + kk * 2 * (128 * 16), 128 * 16, 128);
-                    umma_ts_tf32(tmem_base + slot * SLOT_COLS + 128, tmem_base + slot * SLOT_COLS + kk * 8, bd, idesc2, kk != 0 ? 1u : 0u);
-                }
-                umma_commit(kvdone(slot));
-            }
             __syncwarp();
+            if (lane == 0) mbar_arrive(pready(slot));
             pb = b; pmt = mt; pmd = md;
-            pz = s_z[(par * 2) * 128 + row] + s_z[(par * 2 + 1) * 128 + row];
         }
         if (tl > 0) finish(tl - 1);
-    } else if (warp == NPROD / 32) {
+    } else if (warp == EPW) {
         // ---------------------------------------------------------------- projection UMMA issuer
         if (lane == 0) {
             const uint32_t idesc = make_idesc<false>(128, PX);
@@ -918,41 +923,61 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_attn_kv(const ConvTcParams p) {
                 umma_commit(tfull(slot));
             }
         }
-    } else {
-        // ---------------------------------------------------------------- loader: weights + activation runs (cp.async.bulk)
+    } else if (warp == EPW + 2) {
+        // ---------------------------------------------------------------- context UMMA issuer: S = P * V^T
         if (lane == 0) {
-            uint32_t it = 0;
-            const int chs = p.c0 / 4;
-            const float* src = reinterpret_cast<const float*>(p.in0);
-            for (int t = blockIdx.x; t < total; t += gridDim.x) {
-                const int b = t / mtiles, mt = t - b * mtiles;
-                for (int ks = 0; ks < ksteps; ++ks, ++it) {
-                    const int s = it % STAGES;
+            const uint32_t idesc2 = make_idesc<false>(128, 128);
+            const uint32_t vt0 = smem_u32(vt);
+            int tl = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x, ++tl) {
+                const int slot = tl & 1;
+                const uint32_t tslot = tmem_base + slot * SLOT_COLS;
+                mbar_wait(pready(slot), (tl >> 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int kk = 0; kk < PX / 8; ++kk) {              // K = 8 pixels (32 bytes) per UMMA
+                    const uint64_t bd = make_desc(vt0 + kk * 2 * (128 * 16), 128 * 16, 128);
+                    umma_ts_tf32(tslot + 128, tslot + kk * 8, bd, idesc2, kk != 0 ? 1u : 0u);
+                }
+                umma_commit(kvdone(slot));
+            }
+        }
+    } else {
+        // ---------------------------------------------------------------- loader warp: weights + activation runs (cp.async.bulk)
+        // lane 0 owns the ring protocol and the weight copy; lanes 0-7 each issue the activation runs of one channel chunk
+        // (a single issuing thread was the bottleneck of this kernel: ~20 copies + address math per 48 KB stage).
+        uint32_t it = 0;
+        const int chs = p.c0 / 4;
+        const float* src = reinterpret_cast<const float*>(p.in0);
+        for (int t = blockIdx.x; t < total; t += gridDim.x) {
+            const int b = t / mtiles, mt = t - b * mtiles;
+            const int m0 = mt * PX, m_hi = m0 + PX < HW ? m0 + PX : HW;
+            const int hh0 = m0 / p.W, ww0 = m0 - hh0 * p.W;
+            for (int ks = 0; ks < ksteps; ++ks, ++it) {
+                const int s = it % STAGES;
+                const uint32_t xs = smem_u32(sS) + s * STAGE;
+                if (lane == 0) {
                     mbar_wait(empty(s), ((it / STAGES) & 1) ^ 1);
                     mbar_arrive_expect_tx(full(s), STAGE);
-                    const uint32_t xs = smem_u32(sS) + s * STAGE;
                     bulk_g2s(xs + XS, reinterpret_cast<const uint8_t*>(p.wpk) + (size_t)ks * WS, WS, full(s));
-#pragma unroll 1
-                    for (int k = 0; k < KCH; ++k) {
-                        const int cl = ks * KCH + k;
-                        long long m = (long long)mt * PX;
-                        const long long m_hi = m + PX < HW ? m + PX : HW;
-                        int qx = 0;
-                        while (m < m_hi) {                         // split the flattened run at image-row boundaries
-                            const int hh = (int)(m / p.W), ww = (int)(m - (long long)hh * p.W);
-                            const int n = (int)((p.W - ww) < (m_hi - m) ? (p.W - ww) : (m_hi - m));
-                            bulk_g2s(xs + (k * PX + qx) * 16, src + (((long long)(b * p.H + hh) * chs + cl) * p.W + ww) * 4,
-                                     (uint32_t)n * 16u, full(s));
-                            m += n; qx += n;
-                        }
-                        if (qx < PX) bulk_g2s(xs + (k * PX + qx) * 16, p.zero_page, (uint32_t)(PX - qx) * 16u, full(s));
+                }
+                __syncwarp();
+                if (lane < KCH) {
+                    const int k = lane, cl = ks * KCH + k;
+                    int m = m0, hh = hh0, ww = ww0, qx = 0;
+                    while (m < m_hi) {                             // split the flattened run at image-row boundaries
+                        const int n = (p.W - ww) < (m_hi - m) ? (p.W - ww) : (m_hi - m);
+                        bulk_g2s(xs + (k * PX + qx) * 16, src + (((long long)(b * p.H + hh) * chs + cl) * p.W + ww) * 4,
+                                 (uint32_t)n * 16u, full(s));
+                        m += n; qx += n; ++hh; ww = 0;
                     }
+                    if (qx < PX) bulk_g2s(xs + (k * PX + qx) * 16, p.zero_page, (uint32_t)(PX - qx) * 16u, full(s));
                 }
             }
         }
     }
     __syncthreads();
-    if (warp == NPROD / 32) {
+    if (warp == EPW) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
@@ -970,7 +995,7 @@ static int launch_attn_kv(const ConvTcParams& p, cudaStream_t s) {
     }
     const long long total = (long long)p.B * ((p.H * p.W + kvk::PX - 1) / kvk::PX);
     const int grid = (int)(total < num_sms ? total : num_sms);
-    k_attn_kv<<<grid, NTHREADS, kvk::SMEM, s>>>(p);
+    k_attn_kv<<<grid, kvk::THREADS, kvk::SMEM, s>>>(p);
     return 1;
 }
 int attn_kv_tile_pixels() { return kvk::PX; }
