@@ -623,10 +623,13 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT, KV>::MINB) k_conv_tc
         }
     } else {
         // =========================================================================================================
-        // loader (one thread): weights + A runs by cp.async.bulk.  Every byte of the A tile is written every stage:
+        // loader warp: weights + A runs by cp.async.bulk.  Every byte of the A tile is written every stage:
         // out-of-image rows / columns (the conv's zero padding, the ragged last 1x1 tile) come from a zero page.
         // =========================================================================================================
-        if (lane == 0) {
+        // Lane 0 owns the ring protocol, the border bookkeeping and the weight copy; the (chunk, row) activation runs of a
+        // stage are issued by KCH*HR lanes in parallel (one thread issuing ~10-20 copies + address math per stage was
+        // a measurable part of the pipeline latency).
+        {
             uint32_t it = 0;
             const float* zero = p.zero_page;
             uint32_t stage_pat[STAGES];
@@ -639,69 +642,68 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT, KV>::MINB) k_conv_tc
                                       (size_t)(n0 / NT) * ksteps * B_STAGE_BYTES;
                 for (int ks = 0; ks < ksteps; ++ks, ++it) {
                     const int s = it % STAGES;
-                    mbar_wait(empty(s), ((it / STAGES) & 1) ^ 1);
-                    uint32_t a_tx = BULK ? A_STAGE_BYTES : 0;
-                    if (BULK && GEOM != G_PW) {
-                        // Image-border columns (the conv's zero padding) are never written by the row copies, so they only
-                        // need zeroing when this stage buffer last served a tile with a different border pattern.  With
-                        // the round-robin tile order a CTA normally keeps one pattern, so this (and its proxy fence,
-                        // which would otherwise serialise against the bulk copies in flight) runs a handful of times.
-                        const int wlo = w0 - 1 < 0 ? 0 : w0 - 1, whi = w0 + TPX + 1 > p.W ? p.W : w0 + TPX + 1;
-                        const int qlo = wlo - (w0 - 1), qhi = qlo + (whi - wlo);
-                        const uint32_t pat = (uint32_t)qlo | ((uint32_t)qhi << 8);
-                        if (stage_pat[s] != pat) {
-                            stage_pat[s] = pat;
-                            if (qlo > 0 || qhi < PXP) {
-                                uint8_t* st = sA + s * A_STAGE_BYTES;
-                                for (int k = 0; k < KCH; ++k)
-                                    for (int r = 0; r < HR; ++r) {
-                                        uint4* rowp = reinterpret_cast<uint4*>(st + k * PLANE + (r * PXP) * 16);
-                                        for (int q = 0; q < qlo; ++q) rowp[q] = make_uint4(0u, 0u, 0u, 0u);
-                                        for (int q = qhi; q < PXP; ++q) rowp[q] = make_uint4(0u, 0u, 0u, 0u);
-                                    }
-                                fence_proxy_async();
+                    if (lane == 0) {
+                        mbar_wait(empty(s), ((it / STAGES) & 1) ^ 1);
+                        uint32_t a_tx = BULK ? A_STAGE_BYTES : 0;
+                        if (BULK && GEOM != G_PW) {
+                            // Image-border columns (the conv's zero padding) are never written by the row copies, so they only
+                            // need zeroing when this stage buffer last served a tile with a different border pattern.  With
+                            // the round-robin tile order a CTA normally keeps one pattern, so this (and its proxy fence,
+                            // which would otherwise serialise against the bulk copies in flight) runs a handful of times.
+                            const int wlo = w0 - 1 < 0 ? 0 : w0 - 1, whi = w0 + TPX + 1 > p.W ? p.W : w0 + TPX + 1;
+                            const int qlo = wlo - (w0 - 1), qhi = qlo + (whi - wlo);
+                            const uint32_t pat = (uint32_t)qlo | ((uint32_t)qhi << 8);
+                            if (stage_pat[s] != pat) {
+                                stage_pat[s] = pat;
+                                if (qlo > 0 || qhi < PXP) {
+                                    uint8_t* st = sA + s * A_STAGE_BYTES;
+                                    for (int k = 0; k < KCH; ++k)
+                                        for (int r = 0; r < HR; ++r) {
+                                            uint4* rowp = reinterpret_cast<uint4*>(st + k * PLANE + (r * PXP) * 16);
+                                            for (int q = 0; q < qlo; ++q) rowp[q] = make_uint4(0u, 0u, 0u, 0u);
+                                            for (int q = qhi; q < PXP; ++q) rowp[q] = make_uint4(0u, 0u, 0u, 0u);
+                                        }
+                                    fence_proxy_async();
+                                }
                             }
+                            int vrows = 0;
+                            for (int r = 0; r < HR; ++r) { const int hi = h0 - 1 + r; vrows += (hi >= 0 && hi < p.H) ? 1 : 0; }
+                            a_tx -= (uint32_t)(KCH * vrows * (PXP - (qhi - qlo))) * 16u;
                         }
-                        int vrows = 0;
-                        for (int r = 0; r < HR; ++r) { const int hi = h0 - 1 + r; vrows += (hi >= 0 && hi < p.H) ? 1 : 0; }
-                        a_tx -= (uint32_t)(KCH * vrows * (PXP - (qhi - qlo))) * 16u;
+                        mbar_arrive_expect_tx(full_b(s), B_STAGE_BYTES + a_tx);
+                        bulk_g2s(smem_u32(sB + s * B_STAGE_BYTES), wsrc + (size_t)ks * B_STAGE_BYTES, B_STAGE_BYTES, full_b(s));
                     }
-                    mbar_arrive_expect_tx(full_b(s), B_STAGE_BYTES + a_tx);
-                    bulk_g2s(smem_u32(sB + s * B_STAGE_BYTES), wsrc + (size_t)ks * B_STAGE_BYTES, B_STAGE_BYTES, full_b(s));
-                    if (BULK) {
+                    __syncwarp();
+                    if (BULK && lane < KCH * HR) {
                         const uint32_t a_s = smem_u32(sA) + s * A_STAGE_BYTES;
-#pragma unroll 1
-                        for (int k = 0; k < KCH; ++k) {
-                            const int ck = ks * KCH + k;                     // 16-byte channel chunk index over the concat
-                            const bool second = ck * 4 >= p.c0;
-                            const float* src = reinterpret_cast<const float*>(second ? p.in1 : p.in0);
-                            const int chs = (second ? p.c1 : p.c0) / 4;
-                            const int cl = second ? ck - p.c0 / 4 : ck;
-                            if (GEOM == G_PW) {
-                                for (int r = 0; r < HR; ++r) {
-                                    long long m = (long long)(h0 + r) * TPX;
-                                    const long long m_hi = m >= HW ? m : (m + TPX < HW ? m + TPX : HW);
-                                    int q = 0;
-                                    while (m < m_hi) {                     // split the flattened run at image-row boundaries
-                                        const int hh = (int)(m / p.W), ww = (int)(m - (long long)hh * p.W);
-                                        const int n = (int)((p.W - ww) < (m_hi - m) ? (p.W - ww) : (m_hi - m));
-                                        bulk_g2s(a_s + k * PLANE + (r * PXP + q) * 16,
-                                                 src + (((long long)(b * p.H + hh) * chs + cl) * p.W + ww) * 4, (uint32_t)n * 16u, full_b(s));
-                                        m += n; q += n;
-                                    }
-                                    if (q < PXP) bulk_g2s(a_s + k * PLANE + (r * PXP + q) * 16, zero, (uint32_t)(PXP - q) * 16u, full_b(s));
-                                }
-                            } else {
-                                const int wlo = w0 - 1 < 0 ? 0 : w0 - 1, whi = w0 + TPX + 1 > p.W ? p.W : w0 + TPX + 1;
-                                const int qlo = wlo - (w0 - 1);
-                                for (int r = 0; r < HR; ++r) {
-                                    const int hi = h0 - 1 + r;
-                                    const uint32_t row_s = a_s + k * PLANE + (r * PXP) * 16;
-                                    if (hi < 0 || hi >= p.H) { bulk_g2s(row_s, zero, PXP * 16u, full_b(s)); continue; }
-                                    bulk_g2s(row_s + qlo * 16, src + (((long long)(b * p.H + hi) * chs + cl) * p.W + wlo) * 4,
-                                             (uint32_t)(whi - wlo) * 16u, full_b(s));
+                        const int k = lane / HR, r = lane - k * HR;
+                        const int ck = ks * KCH + k;                     // 16-byte channel chunk index over the concat
+                        const bool second = ck * 4 >= p.c0;
+                        const float* src = reinterpret_cast<const float*>(second ? p.in1 : p.in0);
+                        const int chs = (second ? p.c1 : p.c0) / 4;
+                        const int cl = second ? ck - p.c0 / 4 : ck;
+                        if (GEOM == G_PW) {
+                            long long m = (long long)(h0 + r) * TPX;
+                            const long long m_hi = m >= HW ? m : (m + TPX < HW ? m + TPX : HW);
+                            int q = 0;
+                            if (m < m_hi) {
+                                int hh = (int)(m / p.W), ww = (int)(m - (long long)hh * p.W);
+                                while (m < m_hi) {                     // split the flattened run at image-row boundaries
+                                    const int n = (int)((p.W - ww) < (m_hi - m) ? (p.W - ww) : (m_hi - m));
+                                    bulk_g2s(a_s + k * PLANE + (r * PXP + q) * 16,
+                                             src + (((long long)(b * p.H + hh) * chs + cl) * p.W + ww) * 4, (uint32_t)n * 16u, full_b(s));
+                                    m += n; q += n; ++hh; ww = 0;
                                 }
                             }
+                            if (q < PXP) bulk_g2s(a_s + k * PLANE + (r * PXP + q) * 16, zero, (uint32_t)(PXP - q) * 16u, full_b(s));
+                        } else {
+                            const int wlo = w0 - 1 < 0 ? 0 : w0 - 1, whi = w0 + TPX + 1 > p.W ? p.W : w0 + TPX + 1;
+                            const int qlo = wlo - (w0 - 1);
+                            const int hi = h0 - 1 + r;
+                            const uint32_t row_s = a_s + k * PLANE + (r * PXP) * 16;
+                            if (hi < 0 || hi >= p.H) bulk_g2s(row_s, zero, PXP * 16u, full_b(s));
+                            else bulk_g2s(row_s + qlo * 16, src + (((long long)(b * p.H + hi) * chs + cl) * p.W + wlo) * 4,
+                                          (uint32_t)(whi - wlo) * 16u, full_b(s));
                         }
                     }
                 }
