@@ -387,17 +387,17 @@ int launch_igemm(const IgemmParams& p, cudaStream_t s) {
 // (GradLogPEstimator2d.forward, diffusion.py:181-186 feeding downs[0][0].block1, :56-58)
 // ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_first_conv(const FirstConvParams p) {
-    // CTA = 64 consecutive frames of one mel row x 64 output channels.  The 3-row x 66-frame masked input halo and
-    // the 27x64 weights are staged in shared memory; the 16 KB output block is contiguous in NHWC, so it is
-    // transposed through shared memory and written with fully coalesced 16-byte stores.
+    // CTA = 256 consecutive frames of one mel row x 64 output channels.  The 3-row x 258-frame masked input halo and
+    // the 27x64 weights are staged in shared memory.  A thread owns 16 output channels of 4 frames 64 apart: a weight
+    // quad is read once for 4 frames (8 FMAs per shared-memory load; the one-frame version was LSU-bound), and for a
+    // fixed frame index the lanes of a warp are consecutive frames, so the planar [.][C/4][T][4] stores are 512-byte runs.
     __shared__ __align__(16) float s_w[27 * 64];
-    __shared__ __align__(16) float s_out[64 * 68];
-    __shared__ float s_in[3][3][66];
+    __shared__ float s_in[3][3][258];
     __shared__ float s_b[64];
     __shared__ float s_st[16];
     const int tid = threadIdx.x, b = blockIdx.z, n0 = blockIdx.y * 64;
-    const int wtiles = (p.T + 255) / 256;          // a CTA walks 4 strips of 64 frames, re-using the staged weights
-    const int h = blockIdx.x / wtiles, wbase = (blockIdx.x - h * wtiles) * 256;
+    const int wtiles = (p.T + 255) / 256;
+    const int h = blockIdx.x / wtiles, w0 = (blockIdx.x - h * wtiles) * 256;
     const int K = p.cin * 9;
     const int kreal = p.w_extra ? (p.cin - 1) * 9 : K;       // rows of s_w that come from the shared weight
     for (int i = tid; i < kreal * 64; i += 256) s_w[i] = p.w[(i >> 6) * p.C + n0 + (i & 63)];
@@ -408,10 +408,8 @@ __global__ void __launch_bounds__(256) k_first_conv(const FirstConvParams p) {
     }
     if (tid < 64) s_b[tid] = p.bias[n0 + tid];
     if (tid < 16) s_st[tid] = 0.f;
-    for (int w0 = wbase; w0 < wbase + 256 && w0 < p.T; w0 += 64) {
-    __syncthreads();                                   // previous strip's s_in / s_out readers are done
-    for (int i = tid; i < p.cin * 3 * 66; i += 256) {
-        const int ci = i / 198, rem = i - ci * 198, r = rem / 66, q = rem - r * 66;
+    for (int i = tid; i < p.cin * 3 * 258; i += 256) {
+        const int ci = i / 774, rem = i - ci * 774, r = rem / 258, q = rem - r * 258;
         const int hi = h + r - 1, wi = w0 + q - 1;
         float v = 0.f;
         if (hi >= 0 && hi < p.H && wi >= 0 && wi < p.T) {
@@ -423,64 +421,69 @@ __global__ void __launch_bounds__(256) k_first_conv(const FirstConvParams p) {
         s_in[ci][r][q] = v;
     }
     __syncthreads();
-    const int pxl = tid & 63, cg = tid >> 6;
-    float acc[16];
+    const int pg = tid & 63, cg = tid >> 6;
+    float acc[4][16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = s_b[cg * 16 + j];
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[i][j] = s_b[cg * 16 + j];
     for (int ci = 0; ci < p.cin; ++ci) {
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
-            const float v = s_in[ci][t / 3][pxl + t % 3];
             const float* wr = &s_w[(ci * 9 + t) * 64 + cg * 16];
+            float4 ww[4];
 #pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-                const float4 ww = *reinterpret_cast<const float4*>(wr + j4 * 4);
-                acc[j4 * 4 + 0] = fmaf(v, ww.x, acc[j4 * 4 + 0]);
-                acc[j4 * 4 + 1] = fmaf(v, ww.y, acc[j4 * 4 + 1]);
-                acc[j4 * 4 + 2] = fmaf(v, ww.z, acc[j4 * 4 + 2]);
-                acc[j4 * 4 + 3] = fmaf(v, ww.w, acc[j4 * 4 + 3]);
+            for (int j4 = 0; j4 < 4; ++j4) ww[j4] = *reinterpret_cast<const float4*>(wr + j4 * 4);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float v = s_in[ci][t / 3][pg + 64 * i + t % 3];
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    acc[i][j4 * 4 + 0] = fmaf(v, ww[j4].x, acc[i][j4 * 4 + 0]);
+                    acc[i][j4 * 4 + 1] = fmaf(v, ww[j4].y, acc[i][j4 * 4 + 1]);
+                    acc[i][j4 * 4 + 2] = fmaf(v, ww[j4].z, acc[i][j4 * 4 + 2]);
+                    acc[i][j4 * 4 + 3] = fmaf(v, ww[j4].w, acc[i][j4 * 4 + 3]);
+                }
             }
         }
     }
-    const bool ok = w0 + pxl < p.T;
-#pragma unroll
-    for (int j4 = 0; j4 < 4; ++j4)
-        *reinterpret_cast<float4*>(&s_out[pxl * 68 + cg * 16 + j4 * 4]) = make_float4(acc[j4 * 4], acc[j4 * 4 + 1], acc[j4 * 4 + 2], acc[j4 * 4 + 3]);
     // GN statistics: each half of the thread's 16 channels lies in one group (8 | C/8)
-    const int cpg_ = p.C / kGroups, gb_ = n0 / cpg_;
+    const int cpg = p.C / kGroups, gb = n0 / cpg;
 #pragma unroll
     for (int hf = 0; hf < 2; ++hf) {
         float s = 0.f, q = 0.f;
-        if (ok) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { const float v = acc[hf * 8 + j]; s += v; q = fmaf(v, v, q); }
+        for (int i = 0; i < 4; ++i) {
+            if (w0 + pg + 64 * i < p.T) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { const float v = acc[i][hf * 8 + j]; s += v; q = fmaf(v, v, q); }
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
         if ((tid & 31) == 0) {
-            const int g = (n0 + cg * 16 + hf * 8) / cpg_ - gb_;
+            const int g = (n0 + cg * 16 + hf * 8) / cpg - gb;
             atomicAdd(&s_st[g * 2], s);
             atomicAdd(&s_st[g * 2 + 1], q);
         }
     }
-    __syncthreads();
-    if (p.chw4) {
-        // [B][H][C/4][T][4]: per channel chunk the 64 frames are one contiguous 1 KB run
-        float* obase = p.out + ((((long long)b * p.H + h) * (p.C / 4) + n0 / 4) * p.T + w0) * 4;
-        for (int i = tid; i < 64 * 16; i += 256) {
-            const int ch = i >> 6, q = i & 63;
-            if (w0 + q < p.T) *reinterpret_cast<float4*>(obase + ((long long)ch * p.T + q) * 4) = *reinterpret_cast<const float4*>(&s_out[q * 68 + ch * 4]);
-        }
-    } else {
-        float* obase = p.out + (((long long)b * p.H + h) * p.T + w0) * p.C + n0;
-        for (int i = tid; i < 64 * 16; i += 256) {
-            const int q = i >> 4, c4 = (i & 15) * 4;
-            if (w0 + q < p.T) *reinterpret_cast<float4*>(obase + (long long)q * p.C + c4) = *reinterpret_cast<const float4*>(&s_out[q * 68 + c4]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int w = w0 + pg + 64 * i;
+        if (w >= p.T) continue;
+        if (p.chw4) {
+            float* o = p.out + ((((long long)b * p.H + h) * (p.C / 4) + (n0 + cg * 16) / 4) * p.T + w) * 4;
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4)
+                *reinterpret_cast<float4*>(o + (long long)j4 * p.T * 4) = make_float4(acc[i][j4 * 4], acc[i][j4 * 4 + 1], acc[i][j4 * 4 + 2], acc[i][j4 * 4 + 3]);
+        } else {
+            float* o = p.out + (((long long)b * p.H + h) * p.T + w) * p.C + n0 + cg * 16;
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4)
+                *reinterpret_cast<float4*>(o + j4 * 4) = make_float4(acc[i][j4 * 4], acc[i][j4 * 4 + 1], acc[i][j4 * 4 + 2], acc[i][j4 * 4 + 3]);
         }
     }
-    }   // strips
     __syncthreads();
-    const int cpg = p.C / kGroups, gb = n0 / cpg;
     const int ng = (64 + cpg - 1) / cpg;
     if (p.ostats && tid < ng * 2) atomicAdd(&p.ostats[((long long)b * kGroups + gb + (tid >> 1)) * 2 + (tid & 1)], (double)s_st[tid]);
 }
@@ -834,34 +837,53 @@ int launch_resfinal(const ResFinalParams& p, cudaStream_t s) {
 // ----------------------------------------------------------------------------------------------
 // LinearAttention: merge per-tile partials into the normalised context (diffusion.py:95-96)
 // ----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_attn_ctx(const AttnCtxParams p) {
+// One CTA per (head, sample), 1024 threads: the tile loop is split four ways (and the max pass 32 ways) so that the
+// ~1.4 MB of partials a level-0 sample carries is read with enough loads in flight; partial sums meet in shared memory.
+__global__ void __launch_bounds__(1024) k_attn_ctx(const AttnCtxParams p) {
+    __shared__ float s_red[32 * 33];
     __shared__ float s_M[32];
+    __shared__ __align__(16) float s_acc[3][256][5];
     const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     const float* base = p.kv_part + ((long long)b * p.mtiles * kHeads + h) * kKvPartFloats;
     const long long tstride = (long long)kHeads * kKvPartFloats;
-    if (tid < 32) {
+    {
+        const int w = tid >> 5, lane = tid & 31;
         float mx = -INFINITY;
-        for (int i = 0; i < p.mtiles; ++i) mx = fmaxf(mx, base[i * tstride + tid]);
+        for (int i = w; i < p.mtiles; i += 32) mx = fmaxf(mx, base[i * tstride + lane]);
+        s_red[w * 33 + lane] = mx;
+    }
+    __syncthreads();
+    if (tid < 32) {
+        float mx = s_red[tid];
+        for (int w = 1; w < 32; ++w) mx = fmaxf(mx, s_red[w * 33 + tid]);
         s_M[tid] = mx;
     }
     __syncthreads();
-    const int d = tid >> 3, e0 = (tid & 7) * 4;
+    const int sub = tid >> 8, u = tid & 255;
+    const int d = u >> 3, e0 = (u & 7) * 4;
     const float M = s_M[d];
     float z = 0.f, a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    for (int i = 0; i < p.mtiles; ++i) {
+#pragma unroll 2
+    for (int i = sub; i < p.mtiles; i += 4) {
         const float* pt = base + i * tstride;
         const float f = expf(pt[d] - M);
         z = fmaf(f, pt[32 + d], z);
         const float4 sv = *reinterpret_cast<const float4*>(pt + 64 + d * 32 + e0);
         a0 = fmaf(f, sv.x, a0); a1 = fmaf(f, sv.y, a1); a2 = fmaf(f, sv.z, a2); a3 = fmaf(f, sv.w, a3);
     }
-    const float inv = 1.f / z;
-    float* o = p.ctx + (((long long)b * kHeads + h) * 32 + d) * 32 + e0;
-    *reinterpret_cast<float4*>(o) = make_float4(a0 * inv, a1 * inv, a2 * inv, a3 * inv);
+    if (sub > 0) { float* q = s_acc[sub - 1][u]; q[0] = z; q[1] = a0; q[2] = a1; q[3] = a2; q[4] = a3; }
+    __syncthreads();
+    if (sub == 0) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { const float* q = s_acc[j][u]; z += q[0]; a0 += q[1]; a1 += q[2]; a2 += q[3]; a3 += q[4]; }
+        const float inv = 1.f / z;
+        float* o = p.ctx + (((long long)b * kHeads + h) * 32 + d) * 32 + e0;
+        *reinterpret_cast<float4*>(o) = make_float4(a0 * inv, a1 * inv, a2 * inv, a3 * inv);
+    }
 }
 
 int launch_attn_ctx(const AttnCtxParams& p, cudaStream_t s) {
-    k_attn_ctx<<<dim3(kHeads, p.B), 256, 0, s>>>(p);
+    k_attn_ctx<<<dim3(kHeads, p.B), 1024, 0, s>>>(p);
     return 1;
 }
 
