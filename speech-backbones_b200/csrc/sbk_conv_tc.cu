@@ -192,26 +192,27 @@ using namespace tc;
 //   * NSLOT TMEM accumulator slots: with two slots the epilogue of tile i overlaps the loads + MMAs of tile i+1;
 //   * two CTAs per SM when smem (<= ~108 KB) and TMEM (<= 256 columns) allow, else one CTA with a deeper ring.
 constexpr int pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
-template <int GEOM, int NT, bool KV = false> struct Depth {
+template <int GEOM, int NT> struct Depth {
     static constexpr int STAGE_BYTES = Geo<GEOM>::KCH * Geo<GEOM>::HR * Geo<GEOM>::PXP * 16 + Geo<GEOM>::TAPS * Geo<GEOM>::KCH * NT * 16;
-    static constexpr int SLOT_COLS = KV ? 320 : Geo<GEOM>::NACC * NT;        // KV: D1 (256 px columns) + S (64)
-    static constexpr int EXTRA = KV ? 66 * 1024 : 0;                          // KV: V^T operand tile + reduction scratch
+    static constexpr int SLOT_COLS = Geo<GEOM>::NACC * NT;
     static constexpr int FIT2 = (108 * 1024) / STAGE_BYTES;
-    static constexpr int FIT1 = (220 * 1024 - EXTRA) / STAGE_BYTES;
+    static constexpr int FIT1 = (220 * 1024) / STAGE_BYTES;
     // long-K 3x3 convs (NT = 128) are MMA-bound: one CTA, deep ring, two accumulator slots.  Everything else is
     // epilogue/latency-bound: two CTAs per SM double the epilogue warps; slots as TMEM (256 columns per CTA) allows.
-    static constexpr bool TWO = !KV && FIT2 >= 2 && SLOT_COLS <= 256 && !(GEOM == G_C3 && NT == 128);
-    static constexpr int NSLOT = KV ? 1 : (TWO ? (2 * SLOT_COLS <= 256 ? 2 : 1) : (2 * SLOT_COLS <= 512 ? 2 : 1));
+    static constexpr bool TWO = FIT2 >= 2 && SLOT_COLS <= 256 && !(GEOM == G_C3 && NT == 128);
+    static constexpr int NSLOT = TWO ? (2 * SLOT_COLS <= 256 ? 2 : 1) : (2 * SLOT_COLS <= 512 ? 2 : 1);
     static constexpr int TMEM_COLS = pow2_cols(NSLOT * SLOT_COLS);
     static constexpr int STAGES = TWO ? (FIT2 > 4 ? 4 : FIT2) : (FIT1 > 6 ? 6 : FIT1);
     static constexpr int MINB = TWO ? 2 : 1;
-    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + EXTRA + (2 * STAGES + 2 * NSLOT + 2) * 8 + 16 * 4 + 16 + 3 * NT * 4 + 64;
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + (2 * STAGES + 2 * NSLOT + 2) * 8 + 16 * 4 + 16 + 3 * NT * 4 + 64;
 };
 
-template <int GEOM, bool BF16, int NT, bool KV = false>
-__global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT, KV>::MINB) k_conv_tc(const ConvTcParams p) {
+// RES: ResnetBlock-tail epilogue (1x1 res_conv + Mish(GN(h2raw)) side input), compile-time so that the plain 1x1 /
+// 3x3 instantiations do not pay its registers.
+template <int GEOM, bool BF16, int NT, bool RES = false>
+__global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT>::MINB) k_conv_tc(const ConvTcParams p) {
     using G = Geo<GEOM>;
-    using D = Depth<GEOM, NT, KV>;
+    using D = Depth<GEOM, NT>;
     constexpr int STAGES = D::STAGES, NSLOT = D::NSLOT, SLOT_COLS = D::SLOT_COLS;
     constexpr int LAG = STAGES >= 3 ? STAGES - 2 : 0;      // G_DOWN only: cp.async groups in flight behind the newest
     static_assert(STAGES >= 2, "need at least 2 stages");
@@ -226,8 +227,7 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT, KV>::MINB) k_conv_tc
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sA = smem;                                            // [STAGES][KCH][HR][PXP][16]
     uint8_t* sB = sA + STAGES * A_STAGE_BYTES;                     // [STAGES][TAPS][KCH][NT][16]
-    uint8_t* sX = sB + STAGES * B_STAGE_BYTES;                     // KV scratch (V^T operand + reductions)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sX + D::EXTRA);   // full[S], empty[S], tfull[NSLOT], tempty[NSLOT], fa[S]*, kv
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + STAGES * B_STAGE_BYTES);   // full[S], empty[S], tfull[NSLOT], tempty[NSLOT], fa[S]*, kv
     float* s_st = reinterpret_cast<float*>(bars + 3 * STAGES + 2 * NSLOT + 2);   // [8 groups][2]
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_st + 16);
     float* s_rg = reinterpret_cast<float*>(s_tmem + 4);                          // EPI_RES: mean|scale|beta [NT] each
@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT, KV>::MINB) k_conv_tc
             // ---- epilogue of tile t
             const int slot = tl % NSLOT;
             const uint32_t tslot = tmem_base + slot * SLOT_COLS;
-            if (p.epi == EPI_RES) {
+            if constexpr (RES) {
                 asm volatile("bar.sync 1, 256;" ::: "memory");        // previous tile's readers of s_rg are done
                 const int cpg = p.Cout / kGroups;
                 for (int i = tid; i < NT; i += NPROD) {
@@ -346,8 +346,7 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT, KV>::MINB) k_conv_tc
                 }
                 asm volatile("bar.sync 1, 256;" ::: "memory");
             }
-            mbar_wait(tfull(slot), (tl / NSLOT) & 1);
-            tc_fence_after();
+            bool acc_ready = false;                                // the tfull wait is taken after the epilogue's own loads are in flight
             const int q4 = warp & 3, jrow = warp >> 2;            // TMEM lane quarter / accumulator (output row)
             const int px = q4 * 32 + lane;
             const int Ho = (GEOM == G_DOWN || GEOM == G_UP) ? p.Ho : p.H, Wo = (GEOM == G_DOWN || GEOM == G_UP) ? p.Wo : p.W;
@@ -366,93 +365,7 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT, KV>::MINB) k_conv_tc
                 wo = valid ? (int)(m - (long long)ho * p.W) : 0;
             }
             if (!valid) { ho = 0; wo = 0; }
-        if constexpr (KV) {
-            // LinearAttention pass 1 (diffusion.py:93-96) with the GEMM roles swapped: the main loop computed
-            //   D1[kv channel (TMEM lane)][pixel (column)] = W_kv[128 x C] * X^T        (M = 128, N = 256 pixels)
-            // with lanes 0-31 = k of head h0, 32-63 = v of h0, 64-95 = k of h1, 96-127 = v of h1.  So one thread owns one
-            // channel across all 256 pixels: the softmax max / sum are private reductions over its TMEM columns (no
-            // shuffles, no smem).  P = exp(k - max) is written back to TMEM in place, V^T goes to shared memory as a
-            // K-major operand, and S[d][e] = sum_px P[d,px] V[e,px] is a second UMMA with A = P read from TMEM.
-            // k and v never reach HBM; per 256-pixel tile only (max, sum, S) partials are written.
-            constexpr int NPX = ROWS * TPX;                        // 256 pixels = columns of D1
-            const int q = warp & 3, half = warp >> 2;              // lane quarter (channel block) / pixel half
-            const bool is_k = (q & 1) == 0;
-            const int hh = q >> 1;                                 // head within this N tile
-            const int nvalid = (int)min((long long)NPX, (long long)HW - (long long)h0 * TPX);
-            const uint32_t tq = tslot + ((uint32_t)(q * 32) << 16);
-            float* s_m2 = reinterpret_cast<float*>(sX + 64 * 1024);       // [2 halves][128 lanes] max, then sum
-            uint8_t* vt = sX;                                    // V^T operand: [64 px chunks][64 rows][16 B]
-            const int col0 = half * (NPX / 2);
-            float mx = -INFINITY;
-            if (is_k) {
-#pragma unroll 1
-                for (int c = 0; c < NPX / 2; c += 32) {
-                    uint32_t r[32];
-                    tmem_ld32(tq + col0 + c, r);
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) if (col0 + c + i < nvalid) mx = fmaxf(mx, __uint_as_float(r[i]));
-                }
-                s_m2[half * 128 + q * 32 + lane] = mx;
-            } else {
-                // V^T: row = hh*32 + lane, 4 consecutive pixels per 16-byte chunk
-                const int row = hh * 32 + lane;
-#pragma unroll 1
-                for (int c = 0; c < NPX / 2; c += 32) {
-                    uint32_t r[32];
-                    tmem_ld32(tq + col0 + c, r);
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4)
-                        *reinterpret_cast<uint4*>(vt + ((size_t)((col0 + c + i) / 4) * 64 + row) * 16) = make_uint4(r[i], r[i + 1], r[i + 2], r[i + 3]);
-                }
-            }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            float zsum = 0.f, md = 0.f;
-            if (is_k) {
-                md = fmaxf(s_m2[q * 32 + lane], s_m2[128 + q * 32 + lane]);
-#pragma unroll 1
-                for (int c = 0; c < NPX / 2; c += 32) {
-                    uint32_t r[32];
-                    tmem_ld32(tq + col0 + c, r);
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const float e = (col0 + c + i < nvalid) ? __expf(__uint_as_float(r[i]) - md) : 0.f;
-                        zsum += e;
-                        r[i] = __float_as_uint(e);
-                    }
-                    tmem_st32(tq + col0 + c, r);
-                }
-                tmem_wait_st();
-            }
-            fence_proxy_async();                                   // V^T smem writes -> visible to the tensor core
-            tc_fence_before();
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (is_k) s_m2[half * 128 + q * 32 + lane] = zsum;     // (max values were consumed before the barrier)
-            if (tid == 0) {
-                tc_fence_after();
-                const uint32_t idesc2 = make_idesc<false>(TPX, 64);
-                const uint32_t vt0 = smem_u32(vt);
-#pragma unroll 1
-                for (int kk = 0; kk < NPX / 8; ++kk) {             // K = 8 pixels (32 bytes) per MMA
-                    const uint64_t bd = make_desc(vt0 + kk * 2 * (64 * 16), 64 * 16, 128);
-                    umma_ts_tf32(tslot + NPX, tslot + kk * 8, bd, idesc2, kk != 0 ? 1u : 0u);
-                }
-                umma_commit(kv_bar);
-            }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (is_k && half == 0) {
-                mbar_wait(kv_bar, tl & 1);
-                tc_fence_after();
-                uint32_t r[32];
-                tmem_ld32(tq + NPX + hh * 32, r);                  // S[d = lane][e = 0..31] of head hh
-                float* pt = p.kv_part + (((long long)b * mtiles + mt) * kHeads + (n0 / 64) + hh) * kKvPartFloats;
-                pt[lane] = md;
-                pt[32 + lane] = s_m2[q * 32 + lane] + s_m2[128 + q * 32 + lane];
-#pragma unroll
-                for (int i = 0; i < 32; i += 4)
-                    *reinterpret_cast<float4*>(&pt[64 + lane * 32 + i]) =
-                        make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
-            }
-        } else {
+        {
         const int cpg = p.Cout / kGroups;
         const float* bp = p.bias ? p.bias + (long long)b * p.bias_bstride + n0 : nullptr;
         constexpr int NPH = GEOM == G_UP ? 4 : 1;
@@ -461,12 +374,30 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT, KV>::MINB) k_conv_tc
         const int ho_p = GEOM == G_UP ? ho + (phase >> 1) : ho;
         const int wo_p = GEOM == G_UP ? wo + (phase & 1) : wo;
         const int acc = GEOM == G_UP ? phase * ROWS + jrow : jrow;
-        const float mo = (p.out_mask || p.epi == EPI_RES) ? __ldg(p.mask + (long long)b * p.T + ((long long)wo_p << p.lvl)) : 1.f;
+        const float mo = (p.out_mask || RES) ? __ldg(p.mask + (long long)b * p.T + ((long long)wo_p << p.lvl)) : 1.f;
         // element (b, ho, chunk, wo) of a [B][H][C/4][W][4] tensor; consecutive lanes = consecutive pixels = 16 B apart
         const long long obase = (((long long)(b * Ho + ho_p) * CHo + n0 / 4) * Wo + wo_p) * 4;
         const long long cstride = (long long)Wo * 4;           // floats between consecutive channel chunks
+        // ResnetBlock tail: the h2raw side input does not depend on the accumulators, so chunk block 0 is requested before
+        // the tfull wait and block cb+32 as soon as block cb has been consumed: the global latency hides under the TMEM
+        // load, the Mish math and the stores.  (The attention apply's residual read is a plain streaming add; prefetching
+        // it only cost registers.)
+        constexpr bool SIDE = GEOM == G_PW;                     // the 1x1 convs never carry GN statistics
+        const float* pre_src = RES ? p.rraw : nullptr;
+        const bool pre_on = RES && valid && mo != 0.f;
+        float4 pre[RES ? 8 : 1];
+        if constexpr (RES) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                pre[i] = pre_on ? __ldg(reinterpret_cast<const float4*>(pre_src + obase + i * cstride)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
 #pragma unroll 1
         for (int cb = 0; cb < NT; cb += 32) {
+            if (!acc_ready) {
+                mbar_wait(tfull(slot), (tl / NSLOT) & 1);
+                tc_fence_after();
+                acc_ready = true;
+            }
             uint32_t r[32];
             tmem_ld32(tslot + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(acc * NT + cb), r);
             float v[32];
@@ -476,21 +407,25 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT, KV>::MINB) k_conv_tc
                 v[i] = __uint_as_float(r[i]) + bb.x; v[i + 1] = __uint_as_float(r[i + 1]) + bb.y;
                 v[i + 2] = __uint_as_float(r[i + 2]) + bb.z; v[i + 3] = __uint_as_float(r[i + 3]) + bb.w;
             }
-            if (p.epi == EPI_RES && valid && mo != 0.f) {
+            if constexpr (RES) {
                 // ResnetBlock tail: + Mish(GN(h2raw)) * mask  (diffusion.py:77-78)
-                const float* rp = p.rraw + obase + (cb / 4) * cstride;
+                if (pre_on) {
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    const float4 rv = __ldg(reinterpret_cast<const float4*>(rp + (i / 4) * cstride));
-                    const float rr[4] = {rv.x, rv.y, rv.z, rv.w};
+                    for (int i = 0; i < 32; i += 4) {
+                        const float rr[4] = {pre[i / 4].x, pre[i / 4].y, pre[i / 4].z, pre[i / 4].w};
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int cl = cb + i + e;
-                        v[i + e] += mish_fast((rr[e] - s_rg[cl]) * s_rg[NT + cl] + s_rg[2 * NT + cl]);
+                        for (int e = 0; e < 4; ++e) {
+                            const int cl = cb + i + e;
+                            v[i + e] += mish_fast((rr[e] - s_rg[cl]) * s_rg[NT + cl] + s_rg[2 * NT + cl]);
+                        }
+                    }
+                    if (cb + 32 < NT) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            pre[i] = __ldg(reinterpret_cast<const float4*>(pre_src + obase + ((cb + 32) / 4 + i) * cstride));
                     }
                 }
-            }
-            if (p.addin && valid) {
+            } else if (p.addin && valid) {
                 // fp32-exact residual (attention: x + g*P x): the tensor core only carries the small g*P x term
                 const float* ap = p.addin + obase + (cb / 4) * cstride;
 #pragma unroll
@@ -508,7 +443,7 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT, KV>::MINB) k_conv_tc
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(op + (i / 4) * cstride) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
             }
-            if (p.ostats) {
+            if (!SIDE && p.ostats) {
                 // GroupNorm partials of this 32-column chunk: 8-channel sub-sums first (static register indexing),
                 // then merged to the group width cpg (8 -> 4 groups, 16 -> 2 groups, >= 32 -> 1 group)
                 float s8[4], q8[4];
@@ -543,7 +478,7 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT, KV>::MINB) k_conv_tc
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty(slot));
-            if (p.ostats) {
+            if (GEOM != G_PW && p.ostats) {
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 const int cpg = p.Cout / kGroups, gb = n0 / cpg, ng = (NT + cpg - 1) / cpg;
                 if (tid < ng * 2) {
@@ -577,12 +512,7 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT, KV>::MINB) k_conv_tc
                     for (int kk = 0; kk < KCH / 2; ++kk) {
                         const uint32_t a_st = a0 + s * A_STAGE_BYTES + kk * 2 * PLANE;
                         const uint32_t b_st = b0 + s * B_STAGE_BYTES + kk * 2 * (NT * 16);
-                        if (KV) {
-                            // swapped roles: A = weight tile (128 kv channels), B = the 256-pixel activation tile
-                            const uint64_t wd = make_desc(b_st, NT * 16, 128);
-                            const uint64_t xd = make_desc(a_st, PLANE, 128);
-                            umma<BF16>(tslot, wd, xd, make_idesc<BF16>(TPX, ROWS * TPX), (ks | kk) != 0 ? 1u : 0u);
-                        } else if (GEOM == G_UP) {
+                        if (GEOM == G_UP) {
                             // ho = 2*hi - 1 + kh: parity ph uses (kh=1,dh=0),(kh=3,dh=-1) if ph=0 and (kh=0,dh=+1),(kh=2,dh=0) if ph=1
 #pragma unroll
                             for (int phase = 0; phase < 4; ++phase) {
@@ -718,13 +648,13 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT, KV>::MINB) k_conv_tc
     }
 }
 
-template <int GEOM, bool BF16, int NT, bool KV = false>
+template <int GEOM, bool BF16, int NT, bool RES = false>
 static int launch_tc(const ConvTcParams& p, cudaStream_t s) {
-    using D = Depth<GEOM, NT, KV>;
+    using D = Depth<GEOM, NT>;
     static bool attr_set = false;
     static int num_sms = 0;
     if (!attr_set) {
-        cudaFuncSetAttribute(k_conv_tc<GEOM, BF16, NT, KV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(k_conv_tc<GEOM, BF16, NT, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -737,7 +667,7 @@ static int launch_tc(const ConvTcParams& p, cudaStream_t s) {
     const long long total = (long long)mt * (p.Cout / NT) * p.B;
     const long long cap = (long long)num_sms * D::MINB;             // persistent: one wave of resident CTAs
     const int grid = (int)(total < cap ? total : cap);
-    k_conv_tc<GEOM, BF16, NT, KV><<<grid, NTHREADS, D::SMEM, s>>>(p);
+    k_conv_tc<GEOM, BF16, NT, RES><<<grid, NTHREADS, D::SMEM, s>>>(p);
     return 1;
 }
 
@@ -1020,6 +950,7 @@ int launch_conv_tc(const ConvTcParams& p, cudaStream_t s) {
         case G_C3:   return nt == 128 ? launch_tc<G_C3, false, 128>(p, s) : launch_tc<G_C3, false, 64>(p, s);
         case G_PW:
             if (p.epi == EPI_KV) return launch_attn_kv(p, s);
+            if (p.epi == EPI_RES) return nt == 128 ? launch_tc<G_PW, false, 128, true>(p, s) : launch_tc<G_PW, false, 64, true>(p, s);
             return nt == 128 ? launch_tc<G_PW, false, 128>(p, s) : launch_tc<G_PW, false, 64>(p, s);
         case G_DOWN: return launch_tc<G_DOWN, false, 64>(p, s);
         default:     return launch_tc<G_UP, false, 64>(p, s);
