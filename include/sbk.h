@@ -31,7 +31,9 @@ enum { SBK_OK = 0, SBK_ERR_ARG = 1, SBK_ERR_CUDA = 2, SBK_ERR_STATE = 3, SBK_ERR
 /* arithmetic of the dense contractions (3x3/1x1 convs); GN / softmax / Mish / Euler are always fp32 */
 enum { SBK_PREC_FP32 = 0,   /* CUDA-core FFMA, fp32 operands (bit-faithful class of the CPU reference)   */
        SBK_PREC_TF32 = 1,   /* tcgen05 kind::tf32, fp32 accumulate in TMEM (PyTorch's default GPU class) */
-       SBK_PREC_BF16 = 2 }; /* reserved: bf16 operand tensors are not built yet; sbk_pack() refuses it        */
+       SBK_PREC_BF16 = 2 }; /* tcgen05 kind::f16 on bf16 operand tensors (conv inputs + weights stored as bf16),
+                               fp32 accumulate; raw conv outputs, GN statistics, softmax, sampler state fp32
+                               (BASELINE config 3).  Grad-TTS only: sbk_pack() refuses it for DiffVC        */
 
 enum { SBK_MODEL_GRADTTS = 0, SBK_MODEL_DIFFVC = 1 };
 
@@ -134,6 +136,10 @@ int sbk_debug_capture(sbk_handle* h, int on);
 /* test hook: layout of the intermediates sbk_debug_read returns: 0 = NHWC [B][H][W][C] (fp32 mode),
  * 1 = channel-chunk planar [B][H][C/4][W][4] (tensor-core modes) */
 int sbk_debug_layout(const sbk_handle* h);
+/* test hook: layout of ONE named intermediate (the bf16 mode mixes fp32 raw outputs with bf16 operand tensors):
+ * 0 / 1 as above, 2 = [B][H][C/8][W][8] stored as bf16 (sbk_debug_read widens it to fp32; dst must be host memory),
+ * -1 = unknown name */
+int sbk_debug_op_layout(const sbk_handle* h, const char* name);
 /* test hook: enumerate intermediate names */
 int sbk_debug_num(const sbk_handle* h);
 const char* sbk_debug_name(const sbk_handle* h, int i);

@@ -17,7 +17,7 @@ EXPORTS = [
     "sbk_create", "sbk_destroy", "sbk_set_weight", "sbk_pack", "sbk_num_weights", "sbk_weight_name",
     "sbk_workspace_bytes", "sbk_estimator", "sbk_reverse_diffusion", "sbk_reverse_steps",
     "sbk_reverse_diffusion_host", "sbk_last_launch_count", "sbk_debug_read", "sbk_debug_num",
-    "sbk_debug_name", "sbk_last_error", "sbk_version", "sbk_profile_ops", "sbk_debug_capture", "sbk_debug_layout", "sbk_vc_estimator", "sbk_vc_reverse_diffusion", "sbk_vc_conditioning",
+    "sbk_debug_name", "sbk_last_error", "sbk_version", "sbk_profile_ops", "sbk_debug_capture", "sbk_debug_layout", "sbk_debug_op_layout", "sbk_vc_estimator", "sbk_vc_reverse_diffusion", "sbk_vc_conditioning",
 ]
 
 
@@ -63,6 +63,7 @@ def load_library() -> C.CDLL:
     lib.sbk_debug_num.argtypes = [P]
     lib.sbk_debug_capture.argtypes = [P, I]
     lib.sbk_debug_layout.argtypes = [P]
+    lib.sbk_debug_op_layout.argtypes = [P, C.c_char_p]
     lib.sbk_debug_name.argtypes = [P, I]
     lib.sbk_debug_name.restype = C.c_char_p
     lib.sbk_profile_ops.argtypes = [P, F, F, F, I, C.POINTER(C.c_int)]
@@ -282,7 +283,10 @@ class Engine:
     def debug_capture(self, on=True):
         _check(self.lib.sbk_debug_capture(self.h, 1 if on else 0), "sbk_debug_capture")
 
-    def debug_layout(self):
+    def debug_layout(self, name=None):
+        """0: [B][H][W][C]; 1: [B][H][C/4][W][4]; 2: [B][H][C/8][W][8] (bf16 operand tensor, widened to fp32 by debug_read)."""
+        if name is not None:
+            return int(self.lib.sbk_debug_op_layout(self.h, name.encode()))
         return int(self.lib.sbk_debug_layout(self.h))
 
     def debug_names(self):

@@ -55,6 +55,7 @@ struct Op {
     OpKind kind; std::string name;
     FirstConvParams fc; IgemmParams ig; ConvTcParams tc; GnActParams ga; ResFinalParams rf; AttnCtxParams cx; AttnMixParams mx; FinalParams fn;
     const float* dbg_ptr = nullptr; int64_t dbg_numel = 0;
+    int dbg_fmt = 0;               // layout of the named output: 0 NHWC fp32, 1 [B][H][C/4][W][4] fp32, 2 [B][H][C/8][W][8] bf16
     double flops = 0, bytes = 0;   // algorithmic work of this launch
     float* dbg_copy = nullptr;     // snapshot taken right after the launch when debug capture is on
 };
@@ -298,26 +299,31 @@ static int pack_tc(sbk_handle* h, const std::string& src, const std::string& key
 }
 // k and v rows of to_qkv ('(qkv heads c)': k = rows 128.., v = rows 256..) in k_attn_kv's per-stage shared-memory image
 // [32-channel stage][k|v][16-byte chunk][row = head*32 + c][4], tf32-rounded
-static int pack_tc_kv(sbk_handle* h, const std::string& src, const std::string& key, int C) {
+// (bf16: [64-channel stage][k|v][16-byte chunk][row][8] as bf16)
+static int pack_tc_kv(sbk_handle* h, const std::string& src, const std::string& key, int C, bool bf16) {
     std::vector<float> q((size_t)384 * C);
-    std::vector<uint32_t> m((size_t)256 * C);
     CU(cudaMemcpy(q.data(), h->raw[src], q.size() * sizeof(float), cudaMemcpyDeviceToHost));
-    for (int ks = 0; ks < C / 32; ++ks) for (int kv = 0; kv < 2; ++kv) for (int k = 0; k < 8; ++k)
-        for (int row = 0; row < 128; ++row) for (int e = 0; e < 4; ++e)
-            m[((((size_t)ks * 2 + kv) * 8 + k) * 128 + row) * 4 + e] =
-                f32_to_tf32_rna(q[(size_t)(128 + kv * 128 + row) * C + ks * 32 + k * 4 + e]);
+    const int EPC = bf16 ? 8 : 4, CPS = 8 * EPC;
+    std::vector<uint8_t> m((size_t)256 * C * (bf16 ? 2 : 4));
+    for (int ks = 0; ks < C / CPS; ++ks) for (int kv = 0; kv < 2; ++kv) for (int k = 0; k < 8; ++k)
+        for (int row = 0; row < 128; ++row) for (int e = 0; e < EPC; ++e) {
+            const size_t idx = ((((size_t)ks * 2 + kv) * 8 + k) * 128 + row) * EPC + e;
+            const float w = q[(size_t)(128 + kv * 128 + row) * C + ks * CPS + k * EPC + e];
+            if (bf16) reinterpret_cast<uint16_t*>(m.data())[idx] = f32_to_bf16_rn(w);
+            else reinterpret_cast<uint32_t*>(m.data())[idx] = f32_to_tf32_rna(w);
+        }
     float*& d = h->packed[key];
-    if (!d) { CU(cudaMalloc(&d, m.size() * 4)); h->owned.push_back(d); }
-    CU(cudaMemcpy(d, m.data(), m.size() * 4, cudaMemcpyHostToDevice));
+    if (!d) { CU(cudaMalloc(&d, m.size())); h->owned.push_back(d); }
+    CU(cudaMemcpy(d, m.data(), m.size(), cudaMemcpyHostToDevice));
     return SBK_OK;
 }
 // ConvTranspose2d weight [ci][co][4][4] -> logical [co][ci][kh*4+kw]
-static int pack_tc_up(sbk_handle* h, const std::string& src, const std::string& key, int C) {
+static int pack_tc_up(sbk_handle* h, const std::string& src, const std::string& key, int C, bool bf16) {
     std::vector<float> w((size_t)C * C * 16), m((size_t)C * C * 16);
     CU(cudaMemcpy(w.data(), h->raw[src], w.size() * sizeof(float), cudaMemcpyDeviceToHost));
     for (int ci = 0; ci < C; ++ci) for (int co = 0; co < C; ++co) for (int t = 0; t < 16; ++t)
         m[((size_t)co * C + ci) * 16 + t] = w[((size_t)ci * C + co) * 16 + t];
-    return pack_tc_host(h, m, key, C, C, G_UP, false);
+    return pack_tc_host(h, m, key, C, C, G_UP, bf16);
 }
 static int pack_tc_host(sbk_handle* h, const std::vector<float>& hs, const std::string& key, int cout, int cin, int geom, bool bf16) {
     const int taps = conv_tc_taps(geom);
@@ -379,11 +385,11 @@ extern "C" int sbk_pack(sbk_handle* h) {
         TRY(repack(h, r.prefix + ".block2.block.0.weight", r.prefix + ".block2.w", (size_t)r.cout * 9 * r.cout, conv_pack));
         if (r.cin != r.cout) TRY(repack(h, r.prefix + ".res_conv.weight", r.prefix + ".res.w", (size_t)r.cin * r.cout, conv_pack));
     }
-    if (h->cfg.precision == SBK_PREC_BF16)
-        return fail(SBK_ERR_UNSUPPORTED, "sbk_pack: bf16 operand tensors are not wired up in this build (use fp32 or tf32)");
+    if (h->cfg.precision == SBK_PREC_BF16 && h->cfg.model != SBK_MODEL_GRADTTS)
+        return fail(SBK_ERR_UNSUPPORTED, "sbk_pack: bf16 operand tensors are implemented for the Grad-TTS model only (use fp32 or tf32 for DiffVC)");
     if (h->cfg.precision != SBK_PREC_FP32) {
-        const bool bf = false;
-        const int cps3 = conv_tc_stage_channels(G_C3, 0), cps1 = conv_tc_stage_channels(G_PW, 0);
+        const bool bf = h->cfg.precision == SBK_PREC_BF16;
+        const int cps3 = conv_tc_stage_channels(G_C3, bf ? 1 : 0), cps1 = conv_tc_stage_channels(G_PW, bf ? 1 : 0);
         for (auto& r : h->resnets) {
             if (r.cin % cps3 == 0) TRY(pack_tc(h, r.prefix + ".block1.block.0.weight", r.prefix + ".block1.wtc", r.cout, r.cin, G_C3, bf));
             TRY(pack_tc(h, r.prefix + ".block2.block.0.weight", r.prefix + ".block2.wtc", r.cout, r.cout, G_C3, bf));
@@ -391,14 +397,14 @@ extern "C" int sbk_pack(sbk_handle* h) {
         }
         TRY(pack_tc(h, "estimator.final_block.block.0.weight", "estimator.final_block.wtc", h->cfg.dim, h->cfg.dim, G_C3, bf));
         for (auto& a : h->attns)
-            if (a.c % cps1 == 0) TRY(pack_tc_kv(h, a.prefix + ".fn.fn.to_qkv.weight", a.prefix + ".kv.wtc", a.c));
+            if (a.c % cps1 == 0) TRY(pack_tc_kv(h, a.prefix + ".fn.fn.to_qkv.weight", a.prefix + ".kv.wtc", a.c, bf));
         for (int l = 0; l < 2; ++l) {
             const std::string p = "estimator.downs." + std::to_string(l) + ".3.conv";
             TRY(pack_tc(h, p + ".weight", p + ".wtc", h->cfg.dim << l, h->cfg.dim << l, G_DOWN, bf));
         }
         for (int j = 0; j < 2; ++j) {
             const std::string p = "estimator.ups." + std::to_string(j) + ".3.conv";
-            TRY(pack_tc_up(h, p + ".weight", p + ".wtc", h->cfg.dim << (1 - j)));
+            TRY(pack_tc_up(h, p + ".weight", p + ".wtc", h->cfg.dim << (1 - j), bf));
         }
         if (h->cfg.model == SBK_MODEL_DIFFVC && h->cfg.use_ref_t) {
             const int base = h->cfg.dim_cond / 4;
@@ -458,14 +464,17 @@ static size_t layout(const sbk_handle* h, int B, int T, int tb_rows, Arena& ar, 
     const size_t P[3] = {(size_t)H * T, (size_t)(H / 2) * (T / 2), (size_t)(H / 4) * (T / 4)};
     const int C[3] = {dim, dim * 2, dim * 4};
     auto f = [&](size_t n) { return (float*)ar.take(n * sizeof(float)); };
+    // operand-form tensors (conv inputs): fp32, or bf16 in the bf16 mode; A[] holds the raw conv outputs (always fp32)
+    const size_t osz = c.precision == SBK_PREC_BF16 ? 2 : 4;
+    auto fo = [&](size_t n) { return (float*)ar.take(n * osz); };
     Bufs b{};
     for (int l = 0; l < 3; ++l) {
         const size_t n = (size_t)B * P[l] * C[l];
-        b.A[l] = f(n); b.Bf[l] = f(n); b.X[l] = f(n); b.Y[l] = f(n);
-        b.S[l] = l > 0 ? f(n) : nullptr;
-        b.D[l] = l > 0 ? f((size_t)B * P[l] * C[l - 1]) : nullptr;
+        b.A[l] = f(n); b.Bf[l] = fo(n); b.X[l] = fo(n); b.Y[l] = fo(n);
+        b.S[l] = l > 0 ? fo(n) : nullptr;
+        b.D[l] = l > 0 ? fo((size_t)B * P[l] * C[l - 1]) : nullptr;
     }
-    b.U1 = f((size_t)B * P[1] * C[1]);
+    b.U1 = fo((size_t)B * P[1] * C[1]);
     const size_t mt0 = (P[0] + 127) / 128;
     b.kv_part = f((size_t)B * mt0 * kHeads * kKvPartFloats);
     b.ctx = f((size_t)B * kHeads * 1024);
@@ -536,8 +545,17 @@ static int build_plan(sbk_handle* h, int B, int T, int tb_rows) {
         p.in_lvl = lvl_in; p.out_lvl = lvl_out; p.mask = pl.mask; p.step = pl.step_cur;
         return p;
     };
+    const bool use_tc = c.precision != SBK_PREC_FP32;
+    const bool b16 = c.precision == SBK_PREC_BF16;          // operand tensors in bf16 [B][H][C/8][W][8]
+    const double osz = b16 ? 2.0 : 4.0;                     // bytes per operand-tensor element
+    const int fmt_raw = use_tc ? 1 : 0, fmt_opnd = b16 ? 2 : fmt_raw;
+    const int tc_cps3 = conv_tc_stage_channels(G_C3, b16 ? 1 : 0), tc_cps1 = conv_tc_stage_channels(G_PW, b16 ? 1 : 0);
     auto push = [&](Op& op, const float* dbg, int64_t numel) {
         op.dbg_ptr = dbg; op.dbg_numel = numel;
+        // raw Block-conv outputs (and the attention contexts) are fp32; every other named output is an operand tensor
+        const bool raw_out = op.kind == OP_FIRST || op.kind == OP_CTX || (op.kind == OP_CONVTC && op.tc.geom == G_C3) ||
+                             (op.kind == OP_IGEMM && op.ig.epi == EPI_PLAIN && op.ig.ostats);
+        op.dbg_fmt = raw_out ? fmt_raw : fmt_opnd;
         if (op.kind == OP_IGEMM) {
             const IgemmParams& p = op.ig;
             const double cin = p.c0 + p.c1, opx = (double)B * p.Hout * p.Wout, ipx = (double)B * p.Hin * p.Win;
@@ -557,8 +575,6 @@ static int build_plan(sbk_handle* h, int B, int T, int tb_rows) {
     };
     auto npix = [&](int lvl) { return (int64_t)B * Hs[lvl] * Ws[lvl]; };
 
-    const bool use_tc = c.precision != SBK_PREC_FP32;
-    const int tc_cps3 = conv_tc_stage_channels(G_C3, 0), tc_cps1 = conv_tc_stage_channels(G_PW, 0);
     // In the tensor-core modes every conv input is kept in HBM in "operand form" (already masked; Block activations
     // already GroupNorm-ed/Mish-ed/time-biased), so a conv's A path is a pure copy.  `store_masked` marks outputs
     // whose consumers all multiply by the mask anyway (everything except the tensors fed to LinearAttention, which
@@ -571,9 +587,10 @@ static int build_plan(sbk_handle* h, int B, int T, int tb_rows) {
         p.Ho = p.H; p.Wo = p.W;
         p.wpk = W(wkey); p.bias = bkey.empty() ? nullptr : W(bkey); p.out = out; p.Cout = cout;
         p.epi = EPI_PLAIN; p.ostats = st; p.mask = pl.mask; p.T = T; p.lvl = lvl; p.zero_page = h->d_zero;
+        p.bf16 = b16 ? 1 : 0;
         const double taps = geom == G_PW ? 1.0 : (geom == G_UP ? 4.0 : 9.0);
         op.flops = 2.0 * B * Hs[lvl] * Ws[lvl] * cout * (c0 + c1) * taps;
-        op.bytes = 4.0 * B * Hs[lvl] * Ws[lvl] * (c0 + c1 + cout);
+        op.bytes = (double)B * Hs[lvl] * Ws[lvl] * (osz * (c0 + c1) + (geom == G_C3 ? 4.0 : osz) * cout);
         return op;
     };
     // one Block conv (Conv3x3 + bias + GN statistics of the raw output) on the CUDA-core path
@@ -621,8 +638,8 @@ static int build_plan(sbk_handle* h, int B, int T, int tb_rows) {
                 GnActParams& p = op.ga; memset(&p, 0, sizeof(p));
                 p.raw = A; p.gn = g1; p.tb = pl.tb + h->tb_off[k]; p.tb_stride = pl.tb_stride; p.step = pl.step_cur;
                 p.mask = pl.mask; p.T = T; p.lvl = lvl; p.out = Bb; p.B = B; p.H = Hs[lvl]; p.W = Ws[lvl]; p.C = r.cout;
-                p.round_tf32 = 1; p.chw4 = 1;
-                op.bytes = 8.0 * npix(lvl) * r.cout;
+                p.round_tf32 = b16 ? 0 : 1; p.chw4 = 1; p.out_bf16 = b16 ? 1 : 0;
+                op.bytes = (4.0 + osz) * npix(lvl) * r.cout;
                 push(op, nullptr, 0);
             }
             Op op = tc_conv(r.prefix + ".block2.raw", G_C3, r.prefix + ".block2.wtc", r.prefix + ".block2.block.0.bias", lvl,
@@ -640,7 +657,7 @@ static int build_plan(sbk_handle* h, int B, int T, int tb_rows) {
             ResFinalParams& p = op.rf; memset(&p, 0, sizeof(p));
             p.h2raw = h2; p.gn = g2;
             p.mask = pl.mask; p.T = T; p.lvl = lvl; p.out = out; p.B = B; p.H = Hs[lvl]; p.W = Ws[lvl]; p.C = r.cout;
-            p.out_mask = store_masked ? 1 : 0; p.chw4 = use_tc ? 1 : 0;
+            p.out_mask = store_masked ? 1 : 0; p.chw4 = use_tc ? 1 : 0; p.bf16 = b16 ? 1 : 0;
             if (k == 0) {
                 p.x = nullptr; p.mu = pl.mu; p.xt = pl.xt; p.spk_s = pl.spk_s; p.cin = cin0;
                 p.wres = W(r.prefix + ".res.w"); p.bres = W(r.prefix + ".res_conv.bias");
@@ -649,13 +666,13 @@ static int build_plan(sbk_handle* h, int B, int T, int tb_rows) {
             } else {
                 p.x = in0;
             }
-            op.bytes = 12.0 * npix(lvl) * r.cout;
+            op.bytes = (4.0 + (k == 0 ? 0.0 : osz) + osz) * npix(lvl) * r.cout;
             push(op, out, npix(lvl) * r.cout);
         } else if (use_tc && (c0 + c1) % tc_cps1 == 0 && c0 % tc_cps1 == 0) {
             Op op = tc_conv(r.prefix + ".out", G_PW, r.prefix + ".res.wtc", r.prefix + ".res_conv.bias", lvl,
                             in0, c0, in1, c1, r.cout, out, nullptr);
             op.tc.epi = EPI_RES; op.tc.rraw = h2; op.tc.rgn = g2; op.tc.out_mask = store_masked ? 1 : 0;
-            op.bytes += 4.0 * npix(lvl) * r.cout;
+            op.bytes += 4.0 * npix(lvl) * r.cout;          // + the fp32 h2raw side input
             push(op, out, npix(lvl) * r.cout);
         } else {
             Op op; op.kind = OP_IGEMM; op.name = r.prefix + ".out";
@@ -677,7 +694,7 @@ static int build_plan(sbk_handle* h, int B, int T, int tb_rows) {
             // k/v projection + softmax partials on tensor cores (k_attn_kv): items of 128 pixels x 4 heads
             Op op = tc_conv(a.prefix + ".kvpart", G_PW, a.prefix + ".kv.wtc", "", lvl, x, a.c, nullptr, 0, 256, nullptr, nullptr);
             op.tc.epi = EPI_KV; op.tc.kv_part = bf.kv_part;
-            op.bytes = 4.0 * npix(lvl) * a.c;
+            op.bytes = osz * npix(lvl) * a.c;
             op.flops += 2.0 * npix(lvl) * 4096.0;
             mt = (Hs[lvl] * Ws[lvl] + attn_kv_tile_pixels() - 1) / attn_kv_tile_pixels();
             push(op, nullptr, 0);
@@ -700,15 +717,15 @@ static int build_plan(sbk_handle* h, int B, int T, int tb_rows) {
             p.ctx = bf.ctx; p.wq = W(a.prefix + ".fn.fn.to_qkv.weight"); p.wout = W(a.prefix + ".fn.fn.to_out.weight");
             p.bout = W(a.prefix + ".fn.fn.to_out.bias"); p.g = W(a.prefix + ".fn.g");
             p.w_eff = bf.w_eff; p.b_eff = bf.b_eff; p.B = B; p.C = a.c;
-            if (tc_apply) { p.tc_nt = conv_tc_ntile(G_PW, a.c); p.tc_cps = tc_cps1; }
+            if (tc_apply) { p.tc_nt = conv_tc_ntile(G_PW, a.c); p.tc_cps = tc_cps1; p.tc_bf16 = b16 ? 1 : 0; }
             push(op, nullptr, 0);
         }
         if (tc_apply) {
             // the per-sample (I + g P_b) matrix is written by k_attn_mix directly in the tcgen05 weight-stage layout
             Op op = tc_conv(a.prefix + ".out", G_PW, "", "", lvl, x, a.c, nullptr, 0, a.c, out, nullptr);
-            op.tc.wpk = bf.w_eff; op.tc.w_bstride_bytes = (long long)a.c * a.c * 4; op.tc.bias = bf.b_eff;
+            op.tc.wpk = bf.w_eff; op.tc.w_bstride_bytes = (long long)a.c * a.c * (b16 ? 2 : 4); op.tc.bias = bf.b_eff;
             op.tc.out_mask = 1; op.tc.addin = x;
-            op.bytes += 4.0 * npix(lvl) * a.c;
+            op.bytes += osz * npix(lvl) * a.c;
             push(op, out, npix(lvl) * a.c);
         } else {
             Op op; op.kind = OP_IGEMM; op.name = a.prefix + ".out";
@@ -724,7 +741,7 @@ static int build_plan(sbk_handle* h, int B, int T, int tb_rows) {
             Op op = tc_conv(pre + ".out", geom, pre + ".conv.wtc", pre + ".conv.bias", lvl_in, x, C, nullptr, 0, C, out, nullptr);
             op.tc.Ho = Hs[lvl_out]; op.tc.Wo = Ws[lvl_out]; op.tc.lvl = lvl_out; op.tc.out_mask = 1;
             op.flops = 2.0 * npix(lvl_out) * C * C * (geom == G_UP ? 4.0 : 9.0);
-            op.bytes = 4.0 * C * (npix(lvl_in) + npix(lvl_out));
+            op.bytes = osz * C * (npix(lvl_in) + npix(lvl_out));
             push(op, out, npix(lvl_out) * C);
             return;
         }
@@ -803,8 +820,9 @@ static int run_ops(sbk_handle* h, cudaStream_t s) {
             case OP_GNACT: n += launch_gn_act(op.ga, s); break;
         }
         if (h->capture && op.dbg_ptr && op.dbg_numel > 0) {
-            if (!op.dbg_copy) cudaMalloc(&op.dbg_copy, op.dbg_numel * sizeof(float));
-            cudaMemcpyAsync(op.dbg_copy, op.dbg_ptr, op.dbg_numel * sizeof(float), cudaMemcpyDeviceToDevice, s);
+            const size_t esz = op.dbg_fmt == 2 ? 2 : 4;
+            if (!op.dbg_copy) cudaMalloc(&op.dbg_copy, op.dbg_numel * esz);
+            cudaMemcpyAsync(op.dbg_copy, op.dbg_ptr, op.dbg_numel * esz, cudaMemcpyDeviceToDevice, s);
         }
     }
     return n;
@@ -1274,6 +1292,13 @@ extern "C" int sbk_debug_capture(sbk_handle* h, int on) {
     return SBK_OK;
 }
 extern "C" int sbk_debug_layout(const sbk_handle* h) { return (h && h->cfg.precision != SBK_PREC_FP32) ? 1 : 0; }
+// layout of one named intermediate: 0 [B][H][W][C] fp32, 1 [B][H][C/4][W][4] fp32, 2 [B][H][C/8][W][8] (bf16 in HBM;
+// sbk_debug_read widens it to fp32), -1 unknown name
+extern "C" int sbk_debug_op_layout(const sbk_handle* h, const char* name) {
+    if (!h || !name) return -1;
+    for (auto& op : h->plan.ops) if (op.name == name) return op.dbg_fmt;
+    return -1;
+}
 extern "C" int sbk_debug_num(const sbk_handle* h) { return h ? (int)h->plan.ops.size() : 0; }
 extern "C" const char* sbk_debug_name(const sbk_handle* h, int i) {
     if (!h || i < 0 || i >= (int)h->plan.ops.size()) return nullptr;
@@ -1286,7 +1311,15 @@ extern "C" int sbk_debug_read(sbk_handle* h, const char* name, float* dst, int64
         if (numel) *numel = op.dbg_numel;
         if (dst && op.dbg_ptr && op.dbg_numel > 0) {
             CU(cudaDeviceSynchronize());
-            CU(cudaMemcpy(dst, op.dbg_copy ? op.dbg_copy : op.dbg_ptr, op.dbg_numel * sizeof(float), cudaMemcpyDefault));
+            const void* src = op.dbg_copy ? (const void*)op.dbg_copy : (const void*)op.dbg_ptr;
+            if (op.dbg_fmt == 2) {
+                // bf16 operand tensor: widened to fp32 on the host (dst must be host memory), element order unchanged
+                std::vector<uint16_t> tmp(op.dbg_numel);
+                CU(cudaMemcpy(tmp.data(), src, op.dbg_numel * 2, cudaMemcpyDeviceToHost));
+                for (int64_t i = 0; i < op.dbg_numel; ++i) { const uint32_t u = (uint32_t)tmp[i] << 16; memcpy(&dst[i], &u, 4); }
+            } else {
+                CU(cudaMemcpy(dst, src, op.dbg_numel * sizeof(float), cudaMemcpyDefault));
+            }
         }
         return SBK_OK;
     }

@@ -176,6 +176,15 @@ __device__ __forceinline__ float mish_fast(float x) {
 
 
 
+__device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+// two floats -> packed bf16x2 (round to nearest even), `lo` in the low half = the lower channel index
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
@@ -216,9 +225,12 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT>::MINB) k_conv_tc(con
     constexpr int STAGES = D::STAGES, NSLOT = D::NSLOT, SLOT_COLS = D::SLOT_COLS;
     constexpr int LAG = STAGES >= 3 ? STAGES - 2 : 0;      // G_DOWN only: cp.async groups in flight behind the newest
     static_assert(STAGES >= 2, "need at least 2 stages");
-    static_assert(!BF16, "bf16 operand tensors are not wired up");
     constexpr int HR = G::HR, PXP = G::PXP, TAPS = G::TAPS, KCH = G::KCH;
-    constexpr int CPS = KCH * 4;                           // input channels per stage
+    constexpr int EPC = BF16 ? 8 : 4;                      // elements per 16-byte channel chunk
+    constexpr int CPS = KCH * EPC;                         // input channels per stage
+    // bf16 mode: the raw Block-conv outputs (GroupNorm inputs) stay fp32 [C/4]; every other output is an operand tensor
+    // of a later tensor-core kernel and is written as bf16 [B][H][C/8][W][8]
+    constexpr bool OUT16 = BF16 && GEOM != G_C3;
     constexpr int PLANE = HR * PXP * 16;                   // bytes between K chunks of the A tile
     constexpr int A_STAGE_BYTES = KCH * PLANE;
     constexpr int B_STAGE_BYTES = TAPS * KCH * NT * 16;
@@ -305,15 +317,15 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT>::MINB) k_conv_tc(con
                         const int s = g % STAGES;
                         mbar_wait(empty(s), ((g / STAGES) & 1) ^ 1);
                         const int ck = ks * KCH;
-                        const bool second = ck * 4 >= p.c0;
-                        const float* src = reinterpret_cast<const float*>(second ? p.in1 : p.in0);
-                        const int chs = (second ? p.c1 : p.c0) / 4;
-                        const int c0k = second ? ck - p.c0 / 4 : ck;
+                        const bool second = ck * EPC >= p.c0;
+                        const uint8_t* src = reinterpret_cast<const uint8_t*>(second ? p.in1 : p.in0);
+                        const int chs = (second ? p.c1 : p.c0) / EPC;
+                        const int c0k = second ? ck - p.c0 / EPC : ck;
 #pragma unroll
                         for (int j = 0; j < PER; ++j) {
                             if (sl_dst[j] == 0xFFFFFFFFu) continue;
                             const long long row = sl_off[j] / 1048576, wi = sl_off[j] % 1048576;
-                            const float* gp = src + ((row * chs + c0k + sl_chunk[j]) * p.W + wi) * 4;
+                            const uint8_t* gp = src + ((row * chs + c0k + sl_chunk[j]) * p.W + wi) * 16;
                             cp_async16(a0 + s * A_STAGE_BYTES + sl_dst[j], gp, sl_ok[j] ? 16u : 0u);
                         }
                     }
@@ -378,6 +390,9 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT>::MINB) k_conv_tc(con
         // element (b, ho, chunk, wo) of a [B][H][C/4][W][4] tensor; consecutive lanes = consecutive pixels = 16 B apart
         const long long obase = (((long long)(b * Ho + ho_p) * CHo + n0 / 4) * Wo + wo_p) * 4;
         const long long cstride = (long long)Wo * 4;           // floats between consecutive channel chunks
+        // bf16 outputs: index of the 16-byte chunk (b, ho, n0/8, wo) in a [B][H][C/8][W] grid of chunks; the chunks of one
+        // pixel are Wo apart, consecutive lanes (pixels) are adjacent: a warp store is again 512 contiguous bytes
+        const long long ochunk = OUT16 ? (((long long)(b * Ho + ho_p) * (p.Cout / 8) + n0 / 8) * Wo + wo_p) : 0;
         // ResnetBlock tail: the h2raw side input does not depend on the accumulators, so chunk block 0 is requested before
         // the tfull wait and block cb+32 as soon as block cb has been consumed: the global latency hides under the TMEM
         // load, the Mish math and the stores.  (The attention apply's residual read is a plain streaming add; prefetching
@@ -427,11 +442,21 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT>::MINB) k_conv_tc(con
                 }
             } else if (p.addin && valid) {
                 // fp32-exact residual (attention: x + g*P x): the tensor core only carries the small g*P x term
-                const float* ap = p.addin + obase + (cb / 4) * cstride;
+                if constexpr (OUT16) {
+                    const uint4* ap = reinterpret_cast<const uint4*>(p.addin) + ochunk + (long long)(cb / 8) * Wo;
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    const float4 av = __ldg(reinterpret_cast<const float4*>(ap + (i / 4) * cstride));
-                    v[i] += av.x; v[i + 1] += av.y; v[i + 2] += av.z; v[i + 3] += av.w;
+                    for (int j = 0; j < 4; ++j) {
+                        const uint4 a = __ldg(ap + (long long)j * Wo);
+                        v[8 * j + 0] += bf16_lo(a.x); v[8 * j + 1] += bf16_hi(a.x); v[8 * j + 2] += bf16_lo(a.y); v[8 * j + 3] += bf16_hi(a.y);
+                        v[8 * j + 4] += bf16_lo(a.z); v[8 * j + 5] += bf16_hi(a.z); v[8 * j + 6] += bf16_lo(a.w); v[8 * j + 7] += bf16_hi(a.w);
+                    }
+                } else {
+                    const float* ap = p.addin + obase + (cb / 4) * cstride;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        const float4 av = __ldg(reinterpret_cast<const float4*>(ap + (i / 4) * cstride));
+                        v[i] += av.x; v[i + 1] += av.y; v[i + 2] += av.z; v[i + 3] += av.w;
+                    }
                 }
             }
             if (p.out_mask) {
@@ -439,9 +464,17 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT>::MINB) k_conv_tc(con
                 for (int i = 0; i < 32; ++i) v[i] *= mo;
             }
             if (valid) {
-                float* op = p.out + obase + (cb / 4) * cstride;
+                if constexpr (OUT16) {
+                    uint4* op = reinterpret_cast<uint4*>(p.out) + ochunk + (long long)(cb / 8) * Wo;
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(op + (i / 4) * cstride) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                    for (int j = 0; j < 4; ++j)
+                        op[(long long)j * Wo] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                                           pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+                } else {
+                    float* op = p.out + obase + (cb / 4) * cstride;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(op + (i / 4) * cstride) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                }
             }
             if (!SIDE && p.ostats) {
                 // GroupNorm partials of this 32-column chunk: 8-channel sub-sums first (static register indexing),
@@ -608,10 +641,10 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT>::MINB) k_conv_tc(con
                         const uint32_t a_s = smem_u32(sA) + s * A_STAGE_BYTES;
                         const int k = lane / HR, r = lane - k * HR;
                         const int ck = ks * KCH + k;                     // 16-byte channel chunk index over the concat
-                        const bool second = ck * 4 >= p.c0;
-                        const float* src = reinterpret_cast<const float*>(second ? p.in1 : p.in0);
-                        const int chs = (second ? p.c1 : p.c0) / 4;
-                        const int cl = second ? ck - p.c0 / 4 : ck;
+                        const bool second = ck * EPC >= p.c0;
+                        const uint8_t* src = reinterpret_cast<const uint8_t*>(second ? p.in1 : p.in0);
+                        const int chs = (second ? p.c1 : p.c0) / EPC;
+                        const int cl = second ? ck - p.c0 / EPC : ck;
                         if (GEOM == G_PW) {
                             long long m = (long long)(h0 + r) * TPX;
                             const long long m_hi = m >= HW ? m : (m + TPX < HW ? m + TPX : HW);
@@ -621,7 +654,7 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT>::MINB) k_conv_tc(con
                                 while (m < m_hi) {                     // split the flattened run at image-row boundaries
                                     const int n = (int)((p.W - ww) < (m_hi - m) ? (p.W - ww) : (m_hi - m));
                                     bulk_g2s(a_s + k * PLANE + (r * PXP + q) * 16,
-                                             src + (((long long)(b * p.H + hh) * chs + cl) * p.W + ww) * 4, (uint32_t)n * 16u, full_b(s));
+                                             src + (((long long)(b * p.H + hh) * chs + cl) * p.W + ww) * 16, (uint32_t)n * 16u, full_b(s));
                                     m += n; q += n; ++hh; ww = 0;
                                 }
                             }
@@ -632,7 +665,7 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT>::MINB) k_conv_tc(con
                             const int hi = h0 - 1 + r;
                             const uint32_t row_s = a_s + k * PLANE + (r * PXP) * 16;
                             if (hi < 0 || hi >= p.H) bulk_g2s(row_s, zero, PXP * 16u, full_b(s));
-                            else bulk_g2s(row_s + qlo * 16, src + (((long long)(b * p.H + hi) * chs + cl) * p.W + wlo) * 4,
+                            else bulk_g2s(row_s + qlo * 16, src + (((long long)(b * p.H + hi) * chs + cl) * p.W + wlo) * 16,
                                           (uint32_t)(whi - wlo) * 16u, full_b(s));
                         }
                     }
@@ -704,8 +737,12 @@ constexpr size_t SMEM = (size_t)STAGES * STAGE + VT + RED + NBARS * 8 + 16;
 static_assert(PCOLS == 32 || PCOLS == 64, "one or two 32-column TMEM loads per thread");
 }
 
+// BF16: x is a bf16 operand tensor [B][H][C/8][W][8] and the projection runs as kind::f16 (a stage then carries 64
+// channels); P and V stay fp32 in TMEM / shared memory, so the context UMMA is tf32 in both modes.
+template <bool BF16>
 __global__ void __launch_bounds__(kvk::THREADS, 1) k_attn_kv(const ConvTcParams p) {
     using namespace kvk;
+    constexpr int EPC = BF16 ? 8 : 4;                              // channels per 16-byte chunk
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sS = smem;                                            // [STAGES][X | Wk | Wv]
     uint8_t* vt = sS + STAGES * STAGE;
@@ -716,7 +753,7 @@ __global__ void __launch_bounds__(kvk::THREADS, 1) k_attn_kv(const ConvTcParams 
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int HW = p.H * p.W;
-    const int ksteps = p.c0 / (KCH * 4);
+    const int ksteps = p.c0 / (KCH * EPC);
     const int mtiles = (HW + PX - 1) / PX;
     const int total = p.B * mtiles;
     const uint32_t bar0 = smem_u32(bars);
@@ -828,7 +865,7 @@ __global__ void __launch_bounds__(kvk::THREADS, 1) k_attn_kv(const ConvTcParams 
     } else if (warp == EPW) {
         // ---------------------------------------------------------------- projection UMMA issuer
         if (lane == 0) {
-            const uint32_t idesc = make_idesc<false>(128, PX);
+            const uint32_t idesc = make_idesc<BF16>(128, PX);
             const uint32_t s0 = smem_u32(sS);
             uint32_t it = 0;
             int tl = 0;
@@ -847,8 +884,8 @@ __global__ void __launch_bounds__(kvk::THREADS, 1) k_attn_kv(const ConvTcParams 
                         const uint64_t xd = make_desc(xs + kk * 2 * (PX * 16), PX * 16, 128);
                         const uint64_t kd = make_desc(wk + kk * 2 * (128 * 16), 128 * 16, 128);
                         const uint64_t vd = make_desc(wv + kk * 2 * (128 * 16), 128 * 16, 128);
-                        umma<false>(tslot, kd, xd, idesc, (ks | kk) != 0 ? 1u : 0u);
-                        umma<false>(tslot + 128, vd, xd, idesc, (ks | kk) != 0 ? 1u : 0u);
+                        umma<BF16>(tslot, kd, xd, idesc, (ks | kk) != 0 ? 1u : 0u);
+                        umma<BF16>(tslot + 128, vd, xd, idesc, (ks | kk) != 0 ? 1u : 0u);
                     }
                     umma_commit(empty(s));
                 }
@@ -879,8 +916,8 @@ __global__ void __launch_bounds__(kvk::THREADS, 1) k_attn_kv(const ConvTcParams 
         // lane 0 owns the ring protocol and the weight copy; lanes 0-7 each issue the activation runs of one channel chunk
         // (a single issuing thread was the bottleneck of this kernel: ~20 copies + address math per 48 KB stage).
         uint32_t it = 0;
-        const int chs = p.c0 / 4;
-        const float* src = reinterpret_cast<const float*>(p.in0);
+        const int chs = p.c0 / EPC;
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(p.in0);
         for (int t = blockIdx.x; t < total; t += gridDim.x) {
             const int b = t / mtiles, mt = t - b * mtiles;
             const int m0 = mt * PX, m_hi = m0 + PX < HW ? m0 + PX : HW;
@@ -899,7 +936,7 @@ __global__ void __launch_bounds__(kvk::THREADS, 1) k_attn_kv(const ConvTcParams 
                     int m = m0, hh = hh0, ww = ww0, qx = 0;
                     while (m < m_hi) {                             // split the flattened run at image-row boundaries
                         const int n = (p.W - ww) < (m_hi - m) ? (p.W - ww) : (m_hi - m);
-                        bulk_g2s(xs + (k * PX + qx) * 16, src + (((long long)(b * p.H + hh) * chs + cl) * p.W + ww) * 4,
+                        bulk_g2s(xs + (k * PX + qx) * 16, src + (((long long)(b * p.H + hh) * chs + cl) * p.W + ww) * 16,
                                  (uint32_t)n * 16u, full(s));
                         m += n; qx += n; ++hh; ww = 0;
                     }
@@ -915,11 +952,12 @@ __global__ void __launch_bounds__(kvk::THREADS, 1) k_attn_kv(const ConvTcParams 
     }
 }
 
+template <bool BF16>
 static int launch_attn_kv(const ConvTcParams& p, cudaStream_t s) {
     static bool attr_set = false;
     static int num_sms = 0;
     if (!attr_set) {
-        cudaFuncSetAttribute(k_attn_kv, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(k_attn_kv<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -927,7 +965,7 @@ static int launch_attn_kv(const ConvTcParams& p, cudaStream_t s) {
     }
     const long long total = (long long)p.B * ((p.H * p.W + kvk::PX - 1) / kvk::PX);
     const int grid = (int)(total < num_sms ? total : num_sms);
-    k_attn_kv<<<grid, kvk::THREADS, kvk::SMEM, s>>>(p);
+    k_attn_kv<BF16><<<grid, kvk::THREADS, kvk::SMEM, s>>>(p);
     return 1;
 }
 int attn_kv_tile_pixels() { return kvk::PX; }
@@ -943,18 +981,22 @@ int conv_tc_stage_channels(int geom, int bf16) {
     return (geom == G_PW ? Geo<G_PW>::KCH : Geo<G_C3>::KCH) * epc;
 }
 
-int launch_conv_tc(const ConvTcParams& p, cudaStream_t s) {
+template <bool BF16>
+static int dispatch_conv_tc(const ConvTcParams& p, cudaStream_t s) {
     const int nt = conv_tc_ntile(p.geom, p.Cout);
-    if (p.bf16) return -1;   // bf16 operand tensors are not wired up yet
     switch (p.geom) {
-        case G_C3:   return nt == 128 ? launch_tc<G_C3, false, 128>(p, s) : launch_tc<G_C3, false, 64>(p, s);
+        case G_C3:   return nt == 128 ? launch_tc<G_C3, BF16, 128>(p, s) : launch_tc<G_C3, BF16, 64>(p, s);
         case G_PW:
-            if (p.epi == EPI_KV) return launch_attn_kv(p, s);
-            if (p.epi == EPI_RES) return nt == 128 ? launch_tc<G_PW, false, 128, true>(p, s) : launch_tc<G_PW, false, 64, true>(p, s);
-            return nt == 128 ? launch_tc<G_PW, false, 128>(p, s) : launch_tc<G_PW, false, 64>(p, s);
-        case G_DOWN: return launch_tc<G_DOWN, false, 64>(p, s);
-        default:     return launch_tc<G_UP, false, 64>(p, s);
+            if (p.epi == EPI_KV) return launch_attn_kv<BF16>(p, s);
+            if (p.epi == EPI_RES) return nt == 128 ? launch_tc<G_PW, BF16, 128, true>(p, s) : launch_tc<G_PW, BF16, 64, true>(p, s);
+            return nt == 128 ? launch_tc<G_PW, BF16, 128>(p, s) : launch_tc<G_PW, BF16, 64>(p, s);
+        case G_DOWN: return launch_tc<G_DOWN, BF16, 64>(p, s);
+        default:     return launch_tc<G_UP, BF16, 64>(p, s);
     }
+}
+
+int launch_conv_tc(const ConvTcParams& p, cudaStream_t s) {
+    return p.bf16 ? dispatch_conv_tc<true>(p, s) : dispatch_conv_tc<false>(p, s);
 }
 
 }  // namespace sbk

@@ -51,18 +51,20 @@ struct IgemmParams {
 // kernel's A path is a pure copy.  geom = G_C3 (3x3, pad 1) or G_PW (1x1 over the flattened image).
 struct ConvTcParams {
     int geom;
-    const void* in0; const void* in1; int c0, c1;   // channel concat of two NHWC tensors (fp32, or bf16 when bf16=1)
+    const void* in0; const void* in1; int c0, c1;   // channel concat of two operand tensors: fp32 [B][H][C/4][W][4], or bf16
+                                                    // [B][H][C/8][W][8] when bf16=1 (16-byte channel chunks either way)
     int H, W, B;                                    // input grid
     int Ho, Wo;                                     // output grid (G_DOWN: ~H/2 x W/2, G_UP: 2H x 2W; else = H, W)
     const void* wpk; long long w_bstride_bytes;     // [ntile][kstage][tap][chunk][cout NT][16 B] (+ per-sample stride)
     const float* bias; long long bias_bstride;
-    float* out; int Cout;
+    float* out; int Cout;                           // bf16=1: G_C3 still writes fp32 raw [C/4] (GroupNorm input); the other
+                                                    // geometries write bf16 operand tensors [C/8] through this pointer
     int epi;                                        // EPI_PLAIN | EPI_RES | EPI_KV
     double* ostats;                                 // EPI_PLAIN: GroupNorm statistics of the raw output (nullable)
     const float* mask; int T; int lvl; int out_mask;   // out_mask: multiply the stored output by mask[b][wo << lvl]
     const float* rraw; GnRef rgn;                   // EPI_RES: out = acc + bias + Mish(GN(rraw))*mask
     float* kv_part;                                 // EPI_KV (1x1, NT=128): [B][ceil(HW/256)][4][kKvPartFloats]
-    const float* addin;                             // EPI_PLAIN: out += addin (same shape/layout as out): fp32-exact residual
+    const float* addin;                             // EPI_PLAIN: out += addin (same shape/layout/dtype as out): residual added in fp32
     const float* zero_page;                         // >= 4 KB of zeros in global memory (out-of-image parts of A tiles)
     int bf16;
 };
@@ -74,6 +76,7 @@ struct GnActParams {
     const float* mask; int T; int lvl;
     float* out; int B, H, W, C; int round_tf32;
     int chw4;
+    int out_bf16;               // write the activation as bf16 [B][H][C/8][W][8] (raw stays fp32 [B][H][C/4][W][4])
 };
 
 struct FirstConvParams {        // Block.conv of downs.0.0.block1 on the planar stack([mu, xt(, s)]) * mask
@@ -100,6 +103,7 @@ struct ResFinalParams {         // out = Mish(GN(h2raw))*mask + res(x*mask)
     int B, H, W, C;
     int out_mask;               // store out*mask (operand form for the next conv)
     int chw4;                   // activations are [B][H][C/4][W][4] (tensor-core modes) instead of NHWC
+    int bf16;                   // x and out are bf16 [B][H][C/8][W][8]; h2raw stays fp32 [B][H][C/4][W][4]
 };
 
 struct AttnCtxParams {          // merge per-tile softmax partials -> normalised context [B][4][32][32]
@@ -117,6 +121,7 @@ struct AttnMixParams {          // A_b = I + g * Wout * blockdiag(ctx^T) * Wq ; 
     int B, C;
     int tc_nt, tc_cps;          // != 0: write g*P only (the identity/residual is added in fp32 by the conv epilogue),
                                 // in the tcgen05 1x1 weight-stage layout, tf32-rounded
+    int tc_bf16;                // ... as bf16, 8 input channels per 16-byte chunk (tc_cps = 64)
 };
 
 struct FinalParams {            // final_block GN+Mish, final_conv 1x1 -> 1, mask, Euler(-Maruyama) update

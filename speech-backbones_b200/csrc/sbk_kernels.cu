@@ -804,6 +804,179 @@ __global__ void __launch_bounds__(256) k_gn_act(const GnActParams p) {
     }
 }
 
+// ----------------------------------------------------------------------------------------------
+// bf16 operand tensors (precision = bf16): [B][H][C/8][W][8], one 16-byte chunk = 8 channels of one pixel.
+// Raw conv outputs (the GroupNorm inputs) stay fp32 [B][H][C/4][W][4], so an 8-channel output chunk is fed by
+// two fp32 chunks.  Same walk as the planar fp32 kernels: a CTA owns one output chunk (its GN / time / residual
+// parameters live in registers), a thread owns frame(s) w and walks mel bins four at a time.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack_bf16x2_f(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+__device__ __forceinline__ float bf16_lo_f(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16_hi_f(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+__device__ __forceinline__ uint4 pack8_bf16(const float (&o)[8]) {
+    return make_uint4(pack_bf16x2_f(o[0], o[1]), pack_bf16x2_f(o[2], o[3]), pack_bf16x2_f(o[4], o[5]), pack_bf16x2_f(o[6], o[7]));
+}
+
+__global__ void __launch_bounds__(256) k_gn_act_bf16(const GnActParams p) {
+    extern __shared__ __align__(16) float sm[];
+    float* mean = sm; float* scale = mean + p.C; float* beta = scale + p.C; float* tbv = beta + p.C;
+    const int b = blockIdx.y, tid = threadIdx.x;
+    gn_fill(p.gn, b, p.C, 0, p.C, mean, scale, beta);
+    {
+        const int row = p.tb_per_sample ? b : *p.step;
+        const float* tb = p.tb + (long long)row * p.tb_stride;
+        for (int c = tid; c < p.C; c += 256) tbv[c] = tb[c];
+    }
+    __syncthreads();
+    constexpr int U = 4;
+    const int c4n = p.C >> 2, c8n = p.C >> 3;
+    const int ch = blockIdx.x % c8n, hg = blockIdx.x / c8n, nhg = gridDim.x / c8n;
+    const int tw = p.W >= 256 ? 256 : p.W, nsub = 256 / tw, sub = tid / tw, wl = tid - sub * tw;
+    if (sub >= nsub) return;
+    float pm[8], ps[8], pb[8], pt[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { pm[i] = mean[ch * 8 + i]; ps[i] = scale[ch * 8 + i]; pb[i] = beta[ch * 8 + i]; pt[i] = tbv[ch * 8 + i]; }
+    const float* rawb = p.raw + ((long long)b * p.H * c4n + 2 * ch) * p.W * 4;       // fp32 chunk 2*ch; chunk 2*ch+1 is W*4 floats further
+    uint4* outb = reinterpret_cast<uint4*>(p.out) + ((long long)b * p.H * c8n + ch) * p.W;
+    const int hs4 = c4n * p.W * 4;                                                   // floats between mel bins (raw)
+    const int hs8 = c8n * p.W;                                                       // 16-byte chunks between mel bins (out)
+    for (int w = wl; w < p.W; w += tw) {
+        const float mk = __ldg(p.mask + (long long)b * p.T + ((long long)w << p.lvl));
+        for (int h0 = (hg * nsub + sub) * U; h0 < p.H; h0 += nhg * nsub * U) {
+            float4 r0[U], r1[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const bool live = mk != 0.f && h0 + u < p.H;
+                const float* rp = rawb + (long long)(h0 + u) * hs4 + w * 4;
+                r0[u] = live ? ldg4(rp) : make_float4(0.f, 0.f, 0.f, 0.f);
+                r1[u] = live ? ldg4(rp + p.W * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (h0 + u >= p.H) continue;
+                uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                if (mk != 0.f) {
+                    const float rv[8] = {r0[u].x, r0[u].y, r0[u].z, r0[u].w, r1[u].x, r1[u].y, r1[u].z, r1[u].w};
+                    float y[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) y[i] = mish_fast_f((rv[i] - pm[i]) * ps[i] + pb[i]) + pt[i];
+                    o = pack8_bf16(y);
+                }
+                outb[(long long)(h0 + u) * hs8 + w] = o;
+            }
+        }
+    }
+}
+
+// ResnetBlock tail with bf16 operand tensors: out = Mish(GN(h2raw))*mask + x*mask (identity residual, x bf16) or
+// + W_res(in*mask) + b_res over the planar network inputs (first block).  Same contract as k_resfinal.
+__global__ void __launch_bounds__(256) k_resfinal_bf16(const ResFinalParams p) {
+    extern __shared__ __align__(16) float sm[];
+    float* mean = sm; float* scale = mean + p.C; float* beta = scale + p.C;
+    float* wres = beta + p.C;            // [cin][C] + [C] bias when planar
+    const int b = blockIdx.y, tid = threadIdx.x;
+    gn_fill(p.gn, b, p.C, 0, p.C, mean, scale, beta);
+    if (!p.x) {
+        const int nreal = p.r_extra ? p.cin - 1 : p.cin;
+        for (int i = tid; i < (p.cin + 1) * p.C; i += 256)
+            wres[i] = i < nreal * p.C ? p.wres[i] : (i >= p.cin * p.C ? p.bres[i - p.cin * p.C] : 0.f);
+    }
+    __syncthreads();
+    constexpr int U = 4;
+    const int c4n = p.C >> 2, c8n = p.C >> 3;
+    const int ch = blockIdx.x % c8n, hg = blockIdx.x / c8n, nhg = gridDim.x / c8n;
+    const int tw = p.W >= 256 ? 256 : p.W, nsub = 256 / tw, sub = tid / tw, wl = tid - sub * tw;
+    if (sub >= nsub) return;
+    float pm[8], ps[8], pb[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { pm[i] = mean[ch * 8 + i]; ps[i] = scale[ch * 8 + i]; pb[i] = beta[ch * 8 + i]; }
+    const float* hb = p.h2raw + ((long long)b * p.H * c4n + 2 * ch) * p.W * 4;
+    uint4* outb = reinterpret_cast<uint4*>(p.out) + ((long long)b * p.H * c8n + ch) * p.W;
+    const int hs4 = c4n * p.W * 4, hs8 = c8n * p.W;
+    if (p.x) {
+        const uint4* xb = reinterpret_cast<const uint4*>(p.x) + ((long long)b * p.H * c8n + ch) * p.W;
+        for (int w = wl; w < p.W; w += tw) {
+            const float mk = __ldg(p.mask + (long long)b * p.T + ((long long)w << p.lvl));
+            for (int h0 = (hg * nsub + sub) * U; h0 < p.H; h0 += nhg * nsub * U) {
+                float4 r0[U], r1[U]; uint4 xv[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const bool live = mk != 0.f && h0 + u < p.H;
+                    const float* rp = hb + (long long)(h0 + u) * hs4 + w * 4;
+                    r0[u] = live ? ldg4(rp) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    r1[u] = live ? ldg4(rp + p.W * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    xv[u] = live ? __ldg(xb + (long long)(h0 + u) * hs8 + w) : make_uint4(0u, 0u, 0u, 0u);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (h0 + u >= p.H) continue;
+                    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                    if (mk != 0.f) {
+                        const float rv[8] = {r0[u].x, r0[u].y, r0[u].z, r0[u].w, r1[u].x, r1[u].y, r1[u].z, r1[u].w};
+                        const float xx[8] = {bf16_lo_f(xv[u].x), bf16_hi_f(xv[u].x), bf16_lo_f(xv[u].y), bf16_hi_f(xv[u].y),
+                                             bf16_lo_f(xv[u].z), bf16_hi_f(xv[u].z), bf16_lo_f(xv[u].w), bf16_hi_f(xv[u].w)};
+                        float y[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) y[i] = mish_fast_f((rv[i] - pm[i]) * ps[i] + pb[i]) + xx[i];
+                        o = pack8_bf16(y);
+                    }
+                    outb[(long long)(h0 + u) * hs8 + w] = o;
+                }
+            }
+        }
+        return;
+    }
+    // first ResnetBlock: res_conv over the 2-3 planar network inputs (+ DiffVC's folded conditioning channel)
+    const int nreal = p.r_extra ? p.cin - 1 : p.cin;
+    const float* re = p.r_extra ? p.r_extra + ((long long)(p.extra_per_sample_row ? 0 : *p.step) * p.B + b) * p.C : nullptr;
+    float wb[8], w0[8], w1[8], w2[8], rx[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = ch * 8 + i;
+        wb[i] = wres[p.cin * p.C + c];
+        w0[i] = wres[c];
+        w1[i] = nreal > 1 ? wres[p.C + c] : 0.f;
+        w2[i] = nreal > 2 ? wres[2 * p.C + c] : 0.f;
+        rx[i] = re ? __ldg(re + c) : 0.f;
+    }
+    const bool has_spk = p.cin > 2 && !p.r_extra;
+    for (int w = wl; w < p.W; w += tw) {
+        const float mk = __ldg(p.mask + (long long)b * p.T + ((long long)w << p.lvl));
+        for (int h0 = (hg * nsub + sub) * U; h0 < p.H; h0 += nhg * nsub * U) {
+            float4 r0[U], r1[U]; float i0[U], i1[U], i2[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const bool live = mk != 0.f && h0 + u < p.H;
+                const long long idx = ((long long)b * p.H + h0 + u) * p.T + w;
+                const float* rp = hb + (long long)(h0 + u) * hs4 + w * 4;
+                r0[u] = live ? ldg4(rp) : make_float4(0.f, 0.f, 0.f, 0.f);
+                r1[u] = live ? ldg4(rp + p.W * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                i0[u] = live ? __ldg(p.mu + idx) * mk : 0.f;
+                i1[u] = live ? __ldg(p.xt + idx) * mk : 0.f;
+                i2[u] = (live && has_spk) ? __ldg(p.spk_s + b * p.H + h0 + u) * mk : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (h0 + u >= p.H) continue;
+                const float rv[8] = {r0[u].x, r0[u].y, r0[u].z, r0[u].w, r1[u].x, r1[u].y, r1[u].z, r1[u].w};
+                float y[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float o = fmaf(mk, rx[i], fmaf(i2[u], w2[i], fmaf(i1[u], w1[i], fmaf(i0[u], w0[i], wb[i]))));
+                    if (mk != 0.f) o += mish_fast_f((rv[i] - pm[i]) * ps[i] + pb[i]);
+                    if (p.out_mask) o *= mk;
+                    y[i] = o;
+                }
+                outb[(long long)(h0 + u) * hs8 + w] = pack8_bf16(y);
+            }
+        }
+    }
+}
+
 // planar elementwise kernels: grid.x = (channel chunks) x (mel-bin groups); a 256-thread CTA covers min(W,256) frames x
 // 256/min(W,256) bin sub-groups, each walking 4 bins per pass, ~2 passes per thread.
 static int planar_ew_grid(int H, int W, int C) {
@@ -813,7 +986,19 @@ static int planar_ew_grid(int H, int W, int C) {
     return (C / 4) * nhg;
 }
 
+// bf16 kernels: 8-channel chunks, one 4-bin pass per thread (twice the bytes per pass of the fp32 kernels)
+static int planar_ew_grid_bf16(int H, int W, int C) {
+    const int nsub = W >= 256 ? 1 : 256 / W;
+    int nhg = (H + 4 * nsub - 1) / (4 * nsub);
+    if (nhg < 1) nhg = 1;
+    return (C / 8) * nhg;
+}
+
 int launch_gn_act(const GnActParams& p, cudaStream_t s) {
+    if (p.out_bf16) {
+        k_gn_act_bf16<<<dim3(planar_ew_grid_bf16(p.H, p.W, p.C), p.B), 256, 4 * p.C * sizeof(float), s>>>(p);
+        return 1;
+    }
     const long long n4 = (long long)p.H * p.W * (p.C / 4);
     int gx = (int)((n4 + 256 * 4 * 8 - 1) / (256 * 4 * 8));   // ~8 passes of the 4-way unrolled loop per CTA (amortises the GN table set-up)
     if (gx < 1) gx = 1;
@@ -824,6 +1009,11 @@ int launch_gn_act(const GnActParams& p, cudaStream_t s) {
 }
 
 int launch_resfinal(const ResFinalParams& p, cudaStream_t s) {
+    if (p.bf16) {
+        const size_t smb = (3 * p.C + (p.x ? 0 : (p.cin + 1) * p.C)) * sizeof(float);
+        k_resfinal_bf16<<<dim3(planar_ew_grid_bf16(p.H, p.W, p.C), p.B), 256, smb, s>>>(p);
+        return 1;
+    }
     const long long n4 = (long long)p.H * p.W * (p.C / 4);
     int gx = p.x ? (int)((n4 + 256 * 4 * 8 - 1) / (256 * 4 * 8)) : (int)((n4 + 256 * 4 - 1) / (256 * 4));
     if (gx < 1) gx = 1;
@@ -933,15 +1123,21 @@ __global__ void __launch_bounds__(256) k_attn_mix(const AttnMixParams p) {
         }
         if (p.tc_nt) {
             // tcgen05 1x1 weight image: [ntile][kstage][chunk][cout % NT][4 cin], tf32 (RNA); g*P only (see AttnMixParams)
-            const int NT = p.tc_nt, kch = p.tc_cps / 4, ksteps = C / p.tc_cps;
-            const int ks = cp / p.tc_cps, kc = (cp % p.tc_cps) / 4, e = cp & 3;
+            // (bf16 mode: 8 cin per 16-byte chunk, stored as bf16)
+            const int epc = p.tc_bf16 ? 8 : 4;
+            const int NT = p.tc_nt, kch = p.tc_cps / epc, ksteps = C / p.tc_cps;
+            const int ks = cp / p.tc_cps, kc = (cp % p.tc_cps) / epc, e = cp % epc;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int co = cb + cl0 + i;
                 float v = g * acc[i];
-                uint32_t u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
-                const long long idx = ((((long long)(co / NT) * ksteps + ks) * kch + kc) * NT + (co % NT)) * 4 + e;
-                p.w_eff[(long long)b * C * C + idx] = __uint_as_float(u);
+                const long long idx = ((((long long)(co / NT) * ksteps + ks) * kch + kc) * NT + (co % NT)) * epc + e;
+                if (p.tc_bf16) {
+                    reinterpret_cast<unsigned short*>(p.w_eff)[(long long)b * C * C + idx] = (unsigned short)(pack_bf16x2_f(v, 0.f) & 0xFFFFu);
+                } else {
+                    uint32_t u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+                    p.w_eff[(long long)b * C * C + idx] = __uint_as_float(u);
+                }
             }
         } else {
             float* o = p.w_eff + ((long long)b * C + cp) * C + cb + cl0;

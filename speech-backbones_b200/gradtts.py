@@ -229,12 +229,19 @@ class Diffusion(BaseModule):
     @torch.no_grad()
     def reverse_diffusion(self, z, mask, mu, n_timesteps, stoc=False, spk=None):
         eng = self.engine()
+        # The sampler state (xt, mu, noise, Euler update) is fp32 in every precision mode; reduced-precision callers
+        # (config 3: bf16 tensors in / out) are widened here and the result is cast back to the caller's dtype.
+        io_dtype = z.dtype
+        if io_dtype != torch.float32:
+            z, mask, mu = z.float(), mask.float(), mu.float()
+            spk = None if spk is None else spk.float()
         noise = None
         if stoc:
             # the reference draws torch.randn(z.shape) once per step, in step order (:267)
             noise = torch.stack([torch.randn(z.shape, dtype=z.dtype, device=z.device) for _ in range(n_timesteps)])
         with torch.cuda.device(z.device):
-            return eng.reverse_diffusion(z, mask, mu, n_timesteps, stoc, spk, noise)
+            out = eng.reverse_diffusion(z, mask, mu, n_timesteps, stoc, spk, noise)
+        return out if io_dtype == torch.float32 else out.to(io_dtype)
 
     @torch.no_grad()
     def forward(self, z, mask, mu, n_timesteps, stoc=False, spk=None):

@@ -28,7 +28,8 @@ def rel_l2(a, b):
 
 
 def nhwc_to_nchw(flat, B, H, W, C, layout=0):
-    """layout 0: [B][H][W][C]; layout 1: [B][H][C/4][W][4] (tensor-core modes)."""
-    if layout == 1:
-        return flat.view(B, H, C // 4, W, 4).permute(0, 2, 4, 1, 3).reshape(B, C, H, W).contiguous()
+    """layout 0: [B][H][W][C]; layout 1: [B][H][C/4][W][4] (tensor-core modes); layout 2: [B][H][C/8][W][8] (bf16 operands)."""
+    if layout in (1, 2):
+        e = 4 if layout == 1 else 8
+        return flat.view(B, H, C // e, W, e).permute(0, 2, 4, 1, 3).reshape(B, C, H, W).contiguous()
     return flat.view(B, H, W, C).permute(0, 3, 1, 2).contiguous()
