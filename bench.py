@@ -41,6 +41,35 @@ def load_peaks():
     return dict(hbm_gbs=6650.0, bf16=1400.0, src="fallback")
 
 
+def measure_tf32_matmul_tflops(torch, dev, seconds=1.0):
+    """Sustained cuBLAS TF32 rate on this GPU (torch.matmul 8192^3, fp32 tensors, allow_tf32), back to back for
+    `seconds`: MEASURED_PEAKS.json only carries the bf16 rate, and tf32 is not exactly half of it in practice."""
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a = torch.randn(n, n, device=dev)
+        b = torch.randn(n, n, device=dev)
+        for _ in range(3):
+            a @ b
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        iters, t0 = 0, time.perf_counter()
+        e0.record()
+        while True:
+            for _ in range(10):
+                a @ b
+            iters += 10
+            torch.cuda.synchronize()
+            if time.perf_counter() - t0 > seconds:
+                break
+        e1.record()
+        torch.cuda.synchronize()
+        return 2.0 * n ** 3 * iters / (e0.elapsed_time(e1) * 1e-3) / 1e12
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -268,7 +297,10 @@ def run_ours(args, wl):
     conv = [(n, ms, fl, by) for n, ms, fl, by in prof if n.endswith(".raw")]
     conv_ms, conv_fl, conv_by = (sum(x[i] for x in conv) for i in (1, 2, 3))
     all_ms = sum(x[1] for x in prof)
-    tensor_peak = peaks["bf16"] * 0.5     # tf32 dense = half the measured bf16 rate
+    # bf16 operands: the measured cuBLAS bf16 rate of MEASURED_PEAKS.json.  tf32: that file has no tf32 figure, so the
+    # denominator is the larger of half the bf16 rate and a cuBLAS TF32 matmul timed here (sustained, ~1 s)
+    tf32_here = measure_tf32_matmul_tflops(torch, dev) if args.precision != "bf16" else None
+    tensor_peak = peaks["bf16"] if args.precision == "bf16" else max(peaks["bf16"] * 0.5, tf32_here)
     achieved = conv_fl / (conv_ms * 1e-3) / 1e12
     by_kind = {}
     for n, ms, fl, by in prof:
@@ -286,7 +318,9 @@ def run_ours(args, wl):
         "kernel": "conv3x3 implicit GEMM (25 launches/step)", "bound": "tensor", "achieved": achieved, "peak": tensor_peak,
         "unit": "TFLOP/s", "frac": achieved / tensor_peak, "traffic": traffic, "traffic_source": traffic_src,
         "algorithmic_bytes_per_launch": conv_by / max(1, len(conv)),
-        "peak_note": f"{peaks['src']} cuBLAS bf16 sustained x0.5 (tf32 / fp32-operand tensor rate)",
+        "peak_note": (f"{peaks['src']} cuBLAS bf16 sustained (MEASURED_PEAKS.json)" if args.precision == "bf16" else
+                      f"max(0.5 x {peaks['src']} cuBLAS bf16 sustained = {peaks['bf16'] * 0.5:.1f}, cuBLAS TF32 matmul 8192^3 "
+                      f"sustained measured in this run = {tf32_here:.1f})"),
         "launches": len(conv), "avg_launch_ms": conv_ms / max(1, len(conv)),
         "flop_per_launch_avg": conv_fl / max(1, len(conv)), "share_of_step": conv_ms / all_ms,
         "hbm": {"achieved_gbs": conv_by / (conv_ms * 1e-3) / 1e9, "peak_gbs": peaks["hbm_gbs"],
@@ -314,11 +348,29 @@ def run_ours(args, wl):
         fp32_leg = {"value": B * T / (f0.elapsed_time(f1) * 1e-3), "unit": "mel-frames/s", "dtype": "f32",
                     "note": "same engine, precision=fp32 (CUDA-core FFMA convs), 1 timed call",
                     "rel_l2_of_headline_output_vs_this": rel}
+    # the bf16-operand mode of the same engine (BASELINE config 3's arithmetic), one timed call, for context
+    bf16_leg = None
+    if world == 1 and args.precision == "tf32" and not args.no_fp32_leg:
+        dec16 = Diffusion(cfg.n_feats, cfg.dim, n_spks=cfg.n_spks, precision="bf16").eval()
+        dec16.load_state_dict(sd)
+        dec16 = dec16.to(dev)
+        dec16(zd, md, mud, N, False, spd)
+        torch.cuda.synchronize()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        y16 = dec16(zd, md, mud, N, False, spd)
+        f1.record()
+        torch.cuda.synchronize()
+        ref = y32 if fp32_leg is not None else dec(zd, md, mud, N, False, spd)
+        bf16_leg = {"value": B * T / (f0.elapsed_time(f1) * 1e-3), "unit": "mel-frames/s", "dtype": "bf16",
+                    "note": "same engine, precision=bf16 (bf16 operand tensors + weights, fp32 accumulate/GN/state), 1 timed call",
+                    "rel_l2_vs_fp32_mode": ((y16 - ref).double().norm() / ref.double().norm()).item()}
+        del dec16
     out = {
         "metric": "mel-frames/sec at N=50 reverse-diffusion steps", "value": value, "unit": "mel-frames/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": {"fp32": "f32", "tf32": "tf32"}[args.precision], "data": "synthetic",
+        "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[args.precision], "data": "synthetic",
         "config": {"workload": args.workload, "batch_per_gpu": B, "global_batch": B * world, "frames": T,
                    "n_timesteps": N, "stoc": False, "parallelism": f"dp{world}",
                    "l2": "per-step working set (2.9 GB of activations) exceeds the 126 MB L2; no flush needed",
@@ -332,6 +384,8 @@ def run_ours(args, wl):
     }
     if fp32_leg is not None:
         out["fp32_mode"] = fp32_leg
+    if bf16_leg is not None:
+        out["bf16_mode"] = bf16_leg
     if fps_cpu is not None:
         out["cpu_baseline"] = {"value": fps_cpu, "unit": "mel-frames/s", "cores": threads, "kind": "port",
                                "sample": sample}
@@ -347,9 +401,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="gradtts_b32_t512_n50", choices=sorted(WORKLOADS))
-    ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32"],
+    ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32", "bf16"],
                     help="tf32: tcgen05 tensor cores, fp32 accumulate/IO (PyTorch's default GPU conv arithmetic); "
-                         "fp32: CUDA-core FFMA path")
+                         "fp32: CUDA-core FFMA path; bf16: bf16 operand tensors (BASELINE config 3's arithmetic; not the "
+                         "headline, which is quoted on the fp32 config)")
     ap.add_argument("--no-fp32-leg", action="store_true", help="skip the extra exact-fp32 timing call")
     ap.add_argument("--batch", type=int, default=None, help="override B (debug only; not a valid bench line)")
     ap.add_argument("--frames", type=int, default=None, help="override T (debug only)")

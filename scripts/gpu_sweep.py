@@ -20,7 +20,7 @@ CASES = [  # (label, B, T, N, reps)
     ("single utterance, N=50", 1, 512, 50, 3),
     ("config2: B=32 T=512 N=10", 32, 512, 10, 3),
     ("config2: B=32 T=512 N=50", 32, 512, 50, 3),
-    ("config3 shape (tf32, not bf16): B=128 T=512 N=50 of 1000", 128, 512, 50, 2),
+    ("config3 shape: B=128 T=512 N=50 of 1000", 128, 512, 50, 2),
     ("long horizon: B=32 T=512 N=1000", 32, 512, 1000, 1),
     ("config5 per-GPU share: B=256 T=512 N=50", 256, 512, 50, 1),
 ]

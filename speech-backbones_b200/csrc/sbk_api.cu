@@ -385,8 +385,6 @@ extern "C" int sbk_pack(sbk_handle* h) {
         TRY(repack(h, r.prefix + ".block2.block.0.weight", r.prefix + ".block2.w", (size_t)r.cout * 9 * r.cout, conv_pack));
         if (r.cin != r.cout) TRY(repack(h, r.prefix + ".res_conv.weight", r.prefix + ".res.w", (size_t)r.cin * r.cout, conv_pack));
     }
-    if (h->cfg.precision == SBK_PREC_BF16 && h->cfg.model != SBK_MODEL_GRADTTS)
-        return fail(SBK_ERR_UNSUPPORTED, "sbk_pack: bf16 operand tensors are implemented for the Grad-TTS model only (use fp32 or tf32 for DiffVC)");
     if (h->cfg.precision != SBK_PREC_FP32) {
         const bool bf = h->cfg.precision == SBK_PREC_BF16;
         const int cps3 = conv_tc_stage_channels(G_C3, bf ? 1 : 0), cps1 = conv_tc_stage_channels(G_PW, bf ? 1 : 0);
@@ -412,7 +410,9 @@ extern "C" int sbk_pack(sbk_handle* h) {
             const int ci[5] = {base, base, 2 * base, 2 * base, 4 * base}, co[5] = {2 * base, 4 * base, 4 * base, 8 * base, 8 * base};
             for (int k = 0; k < 5; ++k) {
                 const std::string q = std::string("estimator.ref_block.") + nm[k];
-                TRY(pack_tc(h, q + ".0.weight", q + ".wtc", co[k], ci[k], G_C3, bf));
+                // the hoisted RefBlock branch (sbk_vc_conditioning) runs once per call outside the loop and always uses
+                // tf32 operands with fp32 activations, also when the U-Net itself runs on bf16 operand tensors
+                TRY(pack_tc(h, q + ".0.weight", q + ".wtc", co[k], ci[k], G_C3, false));
             }
             TRY(repack(h, "estimator.ref_block.block11.0.weight", "estimator.ref_block.block11.w", (size_t)9 * 2 * base, first_pack));
         }
@@ -566,7 +566,7 @@ static int build_plan(sbk_handle* h, int B, int T, int tb_rows) {
             op.flops = 2.0 * B * H0 * T * op.fc.C * op.fc.cin * 9;
             op.bytes = 4.0 * B * H0 * T * (op.fc.cin + op.fc.C);
         } else if (op.kind == OP_RESFINAL) {
-            op.bytes = 4.0 * B * op.rf.H * op.rf.W * op.rf.C * 3.0;
+            op.bytes = (4.0 + (op.rf.x ? osz : 0.0) + osz) * B * op.rf.H * op.rf.W * op.rf.C;
         } else if (op.kind == OP_FINAL) {
             op.flops = 2.0 * B * H0 * T * op.fn.C;
             op.bytes = 4.0 * B * H0 * T * (op.fn.C + 3.0);

@@ -213,7 +213,7 @@ template <int GEOM, int NT> struct Depth {
     static constexpr int TMEM_COLS = pow2_cols(NSLOT * SLOT_COLS);
     static constexpr int STAGES = TWO ? (FIT2 > 4 ? 4 : FIT2) : (FIT1 > 6 ? 6 : FIT1);
     static constexpr int MINB = TWO ? 2 : 1;
-    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + (2 * STAGES + 2 * NSLOT + 2) * 8 + 16 * 4 + 16 + 3 * NT * 4 + 64;
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + (3 * STAGES + 2 * NSLOT + 2) * 8 + 128 * 4 + 16 + 3 * NT * 4 + 64;
 };
 
 // RES: ResnetBlock-tail epilogue (1x1 res_conv + Mish(GN(h2raw)) side input), compile-time so that the plain 1x1 /
@@ -240,8 +240,13 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT>::MINB) k_conv_tc(con
     uint8_t* sA = smem;                                            // [STAGES][KCH][HR][PXP][16]
     uint8_t* sB = sA + STAGES * A_STAGE_BYTES;                     // [STAGES][TAPS][KCH][NT][16]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sB + STAGES * B_STAGE_BYTES);   // full[S], empty[S], tfull[NSLOT], tempty[NSLOT], fa[S]*, kv
-    float* s_st = reinterpret_cast<float*>(bars + 3 * STAGES + 2 * NSLOT + 2);   // [8 groups][2]
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_st + 16);
+    // GroupNorm partials of the current tile: one private slot row per epilogue warp (plain read-modify-write by lane 0,
+    // no atomics), summed in a fixed order at the end of the tile and flushed as fp64 -> the totals can only differ between
+    // runs through the order of the fp64 global atomics (1e-16), so the fp32 mean / rstd - and the sampler - are reproducible.
+    // (fp32 smem atomics made the result depend on warp arrival order; fp64 smem atomics fixed that but cost 0.035 ms per
+    // level-0 conv in CAS contention: profiles/r1_ops_tf32_v24_fp64_smem_atomics.txt.)
+    float* s_st = reinterpret_cast<float*>(bars + 3 * STAGES + 2 * NSLOT + 2);   // [8 warps][8 groups][2]
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_st + 128);
     float* s_rg = reinterpret_cast<float*>(s_tmem + 4);                          // EPI_RES: mean|scale|beta [NT] each
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -277,7 +282,7 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT>::MINB) k_conv_tc(con
         fence_barrier_init();
     }
     if (warp == NPROD / 32) tmem_alloc(smem_u32(s_tmem), D::TMEM_COLS);
-    if (tid < 16) s_st[tid] = 0.f;
+    if (tid < 128) s_st[tid] = 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -498,8 +503,8 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT>::MINB) k_conv_tc(con
                         for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
                         if (lane == 0) {
                             const int gl = (n0 + cb + k * (32 / ngrp)) / cpg - n0 / cpg;
-                            atomicAdd(&s_st[gl * 2], s);
-                            atomicAdd(&s_st[gl * 2 + 1], q);
+                            s_st[(warp * 8 + gl) * 2] += s;
+                            s_st[(warp * 8 + gl) * 2 + 1] += q;
                         }
                     }
                 }
@@ -515,8 +520,10 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT>::MINB) k_conv_tc(con
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 const int cpg = p.Cout / kGroups, gb = n0 / cpg, ng = (NT + cpg - 1) / cpg;
                 if (tid < ng * 2) {
-                    atomicAdd(&p.ostats[((long long)b * kGroups + gb + (tid >> 1)) * 2 + (tid & 1)], (double)s_st[tid]);
-                    s_st[tid] = 0.f;
+                    double tot = 0.0;
+#pragma unroll
+                    for (int w8 = 0; w8 < NPROD / 32; ++w8) { tot += (double)s_st[w8 * 16 + tid]; s_st[w8 * 16 + tid] = 0.f; }
+                    atomicAdd(&p.ostats[((long long)b * kGroups + gb + (tid >> 1)) * 2 + (tid & 1)], tot);
                 }
                 asm volatile("bar.sync 1, 256;" ::: "memory");
             }

@@ -344,19 +344,21 @@ __global__ void __launch_bounds__(IG_THREADS, 3) k_igemm(const IgemmParams p) {
     }
     if (p.epi == EPI_PLAIN && p.ostats) {
         // As is free after the main loop's trailing barrier: use it for the per-CTA group partials
-        float* s_st = As;   // [8 groups][2]
-        if (tid < 16) s_st[tid] = 0.f;
+        // (fp64 accumulation: the arrival order of the per-thread fp32 partials then only perturbs the sums at the 1e-16
+        //  level, so the fp32 mean / rstd derived from them - and with them the whole sampler - are reproducible run to run)
+        double* s_st = reinterpret_cast<double*>(As);   // [8 groups][2]
+        if (tid < 16) s_st[tid] = 0.0;
         __syncthreads();
         const int g0 = (n0 + tx * 4) / cpg, g1 = (n0 + 32 + tx * 4) / cpg, gb = n0 / cpg;
-        atomicAdd(&s_st[(g0 - gb) * 2 + 0], st_s[0]);
-        atomicAdd(&s_st[(g0 - gb) * 2 + 1], st_q[0]);
-        atomicAdd(&s_st[(g1 - gb) * 2 + 0], st_s[1]);
-        atomicAdd(&s_st[(g1 - gb) * 2 + 1], st_q[1]);
+        atomicAdd(&s_st[(g0 - gb) * 2 + 0], (double)st_s[0]);
+        atomicAdd(&s_st[(g0 - gb) * 2 + 1], (double)st_q[0]);
+        atomicAdd(&s_st[(g1 - gb) * 2 + 0], (double)st_s[1]);
+        atomicAdd(&s_st[(g1 - gb) * 2 + 1], (double)st_q[1]);
         __syncthreads();
         const int ng = (IG_TN + cpg - 1) / cpg;   // groups this N tile touches (cpg >= 8 -> <= 8)
         if (tid < ng * 2) {
             const int g = gb + (tid >> 1);
-            atomicAdd(&p.ostats[((long long)b * kGroups + g) * 2 + (tid & 1)], (double)s_st[tid]);
+            atomicAdd(&p.ostats[((long long)b * kGroups + g) * 2 + (tid & 1)], s_st[tid]);
         }
     }
 }
@@ -394,7 +396,7 @@ __global__ void __launch_bounds__(256) k_first_conv(const FirstConvParams p) {
     __shared__ __align__(16) float s_w[27 * 64];
     __shared__ float s_in[3][3][258];
     __shared__ float s_b[64];
-    __shared__ float s_st[16];
+    __shared__ double s_st[16];     // fp64: order-insensitive accumulation of the warp partials (reproducible GN statistics)
     const int tid = threadIdx.x, b = blockIdx.z, n0 = blockIdx.y * 64;
     const int wtiles = (p.T + 255) / 256;
     const int h = blockIdx.x / wtiles, w0 = (blockIdx.x - h * wtiles) * 256;
@@ -407,7 +409,7 @@ __global__ void __launch_bounds__(256) k_first_conv(const FirstConvParams p) {
         for (int i = tid; i < 9 * 64; i += 256) s_w[kreal * 64 + i] = we[(i >> 6) * p.C + n0 + (i & 63)];
     }
     if (tid < 64) s_b[tid] = p.bias[n0 + tid];
-    if (tid < 16) s_st[tid] = 0.f;
+    if (tid < 16) s_st[tid] = 0.0;
     for (int i = tid; i < p.cin * 3 * 258; i += 256) {
         const int ci = i / 774, rem = i - ci * 774, r = rem / 258, q = rem - r * 258;
         const int hi = h + r - 1, wi = w0 + q - 1;
@@ -463,8 +465,8 @@ __global__ void __launch_bounds__(256) k_first_conv(const FirstConvParams p) {
         for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
         if ((tid & 31) == 0) {
             const int g = (n0 + cg * 16 + hf * 8) / cpg - gb;
-            atomicAdd(&s_st[g * 2], s);
-            atomicAdd(&s_st[g * 2 + 1], q);
+            atomicAdd(&s_st[g * 2], (double)s);
+            atomicAdd(&s_st[g * 2 + 1], (double)q);
         }
     }
 #pragma unroll
@@ -485,7 +487,7 @@ __global__ void __launch_bounds__(256) k_first_conv(const FirstConvParams p) {
     }
     __syncthreads();
     const int ng = (64 + cpg - 1) / cpg;
-    if (p.ostats && tid < ng * 2) atomicAdd(&p.ostats[((long long)b * kGroups + gb + (tid >> 1)) * 2 + (tid & 1)], (double)s_st[tid]);
+    if (p.ostats && tid < ng * 2) atomicAdd(&p.ostats[((long long)b * kGroups + gb + (tid >> 1)) * 2 + (tid & 1)], s_st[tid]);
 }
 
 int launch_first_conv(const FirstConvParams& p, cudaStream_t s) {
@@ -821,6 +823,10 @@ __device__ __forceinline__ uint4 pack8_bf16(const float (&o)[8]) {
     return make_uint4(pack_bf16x2_f(o[0], o[1]), pack_bf16x2_f(o[2], o[3]), pack_bf16x2_f(o[4], o[5]), pack_bf16x2_f(o[6], o[7]));
 }
 
+// Thread mapping of the two kernels below: a LANE PAIR owns one frame - lane half h handles the fp32 chunk 2*ch+h
+// (4 channels: the same register footprint as the fp32 kernels, so the same 4 CTAs/SM) and writes its 8-byte half of
+// the 16-byte bf16 chunk: loads are two interleaved 256-byte runs per warp, stores one contiguous 256-byte run.
+// (First version: one thread per 8-channel chunk = 92-128 registers, 2 CTAs/SM, 2.8-3.7 TB/s; profiles/r1_ops_bf16_v2.txt.)
 __global__ void __launch_bounds__(256) k_gn_act_bf16(const GnActParams p) {
     extern __shared__ __align__(16) float sm[];
     float* mean = sm; float* scale = mean + p.C; float* beta = scale + p.C; float* tbv = beta + p.C;
@@ -835,38 +841,35 @@ __global__ void __launch_bounds__(256) k_gn_act_bf16(const GnActParams p) {
     constexpr int U = 4;
     const int c4n = p.C >> 2, c8n = p.C >> 3;
     const int ch = blockIdx.x % c8n, hg = blockIdx.x / c8n, nhg = gridDim.x / c8n;
-    const int tw = p.W >= 256 ? 256 : p.W, nsub = 256 / tw, sub = tid / tw, wl = tid - sub * tw;
+    const int half = tid & 1, q = tid >> 1;
+    const int tw = p.W >= 128 ? 128 : p.W, nsub = 128 / tw, sub = q / tw, wl = q - sub * tw;
     if (sub >= nsub) return;
-    float pm[8], ps[8], pb[8], pt[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { pm[i] = mean[ch * 8 + i]; ps[i] = scale[ch * 8 + i]; pb[i] = beta[ch * 8 + i]; pt[i] = tbv[ch * 8 + i]; }
-    const float* rawb = p.raw + ((long long)b * p.H * c4n + 2 * ch) * p.W * 4;       // fp32 chunk 2*ch; chunk 2*ch+1 is W*4 floats further
-    uint4* outb = reinterpret_cast<uint4*>(p.out) + ((long long)b * p.H * c8n + ch) * p.W;
+    const int c4 = 2 * ch + half;                                                    // this thread's fp32 chunk
+    const float4 pm = reinterpret_cast<const float4*>(mean)[c4], ps = reinterpret_cast<const float4*>(scale)[c4];
+    const float4 pb = reinterpret_cast<const float4*>(beta)[c4], pt = reinterpret_cast<const float4*>(tbv)[c4];
+    const float* rawb = p.raw + ((long long)b * p.H * c4n + c4) * p.W * 4;
+    uint2* outb = reinterpret_cast<uint2*>(p.out) + (((long long)b * p.H * c8n + ch) * p.W) * 2 + half;
     const int hs4 = c4n * p.W * 4;                                                   // floats between mel bins (raw)
-    const int hs8 = c8n * p.W;                                                       // 16-byte chunks between mel bins (out)
+    const int hs8 = c8n * p.W * 2;                                                   // 8-byte units between mel bins (out)
     for (int w = wl; w < p.W; w += tw) {
         const float mk = __ldg(p.mask + (long long)b * p.T + ((long long)w << p.lvl));
         for (int h0 = (hg * nsub + sub) * U; h0 < p.H; h0 += nhg * nsub * U) {
-            float4 r0[U], r1[U];
+            float4 r[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const bool live = mk != 0.f && h0 + u < p.H;
-                const float* rp = rawb + (long long)(h0 + u) * hs4 + w * 4;
-                r0[u] = live ? ldg4(rp) : make_float4(0.f, 0.f, 0.f, 0.f);
-                r1[u] = live ? ldg4(rp + p.W * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+            for (int u = 0; u < U; ++u)
+                r[u] = (mk != 0.f && h0 + u < p.H) ? ldg4(rawb + (long long)(h0 + u) * hs4 + w * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 if (h0 + u >= p.H) continue;
-                uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                uint2 o = make_uint2(0u, 0u);
                 if (mk != 0.f) {
-                    const float rv[8] = {r0[u].x, r0[u].y, r0[u].z, r0[u].w, r1[u].x, r1[u].y, r1[u].z, r1[u].w};
-                    float y[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) y[i] = mish_fast_f((rv[i] - pm[i]) * ps[i] + pb[i]) + pt[i];
-                    o = pack8_bf16(y);
+                    const float y0 = mish_fast_f((r[u].x - pm.x) * ps.x + pb.x) + pt.x;
+                    const float y1 = mish_fast_f((r[u].y - pm.y) * ps.y + pb.y) + pt.y;
+                    const float y2 = mish_fast_f((r[u].z - pm.z) * ps.z + pb.z) + pt.z;
+                    const float y3 = mish_fast_f((r[u].w - pm.w) * ps.w + pb.w) + pt.w;
+                    o = make_uint2(pack_bf16x2_f(y0, y1), pack_bf16x2_f(y2, y3));
                 }
-                outb[(long long)(h0 + u) * hs8 + w] = o;
+                outb[(long long)(h0 + u) * hs8 + w * 2] = o;
             }
         }
     }
@@ -874,13 +877,15 @@ __global__ void __launch_bounds__(256) k_gn_act_bf16(const GnActParams p) {
 
 // ResnetBlock tail with bf16 operand tensors: out = Mish(GN(h2raw))*mask + x*mask (identity residual, x bf16) or
 // + W_res(in*mask) + b_res over the planar network inputs (first block).  Same contract as k_resfinal.
-__global__ void __launch_bounds__(256) k_resfinal_bf16(const ResFinalParams p) {
+// (PLANAR is a template parameter so that the streaming identity variant does not pay the planar variant's registers.)
+template <bool PLANAR>
+__global__ void __launch_bounds__(256, PLANAR ? 2 : 4) k_resfinal_bf16(const ResFinalParams p) {
     extern __shared__ __align__(16) float sm[];
     float* mean = sm; float* scale = mean + p.C; float* beta = scale + p.C;
     float* wres = beta + p.C;            // [cin][C] + [C] bias when planar
     const int b = blockIdx.y, tid = threadIdx.x;
     gn_fill(p.gn, b, p.C, 0, p.C, mean, scale, beta);
-    if (!p.x) {
+    if constexpr (PLANAR) {
         const int nreal = p.r_extra ? p.cin - 1 : p.cin;
         for (int i = tid; i < (p.cin + 1) * p.C; i += 256)
             wres[i] = i < nreal * p.C ? p.wres[i] : (i >= p.cin * p.C ? p.bres[i - p.cin * p.C] : 0.f);
@@ -889,72 +894,62 @@ __global__ void __launch_bounds__(256) k_resfinal_bf16(const ResFinalParams p) {
     constexpr int U = 4;
     const int c4n = p.C >> 2, c8n = p.C >> 3;
     const int ch = blockIdx.x % c8n, hg = blockIdx.x / c8n, nhg = gridDim.x / c8n;
-    const int tw = p.W >= 256 ? 256 : p.W, nsub = 256 / tw, sub = tid / tw, wl = tid - sub * tw;
+    const int half = tid & 1, q = tid >> 1;
+    const int tw = p.W >= 128 ? 128 : p.W, nsub = 128 / tw, sub = q / tw, wl = q - sub * tw;
     if (sub >= nsub) return;
-    float pm[8], ps[8], pb[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { pm[i] = mean[ch * 8 + i]; ps[i] = scale[ch * 8 + i]; pb[i] = beta[ch * 8 + i]; }
-    const float* hb = p.h2raw + ((long long)b * p.H * c4n + 2 * ch) * p.W * 4;
-    uint4* outb = reinterpret_cast<uint4*>(p.out) + ((long long)b * p.H * c8n + ch) * p.W;
-    const int hs4 = c4n * p.W * 4, hs8 = c8n * p.W;
-    if (p.x) {
-        const uint4* xb = reinterpret_cast<const uint4*>(p.x) + ((long long)b * p.H * c8n + ch) * p.W;
+    const int c4 = 2 * ch + half;
+    const float4 pm = reinterpret_cast<const float4*>(mean)[c4], ps = reinterpret_cast<const float4*>(scale)[c4];
+    const float4 pb = reinterpret_cast<const float4*>(beta)[c4];
+    const float* hb = p.h2raw + ((long long)b * p.H * c4n + c4) * p.W * 4;
+    uint2* outb = reinterpret_cast<uint2*>(p.out) + (((long long)b * p.H * c8n + ch) * p.W) * 2 + half;
+    const int hs4 = c4n * p.W * 4, hs8 = c8n * p.W * 2;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if constexpr (!PLANAR) {
+        const uint2* xb = reinterpret_cast<const uint2*>(p.x) + (((long long)b * p.H * c8n + ch) * p.W) * 2 + half;
         for (int w = wl; w < p.W; w += tw) {
             const float mk = __ldg(p.mask + (long long)b * p.T + ((long long)w << p.lvl));
             for (int h0 = (hg * nsub + sub) * U; h0 < p.H; h0 += nhg * nsub * U) {
-                float4 r0[U], r1[U]; uint4 xv[U];
+                float4 r[U]; uint2 xv[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const bool live = mk != 0.f && h0 + u < p.H;
-                    const float* rp = hb + (long long)(h0 + u) * hs4 + w * 4;
-                    r0[u] = live ? ldg4(rp) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    r1[u] = live ? ldg4(rp + p.W * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    xv[u] = live ? __ldg(xb + (long long)(h0 + u) * hs8 + w) : make_uint4(0u, 0u, 0u, 0u);
+                    r[u] = live ? ldg4(hb + (long long)(h0 + u) * hs4 + w * 4) : z4;
+                    xv[u] = live ? __ldg(xb + (long long)(h0 + u) * hs8 + w * 2) : make_uint2(0u, 0u);
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     if (h0 + u >= p.H) continue;
-                    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                    uint2 o = make_uint2(0u, 0u);
                     if (mk != 0.f) {
-                        const float rv[8] = {r0[u].x, r0[u].y, r0[u].z, r0[u].w, r1[u].x, r1[u].y, r1[u].z, r1[u].w};
-                        const float xx[8] = {bf16_lo_f(xv[u].x), bf16_hi_f(xv[u].x), bf16_lo_f(xv[u].y), bf16_hi_f(xv[u].y),
-                                             bf16_lo_f(xv[u].z), bf16_hi_f(xv[u].z), bf16_lo_f(xv[u].w), bf16_hi_f(xv[u].w)};
-                        float y[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) y[i] = mish_fast_f((rv[i] - pm[i]) * ps[i] + pb[i]) + xx[i];
-                        o = pack8_bf16(y);
+                        const float y0 = mish_fast_f((r[u].x - pm.x) * ps.x + pb.x) + bf16_lo_f(xv[u].x);
+                        const float y1 = mish_fast_f((r[u].y - pm.y) * ps.y + pb.y) + bf16_hi_f(xv[u].x);
+                        const float y2 = mish_fast_f((r[u].z - pm.z) * ps.z + pb.z) + bf16_lo_f(xv[u].y);
+                        const float y3 = mish_fast_f((r[u].w - pm.w) * ps.w + pb.w) + bf16_hi_f(xv[u].y);
+                        o = make_uint2(pack_bf16x2_f(y0, y1), pack_bf16x2_f(y2, y3));
                     }
-                    outb[(long long)(h0 + u) * hs8 + w] = o;
+                    outb[(long long)(h0 + u) * hs8 + w * 2] = o;
                 }
             }
         }
-        return;
-    }
+    } else {
     // first ResnetBlock: res_conv over the 2-3 planar network inputs (+ DiffVC's folded conditioning channel)
     const int nreal = p.r_extra ? p.cin - 1 : p.cin;
     const float* re = p.r_extra ? p.r_extra + ((long long)(p.extra_per_sample_row ? 0 : *p.step) * p.B + b) * p.C : nullptr;
-    float wb[8], w0[8], w1[8], w2[8], rx[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int c = ch * 8 + i;
-        wb[i] = wres[p.cin * p.C + c];
-        w0[i] = wres[c];
-        w1[i] = nreal > 1 ? wres[p.C + c] : 0.f;
-        w2[i] = nreal > 2 ? wres[2 * p.C + c] : 0.f;
-        rx[i] = re ? __ldg(re + c) : 0.f;
-    }
+    const float4 wb = reinterpret_cast<const float4*>(wres + p.cin * p.C)[c4];
+    const float4 w0 = reinterpret_cast<const float4*>(wres)[c4];
+    const float4 w1 = nreal > 1 ? reinterpret_cast<const float4*>(wres + p.C)[c4] : z4;
+    const float4 w2 = nreal > 2 ? reinterpret_cast<const float4*>(wres + 2 * p.C)[c4] : z4;
+    const float4 rx = re ? ldg4(re + c4 * 4) : z4;
     const bool has_spk = p.cin > 2 && !p.r_extra;
     for (int w = wl; w < p.W; w += tw) {
         const float mk = __ldg(p.mask + (long long)b * p.T + ((long long)w << p.lvl));
         for (int h0 = (hg * nsub + sub) * U; h0 < p.H; h0 += nhg * nsub * U) {
-            float4 r0[U], r1[U]; float i0[U], i1[U], i2[U];
+            float4 r[U]; float i0[U], i1[U], i2[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const bool live = mk != 0.f && h0 + u < p.H;
                 const long long idx = ((long long)b * p.H + h0 + u) * p.T + w;
-                const float* rp = hb + (long long)(h0 + u) * hs4 + w * 4;
-                r0[u] = live ? ldg4(rp) : make_float4(0.f, 0.f, 0.f, 0.f);
-                r1[u] = live ? ldg4(rp + p.W * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                r[u] = live ? ldg4(hb + (long long)(h0 + u) * hs4 + w * 4) : z4;
                 i0[u] = live ? __ldg(p.mu + idx) * mk : 0.f;
                 i1[u] = live ? __ldg(p.xt + idx) * mk : 0.f;
                 i2[u] = (live && has_spk) ? __ldg(p.spk_s + b * p.H + h0 + u) * mk : 0.f;
@@ -962,18 +957,22 @@ __global__ void __launch_bounds__(256) k_resfinal_bf16(const ResFinalParams p) {
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 if (h0 + u >= p.H) continue;
-                const float rv[8] = {r0[u].x, r0[u].y, r0[u].z, r0[u].w, r1[u].x, r1[u].y, r1[u].z, r1[u].w};
-                float y[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    float o = fmaf(mk, rx[i], fmaf(i2[u], w2[i], fmaf(i1[u], w1[i], fmaf(i0[u], w0[i], wb[i]))));
-                    if (mk != 0.f) o += mish_fast_f((rv[i] - pm[i]) * ps[i] + pb[i]);
-                    if (p.out_mask) o *= mk;
-                    y[i] = o;
+                float4 o;
+                o.x = fmaf(mk, rx.x, fmaf(i2[u], w2.x, fmaf(i1[u], w1.x, fmaf(i0[u], w0.x, wb.x))));
+                o.y = fmaf(mk, rx.y, fmaf(i2[u], w2.y, fmaf(i1[u], w1.y, fmaf(i0[u], w0.y, wb.y))));
+                o.z = fmaf(mk, rx.z, fmaf(i2[u], w2.z, fmaf(i1[u], w1.z, fmaf(i0[u], w0.z, wb.z))));
+                o.w = fmaf(mk, rx.w, fmaf(i2[u], w2.w, fmaf(i1[u], w1.w, fmaf(i0[u], w0.w, wb.w))));
+                if (mk != 0.f) {
+                    o.x += mish_fast_f((r[u].x - pm.x) * ps.x + pb.x);
+                    o.y += mish_fast_f((r[u].y - pm.y) * ps.y + pb.y);
+                    o.z += mish_fast_f((r[u].z - pm.z) * ps.z + pb.z);
+                    o.w += mish_fast_f((r[u].w - pm.w) * ps.w + pb.w);
                 }
-                outb[(long long)(h0 + u) * hs8 + w] = pack8_bf16(y);
+                if (p.out_mask) { o.x *= mk; o.y *= mk; o.z *= mk; o.w *= mk; }
+                outb[(long long)(h0 + u) * hs8 + w * 2] = make_uint2(pack_bf16x2_f(o.x, o.y), pack_bf16x2_f(o.z, o.w));
             }
         }
+    }
     }
 }
 
@@ -986,10 +985,10 @@ static int planar_ew_grid(int H, int W, int C) {
     return (C / 4) * nhg;
 }
 
-// bf16 kernels: 8-channel chunks, one 4-bin pass per thread (twice the bytes per pass of the fp32 kernels)
+// bf16 kernels: 8-channel chunks, a lane pair per frame (128 frames per CTA pass), ~2 four-bin passes per thread
 static int planar_ew_grid_bf16(int H, int W, int C) {
-    const int nsub = W >= 256 ? 1 : 256 / W;
-    int nhg = (H + 4 * nsub - 1) / (4 * nsub);
+    const int nsub = W >= 128 ? 1 : 128 / W;
+    int nhg = (H + 8 * nsub - 1) / (8 * nsub);
     if (nhg < 1) nhg = 1;
     return (C / 8) * nhg;
 }
@@ -1011,7 +1010,8 @@ int launch_gn_act(const GnActParams& p, cudaStream_t s) {
 int launch_resfinal(const ResFinalParams& p, cudaStream_t s) {
     if (p.bf16) {
         const size_t smb = (3 * p.C + (p.x ? 0 : (p.cin + 1) * p.C)) * sizeof(float);
-        k_resfinal_bf16<<<dim3(planar_ew_grid_bf16(p.H, p.W, p.C), p.B), 256, smb, s>>>(p);
+        if (p.x) k_resfinal_bf16<false><<<dim3(planar_ew_grid_bf16(p.H, p.W, p.C), p.B), 256, smb, s>>>(p);
+        else k_resfinal_bf16<true><<<dim3(planar_ew_grid_bf16(p.H, p.W, p.C), p.B), 256, smb, s>>>(p);
         return 1;
     }
     const long long n4 = (long long)p.H * p.W * (p.C / 4);
@@ -1082,8 +1082,13 @@ int launch_attn_ctx(const AttnCtxParams& p, cudaStream_t s) {
 // 1x1 conv:  x + g*(Wout blockdiag(ctx_h^T) Wq x + bout) = (I + g P_b) x + g bout.
 // This kernel builds (I + g P_b) in the implicit-GEMM weight layout [ci][co].
 __global__ void __launch_bounds__(256) k_attn_mix(const AttnMixParams p) {
-    __shared__ float s_ctx[kHeads * 32 * 33];
-    __shared__ __align__(16) float s_mb[128 * 32];     // Mb transposed: [j = h*32+d][cl]
+    // 48 KB static: Mb transposed [j = h*32+d][cl] (16 KB) + a 32 KB union: the contexts in phase 1, a 128 x 64 tile of Wq
+    // in phase 2 (Wq used to be read from global inside the j loop: 128 dependent L2 round trips per 64 input channels made
+    // this tiny kernel 80 us at C = 256)
+    __shared__ __align__(16) float s_mb[128 * 32];
+    __shared__ __align__(16) float s_u[128 * 64];
+    float* s_ctx = s_u;                                 // [kHeads*32][33]
+    float* s_wq = s_u;                                  // [128][64]
     const int cb = blockIdx.x * 32, b = blockIdx.y, tid = threadIdx.x, C = p.C;
     for (int i = tid; i < kHeads * 32 * 32; i += 256)
         s_ctx[(i >> 5) * 33 + (i & 31)] = p.ctx[(long long)b * kHeads * 1024 + i];
@@ -1105,17 +1110,24 @@ __global__ void __launch_bounds__(256) k_attn_mix(const AttnMixParams p) {
             s_mb[j * 32 + cl] = (a0 + a1) + (a2 + a3);
         }
     }
-    __syncthreads();
     const float g = __ldg(p.g);
     // P[cl][c'] = sum_j Mb[cl][j] * Wq[j][c']: thread = (input channel c' within a block of 64, group of 8 output rows)
-    const int cq = tid >> 6, cl0 = cq * 8;
-    for (int cp = tid & 63; cp < C; cp += 64) {
+    const int cq = tid >> 6, cl0 = cq * 8, cpl = tid & 63;
+    for (int cp0 = 0; cp0 < C; cp0 += 64) {
+        __syncthreads();                                // phase 1 readers of s_ctx / previous block's readers of s_wq are done
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {                   // 128 rows x 16 float4, coalesced 256-byte rows
+            const int idx = tid + i * 256, row = idx >> 4, c4 = idx & 15;
+            *reinterpret_cast<float4*>(&s_wq[row * 64 + c4 * 4]) = ldg4(p.wq + (long long)row * C + cp0 + c4 * 4);
+        }
+        __syncthreads();
+        const int cp = cp0 + cpl;
         float acc[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-#pragma unroll 4
+#pragma unroll 8
         for (int j = 0; j < kAttnHidden; ++j) {
-            const float wq = __ldg(p.wq + (long long)j * C + cp);
+            const float wq = s_wq[j * 64 + cpl];
             const float4 m0 = *reinterpret_cast<const float4*>(&s_mb[j * 32 + cl0]);
             const float4 m1 = *reinterpret_cast<const float4*>(&s_mb[j * 32 + cl0 + 4]);
             acc[0] = fmaf(m0.x, wq, acc[0]); acc[1] = fmaf(m0.y, wq, acc[1]); acc[2] = fmaf(m0.z, wq, acc[2]); acc[3] = fmaf(m0.w, wq, acc[3]);

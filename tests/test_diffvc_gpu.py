@@ -13,7 +13,8 @@ from speech_backbones_b200.spec import DiffVCConfig, diffvc_param_spec, syntheti
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-TOL = {"fp32": (1e-4, 2e-3), "tf32": (4e-3, 1e-2)}        # (estimator call, trajectory)
+# bf16: the U-Net runs on bf16 operand tensors (the hoisted conditioning branch stays tf32)
+TOL = {"fp32": (1e-4, 2e-3), "tf32": (4e-3, 1e-2), "bf16": (3e-2, 4e-2)}        # (estimator call, trajectory)
 
 
 @pytest.fixture(scope="module")
@@ -43,7 +44,7 @@ def _inputs(g, c):
     return synthetic_diffvc_inputs(c["B"], c["T"], c["Tr"], seed=g["seed"], ragged=c["ragged"])
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
 def test_vc_estimator_vs_reference_golden(vc_engines, vc_golden, precision):
     eng, cfg, sd = vc_engines(precision)
     for c in [c for c in vc_golden["cases"] if c["kind"] == "est"]:
@@ -59,7 +60,7 @@ def test_vc_estimator_vs_reference_golden(vc_engines, vc_golden, precision):
         assert (y * (1 - mask)).abs().max().item() == 0.0
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
 def test_vc_samplers_vs_reference_golden(vc_engines, vc_golden, precision):
     eng, cfg, sd = vc_engines(precision)
     for c in [c for c in vc_golden["cases"] if c["kind"] == "traj"]:

@@ -205,12 +205,13 @@ def test_config2_shape_properties(engines):
 # Tolerances follow the operand rounding (measured by emulation on the reference):
 # tf32 (10-bit mantissa) ~1e-3 per estimator call, bf16 (8-bit) ~9e-3; GN/softmax/Mish/Euler stay fp32.
 # bf16 mode: conv inputs AND the residual stream are stored as bf16 (8-bit mantissa, 2^-9 relative rounding per store),
-# accumulation / GN statistics / raw conv outputs / sampler state fp32.
-TC_TOL = {"tf32": (4e-3, 8e-3), "bf16": (3e-2, 3e-2)}       # (per estimator call / stage, trajectory)
+# accumulation / GN statistics / raw conv outputs / sampler state fp32.  Measured on B200: 1.07-1.27e-2 per estimator call,
+# <= 1.2e-2 per stage, 3.1-5.5e-3 on trajectories, 3.7e-2 on the |xt| x100 stress case (SURVEY 8c predicted 9e-3 / 3-5e-3).
+TC_TOL = {"tf32": (4e-3, 8e-3), "bf16": (2e-2, 1e-2)}       # (per estimator call / stage, trajectory)
 # The |xt| x100 stress case drives the attention logits k to O(100): softmax turns the tf32 operand rounding of the
 # k projection (|k| * 2^-11 absolute) into a relative error of the same size in p = exp(k - max), so this one case
 # gets a wider bound (measured 4.7e-3; the reference's own TF32 GPU path has the same sensitivity).
-TC_TOL_STRESS = {"tf32": 1e-2, "bf16": 8e-2}
+TC_TOL_STRESS = {"tf32": 1e-2, "bf16": 6e-2}
 
 
 @pytest.mark.parametrize("precision", ["tf32", "bf16"])
@@ -274,8 +275,8 @@ def test_bf16_multispeaker_module_and_bf16_io(golden):
 
 
 def test_bf16_tracks_tf32_at_config_shapes(engines):
-    """bf16 vs tf32 engines on the same inputs at a config-2-like width (T=512): the two tensor-core modes must agree to
-    bf16 rounding, padded frames must be exactly zero, and batch entries must not interact."""
+    """bf16 vs tf32 engines on the same inputs at config 2's width (T=512): the two tensor-core modes must agree to bf16
+    rounding and padded frames must be exactly zero."""
     z, mask, mu, _, _ = synthetic_inputs(3, 512, ragged=True)
     t = torch.tensor([0.9, 0.5, 0.1])
     e16, e32 = engines(1, True, 1234, "bf16"), engines(1, True, 1234, "tf32")
@@ -283,18 +284,27 @@ def test_bf16_tracks_tf32_at_config_shapes(engines):
     y32 = e32.estimator((z * mask).cuda(), mask.cuda(), mu.cuda(), t.cuda()).cpu()
     assert rel_l2(y16, y32) <= TC_TOL["bf16"][0]
     assert (y16 * (1 - mask)).abs().max().item() == 0.0
-    y1 = e16.estimator((z * mask)[1:2].cuda(), mask[1:2].cuda(), mu[1:2].cuda(), t[1:2].cuda()).cpu()
-    assert rel_l2(y1, y16[1:2]) < 1e-5
 
 
-def test_bf16_is_refused_loudly_for_diffvc(sbk_lib):
-    from speech_backbones_b200.binding import Engine
-    from speech_backbones_b200.spec import DiffVCConfig, diffvc_param_spec
-    cfg = DiffVCConfig()
-    e = Engine(80, cfg.dim_unet, model="diffvc", dim_cond=cfg.dim_spk, precision="bf16")
-    with pytest.raises(RuntimeError, match="bf16"):
-        e.load_state_dict(synthetic_state_dict(cfg, 1234, spec=diffvc_param_spec(cfg)))
-    e.close()
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
+def test_reproducible_and_batch_independent(engines, precision):
+    """Same call twice -> same result; an utterance alone -> the same rows as inside a batch.  GroupNorm statistics are
+    accumulated in fp64 (smem + global atomics), so the summation order cannot move the fp32 mean / rstd: before that
+    change the 1e-8 order noise was amplified by operand-rounding flips through this random-weight U-Net to 6e-4 (tf32)
+    and 7e-3 (bf16) per call (profiles/r1_batch_dep_before.log)."""
+    z, mask, mu, _, _ = synthetic_inputs(3, 512, ragged=True)
+    t = torch.tensor([0.9, 0.5, 0.1])
+    eng = engines(1, True, 1234, precision)
+    xt = (z * mask).cuda()
+    a = eng.estimator(xt, mask.cuda(), mu.cuda(), t.cuda()).cpu()
+    b = eng.estimator(xt, mask.cuda(), mu.cuda(), t.cuda()).cpu()
+    one = eng.estimator(xt[1:2], mask[1:2].cuda(), mu[1:2].cuda(), t[1:2].cuda()).cpu()
+    print(precision, "run-to-run", rel_l2(b, a), "alone vs in batch", rel_l2(one, a[1:2]))
+    assert rel_l2(b, a) < 1e-6
+    assert rel_l2(one, a[1:2]) < 1e-6
+    n1 = eng.reverse_diffusion(z.cuda(), mask.cuda(), mu.cuda(), 10).cpu()
+    n2 = eng.reverse_diffusion(z.cuda(), mask.cuda(), mu.cuda(), 10).cpu()
+    assert rel_l2(n2, n1) < 1e-6
 
 
 def test_oversize_batch_is_sliced(engines):
