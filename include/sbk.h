@@ -119,6 +119,23 @@ int sbk_reverse_steps(sbk_handle* h, float* xt, const float* mask, const float* 
 int sbk_reverse_diffusion_host(sbk_handle* h, const float* z, const float* mask, const float* mu, const float* spk,
                                const float* noise, float* out, int B, int T, int n_timesteps, int stoc);
 
+/* ---- the step before the path: GradTTS.forward, Grad-TTS/model/tts.py:82-94 -----------------
+ * From the encoder outputs build, in ONE pass and without materialising [B,Tx,Ty] intermediates,
+ *   attn  = generate_path(w_ceil, x_mask (x) y_mask)            (model/utils.py:26-39, tts.py:83-85)
+ *   mu_y  = (attn^T @ mu_x^T)^T  - a 0/1 matrix product, i.e. an exact gather of encoder frames   (tts.py:88-89)
+ *   z     = mu_y + noise / temperature                          (tts.py:94; IEEE division as on the reference's CPU path)
+ *   y_mask = sequence_mask(y_lengths, Ty)                       (tts.py:83)
+ * mu_x: [B,F,Tx]; w_ceil: [B,Tx] = ceil(exp(logw) * x_mask) * length_scale (tts.py:77-78, computed by the caller with the
+ * reference's own ops so that the token durations are the reference's bit for bit); x_mask: [B,Tx] in {0,1};
+ * y_lengths: [B] int64 = clamp_min(sum(w_ceil), 1) (tts.py:79); Ty = fix_len_compatibility(max(y_lengths)) (tts.py:80-81).
+ * noise_tf: [B][Ty][F] standard normal draws - the MEMORY order in which the reference's randn_like(mu_y) fills its
+ * transposed mu_y - or NULL (then z = mu_y).  Outputs: mu_y, z: [B,F,Ty] contiguous (the layout sbk_reverse_diffusion
+ * takes); y_mask: [B,Ty]; attn: NULL or [B,Tx,Ty].  Cumulative durations are accumulated sequentially in double and rounded
+ * to fp32 per prefix, exactly as torch.cumsum does on the reference's CPU path.  No handle: the op has no weights.  Device pointers; asynchronous on `stream`. */
+int sbk_prior_expand(const float* mu_x, const float* w_ceil, const float* x_mask, const int64_t* y_lengths,
+                     const float* noise_tf, float temperature, int B, int F, int Tx, int Ty,
+                     float* mu_y, float* z, float* y_mask, float* attn, void* stream);
+
 /* number of kernel launches the last sbk_estimator / sbk_reverse_* call enqueued (graph nodes count) */
 int64_t sbk_last_launch_count(const sbk_handle* h);
 

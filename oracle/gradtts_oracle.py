@@ -158,3 +158,52 @@ def reverse_diffusion(p, cfg, z, mask, mu, n_timesteps, stoc=False, spk=None, no
             dxt = 0.5 * (mu - xt - est) * bt * h
         xt = (xt - dxt) * mask
     return xt
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The step before the path: GradTTS.forward between the text encoder and the decoder
+# ---------------------------------------------------------------------------------------------------------------
+def sequence_mask(length, max_length=None):
+    """model/utils.py:6-10."""
+    if max_length is None:
+        max_length = length.max()
+    x = torch.arange(int(max_length), dtype=length.dtype, device=length.device)
+    return x.unsqueeze(0) < length.unsqueeze(1)
+
+
+def fix_len_compatibility(length, num_downsamplings_in_unet=2):
+    """model/utils.py:13-17."""
+    while length % (2 ** num_downsamplings_in_unet) != 0:
+        length += 1
+    return length
+
+
+def generate_path(duration, mask):
+    """model/utils.py:26-39: path[b,i,t] = [t < cum_i] - [t < cum_(i-1)], times mask."""
+    b, t_x, t_y = mask.shape
+    cum_duration = torch.cumsum(duration, 1)
+    path = sequence_mask(cum_duration.view(b * t_x), t_y).to(mask.dtype).view(b, t_x, t_y)
+    path = path - F.pad(path, [0, 0, 1, 0, 0, 0])[:, :-1]
+    return path * mask
+
+
+def prior_expand(mu_x, logw, x_mask, length_scale=1.0, temperature=1.0, noise_tf=None):
+    """model/tts.py:77-94.  mu_x [B,F,Tx], logw / x_mask [B,1,Tx]; noise_tf [B,Ty,F] = the draws of `randn_like(mu_y)`
+    in the memory order of the reference's transposed mu_y (drawn from the global generator when None).
+    Returns dict(y_lengths, y_max_length, y_mask [B,1,Ty], attn [B,1,Tx,Ty], mu_y [B,F,Ty], z [B,F,Ty])."""
+    w = torch.exp(logw) * x_mask                                            # :77
+    w_ceil = torch.ceil(w) * length_scale                                   # :78
+    y_lengths = torch.clamp_min(torch.sum(w_ceil, [1, 2]), 1).long()        # :79
+    y_max_length = int(y_lengths.max())                                     # :80
+    y_max_length_ = fix_len_compatibility(y_max_length)                     # :81
+    y_mask = sequence_mask(y_lengths, y_max_length_).unsqueeze(1).to(x_mask.dtype)              # :83
+    attn_mask = x_mask.unsqueeze(-1) * y_mask.unsqueeze(2)                                      # :84
+    attn = generate_path(w_ceil.squeeze(1), attn_mask.squeeze(1)).unsqueeze(1)                  # :85
+    mu_y = torch.matmul(attn.squeeze(1).transpose(1, 2), mu_x.transpose(1, 2)).transpose(1, 2)  # :88-89
+    if noise_tf is None:
+        noise = torch.randn_like(mu_y)                                      # :94 (fills mu_y's transposed memory order)
+    else:
+        noise = noise_tf.transpose(1, 2)
+    z = mu_y + noise / temperature                                          # :94
+    return dict(w_ceil=w_ceil, y_lengths=y_lengths, y_max_length=y_max_length, y_mask=y_mask, attn=attn,
+                mu_y=mu_y.contiguous(), z=z.contiguous())

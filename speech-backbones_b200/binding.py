@@ -18,6 +18,7 @@ EXPORTS = [
     "sbk_workspace_bytes", "sbk_estimator", "sbk_reverse_diffusion", "sbk_reverse_steps",
     "sbk_reverse_diffusion_host", "sbk_last_launch_count", "sbk_debug_read", "sbk_debug_num",
     "sbk_debug_name", "sbk_last_error", "sbk_version", "sbk_profile_ops", "sbk_debug_capture", "sbk_debug_layout", "sbk_debug_op_layout", "sbk_vc_estimator", "sbk_vc_reverse_diffusion", "sbk_vc_conditioning",
+    "sbk_prior_expand",
 ]
 
 
@@ -57,6 +58,7 @@ def load_library() -> C.CDLL:
     lib.sbk_vc_conditioning.argtypes = [P, F, F, F, F, F, I, I, I, P]
     lib.sbk_reverse_steps.argtypes = [P, F, F, F, F, F, I, I, I, I, I, I, P]
     lib.sbk_reverse_diffusion_host.argtypes = [P, F, F, F, F, F, F, I, I, I, I]
+    lib.sbk_prior_expand.argtypes = [F, F, F, F, F, C.c_float, I, I, I, I, F, F, F, F, P]
     lib.sbk_last_launch_count.argtypes = [P]
     lib.sbk_last_launch_count.restype = C.c_int64
     lib.sbk_debug_read.argtypes = [P, C.c_char_p, F, C.POINTER(C.c_int64)]
@@ -86,6 +88,39 @@ def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
     if t.dtype != torch.float32:
         raise RuntimeError(f"{name}: expected float32, got {t.dtype}")
     return t.contiguous()
+
+
+def prior_expand(mu_x, w_ceil, x_mask, y_lengths, Ty, noise_tf=None, temperature=1.0, want_attn=True):
+    """sbk_prior_expand (GradTTS.forward, tts.py:82-94): alignment path, aligned prior mu_y, terminal sample z, y_mask.
+    mu_x [B,F,Tx], w_ceil / x_mask [B,Tx] fp32, y_lengths [B] int64, noise_tf [B,Ty,F] or None; all CUDA tensors.
+    Returns (mu_y [B,F,Ty], z [B,F,Ty], y_mask [B,1,Ty], attn [B,1,Tx,Ty] or None)."""
+    lib = load_library()
+    for n, t in (("mu_x", mu_x), ("w_ceil", w_ceil), ("x_mask", x_mask), ("y_lengths", y_lengths)):
+        if not t.is_cuda:
+            raise RuntimeError(f"{n} must be a CUDA tensor: the glue kernel has no CPU path")
+    B, Fm, Tx = mu_x.shape
+    mu_x, w_ceil, x_mask = _f32c(mu_x, "mu_x"), _f32c(w_ceil, "w_ceil"), _f32c(x_mask, "x_mask")
+    if tuple(w_ceil.shape) != (B, Tx) or tuple(x_mask.shape) != (B, Tx) or tuple(y_lengths.shape) != (B,):
+        raise RuntimeError(f"shape mismatch: mu_x {tuple(mu_x.shape)}, w_ceil {tuple(w_ceil.shape)}, x_mask {tuple(x_mask.shape)}, "
+                           f"y_lengths {tuple(y_lengths.shape)}")
+    if y_lengths.dtype != torch.int64:
+        raise RuntimeError(f"y_lengths: expected int64, got {y_lengths.dtype}")
+    y_lengths = y_lengths.contiguous()
+    if noise_tf is not None:
+        noise_tf = _f32c(noise_tf, "noise_tf")
+        if tuple(noise_tf.shape) != (B, Ty, Fm):
+            raise RuntimeError(f"noise_tf shape {tuple(noise_tf.shape)} != {(B, Ty, Fm)} (memory order of randn_like(mu_y))")
+    dev = mu_x.device
+    mu_y = torch.empty((B, Fm, Ty), dtype=torch.float32, device=dev)
+    z = torch.empty_like(mu_y)
+    y_mask = torch.empty((B, 1, Ty), dtype=torch.float32, device=dev)
+    attn = torch.empty((B, 1, Tx, Ty), dtype=torch.float32, device=dev) if want_attn else None
+    with torch.cuda.device(dev):
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _check(lib.sbk_prior_expand(_ptr(mu_x), _ptr(w_ceil), _ptr(x_mask), _ptr(y_lengths), _ptr(noise_tf),
+                                    C.c_float(float(temperature)), B, Fm, Tx, int(Ty), _ptr(mu_y), _ptr(z), _ptr(y_mask),
+                                    _ptr(attn), stream), "sbk_prior_expand")
+    return mu_y, z, y_mask, attn
 
 
 class Engine:

@@ -1284,6 +1284,22 @@ extern "C" int sbk_vc_conditioning(sbk_handle* h, const float* ref, const float*
     return SBK_OK;
 }
 
+extern "C" int sbk_prior_expand(const float* mu_x, const float* w_ceil, const float* x_mask, const int64_t* y_lengths,
+                                const float* noise_tf, float temperature, int B, int F, int Tx, int Ty,
+                                float* mu_y, float* z, float* y_mask, float* attn, void* stream) {
+    if (!mu_x || !w_ceil || !x_mask || !y_lengths || !mu_y || !z || !y_mask) return fail(SBK_ERR_ARG, "sbk_prior_expand: null argument");
+    if (B <= 0 || F <= 0 || Tx <= 0 || Ty <= 0) return fail(SBK_ERR_ARG, "sbk_prior_expand: bad sizes B=%d F=%d Tx=%d Ty=%d", B, F, Tx, Ty);
+    if (Tx > 12000) return fail(SBK_ERR_ARG, "sbk_prior_expand: Tx=%d exceeds the 12000-token shared-memory table", Tx);
+    if (noise_tf && !(temperature > 0.f)) return fail(SBK_ERR_ARG, "sbk_prior_expand: temperature must be > 0");
+    PriorExpandParams p;
+    p.mu_x = mu_x; p.w_ceil = w_ceil; p.x_mask = x_mask; p.y_len = reinterpret_cast<const long long*>(y_lengths);
+    p.noise_tf = noise_tf; p.temperature = temperature; p.B = B; p.F = F; p.Tx = Tx; p.Ty = Ty;
+    p.mu_y = mu_y; p.z = z; p.y_mask = y_mask; p.attn = attn;
+    launch_prior_expand(p, (cudaStream_t)stream);
+    CU(cudaGetLastError());
+    return SBK_OK;
+}
+
 extern "C" int64_t sbk_last_launch_count(const sbk_handle* h) { return h ? h->last_launches : 0; }
 
 extern "C" int sbk_debug_capture(sbk_handle* h, int on) {

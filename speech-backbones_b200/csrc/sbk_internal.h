@@ -195,6 +195,21 @@ int launch_chan_stats(const ChanStatsParams& p, cudaStream_t s);
 int launch_in_glu(const InGluParams& p, cudaStream_t s);
 int launch_vc_cond(const VcCondParams& p, cudaStream_t s);
 
+// GradTTS.forward glue before the decoder (Grad-TTS/model/tts.py:82-94): alignment path + aligned prior + terminal sample
+struct PriorExpandParams {
+    const float* mu_x;          // [B][F][Tx]
+    const float* w_ceil;        // [B][Tx]
+    const float* x_mask;        // [B][Tx]
+    const long long* y_len;     // [B]
+    const float* noise_tf;      // [B][Ty][F] or nullptr
+    float temperature;
+    int B, F, Tx, Ty;
+    float* mu_y; float* z;      // [B][F][Ty]
+    float* y_mask;              // [B][Ty]
+    float* attn;                // [B][Tx][Ty] or nullptr
+};
+int launch_prior_expand(const PriorExpandParams& p, cudaStream_t s);
+
 struct StepBeginParams { double* stats; int n_doubles; int* step_cur; int* step_next; };
 
 // launchers (all asynchronous on `s`); return the number of kernels launched

@@ -819,9 +819,6 @@ __device__ __forceinline__ uint32_t pack_bf16x2_f(float lo, float hi) {
 }
 __device__ __forceinline__ float bf16_lo_f(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16_hi_f(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
-__device__ __forceinline__ uint4 pack8_bf16(const float (&o)[8]) {
-    return make_uint4(pack_bf16x2_f(o[0], o[1]), pack_bf16x2_f(o[2], o[3]), pack_bf16x2_f(o[4], o[5]), pack_bf16x2_f(o[6], o[7]));
-}
 
 // Thread mapping of the two kernels below: a LANE PAIR owns one frame - lane half h handles the fp32 chunk 2*ch+h
 // (4 channels: the same register footprint as the fp32 kernels, so the same 4 CTAs/SM) and writes its 8-byte half of
@@ -1516,6 +1513,56 @@ int launch_vc_cond(const VcCondParams& p, cudaStream_t s) {
 }
 
 // zero the GroupNorm statistics arena and advance the device-side step counter
+// ----------------------------------------------------------------------------------------------
+// GradTTS.forward, the lines between the text encoder and the decoder (Grad-TTS/model/tts.py:82-94, model/utils.py:26-39).
+// The reference builds the 0/1 alignment `attn` [B,Tx,Ty] with five full-size elementwise passes (zeros, sequence_mask over
+// B*Tx rows, pad, subtract, mask) and then multiplies it with mu_x as a dense batched GEMM.  attn^T @ mu_x^T with a 0/1
+// matrix that has at most one 1 per output frame is a gather, so one thread per output frame finds its token by binary
+// search in the cumulative durations and copies that token's F features: one pass, exact.
+//   path[i][t] = [t < cum_i] - [t < cum_(i-1)]  (float compares against the frame index, utils.py:33-37), * x_mask_i * y_mask_t
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_prior_expand(const PriorExpandParams p) {
+    extern __shared__ __align__(16) float s_cum[];         // [Tx] cumulative durations of this sample
+    const int b = blockIdx.y, tid = threadIdx.x;
+    if (tid == 0) {
+        // torch.cumsum on the CPU reference accumulates sequentially in double (at::acc_type<float, false>) and rounds each
+        // prefix to fp32; durations are non-integers when length_scale != 1 and prefixes such as 100 x 0.91 land next to
+        // an integer, so the accumulation type decides which frame a token boundary falls on
+        double c = 0.0;
+        const float* w = p.w_ceil + (long long)b * p.Tx;
+        for (int i = 0; i < p.Tx; ++i) { c += (double)w[i]; s_cum[i] = (float)c; }
+    }
+    __syncthreads();
+    const int t = blockIdx.x * 256 + tid;
+    if (t >= p.Ty) return;
+    const float tf = (float)t;
+    // first token whose cumulative duration exceeds t (cum is non-decreasing): path[i][t] = 1 exactly for that token
+    int lo = 0, hi = p.Tx;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (tf < s_cum[mid]) hi = mid; else lo = mid + 1; }
+    const int tok = lo;                                    // == Tx: frame beyond the last token
+    const float ym = (long long)t < p.y_len[b] ? 1.f : 0.f;
+    const float am = tok < p.Tx ? __ldg(p.x_mask + (long long)b * p.Tx + tok) * ym : 0.f;   // attn_mask at (tok, t)
+    p.y_mask[(long long)b * p.Ty + t] = ym;
+    const float* mx = p.mu_x + (long long)b * p.F * p.Tx + (tok < p.Tx ? tok : 0);
+    const float* nz = p.noise_tf ? p.noise_tf + ((long long)b * p.Ty + t) * p.F : nullptr;
+    for (int f = 0; f < p.F; ++f) {
+        // attn is exactly 0 or 1: the reference's matmul adds one product and Tx-1 zeros
+        const float m = am != 0.f ? __ldg(mx + (long long)f * p.Tx) * am : 0.f;
+        const long long o = ((long long)b * p.F + f) * p.Ty + t;
+        p.mu_y[o] = m;
+        p.z[o] = nz ? m + __fdiv_rn(nz[f], p.temperature) : m;
+    }
+    if (p.attn) {
+        float* ap = p.attn + (long long)b * p.Tx * p.Ty + t;
+        for (int i = 0; i < p.Tx; ++i) ap[(long long)i * p.Ty] = (i == tok) ? am : 0.f;
+    }
+}
+
+int launch_prior_expand(const PriorExpandParams& p, cudaStream_t s) {
+    k_prior_expand<<<dim3((p.Ty + 255) / 256, p.B), 256, (size_t)p.Tx * sizeof(float), s>>>(p);
+    return 1;
+}
+
 __global__ void k_step_begin(const StepBeginParams p) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < p.n_doubles) p.stats[i] = 0.0;

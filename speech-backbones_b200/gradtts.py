@@ -19,7 +19,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .binding import Engine
+from .binding import Engine, prior_expand
 
 
 class BaseModule(nn.Module):
@@ -271,3 +271,52 @@ class Diffusion(BaseModule):
     def compute_loss(self, x0, mask, mu, spk=None, offset=1e-5):
         t = torch.rand(x0.shape[0], dtype=x0.dtype, device=x0.device, requires_grad=False)
         return self.loss_t(x0, mask, mu, torch.clamp(t, offset, 1.0 - offset), spk)
+
+
+# ---- the step before the path: GradTTS.forward between the text encoder and the decoder (tts.py:77-99) ----------------
+def fix_len_compatibility(length, num_downsamplings_in_unet=2):
+    """Grad-TTS/model/utils.py:13-17."""
+    while length % (2 ** num_downsamplings_in_unet) != 0:
+        length += 1
+    return length
+
+
+def reference_order_noise(B, n_feats, Ty, dtype, device):
+    """The draws of the reference's `torch.randn_like(mu_y)` (tts.py:94) as a contiguous [B,Ty,n_feats] tensor.
+    There mu_y is `matmul(...).transpose(1, 2)`, a [B,n_feats,Ty] VIEW with strides (Ty*n_feats, 1, n_feats); randn_like
+    keeps those strides and torch's generators fill strided tensors differently from contiguous ones, so the only way to
+    get the same numbers from the same generator state is to make the same call on a tensor with the same strides."""
+    proto = torch.empty((B, Ty, n_feats), dtype=dtype, device=device).transpose(1, 2)
+    noise = torch.randn_like(proto)
+    return noise.transpose(1, 2)            # the same memory, now a contiguous [B,Ty,n_feats] tensor
+
+
+@torch.no_grad()
+def synthesize_from_encoder(decoder, mu_x, logw, x_mask, n_timesteps, temperature=1.0, stoc=False, spk=None,
+                            length_scale=1.0, want_attn=True):
+    """Drop-in for Grad-TTS/model/tts.py:77-99 - everything `GradTTS.forward` does after `self.encoder(...)`:
+
+        mu_x, logw, x_mask = self.encoder(x, x_lengths, spk)
+        return synthesize_from_encoder(self.decoder, mu_x, logw, x_mask, n_timesteps, temperature, stoc, spk, length_scale)
+
+    The durations and output lengths (tts.py:77-81) are the reference's own four tiny ops on [B,1,Tx] tensors; the ONE
+    host synchronisation (`int(y_lengths.max())`) is kept because it fixes the SHAPE of what the method returns.
+    Everything sized [B,Tx,Ty] or [B,F,Ty] - generate_path, the 0/1 matmul, the terminal sample - is one libsbk kernel
+    (`sbk_prior_expand`) that writes mu_y / z / y_mask in the layout the sampler reads.  The noise is drawn by torch with
+    the reference's own call on a tensor with the reference's strides (`reference_order_noise`), so with the same
+    generator state z equals the reference's z bit for bit.  Returns (encoder_outputs, decoder_outputs, attn) like the reference."""
+    if not mu_x.is_cuda:
+        raise RuntimeError("synthesize_from_encoder runs only on a CUDA device (sm_100a); there is no CPU fallback")
+    B, Fm, Tx = mu_x.shape
+    w = torch.exp(logw) * x_mask                                                   # :77
+    w_ceil = torch.ceil(w) * length_scale                                          # :78
+    y_lengths = torch.clamp_min(torch.sum(w_ceil, [1, 2]), 1).long()               # :79
+    y_max_length = int(y_lengths.max())                                            # :80 (host sync: output shape)
+    y_max_length_ = fix_len_compatibility(y_max_length)                            # :81
+    noise_tf = reference_order_noise(B, Fm, y_max_length_, mu_x.dtype, mu_x.device)  # :94, the reference's draws
+    mu_y, z, y_mask, attn = prior_expand(mu_x, w_ceil.reshape(B, Tx), x_mask.reshape(B, Tx).to(torch.float32), y_lengths,
+                                         y_max_length_, noise_tf, temperature, want_attn)
+    decoder_outputs = decoder(z, y_mask, mu_y, n_timesteps, stoc, spk)             # :96
+    # (the reference slices attn's dim 2 - the token axis - with the frame count, tts.py:99; kept as is)
+    return (mu_y[:, :, :y_max_length], decoder_outputs[:, :, :y_max_length],
+            None if attn is None else attn[:, :, :y_max_length])

@@ -198,6 +198,18 @@ def synthetic_inputs(B: int, T: int, n_feats: int = 80, seed: int = 1234, ragged
     return z, mask, mu, spk, lengths
 
 
+def synthetic_encoder_outputs(B: int, Tx: int, x_lengths, dur_mean: float = 1.0, n_feats: int = 80, seed: int = 1234):
+    """Seeded stand-ins for the text encoder's outputs (Grad-TTS/model/tts.py:75): mu_x [B,n_feats,Tx],
+    logw [B,1,Tx] (log durations ~ N(dur_mean, 0.5)), x_mask [B,1,Tx] from `x_lengths`; masked positions are zeroed the
+    way the encoder leaves them."""
+    g = torch.Generator().manual_seed(_key_seed(seed, f"encoder_outputs/{B}/{Tx}"))
+    lengths = torch.tensor(list(x_lengths), dtype=torch.long)
+    x_mask = (torch.arange(Tx)[None, :] < lengths[:, None]).to(torch.float32)[:, None, :]
+    mu_x = torch.randn(B, n_feats, Tx, generator=g) * x_mask
+    logw = (torch.randn(B, 1, Tx, generator=g) * 0.5 + dur_mean) * x_mask
+    return mu_x, logw, x_mask
+
+
 def synthetic_noise(N: int, B: int, T: int, n_feats: int = 80, seed: int = 1234) -> torch.Tensor:
     """Pre-drawn per-step noise [N,B,n_feats,T] for the stochastic sampler (diffusion.py:267)."""
     return synthetic_tensor(seed, f"noise:{N}x{B}x{T}", (N, B, n_feats, T))
