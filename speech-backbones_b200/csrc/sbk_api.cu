@@ -31,6 +31,8 @@ static int fail(int code, const char* fmt, ...) {
             return fail(SBK_ERR_CUDA, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
+#define TRY_RC(x) do { int rc__ = (x); if (rc__ != SBK_OK) return rc__; } while (0)
+
 namespace {
 
 struct WSpec { std::string name; std::vector<int64_t> shape; };
@@ -290,12 +292,16 @@ static uint16_t f32_to_bf16_rn(float x) {
     u += 0x7FFFu + ((u >> 16) & 1u);
     return (uint16_t)(u >> 16);
 }
-static int pack_tc_host(sbk_handle* h, const std::vector<float>& hs, const std::string& key, int cout, int cin, int geom, bool bf16);
+static int pack_tc_host(sbk_handle* h, const std::vector<float>& hs, const std::string& key, int cout, int cin, int geom, bool bf16, int nt_override = 0);
 static int pack_tc(sbk_handle* h, const std::string& src, const std::string& key, int cout, int cin, int geom, bool bf16) {
     const int taps = conv_tc_taps(geom);
     std::vector<float> hs((size_t)cout * cin * taps);
     CU(cudaMemcpy(hs.data(), h->raw[src], hs.size() * sizeof(float), cudaMemcpyDeviceToHost));
-    return pack_tc_host(h, hs, key, cout, cin, geom, bf16);
+    TRY_RC(pack_tc_host(h, hs, key, cout, cin, geom, bf16));
+    // 3x3 convs with >= 128 output channels also get a 64-wide N-tile image: small batches have too few 128-wide tiles to
+    // fill 148 SMs (B=1, level 2: 20 tiles), so the planner switches those launches to twice as many half-width tiles
+    if (geom == G_C3 && conv_tc_ntile(geom, cout) == 128) TRY_RC(pack_tc_host(h, hs, key + "64", cout, cin, geom, bf16, 64));
+    return SBK_OK;
 }
 // k and v rows of to_qkv ('(qkv heads c)': k = rows 128.., v = rows 256..) in k_attn_kv's per-stage shared-memory image
 // [32-channel stage][k|v][16-byte chunk][row = head*32 + c][4], tf32-rounded
@@ -325,9 +331,9 @@ static int pack_tc_up(sbk_handle* h, const std::string& src, const std::string& 
         m[((size_t)co * C + ci) * 16 + t] = w[((size_t)ci * C + co) * 16 + t];
     return pack_tc_host(h, m, key, C, C, G_UP, bf16);
 }
-static int pack_tc_host(sbk_handle* h, const std::vector<float>& hs, const std::string& key, int cout, int cin, int geom, bool bf16) {
+static int pack_tc_host(sbk_handle* h, const std::vector<float>& hs, const std::string& key, int cout, int cin, int geom, bool bf16, int nt_override) {
     const int taps = conv_tc_taps(geom);
-    const int NT = conv_tc_ntile(geom, cout), CPS = conv_tc_stage_channels(geom, bf16 ? 1 : 0), EPC = bf16 ? 8 : 4, KCHK = CPS / EPC;
+    const int NT = nt_override ? nt_override : conv_tc_ntile(geom, cout), CPS = conv_tc_stage_channels(geom, bf16 ? 1 : 0), EPC = bf16 ? 8 : 4, KCHK = CPS / EPC;
     const int ksteps = cin / CPS;
     const size_t esz = bf16 ? 2 : 4;
     std::vector<uint8_t> hd((size_t)cout * cin * taps * esz);
@@ -546,6 +552,8 @@ static int build_plan(sbk_handle* h, int B, int T, int tb_rows) {
         return p;
     };
     const bool use_tc = c.precision != SBK_PREC_FP32;
+    int num_sms = 148;
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, c.device);
     const bool b16 = c.precision == SBK_PREC_BF16;          // operand tensors in bf16 [B][H][C/8][W][8]
     const double osz = b16 ? 2.0 : 4.0;                     // bytes per operand-tensor element
     const int fmt_raw = use_tc ? 1 : 0, fmt_opnd = b16 ? 2 : fmt_raw;
@@ -588,6 +596,11 @@ static int build_plan(sbk_handle* h, int B, int T, int tb_rows) {
         p.wpk = W(wkey); p.bias = bkey.empty() ? nullptr : W(bkey); p.out = out; p.Cout = cout;
         p.epi = EPI_PLAIN; p.ostats = st; p.mask = pl.mask; p.T = T; p.lvl = lvl; p.zero_page = h->d_zero;
         p.bf16 = b16 ? 1 : 0;
+        if (geom == G_C3 && conv_tc_ntile(geom, cout) == 128) {
+            // tiles of 2 rows x 128 pixels x 128 channels; when they cannot fill half the SMs, use 64-wide N tiles instead
+            const long long tiles = (long long)B * ((Ws[lvl] + 127) / 128) * ((Hs[lvl] + 1) / 2) * (cout / 128);
+            if (tiles * 2 <= num_sms && h->packed.count(wkey + "64")) { p.nt = 64; p.wpk = W(wkey + "64"); }
+        }
         const double taps = geom == G_PW ? 1.0 : (geom == G_UP ? 4.0 : 9.0);
         op.flops = 2.0 * B * Hs[lvl] * Ws[lvl] * cout * (c0 + c1) * taps;
         op.bytes = (double)B * Hs[lvl] * Ws[lvl] * (osz * (c0 + c1) + (geom == G_C3 ? 4.0 : osz) * cout);

@@ -990,7 +990,7 @@ int conv_tc_stage_channels(int geom, int bf16) {
 
 template <bool BF16>
 static int dispatch_conv_tc(const ConvTcParams& p, cudaStream_t s) {
-    const int nt = conv_tc_ntile(p.geom, p.Cout);
+    const int nt = (p.nt == 64 && p.geom == G_C3) ? 64 : conv_tc_ntile(p.geom, p.Cout);
     switch (p.geom) {
         case G_C3:   return nt == 128 ? launch_tc<G_C3, BF16, 128>(p, s) : launch_tc<G_C3, BF16, 64>(p, s);
         case G_PW:

@@ -67,6 +67,8 @@ struct ConvTcParams {
     const float* addin;                             // EPI_PLAIN: out += addin (same shape/layout/dtype as out): residual added in fp32
     const float* zero_page;                         // >= 4 KB of zeros in global memory (out-of-image parts of A tiles)
     int bf16;
+    int nt;                                         // N tile override (64) for launches with too few 128-wide tiles to fill the
+                                                    // GPU (small batches); 0 = conv_tc_ntile(geom, Cout).  The weights must be packed for it.
 };
 
 // Block activation between the two convs of a ResnetBlock, written once in operand form (diffusion.py:57,76):
