@@ -210,6 +210,45 @@ def synthetic_encoder_outputs(B: int, Tx: int, x_lengths, dur_mean: float = 1.0,
     return mu_x, logw, x_mask
 
 
+HIFIGAN_V1 = dict(upsample_rates=[8, 8, 2, 2], upsample_kernel_sizes=[16, 16, 4, 4], upsample_initial_channel=512,
+                  resblock_kernel_sizes=[3, 7, 11], resblock_dilation_sizes=[[1, 3, 5], [1, 3, 5], [1, 3, 5]], num_mels=80)
+
+
+def hifigan_param_spec(h=None):
+    """[(name, shape)] of the HiFi-GAN V1 generator's state_dict after remove_weight_norm
+    (Grad-TTS/hifi-gan/models.py:77-101, Grad-TTS/checkpts/hifigan-config.json; inference.py:60-63)."""
+    h = h or HIFIGAN_V1
+    c0 = h["upsample_initial_channel"]
+    spec = [("conv_pre.weight", (c0, h["num_mels"], 7)), ("conv_pre.bias", (c0,))]
+    for i, k in enumerate(h["upsample_kernel_sizes"]):
+        spec += [(f"ups.{i}.weight", (c0 // 2 ** i, c0 // 2 ** (i + 1), k)), (f"ups.{i}.bias", (c0 // 2 ** (i + 1),))]
+    n, ch = 0, c0
+    for i in range(len(h["upsample_rates"])):
+        ch = c0 // 2 ** (i + 1)
+        for k, d in zip(h["resblock_kernel_sizes"], h["resblock_dilation_sizes"]):
+            for grp in ("convs1", "convs2"):
+                for j in range(len(d)):
+                    spec += [(f"resblocks.{n}.{grp}.{j}.weight", (ch, ch, k)), (f"resblocks.{n}.{grp}.{j}.bias", (ch,))]
+            n += 1
+    return spec + [("conv_post.weight", (1, ch, 7)), ("conv_post.bias", (1,))]
+
+
+def synthetic_hifigan_state_dict(seed: int = 1234):
+    """Seeded weights for the HiFi-GAN V1 generator after remove_weight_norm: the reference ships no vocoder checkpoint.
+    He-style scales (std = 1/sqrt(fan_in)) keep the activations O(1) through the 15-conv-deep residual stacks, so the tanh
+    output is neither saturated nor vanishing."""
+    import math
+    sd = {}
+    for name, shape in hifigan_param_spec():
+        g = torch.Generator().manual_seed(_key_seed(seed, "hifigan/" + name))
+        if name.endswith(".bias"):
+            sd[name] = torch.randn(shape, generator=g) * 0.02
+        else:
+            fan_in = shape[1] * shape[2] if not name.startswith("ups.") else shape[0] * shape[2] / 4.0
+            sd[name] = torch.randn(shape, generator=g) / math.sqrt(fan_in)
+    return sd
+
+
 def synthetic_noise(N: int, B: int, T: int, n_feats: int = 80, seed: int = 1234) -> torch.Tensor:
     """Pre-drawn per-step noise [N,B,n_feats,T] for the stochastic sampler (diffusion.py:267)."""
     return synthetic_tensor(seed, f"noise:{N}x{B}x{T}", (N, B, n_feats, T))
