@@ -691,19 +691,15 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT>::MINB) k_conv_tc(con
 template <int GEOM, bool BF16, int NT, bool RES = false>
 static int launch_tc(const ConvTcParams& p, cudaStream_t s) {
     using D = Depth<GEOM, NT>;
-    // per-device caches: the dynamic shared-memory opt-in is a per-device function attribute, and a process may drive more
-    // than one GPU (one handle per device)
-    static bool attr_set[64] = {};
-    static int sms[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    dev &= 63;
-    if (!attr_set[dev]) {
+    static bool attr_set = false;
+    static int num_sms = 0;
+    if (!attr_set) {
         cudaFuncSetAttribute(k_conv_tc<GEOM, BF16, NT, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
-        attr_set[dev] = true;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        attr_set = true;
     }
-    const int num_sms = sms[dev];
     int mt;
     if (GEOM == G_C3 || GEOM == G_UP) mt = ((p.W + TPX - 1) / TPX) * ((p.H + ROWS - 1) / ROWS);
     else if (GEOM == G_DOWN) mt = ((p.Wo + TPX - 1) / TPX) * ((p.Ho + ROWS - 1) / ROWS);
@@ -965,17 +961,15 @@ __global__ void __launch_bounds__(kvk::THREADS, 1) k_attn_kv(const ConvTcParams 
 
 template <bool BF16>
 static int launch_attn_kv(const ConvTcParams& p, cudaStream_t s) {
-    static bool attr_set[64] = {};
-    static int sms[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    dev &= 63;
-    if (!attr_set[dev]) {
+    static bool attr_set = false;
+    static int num_sms = 0;
+    if (!attr_set) {
         cudaFuncSetAttribute(k_attn_kv<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
-        attr_set[dev] = true;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        attr_set = true;
     }
-    const int num_sms = sms[dev];
     const long long total = (long long)p.B * ((p.H * p.W + kvk::PX - 1) / kvk::PX);
     const int grid = (int)(total < num_sms ? total : num_sms);
     k_attn_kv<BF16><<<grid, kvk::THREADS, kvk::SMEM, s>>>(p);
