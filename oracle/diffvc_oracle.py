@@ -136,3 +136,33 @@ def reverse_diffusion(p, cfg, z, mask, mean, ref, ref_mask, mean_ref, c, n_times
             dxt = dxt + eps * sigma
         xt = (xt - dxt) * mask
     return xt
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The step before the path (DiffVC): DiffVC.forward between the encoders and the decoder
+# ---------------------------------------------------------------------------------------------------------------
+def prepare_decoder_inputs(cfg, x, x_lengths, mean, noise=None):
+    """DiffVC/model/vc.py:104,107,110-123 as written there (the per-sample copy loop included).
+    Returns dict(x_mask, mean_x, max_length, x_mask_new, mean_new, z)."""
+    def sequence_mask(length, max_length=None):                  # DiffVC/model/utils.py
+        if max_length is None:
+            max_length = length.max()
+        r = torch.arange(int(max_length), dtype=length.dtype, device=length.device)
+        return r.unsqueeze(0) < length.unsqueeze(1)
+
+    x_mask = sequence_mask(x_lengths).unsqueeze(1).to(x.dtype)                                   # :104
+    g = _gamma(cfg, 0, 1.0)
+    mean_x = (x * g + mean * (1.0 - g)) * x_mask                                                 # :107, diffusion.py:151-155
+    b = x.shape[0]
+    max_length = int(x_lengths.max())
+    max_length_new = max_length
+    while max_length_new % 4 != 0:
+        max_length_new += 1
+    x_mask_new = sequence_mask(x_lengths, max_length_new).unsqueeze(1).to(x.dtype)
+    mean_new = torch.zeros((b, x.shape[1], max_length_new), dtype=x.dtype)
+    mean_x_new = torch.zeros((b, x.shape[1], max_length_new), dtype=x.dtype)
+    for i in range(b):
+        mean_new[i, :, :x_lengths[i]] = mean[i, :, :x_lengths[i]]
+        mean_x_new[i, :, :x_lengths[i]] = mean_x[i, :, :x_lengths[i]]
+    z = mean_x_new + (torch.randn_like(mean_x_new) if noise is None else noise)
+    return dict(x_mask=x_mask, mean_x=mean_x, max_length=max_length, x_mask_new=x_mask_new, mean_new=mean_new, z=z)

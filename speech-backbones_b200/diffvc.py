@@ -209,3 +209,45 @@ class Diffusion(BaseModule):
     def compute_loss(self, x0, mask, mean, x_ref, mean_ref, c, offset=1e-5):
         t = torch.rand(x0.shape[0], dtype=x0.dtype, device=x0.device, requires_grad=False)
         return self.loss_t(x0, mask, mean, x_ref, mean_ref, c, torch.clamp(t, offset, 1.0 - offset))
+
+
+# ---- the step before the path: DiffVC.forward between the encoders and the decoder (DiffVC/model/vc.py:107-127) -------
+def fix_len_compatibility(length, num_downsamplings_in_unet=2):
+    """DiffVC/model/utils.py (same helper as Grad-TTS/model/utils.py:13-17)."""
+    while length % (2 ** num_downsamplings_in_unet) != 0:
+        length += 1
+    return length
+
+
+@torch.no_grad()
+def convert_from_encoder(decoder, x, x_lengths, mean, x_ref, x_ref_mask, mean_ref, c, n_timesteps, mode="ml"):
+    """Drop-in for DiffVC/model/vc.py:107,110-127 - what `DiffVC.forward` does once `mean = self.encoder(x, x_mask)` and
+    `mean_ref = self.encoder(x_ref, x_ref_mask)` exist:
+
+        return convert_from_encoder(self.decoder, x, x_lengths, mean, x_ref, x_ref_mask, mean_ref, c, n_timesteps, mode)
+
+    The reference re-pads `mean` and `mean_x` to a length the U-Net accepts with a Python loop over the batch that indexes
+    `x_lengths[i]` on the host: 2B slice copies and B device-to-host synchronisations per call (vc.py:118-120).  Here the same
+    tensors are one masked pad each (bit-identical: a copy of the valid prefix into zeros), the only synchronisation left is
+    `int(x_lengths.max())`, which fixes the SHAPE of the returned tensor, and the noise draw is the reference's own call
+    (`randn_like` of a contiguous [B,n_feats,T'] tensor), so the generator stream is unchanged.  Returns (mean_x, y)."""
+    b, n_feats, t_in = x.shape
+    max_length = int(x_lengths.max())                                              # :111 (host sync: output shape)
+    if t_in != max_length:                                                         # the reference's x_mask (:104) has max_length frames
+        raise RuntimeError(f"x has {t_in} frames but max(x_lengths) = {max_length}: DiffVC.forward expects a batch padded to its longest item")
+    max_length_new = fix_len_compatibility(max_length)                             # :112
+    frames = torch.arange(max_length_new, device=x.device)
+    x_mask_new = (frames.unsqueeze(0) < x_lengths.unsqueeze(1)).unsqueeze(1).to(x.dtype)        # :113
+    x_mask = x_mask_new[:, :, :max_length]                                         # :104
+    mean_x = decoder.compute_diffused_mean(x, x_mask, mean, 1.0)                   # :107
+
+    def repad(v):                                                                  # :114-120 without the per-sample loop
+        out = torch.zeros((b, n_feats, max_length_new), dtype=x.dtype, device=x.device)
+        out[:, :, :max_length] = torch.where(x_mask != 0, v, out[:, :, :max_length])
+        return out
+
+    mean_new, mean_x_new = repad(mean), repad(mean_x)
+    z = mean_x_new
+    z += torch.randn_like(mean_x_new, device=mean_x_new.device)                    # :122-123
+    y = decoder(z, x_mask_new, mean_new, x_ref, x_ref_mask, mean_ref, c, n_timesteps, mode)     # :125
+    return mean_x, y[:, :, :max_length]
