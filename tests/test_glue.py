@@ -66,6 +66,20 @@ def test_oracle_prior_expand_properties():
     del noise
 
 
+def test_product_glue_has_no_cpu_path(sbk_lib):
+    """The product entry points refuse CPU tensors loudly (no fallback): binding.prior_expand and synthesize_from_encoder."""
+    from speech_backbones_b200 import gradtts as G
+    from speech_backbones_b200.binding import prior_expand
+    mu_x, logw, x_mask = synthetic_encoder_outputs(1, 6, [6], 0.5, seed=1)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        prior_expand(mu_x, torch.ones(1, 6), x_mask.reshape(1, 6), torch.tensor([6]), 8)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        G.synthesize_from_encoder(lambda *a: None, mu_x, logw, x_mask, 2)
+    assert G.fix_len_compatibility(5) == 8 and G.fix_len_compatibility(8) == 8
+    n = G.reference_order_noise(2, 80, 12, torch.float32, "cpu")
+    assert n.shape == (2, 12, 80) and n.is_contiguous()
+
+
 # ---------------------------------------------------------------------------------------------------------------- GPU
 @pytest.mark.gpu
 @pytest.mark.parametrize("idx", range(5))
