@@ -28,6 +28,9 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     # BASELINE.json configs[1]: Grad-TTS batch=32, T~512, N=50, fp32, 1xB200
     "gradtts_b32_t512_n50": dict(B=32, T=512, N=50, n_spks=1),
+    # BASELINE.json configs[4]'s per-GPU share (2048 utterances over 8 GPUs = 256 per GPU); not the default bench line:
+    #   torchrun --nproc-per-node 8 bench.py --gpus 8 --workload gradtts_b256_t512_n50 --steps 2 --warmup 3 --no-fp32-leg
+    "gradtts_b256_t512_n50": dict(B=256, T=512, N=50, n_spks=1),
 }
 FLOP_PER_FRAME_STEP = 134.15e6      # 67,077,120 MAC per mel frame per reverse step
 IDEAL_BYTES_PER_FRAME_STEP = 713280.0
