@@ -376,7 +376,7 @@ def run_ours(args, wl):
         "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[args.precision], "data": "synthetic",
         "config": {"workload": args.workload, "batch_per_gpu": B, "global_batch": B * world, "frames": T,
                    "n_timesteps": N, "stoc": False, "parallelism": f"dp{world}",
-                   "l2": "per-step working set (2.9 GB of activations) exceeds the 126 MB L2; no flush needed",
+                   "l2": f"per-step working set ({eng.workspace_bytes(B, T) / 1e9:.1f} GB of activations) exceeds the 126 MB L2; no flush needed",
                    "weights": "synthetic seeded (no checkpoints ship with the reference)",
                    "weight_broadcast_s": round(bcast_s, 4)},
         "frame_steps_per_s": value * N,
