@@ -57,6 +57,21 @@ def test_c_abi_argument_errors(sbk_lib):
     eng.close()
 
 
+def test_prior_expand_argument_errors(sbk_lib):
+    """sbk_prior_expand validates its arguments before touching the GPU (return code + sbk_last_error, no exceptions)."""
+    buf = (C.c_float * 16)()
+    lens = (C.c_int64 * 1)(4)
+    f = sbk_lib.sbk_prior_expand
+    assert f(None, buf, buf, lens, None, C.c_float(1.0), 1, 1, 4, 4, buf, buf, buf, None, None) != 0
+    assert b"null" in sbk_lib.sbk_last_error()
+    assert f(buf, buf, buf, lens, None, C.c_float(1.0), 1, 1, 0, 4, buf, buf, buf, None, None) != 0
+    assert b"bad sizes" in sbk_lib.sbk_last_error()
+    assert f(buf, buf, buf, lens, None, C.c_float(1.0), 1, 1, 20000, 4, buf, buf, buf, None, None) != 0
+    assert b"12000" in sbk_lib.sbk_last_error()
+    assert f(buf, buf, buf, lens, buf, C.c_float(0.0), 1, 1, 4, 4, buf, buf, buf, None, None) != 0
+    assert b"temperature" in sbk_lib.sbk_last_error()
+
+
 def test_module_state_dict_is_reference_compatible():
     from speech_backbones_b200.gradtts import Diffusion
     for n_spks in (1, 4):
