@@ -47,6 +47,33 @@ def test_measured_gpu_error_is_explained_by_operand_rounding(golden, mode):
     assert seen == len(MEASURED)
 
 
+# rel-L2 of whole trajectories (N reverse steps) vs the reference, measured on the GPU (same log)
+MEASURED_TRAJ = {
+    "kindtraj-n_spks1-B2-T32-raggedTrue-N1-stocFalse": dict(tf32=7.011e-4, bf16=4.932e-3),
+    "kindtraj-n_spks1-B2-T32-raggedTrue-N10-stocFalse": dict(tf32=6.490e-4, bf16=4.127e-3),
+    "kindtraj-n_spks1-B2-T32-raggedTrue-N5-stocTrue": dict(tf32=8.297e-4, bf16=5.483e-3),
+    "kindtraj-n_spks1-B1-T128-raggedFalse-N10-stocFalse": dict(tf32=5.761e-4, bf16=3.568e-3),
+}
+
+
+@pytest.mark.parametrize("mode", ["tf32", "bf16"])
+def test_measured_trajectory_error_is_explained_by_operand_rounding(golden, mode):
+    from helpers import stoc_noise
+    seen = 0
+    for c in golden["cases"]:
+        if c["kind"] != "traj" or case_id(c) not in MEASURED_TRAJ:
+            continue
+        cfg, sd, z, mask, mu, spk = case_inputs(golden, c)
+        noise = stoc_noise(golden, c) if c["stoc"] else None
+        with operand_rounding(mode, sd), torch.no_grad():
+            y = O.reverse_diffusion(sd, cfg, z, mask, mu, c["N"], c["stoc"], spk, noise=noise)
+        predicted, measured = rel_l2(y, c["out"]), MEASURED_TRAJ[case_id(c)][mode]
+        print(f"{mode} {case_id(c)}: model {predicted:.3e}  GPU {measured:.3e}  ratio {measured / predicted:.3f}")
+        assert abs(measured / predicted - 1.0) <= 0.15, case_id(c)
+        seen += 1
+    assert seen == len(MEASURED_TRAJ)
+
+
 def test_patch_is_removed_afterwards(golden):
     c = next(c for c in golden["cases"] if c["kind"] == "est" and c["n_spks"] == 1)
     cfg, sd, z, mask, mu, spk = case_inputs(golden, c)
