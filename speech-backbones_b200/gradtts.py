@@ -293,7 +293,7 @@ def reference_order_noise(B, n_feats, Ty, dtype, device):
 
 @torch.no_grad()
 def synthesize_from_encoder(decoder, mu_x, logw, x_mask, n_timesteps, temperature=1.0, stoc=False, spk=None,
-                            length_scale=1.0, want_attn=True):
+                            length_scale=1.0, want_attn=True, noise_tf=None):
     """Drop-in for Grad-TTS/model/tts.py:77-99 - everything `GradTTS.forward` does after `self.encoder(...)`:
 
         mu_x, logw, x_mask = self.encoder(x, x_lengths, spk)
@@ -313,7 +313,8 @@ def synthesize_from_encoder(decoder, mu_x, logw, x_mask, n_timesteps, temperatur
     y_lengths = torch.clamp_min(torch.sum(w_ceil, [1, 2]), 1).long()               # :79
     y_max_length = int(y_lengths.max())                                            # :80 (host sync: output shape)
     y_max_length_ = fix_len_compatibility(y_max_length)                            # :81
-    noise_tf = reference_order_noise(B, Fm, y_max_length_, mu_x.dtype, mu_x.device)  # :94, the reference's draws
+    if noise_tf is None:                                                           # (tests may inject pre-drawn noise [B,Ty,F])
+        noise_tf = reference_order_noise(B, Fm, y_max_length_, mu_x.dtype, mu_x.device)  # :94, the reference's draws
     mu_y, z, y_mask, attn = prior_expand(mu_x, w_ceil.reshape(B, Tx), x_mask.reshape(B, Tx).to(torch.float32), y_lengths,
                                          y_max_length_, noise_tf, temperature, want_attn)
     decoder_outputs = decoder(z, y_mask, mu_y, n_timesteps, stoc, spk)             # :96
