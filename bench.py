@@ -121,56 +121,87 @@ def _ncpu():
         return os.cpu_count()
 
 
-_THREADS = None
+# ---- the CPU arm: the UNMODIFIED reference (oracle/_ref bytecode or /root/reference) when present, else the oracle port ------
+CPU_SAMPLE_B = 8          # utterances of the workload's T per timed sample (B >= 8, >= 3 Euler steps, not extrapolated from B=2)
+CPU_SAMPLE_STEPS = 3
+_CPU = {}
 
 
-def pick_cpu_threads(torch, O, cfg, sd):
-    """The reference arm gets all the host threads it can USE: sweep the thread count on a tiny problem and keep
-    the fastest (on many-core boxes PyTorch's CPU convs slow down badly when oversubscribed)."""
-    global _THREADS
-    if _THREADS is not None:
-        torch.set_num_threads(_THREADS)
-        return _THREADS
-    from speech_backbones_b200 import synthetic_inputs
-    z, mask, mu, spk, _ = synthetic_inputs(1, 128, n_spks=cfg.n_spks)
-    n = _ncpu()
-    cands = sorted({c for c in (4, 8, 16, 32, 64, n) if c <= n})
-    best, best_t = cands[0], float("inf")
-    for c in cands:
-        torch.set_num_threads(c)
-        O.reverse_diffusion(sd, cfg, z, mask, mu, 1, False, spk)
-        t0 = time.perf_counter()
-        O.reverse_diffusion(sd, cfg, z, mask, mu, 1, False, spk)
-        dt = time.perf_counter() - t0
-        if dt < best_t:
-            best, best_t = c, dt
-    _THREADS = best
-    torch.set_num_threads(best)
-    return best
-
-
-def cpu_reference_sample(wl, torch, n_steps=2, b_sample=2, repeats=1):
-    """Time the CPU oracle (port of the reference PyTorch path) on a bounded sample of the workload:
-    `b_sample` utterances at the workload's T for `n_steps` Euler steps, after one warm-up step.
-    Cost is linear in B and in N (the loop body is step-independent, diffusion.py:258-274)."""
-    from oracle import gradtts_oracle as O
-    from speech_backbones_b200 import UNetConfig, synthetic_inputs, synthetic_state_dict
+def _cpu_runner(wl, torch):
+    """Build once: (fn(z, mask, mu, n_steps, spk) -> mel, kind, description).  The reference's own `Diffusion` module
+    (Grad-TTS/model/diffusion.py:227-279) with the bench's synthetic weights loaded strictly, run on the host cores."""
+    if "fn" in _CPU:
+        return _CPU["fn"], _CPU["kind"], _CPU["what"]
+    from oracle import ref_import
+    from speech_backbones_b200 import UNetConfig, synthetic_state_dict
     cfg = UNetConfig(n_spks=wl["n_spks"])
     sd = synthetic_state_dict(cfg)
-    threads = pick_cpu_threads(torch, O, cfg, sd)
-    z, mask, mu, spk, _ = synthetic_inputs(b_sample, wl["T"], n_spks=cfg.n_spks)
-    O.reverse_diffusion(sd, cfg, z, mask, mu, 1, False, spk)                    # warm-up
-    best = float("inf")
-    for _ in range(repeats):
+    if ref_import.available("gradtts"):
+        md = ref_import.import_model("gradtts")
+        dec = md.Diffusion(cfg.n_feats, cfg.dim, n_spks=cfg.n_spks, spk_emb_dim=cfg.spk_emb_dim).eval()
+        dec.load_state_dict(sd, strict=True)
+
+        def fn(z, mask, mu, n, spk):
+            return dec(z, mask, mu, n, False, spk)
+        kind, what = "reference", f"unmodified reference Diffusion.forward ({ref_import.kind('gradtts')})"
+    else:
+        from oracle import gradtts_oracle as O
+
+        def fn(z, mask, mu, n, spk):
+            return O.reverse_diffusion(sd, cfg, z, mask, mu, n, False, spk)
+        kind, what = "port", "oracle port of the reference (oracle/gradtts_oracle.py; oracle/_ref not built)"
+    _CPU.update(fn=fn, kind=kind, what=what, cfg=cfg)
+    return fn, kind, what
+
+
+def pick_cpu_threads(torch, fn, inputs):
+    """The CPU arm gets all the host threads it can USE: the thread count is swept AT THE SAMPLE'S OWN SHAPE (one Euler
+    step each, after one untimed step) up to every usable core, and the fastest is kept (PyTorch's CPU convs slow down
+    when oversubscribed on many-core boxes)."""
+    if "threads" in _CPU:
+        torch.set_num_threads(_CPU["threads"])
+        return _CPU["threads"], _CPU["sweep"]
+    z, mask, mu, spk = inputs
+    n = _ncpu()
+    cands = sorted({c for c in (8, 16, 32, 48, 64, 96, 128, n) if c <= n})
+    sweep, best, best_t = {}, cands[0], float("inf")
+    torch.set_num_threads(cands[0])
+    fn(z, mask, mu, 1, spk)                                                      # page in / allocator warm-up
+    for c in cands:
+        torch.set_num_threads(c)
+        fn(z, mask, mu, 1, spk)
         t0 = time.perf_counter()
-        O.reverse_diffusion(sd, cfg, z, mask, mu, n_steps, False, spk)
-        best = min(best, time.perf_counter() - t0)
-    sec_per_frame_step = best / (b_sample * wl["T"] * n_steps)
+        fn(z, mask, mu, 1, spk)
+        dt = time.perf_counter() - t0
+        sweep[c] = round(dt, 3)
+        if dt < best_t:
+            best, best_t = c, dt
+    _CPU.update(threads=best, sweep=sweep)
+    torch.set_num_threads(best)
+    return best, sweep
+
+
+def cpu_reference_sample(wl, torch):
+    """ONE sample definition for both the `--impl reference` arm and the `cpu_baseline` leg: CPU_SAMPLE_B utterances at the
+    workload's T for CPU_SAMPLE_STEPS Euler steps (one call of the reference's `Diffusion.forward` with n_timesteps =
+    CPU_SAMPLE_STEPS; the loop body is step-independent, diffusion.py:258-274), timed in full, after a warm-up call.
+    mel-frames/s at the workload's N = frames / (seconds per frame-step x N)."""
+    from speech_backbones_b200 import synthetic_inputs
+    fn, kind, what = _cpu_runner(wl, torch)
+    b, n_steps = min(CPU_SAMPLE_B, wl["B"]), CPU_SAMPLE_STEPS
+    z, mask, mu, spk, _ = synthetic_inputs(b, wl["T"], n_spks=wl["n_spks"])
+    with torch.no_grad():
+        threads, sweep = pick_cpu_threads(torch, fn, (z, mask, mu, spk))
+        t0 = time.perf_counter()
+        y = fn(z, mask, mu, n_steps, spk)
+        dt = time.perf_counter() - t0
+    assert torch.isfinite(y).all()
+    sec_per_frame_step = dt / (b * wl["T"] * n_steps)
     frames_per_sec = 1.0 / (sec_per_frame_step * wl["N"])
-    sample = (f"oracle port (PyTorch CPU fp32, {threads} threads = fastest of a sweep up to {_ncpu()} usable cores), "
-              f"B={b_sample} x T={wl['T']} for {n_steps} of N={wl['N']} Euler steps ({best:.2f} s), "
-              f"scaled linearly in B and N")
-    return frames_per_sec, sec_per_frame_step, sample, threads
+    sample = (f"{what}, PyTorch CPU fp32, {threads} threads (fastest of a sweep at this shape: {sweep} s per Euler step; "
+              f"{_ncpu()} usable cores); B={b} x T={wl['T']}, {n_steps} Euler steps timed in full ({dt:.2f} s); "
+              f"mel-frames/s at N={wl['N']} = B*T / (s per step * N)")
+    return frames_per_sec, sec_per_frame_step, sample, threads, kind
 
 
 def run_reference(args, wl):
@@ -180,23 +211,58 @@ def run_reference(args, wl):
         return
     vals = []
     for i in range(args.warmup + args.steps):
-        fps, spfs, sample, threads = cpu_reference_sample(wl, torch, n_steps=2, b_sample=2)
+        fps, spfs, sample, threads, kind = cpu_reference_sample(wl, torch)
         if i >= args.warmup:
             vals.append((fps, spfs))
-    fps = statistics.mean(v[0] for v in vals)
-    ms_full = statistics.mean(v[1] for v in vals) * wl["B"] * wl["T"] * wl["N"] * 1e3
+    fps = statistics.median(v[0] for v in vals)
+    ms_full = statistics.median(v[1] for v in vals) * wl["B"] * wl["T"] * wl["N"] * 1e3
     out = {
         "impl": "reference", "metric": "mel-frames/sec at N=50 reverse-diffusion steps", "value": fps,
         "unit": "mel-frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_full, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "batch_per_gpu": wl["B"], "frames": wl["T"], "n_timesteps": wl["N"],
-                   "note": "CPU reference arm: each step is a bounded sample, ms_per_step is the extrapolated full step"},
-        "cpu_baseline": {"value": fps, "unit": "mel-frames/s", "cores": threads, "kind": "port", "sample": sample},
+        "config": bench_config(args, wl, int(os.environ.get("WORLD_SIZE", "1")),
+                               note="CPU reference arm: each bench step is one bounded sample (see cpu_baseline.sample); "
+                                    "ms_per_step is that rate applied to the full workload"),
+        "cpu_baseline": {"value": fps, "unit": "mel-frames/s", "cores": threads, "kind": kind, "sample": sample,
+                         "spread": {"min": min(v[0] for v in vals), "max": max(v[0] for v in vals), "n": len(vals)}},
         "e2e": {"value": fps, "unit": "mel-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(out), flush=True)
+
+
+def bench_config(args, wl, world, **extra):
+    """The `config` object: identical keys in both arms (the driver compares them)."""
+    cfg = {"workload": args.workload, "batch_per_gpu": wl["B"], "global_batch": wl["B"] * world, "frames": wl["T"],
+           "n_timesteps": wl["N"], "stoc": False, "parallelism": f"dp{world}"}
+    cfg.update(extra)
+    return cfg
+
+
+# per-mode arithmetic + the parity bound its tests hold it to (tests/test_fp32x3_gpu.py, tests/test_parity_gpu.py)
+MODES = {
+    "fp32x3": dict(dtype="f32", what="fp32-class on tcgen05: 3xTF32 operand splits, fp32 accumulate; exact fp32 GN/Mish/softmax/context/Euler",
+                   tol="rel-L2 <= 1e-5 per estimator call vs the reference's fp32 CPU outputs (13 goldens), <= 2e-4 on N<=50 trajectories",
+                   mma_per_mac=3),
+    "tf32": dict(dtype="tf32", what="tcgen05 kind::tf32 operands (PyTorch's default GPU conv arithmetic), fp32 accumulate / GN / softmax / Euler",
+                 tol="rel-L2 <= 4e-3 per estimator call (measured 1.5e-3), <= 8e-3 on trajectories", mma_per_mac=1),
+    "bf16": dict(dtype="bf16", what="bf16 operand tensors + weights on tcgen05 kind::f16 (BASELINE config 3's arithmetic), fp32 accumulate / GN / state",
+                 tol="rel-L2 <= 2e-2 per estimator call (measured 1.1e-2), <= 1e-2 on trajectories", mma_per_mac=1),
+    "fp32": dict(dtype="f32", what="CUDA-core FFMA implicit GEMM (the round-1 exact mode; kept as a second opinion)",
+                 tol="rel-L2 <= 1e-4 per estimator call (measured 0.6-2.6e-6)", mma_per_mac=0),
+}
+
+
+def csrc_digest():
+    """sha256 over the kernel sources: ties measured side files (profiles/r2_traffic_*.json) to the binary being benched."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "speech-backbones_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".h")):
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
 
 
 def run_ours(args, wl):
@@ -218,7 +284,7 @@ def run_ours(args, wl):
         dist.barrier()
     from speech_backbones_b200 import UNetConfig, estimator_param_spec, synthetic_inputs, synthetic_state_dict
     from speech_backbones_b200.gradtts import Diffusion
-    from speech_backbones_b200.sharded import broadcast_state_dict
+    from speech_backbones_b200.sharded import broadcast_state_dict, sharded_sample
 
     B, T, N = wl["B"], wl["T"], wl["N"]
     cfg = UNetConfig(n_spks=wl["n_spks"])
@@ -229,46 +295,63 @@ def run_ours(args, wl):
         sd = broadcast_state_dict(sd, estimator_param_spec(cfg), dev)
         torch.cuda.synchronize()
     bcast_s = time.perf_counter() - t0
-    dec = Diffusion(cfg.n_feats, cfg.dim, n_spks=cfg.n_spks, precision=args.precision).eval()
-    dec.load_state_dict(sd)
-    dec = dec.to(dev)
-    eng = dec.engine()
 
     z, mask, mu, spk, _ = synthetic_inputs(B, T, seed=1234 + rank, n_spks=cfg.n_spks)
     zd, md, mud = z.to(dev), mask.to(dev), mu.to(dev)
     spd = None if spk is None else spk.to(dev)
     gathered = torch.empty((world * B, cfg.n_feats, T), dtype=torch.float32, device=dev) if world > 1 else None
 
-    def one_call():
-        y = dec(zd, md, mud, N, False, spd)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, y)       # output mel gather over NVLink
-        return y
-
     def fence():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        one_call()
-    fence()
-    clocks = ClockSampler(local) if rank == 0 else None
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    launches = 0
-    for _ in range(args.steps):
-        one_call()
-        launches += eng.last_launch_count()
-    e1.record()
-    fence()
-    ms_total = e0.elapsed_time(e1)
-    clk = clocks.stop() if clocks else None
-    tms = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms_step = tms.item() / args.steps
-    value = world * B * T / (ms_step * 1e-3)
+    def make(precision):
+        d = Diffusion(cfg.n_feats, cfg.dim, n_spks=cfg.n_spks, precision=precision).eval()
+        d.load_state_dict(sd)
+        return d.to(dev)
+
+    def time_mode(dec_, steps, warmup, sample_clocks=False):
+        """W untimed + K timed `Diffusion.forward` calls (+ the output all-gather when world > 1), CUDA events on the
+        launching stream, barrier + synchronize on both sides, MAX over ranks.  Also times the gather alone per call."""
+        eng_ = dec_.engine()
+        y = None
+        for _ in range(warmup):
+            y = dec_(zd, md, mud, N, False, spd)
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, y)
+        fence()
+        clocks = ClockSampler(local) if (sample_clocks and rank == 0) else None
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * steps + 2)]
+        launches = 0
+        ev[0].record()
+        for i in range(steps):
+            y = dec_(zd, md, mud, N, False, spd)
+            launches += eng_.last_launch_count()
+            ev[1 + 2 * i].record()
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, y)       # output mel gather over NVLink
+            ev[2 + 2 * i].record()
+        ev[2 * steps + 1].record()
+        fence()
+        clk = clocks.stop() if clocks else None
+        ms_total = ev[0].elapsed_time(ev[2 * steps + 1])
+        gather_ms = sum(ev[1 + 2 * i].elapsed_time(ev[2 + 2 * i]) for i in range(steps)) / steps
+        tms = torch.tensor([ms_total, gather_ms], dtype=torch.float64, device=dev)
+        per_rank = None
+        if world > 1:
+            allr = [torch.zeros_like(tms) for _ in range(world)]
+            dist.all_gather(allr, tms)
+            per_rank = [{"rank": r, "ms_per_step": round(v[0].item() / steps, 3), "gather_ms": round(v[1].item(), 3)} for r, v in enumerate(allr)]
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms_step = tms[0].item() / steps
+        return dict(ms_step=ms_step, value=world * B * T / (ms_step * 1e-3), launches=launches, clocks=clk, y=y,
+                    per_rank=per_rank, gather_ms_max=tms[1].item())
+
+    dec = make(args.precision)
+    eng = dec.engine()
+    head = time_mode(dec, args.steps, args.warmup, sample_clocks=True)
+    ms_step, value, launches, clk = head["ms_step"], head["value"], head["launches"], head["clocks"]
 
     # ---- end to end through the host-buffer entry point (pinned host memory in/out, copies inside the timed region)
     zh, mh, muh = z.pin_memory(), mask.pin_memory(), mu.pin_memory()
@@ -289,6 +372,39 @@ def run_ours(args, wl):
     h2d = (zh.numel() + mh.numel() + muh.numel() + (0 if sph is None else sph.numel())) * 4
     d2h = outh.numel() * 4
 
+    # ---- BASELINE config 5 as written (2048 utterances = 256 per GPU over 8 GPUs) through sharded.sharded_sample over NCCL
+    config5 = None
+    if world == 8 and not args.no_config5:
+        B5 = 256
+        z5, m5, mu5, _, _ = synthetic_inputs(B5 * world, T, seed=4321, n_spks=1) if rank == 0 else (None,) * 5
+        shape5 = (B5 * world, cfg.n_feats, T)
+        ins = []
+        for t_, shp in ((z5, shape5), (m5, (B5 * world, 1, T)), (mu5, shape5)):
+            buf = t_.to(dev) if rank == 0 else torch.empty(shp, dtype=torch.float32, device=dev)
+            dist.broadcast(buf, 0)
+            ins.append(buf)
+        del z5, m5, mu5
+        lo, hi = rank * B5, (rank + 1) * B5
+
+        def compute(a, b_):
+            return dec(ins[0][a:b_], ins[1][a:b_], ins[2][a:b_], N, False, None)
+        sharded_sample(compute, B5 * world, shape5[1:], dev)                   # warm-up (plan for B=256)
+        fence()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        y5 = sharded_sample(compute, B5 * world, shape5[1:], dev)
+        c1.record()
+        fence()
+        t5 = torch.tensor([c0.elapsed_time(c1)], dtype=torch.float64, device=dev)
+        all5 = [torch.zeros_like(t5) for _ in range(world)]
+        dist.all_gather(all5, t5)
+        dist.all_reduce(t5, op=dist.ReduceOp.MAX)
+        config5 = {"workload": "BASELINE config 5: 2048 utterances x T=512, N=50, 256 per GPU, sharded_sample over NCCL (1 timed call)",
+                   "value": B5 * world * T / (t5.item() * 1e-3), "unit": "mel-frames/s", "ms": t5.item(),
+                   "per_rank_ms": [round(v.item(), 2) for v in all5], "finite": bool(torch.isfinite(y5).all().item()),
+                   "gathered_shape": list(y5.shape)}
+        del ins, y5
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -296,14 +412,19 @@ def run_ours(args, wl):
 
     # ---- roofline of the dominant kernel class, one CUDA event pair per launch
     peaks = load_peaks()
+    mode = MODES[args.precision]
+    dec(zd, md, mud, 1, False, spd)                                            # (config 5 may have re-planned for B=256)
     prof = eng.profile_ops()
     conv = [(n, ms, fl, by) for n, ms, fl, by in prof if n.endswith(".raw")]
     conv_ms, conv_fl, conv_by = (sum(x[i] for x in conv) for i in (1, 2, 3))
     all_ms = sum(x[1] for x in prof)
-    # bf16 operands: the measured cuBLAS bf16 rate of MEASURED_PEAKS.json.  tf32: that file has no tf32 figure, so the
-    # denominator is the larger of half the bf16 rate and a cuBLAS TF32 matmul timed here (sustained, ~1 s)
+    # bf16 operands: the measured cuBLAS bf16 rate of MEASURED_PEAKS.json.  tf32 / fp32x3: that file has no tf32 figure, so
+    # the tf32 rate is the larger of half the bf16 rate and a cuBLAS TF32 matmul timed here (sustained, ~1 s); an fp32x3
+    # MAC costs three tf32 MMAs, so its algorithmic peak is a third of that
     tf32_here = measure_tf32_matmul_tflops(torch, dev) if args.precision != "bf16" else None
-    tensor_peak = peaks["bf16"] if args.precision == "bf16" else max(peaks["bf16"] * 0.5, tf32_here)
+    mma_peak = peaks["bf16"] if args.precision == "bf16" else max(peaks["bf16"] * 0.5, tf32_here)
+    per_mac = max(1, mode["mma_per_mac"])
+    tensor_peak = mma_peak / per_mac
     achieved = conv_fl / (conv_ms * 1e-3) / 1e12
     by_kind = {}
     for n, ms, fl, by in prof:
@@ -311,87 +432,72 @@ def run_ours(args, wl):
              "attention" if (".2." in n or "mid_attn" in n) else "resample" if ".3." in n else
              "final_euler" if n == "estimator.out" else "resblock_tail")
         by_kind[k] = by_kind.get(k, 0.0) + ms
-    # DRAM bytes per launch of the same kernel class from the committed ncu capture (scripts/ncu_traffic.py), if present
+    # DRAM bytes per launch of the same kernel class from an ncu capture OF THIS BINARY (scripts/ncu_traffic.py writes the
+    # csrc digest next to the bytes); a capture of other kernels is not reported
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r1_traffic_conv3x3.json")
-    if os.path.exists(tpath) and args.precision == "tf32" and (B, T) == (32, 512):
+    tpath = os.path.join(ROOT, "profiles", f"r2_traffic_conv3x3_{args.precision}.json")
+    if os.path.exists(tpath) and (B, T) == (32, 512):
         tj = json.load(open(tpath))
-        traffic, traffic_src = tj["dram_bytes_per_launch"], "profiles/r1_traffic_conv3x3.json (ncu dram__bytes_read+write, %d launches)" % tj["launches"]
+        if tj.get("csrc_digest") == csrc_digest():
+            traffic, traffic_src = tj["dram_bytes_per_launch"], f"profiles/{os.path.basename(tpath)} (ncu dram__bytes_read+write, {tj['launches']} launches, csrc {tj['csrc_digest']})"
+        else:
+            traffic_src = f"not reported: profiles/{os.path.basename(tpath)} was captured from other kernel sources (csrc {tj.get('csrc_digest')} != {csrc_digest()})"
     roofline = {
         "kernel": "conv3x3 implicit GEMM (25 launches/step)", "bound": "tensor", "achieved": achieved, "peak": tensor_peak,
         "unit": "TFLOP/s", "frac": achieved / tensor_peak, "traffic": traffic, "traffic_source": traffic_src,
         "algorithmic_bytes_per_launch": conv_by / max(1, len(conv)),
         "peak_note": (f"{peaks['src']} cuBLAS bf16 sustained (MEASURED_PEAKS.json)" if args.precision == "bf16" else
-                      f"max(0.5 x {peaks['src']} cuBLAS bf16 sustained = {peaks['bf16'] * 0.5:.1f}, cuBLAS TF32 matmul 8192^3 "
-                      f"sustained measured in this run = {tf32_here:.1f})"),
+                      f"tf32 MMA rate = max(0.5 x {peaks['src']} cuBLAS bf16 sustained = {peaks['bf16'] * 0.5:.1f}, cuBLAS TF32 matmul 8192^3 "
+                      f"sustained measured in this run = {tf32_here:.1f}) TFLOP/s, divided by {per_mac} tf32 MMA(s) per algorithmic MAC in mode {args.precision}"),
+        "mma_issue_tflops": achieved * per_mac,
         "launches": len(conv), "avg_launch_ms": conv_ms / max(1, len(conv)),
         "flop_per_launch_avg": conv_fl / max(1, len(conv)), "share_of_step": conv_ms / all_ms,
         "hbm": {"achieved_gbs": conv_by / (conv_ms * 1e-3) / 1e9, "peak_gbs": peaks["hbm_gbs"],
                 "frac": conv_by / (conv_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]},
         "step_ms_by_kind": {k: round(v, 4) for k, v in by_kind.items()},
         "whole_step": {"tflops": FLOP_PER_FRAME_STEP * B * T / (ms_step / N * 1e-3) / 1e12,
+                       "frac_of_tensor_peak": FLOP_PER_FRAME_STEP * B * T / (ms_step / N * 1e-3) / 1e12 / tensor_peak,
                        "ideal_hbm_gbs": IDEAL_BYTES_PER_FRAME_STEP * B * T / (ms_step / N * 1e-3) / 1e9},
     }
-    fps_cpu, _, sample, threads = cpu_reference_sample(wl, torch, n_steps=3, b_sample=2) if world == 1 else (None,) * 4
-    # the exact-fp32 CUDA-core mode of the same engine, one timed call (context for the tf32 headline)
-    fp32_leg = None
-    if world == 1 and args.precision != "fp32" and not args.no_fp32_leg:
-        dec32 = Diffusion(cfg.n_feats, cfg.dim, n_spks=cfg.n_spks, precision="fp32").eval()
-        dec32.load_state_dict(sd)
-        dec32 = dec32.to(dev)
-        dec32(zd, md, mud, N, False, spd)
-        torch.cuda.synchronize()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record()
-        y32 = dec32(zd, md, mud, N, False, spd)
-        f1.record()
-        torch.cuda.synchronize()
-        ytc = dec(zd, md, mud, N, False, spd)
-        rel = ((ytc - y32).double().norm() / y32.double().norm()).item()
-        fp32_leg = {"value": B * T / (f0.elapsed_time(f1) * 1e-3), "unit": "mel-frames/s", "dtype": "f32",
-                    "note": "same engine, precision=fp32 (CUDA-core FFMA convs), 1 timed call",
-                    "rel_l2_of_headline_output_vs_this": rel}
-    # the bf16-operand mode of the same engine (BASELINE config 3's arithmetic), one timed call, for context
-    bf16_leg = None
-    if world == 1 and args.precision == "tf32" and not args.no_fp32_leg:
-        dec16 = Diffusion(cfg.n_feats, cfg.dim, n_spks=cfg.n_spks, precision="bf16").eval()
-        dec16.load_state_dict(sd)
-        dec16 = dec16.to(dev)
-        dec16(zd, md, mud, N, False, spd)
-        torch.cuda.synchronize()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record()
-        y16 = dec16(zd, md, mud, N, False, spd)
-        f1.record()
-        torch.cuda.synchronize()
-        ref = y32 if fp32_leg is not None else dec(zd, md, mud, N, False, spd)
-        bf16_leg = {"value": B * T / (f0.elapsed_time(f1) * 1e-3), "unit": "mel-frames/s", "dtype": "bf16",
-                    "note": "same engine, precision=bf16 (bf16 operand tensors + weights, fp32 accumulate/GN/state), 1 timed call",
-                    "rel_l2_vs_fp32_mode": ((y16 - ref).double().norm() / ref.double().norm()).item()}
-        del dec16
+    # ---- the other precision modes of the same engine, timed with the SAME --steps / --warmup (first-class legs)
+    legs = {}
+    if world == 1 and not args.no_extra_legs:
+        y_head = head["y"]
+        for prec in [m for m in ("fp32x3", "tf32", "bf16") if m != args.precision]:
+            d2 = make(prec)
+            r = time_mode(d2, args.steps, args.warmup)
+            legs[prec] = {"value": r["value"], "unit": "mel-frames/s", "ms_per_step": r["ms_step"], "dtype": MODES[prec]["dtype"],
+                          "steps": args.steps, "warmup": args.warmup, "arithmetic": MODES[prec]["what"], "tolerance": MODES[prec]["tol"],
+                          "rel_l2_of_output_vs_headline_mode": ((r["y"] - y_head).double().norm() / y_head.double().norm()).item()}
+            d2._engine.close()
+            del d2, r
+            torch.cuda.empty_cache()
+    cpu = cpu_reference_sample(wl, torch) if world == 1 else None
     out = {
         "metric": "mel-frames/sec at N=50 reverse-diffusion steps", "value": value, "unit": "mel-frames/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[args.precision], "data": "synthetic",
-        "config": {"workload": args.workload, "batch_per_gpu": B, "global_batch": B * world, "frames": T,
-                   "n_timesteps": N, "stoc": False, "parallelism": f"dp{world}",
-                   "l2": f"per-step working set ({eng.workspace_bytes(B, T) / 1e9:.1f} GB of activations) exceeds the 126 MB L2; no flush needed",
-                   "weights": "synthetic seeded (no checkpoints ship with the reference)",
-                   "weight_broadcast_s": round(bcast_s, 4)},
+        "dtype": mode["dtype"], "data": "synthetic",
+        "config": bench_config(args, wl, world, precision_mode=args.precision, arithmetic=mode["what"], tolerance=mode["tol"],
+                               l2=f"per-step working set ({eng.workspace_bytes(B, T) / 1e9:.1f} GB of activations) exceeds the 126 MB L2; no flush needed",
+                               weights="synthetic seeded (no checkpoints ship with the reference)",
+                               weight_broadcast_s=round(bcast_s, 4)),
         "frame_steps_per_s": value * N,
         "e2e": {"value": e2e_value, "unit": "mel-frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,
         "clocks": clk,
         "roofline": roofline,
     }
-    if fp32_leg is not None:
-        out["fp32_mode"] = fp32_leg
-    if bf16_leg is not None:
-        out["bf16_mode"] = bf16_leg
-    if fps_cpu is not None:
-        out["cpu_baseline"] = {"value": fps_cpu, "unit": "mel-frames/s", "cores": threads, "kind": "port",
-                               "sample": sample}
+    if legs:
+        out["modes"] = legs
+    if head["per_rank"] is not None:
+        out["per_rank"] = head["per_rank"]
+        out["gather_ms_max"] = head["gather_ms_max"]
+    if config5 is not None:
+        out["config5"] = config5
+    if cpu is not None:
+        fps_cpu, _, sample, threads, kind = cpu
+        out["cpu_baseline"] = {"value": fps_cpu, "unit": "mel-frames/s", "cores": threads, "kind": kind, "sample": sample}
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -404,11 +510,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="gradtts_b32_t512_n50", choices=sorted(WORKLOADS))
-    ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32", "bf16"],
-                    help="tf32: tcgen05 tensor cores, fp32 accumulate/IO (PyTorch's default GPU conv arithmetic); "
-                         "fp32: CUDA-core FFMA path; bf16: bf16 operand tensors (BASELINE config 3's arithmetic; not the "
-                         "headline, which is quoted on the fp32 config)")
-    ap.add_argument("--no-fp32-leg", action="store_true", help="skip the extra exact-fp32 timing call")
+    ap.add_argument("--precision", default="fp32x3", choices=["fp32x3", "fp32", "tf32", "bf16"],
+                    help="fp32x3 (default, the headline: BASELINE config 2 is fp32): fp32-class arithmetic on tcgen05 (3xTF32); "
+                         "tf32: plain tf32 operands (PyTorch's default GPU conv arithmetic); bf16: bf16 operand tensors "
+                         "(BASELINE config 3's arithmetic); fp32: the CUDA-core FFMA path")
+    ap.add_argument("--no-extra-legs", "--no-fp32-leg", dest="no_extra_legs", action="store_true",
+                    help="skip the other precision modes' legs (each is timed with the same --steps/--warmup)")
+    ap.add_argument("--no-config5", action="store_true", help="at 8 GPUs: skip the BASELINE config 5 leg (B=256 per GPU)")
     ap.add_argument("--batch", type=int, default=None, help="override B (debug only; not a valid bench line)")
     ap.add_argument("--frames", type=int, default=None, help="override T (debug only)")
     ap.add_argument("--n-timesteps", type=int, default=None, help="override N (debug only)")

@@ -31,9 +31,13 @@ enum { SBK_OK = 0, SBK_ERR_ARG = 1, SBK_ERR_CUDA = 2, SBK_ERR_STATE = 3, SBK_ERR
 /* arithmetic of the dense contractions (3x3/1x1 convs); GN / softmax / Mish / Euler are always fp32 */
 enum { SBK_PREC_FP32 = 0,   /* CUDA-core FFMA, fp32 operands (bit-faithful class of the CPU reference)   */
        SBK_PREC_TF32 = 1,   /* tcgen05 kind::tf32, fp32 accumulate in TMEM (PyTorch's default GPU class) */
-       SBK_PREC_BF16 = 2 }; /* tcgen05 kind::f16 on bf16 operand tensors (conv inputs + weights stored as bf16),
+       SBK_PREC_BF16 = 2,   /* tcgen05 kind::f16 on bf16 operand tensors (conv inputs + weights stored as bf16),
                                fp32 accumulate; raw conv outputs, GN statistics, softmax, sampler state fp32
-                               (BASELINE config 3).  Grad-TTS only: sbk_pack() refuses it for DiffVC        */
+                               (BASELINE config 3); both models                                             */
+       SBK_PREC_FP32X3 = 3 };/* fp32-class arithmetic on tcgen05 ("3xTF32"): every operand is split x = x_hi + x_lo
+                               (tf32 each), x_lo*w_hi + x_hi*w_lo + x_hi*w_hi accumulated in fp32 in TMEM; softmax /
+                               context / Mish / GN exact fp32.  The default of the drop-in modules: matches the
+                               reference's fp32 CPU arithmetic to ~1e-6 per estimator call                   */
 
 enum { SBK_MODEL_GRADTTS = 0, SBK_MODEL_DIFFVC = 1 };
 

@@ -10,7 +10,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsbk.so")
 
-PREC = {"fp32": 0, "tf32": 1, "bf16": 2}
+PREC = {"fp32": 0, "tf32": 1, "bf16": 2, "fp32x3": 3}
 MODEL = {"gradtts": 0, "diffvc": 1}
 
 EXPORTS = [
@@ -127,7 +127,7 @@ class Engine:
     """One sbk_handle: a (device, configuration) pair owning packed weights, workspace and graphs."""
 
     def __init__(self, n_feats=80, dim=64, n_spks=1, spk_emb_dim=64, beta_min=0.05, beta_max=20.0,
-                 pe_scale=1000.0, device=0, precision="fp32", use_graph=True, model="gradtts", dim_cond=0,
+                 pe_scale=1000.0, device=0, precision="fp32x3", use_graph=True, model="gradtts", dim_cond=0,
                  use_ref_t=True):
         self.lib = load_library()
         self.cfg = SbkConfig(MODEL[model], n_feats, dim, n_spks, spk_emb_dim, beta_min, beta_max, pe_scale,

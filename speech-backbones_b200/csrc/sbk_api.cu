@@ -52,10 +52,11 @@ struct Arena {
     }
 };
 
-enum OpKind { OP_FIRST, OP_IGEMM, OP_RESFINAL, OP_CTX, OP_MIX, OP_FINAL, OP_CONVTC, OP_GNACT };
+enum OpKind { OP_FIRST, OP_IGEMM, OP_RESFINAL, OP_CTX, OP_MIX, OP_FINAL, OP_CONVTC, OP_GNACT, OP_KVCTX };
 struct Op {
     OpKind kind; std::string name;
     FirstConvParams fc; IgemmParams ig; ConvTcParams tc; GnActParams ga; ResFinalParams rf; AttnCtxParams cx; AttnMixParams mx; FinalParams fn;
+    KvCtxParams kc;
     const float* dbg_ptr = nullptr; int64_t dbg_numel = 0;
     int dbg_fmt = 0;               // layout of the named output: 0 NHWC fp32, 1 [B][H][C/4][W][4] fp32, 2 [B][H][C/8][W][8] bf16
     double flops = 0, bytes = 0;   // algorithmic work of this launch
@@ -64,7 +65,7 @@ struct Op {
 
 struct Plan {
     int B = 0, T = 0, tb_rows = 0, noise_cap_steps = 0;
-    void* mem = nullptr; size_t bytes = 0;
+    void* mem = nullptr; size_t bytes = 0, cap = 0;   // arena: grow-only (cap) across (B,T) changes, `bytes` in use
     std::vector<Op> ops;
     int final_op = -1;
     // owned buffers
@@ -212,10 +213,13 @@ extern "C" int sbk_create(const sbk_config* cfg, sbk_handle** out) {
     if (!cfg || !out) return fail(SBK_ERR_ARG, "sbk_create: null argument");
     if (cfg->model != SBK_MODEL_GRADTTS && cfg->model != SBK_MODEL_DIFFVC) return fail(SBK_ERR_UNSUPPORTED, "sbk_create: model %d not supported", cfg->model);
     if (cfg->model == SBK_MODEL_DIFFVC && (cfg->dim_cond <= 0 || cfg->dim_cond % 4 != 0)) return fail(SBK_ERR_ARG, "sbk_create: DiffVC needs dim_cond > 0 (multiple of 4), got %d", cfg->dim_cond);
+    if (cfg->model == SBK_MODEL_DIFFVC && cfg->use_ref_t && cfg->dim_cond % 128 != 0)
+        return fail(SBK_ERR_ARG, "sbk_create: the native RefBlock needs dim_cond to be a multiple of 128 (its first conv writes 64-channel "
+                                 "tiles and every conv reads 32-channel K stages), got %d", cfg->dim_cond);
     if (cfg->dim <= 0 || cfg->dim % 64 != 0) return fail(SBK_ERR_ARG, "sbk_create: dim must be a positive multiple of 64 (got %d)", cfg->dim);
     if (cfg->n_feats <= 0 || cfg->n_feats % 4 != 0) return fail(SBK_ERR_ARG, "sbk_create: n_feats must be a multiple of 4 (two stride-2 levels), got %d", cfg->n_feats);
     if (cfg->n_spks < 1 || cfg->spk_emb_dim <= 0) return fail(SBK_ERR_ARG, "sbk_create: bad speaker configuration");
-    if (cfg->precision < SBK_PREC_FP32 || cfg->precision > SBK_PREC_BF16) return fail(SBK_ERR_ARG, "sbk_create: unknown precision %d", cfg->precision);
+    if (cfg->precision < SBK_PREC_FP32 || cfg->precision > SBK_PREC_FP32X3) return fail(SBK_ERR_ARG, "sbk_create: unknown precision %d", cfg->precision);
     sbk_handle* h = new sbk_handle();
     h->cfg = *cfg;
     build_spec(h);
@@ -223,12 +227,16 @@ extern "C" int sbk_create(const sbk_config* cfg, sbk_handle** out) {
     return SBK_OK;
 }
 
-static void free_plan(sbk_handle* h) {
+// drop the launch plan and its graphs; the arena allocation survives unless `release_arena` (it is grow-only: a new
+// (B,T) whose layout fits the existing capacity is laid out inside it without a cudaFree/cudaMalloc pair)
+static void free_plan(sbk_handle* h, bool release_arena = true) {
     Plan& p = h->plan;
     for (int i = 0; i < 4; ++i) if (p.gexec[i]) { cudaGraphExecDestroy(p.gexec[i]); p.gexec[i] = nullptr; }
     for (auto& op : p.ops) if (op.dbg_copy) cudaFree(op.dbg_copy);
-    if (p.mem) cudaFree(p.mem);
+    void* mem = p.mem; const size_t cap = p.cap;
+    if (mem && release_arena) { cudaFree(mem); mem = nullptr; }
     p = Plan();
+    if (mem) { p.mem = mem; p.cap = cap; }
 }
 
 extern "C" void sbk_destroy(sbk_handle* h) {
@@ -293,6 +301,8 @@ static uint16_t f32_to_bf16_rn(float x) {
     return (uint16_t)(u >> 16);
 }
 static int pack_tc_host(sbk_handle* h, const std::vector<float>& hs, const std::string& key, int cout, int cin, int geom, bool bf16, int nt_override = 0);
+// fp32x3 handles (and the CUDA-core fp32 handles' RefBlock branch) pack every tensor-core weight as (hi, lo) stage pairs
+static bool packs_x3(const sbk_handle* h) { return h->cfg.precision == SBK_PREC_FP32X3 || h->cfg.precision == SBK_PREC_FP32; }
 static int pack_tc(sbk_handle* h, const std::string& src, const std::string& key, int cout, int cin, int geom, bool bf16) {
     const int taps = conv_tc_taps(geom);
     std::vector<float> hs((size_t)cout * cin * taps);
@@ -323,6 +333,14 @@ static int pack_tc_kv(sbk_handle* h, const std::string& src, const std::string& 
     CU(cudaMemcpy(d, m.data(), m.size(), cudaMemcpyHostToDevice));
     return SBK_OK;
 }
+// fp32x3 mode: the k|v rows of to_qkv (rows 128..383) as a plain 1x1 conv [256][C] for the 3xTF32 conv kernel; its fp32
+// output [B][H][64][W][4] feeds k_kv_ctx
+static int pack_tc_kvx(sbk_handle* h, const std::string& src, const std::string& key, int C) {
+    std::vector<float> q((size_t)384 * C);
+    CU(cudaMemcpy(q.data(), h->raw[src], q.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    std::vector<float> kv(q.begin() + (size_t)128 * C, q.end());
+    return pack_tc_host(h, kv, key, 256, C, G_PW, false);
+}
 // ConvTranspose2d weight [ci][co][4][4] -> logical [co][ci][kh*4+kw]
 static int pack_tc_up(sbk_handle* h, const std::string& src, const std::string& key, int C, bool bf16) {
     std::vector<float> w((size_t)C * C * 16), m((size_t)C * C * 16);
@@ -336,11 +354,21 @@ static int pack_tc_host(sbk_handle* h, const std::vector<float>& hs, const std::
     const int NT = nt_override ? nt_override : conv_tc_ntile(geom, cout), CPS = conv_tc_stage_channels(geom, bf16 ? 1 : 0), EPC = bf16 ? 8 : 4, KCHK = CPS / EPC;
     const int ksteps = cin / CPS;
     const size_t esz = bf16 ? 2 : 4;
-    std::vector<uint8_t> hd((size_t)cout * cin * taps * esz);
+    const bool x3 = !bf16 && packs_x3(h);
+    std::vector<uint8_t> hd((size_t)cout * cin * taps * esz * (x3 ? 2 : 1));
     for (int nt = 0; nt < cout / NT; ++nt) for (int ks = 0; ks < ksteps; ++ks) for (int tap = 0; tap < taps; ++tap)
         for (int k = 0; k < KCHK; ++k) for (int col = 0; col < NT; ++col) for (int e = 0; e < EPC; ++e) {
             const int co = nt * NT + col, ci = ks * CPS + k * EPC + e;
             const float w = hs[((size_t)co * cin + ci) * taps + tap];
+            if (x3) {
+                // [ntile][kstage][hi|lo][tap][chunk][co % NT][4]: w = hi + lo, both tf32 (RNA), residual ~2^-22 |w|
+                const size_t ih = ((((((size_t)nt * ksteps + ks) * 2) * taps + tap) * KCHK + k) * NT + col) * EPC + e;
+                const uint32_t uh = f32_to_tf32_rna(w);
+                float fh; memcpy(&fh, &uh, 4);
+                reinterpret_cast<uint32_t*>(hd.data())[ih] = uh;
+                reinterpret_cast<uint32_t*>(hd.data())[ih + (size_t)taps * KCHK * NT * EPC] = f32_to_tf32_rna(w - fh);
+                continue;
+            }
             const size_t idx = (((((size_t)nt * ksteps + ks) * taps + tap) * KCHK + k) * NT + col) * EPC + e;
             if (bf16) reinterpret_cast<uint16_t*>(hd.data())[idx] = f32_to_bf16_rn(w);
             else reinterpret_cast<uint32_t*>(hd.data())[idx] = f32_to_tf32_rna(w);
@@ -391,6 +419,7 @@ extern "C" int sbk_pack(sbk_handle* h) {
         TRY(repack(h, r.prefix + ".block2.block.0.weight", r.prefix + ".block2.w", (size_t)r.cout * 9 * r.cout, conv_pack));
         if (r.cin != r.cout) TRY(repack(h, r.prefix + ".res_conv.weight", r.prefix + ".res.w", (size_t)r.cin * r.cout, conv_pack));
     }
+    const bool x3 = h->cfg.precision == SBK_PREC_FP32X3;
     if (h->cfg.precision != SBK_PREC_FP32) {
         const bool bf = h->cfg.precision == SBK_PREC_BF16;
         const int cps3 = conv_tc_stage_channels(G_C3, bf ? 1 : 0), cps1 = conv_tc_stage_channels(G_PW, bf ? 1 : 0);
@@ -401,7 +430,10 @@ extern "C" int sbk_pack(sbk_handle* h) {
         }
         TRY(pack_tc(h, "estimator.final_block.block.0.weight", "estimator.final_block.wtc", h->cfg.dim, h->cfg.dim, G_C3, bf));
         for (auto& a : h->attns)
-            if (a.c % cps1 == 0) TRY(pack_tc_kv(h, a.prefix + ".fn.fn.to_qkv.weight", a.prefix + ".kv.wtc", a.c, bf));
+            if (a.c % cps1 == 0) {
+                if (x3) TRY(pack_tc_kvx(h, a.prefix + ".fn.fn.to_qkv.weight", a.prefix + ".kvx.wtc", a.c));
+                else TRY(pack_tc_kv(h, a.prefix + ".fn.fn.to_qkv.weight", a.prefix + ".kv.wtc", a.c, bf));
+            }
         for (int l = 0; l < 2; ++l) {
             const std::string p = "estimator.downs." + std::to_string(l) + ".3.conv";
             TRY(pack_tc(h, p + ".weight", p + ".wtc", h->cfg.dim << l, h->cfg.dim << l, G_DOWN, bf));
@@ -410,18 +442,19 @@ extern "C" int sbk_pack(sbk_handle* h) {
             const std::string p = "estimator.ups." + std::to_string(j) + ".3.conv";
             TRY(pack_tc_up(h, p + ".weight", p + ".wtc", h->cfg.dim << (1 - j), bf));
         }
-        if (h->cfg.model == SBK_MODEL_DIFFVC && h->cfg.use_ref_t) {
-            const int base = h->cfg.dim_cond / 4;
-            const char* nm[5] = {"block12", "block21", "block22", "block31", "block32"};
-            const int ci[5] = {base, base, 2 * base, 2 * base, 4 * base}, co[5] = {2 * base, 4 * base, 4 * base, 8 * base, 8 * base};
-            for (int k = 0; k < 5; ++k) {
-                const std::string q = std::string("estimator.ref_block.") + nm[k];
-                // the hoisted RefBlock branch (sbk_vc_conditioning) runs once per call outside the loop and always uses
-                // tf32 operands with fp32 activations, also when the U-Net itself runs on bf16 operand tensors
-                TRY(pack_tc(h, q + ".0.weight", q + ".wtc", co[k], ci[k], G_C3, false));
-            }
-            TRY(repack(h, "estimator.ref_block.block11.0.weight", "estimator.ref_block.block11.w", (size_t)9 * 2 * base, first_pack));
+    }
+    if (h->cfg.model == SBK_MODEL_DIFFVC && h->cfg.use_ref_t) {
+        const int base = h->cfg.dim_cond / 4;
+        const char* nm[5] = {"block12", "block21", "block22", "block31", "block32"};
+        const int ci[5] = {base, base, 2 * base, 2 * base, 4 * base}, co[5] = {2 * base, 4 * base, 4 * base, 8 * base, 8 * base};
+        for (int k = 0; k < 5; ++k) {
+            const std::string q = std::string("estimator.ref_block.") + nm[k];
+            // the hoisted RefBlock branch (sbk_vc_conditioning) runs once per call outside the loop, on the tensor cores in
+            // every precision: tf32 operands with fp32 activations for the tf32 / bf16 handles, 3xTF32 (hi, lo) pairs for
+            // the fp32-class handles (fp32x3 and the CUDA-core fp32 mode, whose U-Net kernels have no InstanceNorm/GLU path)
+            TRY(pack_tc(h, q + ".0.weight", q + ".wtc", co[k], ci[k], G_C3, false));
         }
+        TRY(repack(h, "estimator.ref_block.block11.0.weight", "estimator.ref_block.block11.w", (size_t)9 * 2 * base, first_pack));
     }
     for (auto& a : h->attns) TRY(repack(h, a.prefix + ".fn.fn.to_qkv.weight", a.prefix + ".kv.w", (size_t)a.c * 256, kv_pack));
     for (int l = 0; l < 2; ++l) {
@@ -449,7 +482,7 @@ extern "C" int sbk_pack(sbk_handle* h) {
         h->owned.push_back(h->d_zero);
         CU(cudaMemset(h->d_zero, 0, 8192));
     }
-    free_plan(h);   // packed pointers may have changed
+    free_plan(h, false);   // packed pointers may have changed; the arena itself stays
     h->is_packed = true;
     return SBK_OK;
 }
@@ -461,6 +494,8 @@ namespace {
 struct Bufs {
     float *A[3], *Bf[3], *X[3], *Y[3], *S[3], *D[3], *U1;
     float *kv_part, *ctx, *w_eff, *b_eff;
+    float* kvraw;                              // fp32x3: the k|v projection [B][H0][64][W0][4]
+    std::map<const void*, float*> lo;          // fp32x3: operand tensor -> its x_lo twin
 };
 }
 
@@ -472,8 +507,13 @@ static size_t layout(const sbk_handle* h, int B, int T, int tb_rows, Arena& ar, 
     auto f = [&](size_t n) { return (float*)ar.take(n * sizeof(float)); };
     // operand-form tensors (conv inputs): fp32, or bf16 in the bf16 mode; A[] holds the raw conv outputs (always fp32)
     const size_t osz = c.precision == SBK_PREC_BF16 ? 2 : 4;
-    auto fo = [&](size_t n) { return (float*)ar.take(n * osz); };
+    const bool x3 = c.precision == SBK_PREC_FP32X3;
     Bufs b{};
+    auto fo = [&](size_t n) {
+        float* r = (float*)ar.take(n * osz);
+        if (x3) { float* l = (float*)ar.take(n * osz); if (r) b.lo[r] = l; }
+        return r;
+    };
     for (int l = 0; l < 3; ++l) {
         const size_t n = (size_t)B * P[l] * C[l];
         b.A[l] = f(n); b.Bf[l] = fo(n); b.X[l] = fo(n); b.Y[l] = fo(n);
@@ -484,8 +524,9 @@ static size_t layout(const sbk_handle* h, int B, int T, int tb_rows, Arena& ar, 
     const size_t mt0 = (P[0] + 127) / 128;
     b.kv_part = f((size_t)B * mt0 * kHeads * kKvPartFloats);
     b.ctx = f((size_t)B * kHeads * 1024);
-    b.w_eff = f((size_t)B * C[2] * C[2]);
+    b.w_eff = f((size_t)B * C[2] * C[2] * (x3 ? 2 : 1));
     b.b_eff = f(C[2]);
+    b.kvraw = x3 ? f((size_t)B * P[0] * 256) : nullptr;
     if (bf) *bf = b;
     Plan dummy;
     Plan& p = pl ? *pl : dummy;
@@ -515,12 +556,23 @@ extern "C" size_t sbk_workspace_bytes(const sbk_handle* h, int B, int T) {
 }
 
 static int build_plan(sbk_handle* h, int B, int T, int tb_rows) {
-    free_plan(h);
+    free_plan(h, false);
     Plan& pl = h->plan;
     const sbk_config& c = h->cfg;
     Arena probe;
     const size_t bytes = layout(h, B, T, tb_rows, probe, nullptr, nullptr);
-    CU(cudaMalloc(&pl.mem, bytes));
+    if (bytes > pl.cap) {
+        // grow-only arena: utterance lengths change from call to call, and a cudaFree/cudaMalloc pair is a device-wide sync
+        if (pl.mem) { cudaFree(pl.mem); pl.mem = nullptr; pl.cap = 0; }
+        const cudaError_t e = cudaMalloc(&pl.mem, bytes);
+        if (e != cudaSuccess) {
+            pl.mem = nullptr;
+            cudaGetLastError();
+            return fail(SBK_ERR_CUDA, "out of memory: the (B=%d, T=%d) workspace needs %zu bytes (%s); free cached blocks "
+                                      "(torch.cuda.empty_cache()) or split the batch", B, T, bytes, cudaGetErrorString(e));
+        }
+        pl.cap = bytes;
+    }
     pl.bytes = bytes;
     Arena ar; ar.base = (char*)pl.mem; ar.cap = bytes;
     Bufs bf;
@@ -552,6 +604,8 @@ static int build_plan(sbk_handle* h, int B, int T, int tb_rows) {
         return p;
     };
     const bool use_tc = c.precision != SBK_PREC_FP32;
+    const bool x3 = c.precision == SBK_PREC_FP32X3;
+    auto LO = [&](const void* q) -> float* { auto it = bf.lo.find(q); return it == bf.lo.end() ? nullptr : it->second; };
     int num_sms = 148;
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, c.device);
     const bool b16 = c.precision == SBK_PREC_BF16;          // operand tensors in bf16 [B][H][C/8][W][8]
@@ -596,6 +650,7 @@ static int build_plan(sbk_handle* h, int B, int T, int tb_rows) {
         p.wpk = W(wkey); p.bias = bkey.empty() ? nullptr : W(bkey); p.out = out; p.Cout = cout;
         p.epi = EPI_PLAIN; p.ostats = st; p.mask = pl.mask; p.T = T; p.lvl = lvl; p.zero_page = h->d_zero;
         p.bf16 = b16 ? 1 : 0;
+        if (x3) { p.x3 = 1; p.in0_lo = LO(in0); p.in1_lo = LO(in1); p.out_lo = geom != G_C3 ? LO(out) : nullptr; }
         if (geom == G_C3 && conv_tc_ntile(geom, cout) == 128) {
             // tiles of 2 rows x 128 pixels x 128 channels; when they cannot fill half the SMs, use 64-wide N tiles instead
             const long long tiles = (long long)B * ((Ws[lvl] + 127) / 128) * ((Hs[lvl] + 1) / 2) * (cout / 128);
@@ -651,7 +706,7 @@ static int build_plan(sbk_handle* h, int B, int T, int tb_rows) {
                 GnActParams& p = op.ga; memset(&p, 0, sizeof(p));
                 p.raw = A; p.gn = g1; p.tb = pl.tb + h->tb_off[k]; p.tb_stride = pl.tb_stride; p.step = pl.step_cur;
                 p.mask = pl.mask; p.T = T; p.lvl = lvl; p.out = Bb; p.B = B; p.H = Hs[lvl]; p.W = Ws[lvl]; p.C = r.cout;
-                p.round_tf32 = b16 ? 0 : 1; p.chw4 = 1; p.out_bf16 = b16 ? 1 : 0;
+                p.round_tf32 = (b16 || x3) ? 0 : 1; p.chw4 = 1; p.out_bf16 = b16 ? 1 : 0; p.out_lo = LO(Bb);
                 op.bytes = (4.0 + osz) * npix(lvl) * r.cout;
                 push(op, nullptr, 0);
             }
@@ -670,7 +725,7 @@ static int build_plan(sbk_handle* h, int B, int T, int tb_rows) {
             ResFinalParams& p = op.rf; memset(&p, 0, sizeof(p));
             p.h2raw = h2; p.gn = g2;
             p.mask = pl.mask; p.T = T; p.lvl = lvl; p.out = out; p.B = B; p.H = Hs[lvl]; p.W = Ws[lvl]; p.C = r.cout;
-            p.out_mask = store_masked ? 1 : 0; p.chw4 = use_tc ? 1 : 0; p.bf16 = b16 ? 1 : 0;
+            p.out_mask = store_masked ? 1 : 0; p.chw4 = use_tc ? 1 : 0; p.bf16 = b16 ? 1 : 0; p.out_lo = LO(out);
             if (k == 0) {
                 p.x = nullptr; p.mu = pl.mu; p.xt = pl.xt; p.spk_s = pl.spk_s; p.cin = cin0;
                 p.wres = W(r.prefix + ".res.w"); p.bres = W(r.prefix + ".res_conv.bias");
@@ -703,7 +758,19 @@ static int build_plan(sbk_handle* h, int B, int T, int tb_rows) {
         const AttnInfo& a = h->attns[k];
         int mt = igemm_mtiles(G_PW, Hs[lvl], Ws[lvl], Hs[lvl], Ws[lvl]);
         const bool tc_apply = use_tc && a.c % tc_cps1 == 0;
-        if (tc_apply) {
+        if (tc_apply && x3) {
+            // fp32-class attention: k|v projection as a 3xTF32 1x1 conv (fp32 result in HBM), then the softmax / context
+            // partials in exact fp32 on CUDA cores (k_kv_ctx): a tf32 P*V^T product would leave a 2^-12-class error in ctx
+            Op op = tc_conv(a.prefix + ".kvraw", G_PW, a.prefix + ".kvx.wtc", "", lvl, x, a.c, nullptr, 0, 256, bf.kvraw, nullptr);
+            op.bytes = 4.0 * npix(lvl) * (a.c * 2.0 + 256.0);
+            push(op, nullptr, 0);
+            Op kc; kc.kind = OP_KVCTX; kc.name = a.prefix + ".kvpart";
+            mt = (Hs[lvl] * Ws[lvl] + kv_ctx_chunk_pixels() - 1) / kv_ctx_chunk_pixels();
+            kc.kc.kv = bf.kvraw; kc.kc.kv_part = bf.kv_part; kc.kc.B = B; kc.kc.H = Hs[lvl]; kc.kc.W = Ws[lvl];
+            kc.kc.chunk_px = kv_ctx_chunk_pixels(); kc.kc.nchunks = mt;
+            kc.flops = 2.0 * npix(lvl) * 4096.0; kc.bytes = 4.0 * npix(lvl) * 256.0;
+            push(kc, nullptr, 0);
+        } else if (tc_apply) {
             // k/v projection + softmax partials on tensor cores (k_attn_kv): items of 128 pixels x 4 heads
             Op op = tc_conv(a.prefix + ".kvpart", G_PW, a.prefix + ".kv.wtc", "", lvl, x, a.c, nullptr, 0, 256, nullptr, nullptr);
             op.tc.epi = EPI_KV; op.tc.kv_part = bf.kv_part;
@@ -730,13 +797,13 @@ static int build_plan(sbk_handle* h, int B, int T, int tb_rows) {
             p.ctx = bf.ctx; p.wq = W(a.prefix + ".fn.fn.to_qkv.weight"); p.wout = W(a.prefix + ".fn.fn.to_out.weight");
             p.bout = W(a.prefix + ".fn.fn.to_out.bias"); p.g = W(a.prefix + ".fn.g");
             p.w_eff = bf.w_eff; p.b_eff = bf.b_eff; p.B = B; p.C = a.c;
-            if (tc_apply) { p.tc_nt = conv_tc_ntile(G_PW, a.c); p.tc_cps = tc_cps1; p.tc_bf16 = b16 ? 1 : 0; }
+            if (tc_apply) { p.tc_nt = conv_tc_ntile(G_PW, a.c); p.tc_cps = tc_cps1; p.tc_bf16 = b16 ? 1 : 0; p.tc_x3 = x3 ? 1 : 0; }
             push(op, nullptr, 0);
         }
         if (tc_apply) {
             // the per-sample (I + g P_b) matrix is written by k_attn_mix directly in the tcgen05 weight-stage layout
             Op op = tc_conv(a.prefix + ".out", G_PW, "", "", lvl, x, a.c, nullptr, 0, a.c, out, nullptr);
-            op.tc.wpk = bf.w_eff; op.tc.w_bstride_bytes = (long long)a.c * a.c * (b16 ? 2 : 4); op.tc.bias = bf.b_eff;
+            op.tc.wpk = bf.w_eff; op.tc.w_bstride_bytes = (long long)a.c * a.c * (b16 ? 2 : (x3 ? 8 : 4)); op.tc.bias = bf.b_eff;
             op.tc.out_mask = 1; op.tc.addin = x;
             op.bytes += osz * npix(lvl) * a.c;
             push(op, out, npix(lvl) * a.c);
@@ -809,7 +876,7 @@ static int build_plan(sbk_handle* h, int B, int T, int tb_rows) {
         p.raw = bf.A[0]; p.gn = gnref(stf, "estimator.final_block", C1, 0);
         p.wfin = W("estimator.final_conv.weight"); p.bfin = W("estimator.final_conv.bias");
         p.mask = pl.mask; p.mu = pl.mu; p.xt_in = pl.xt; p.xt_out = pl.xt;
-        p.coef = pl.coef; p.step = pl.step_cur; p.B = B; p.H = H0; p.T = T; p.C = C1; p.chw4 = use_tc ? 1 : 0;
+        p.coef = pl.coef; p.step = pl.step_cur; p.B = B; p.H = H0; p.T = T; p.C = C1; p.chw4 = use_tc ? 1 : 0; p.exact = x3 ? 1 : 0;
         pl.final_op = (int)pl.ops.size();
         push(op, nullptr, 0);
     }
@@ -817,21 +884,31 @@ static int build_plan(sbk_handle* h, int B, int T, int tb_rows) {
     return SBK_OK;
 }
 
+static int launch_op(const Op& op, cudaStream_t s) {
+    switch (op.kind) {
+        case OP_FIRST: return launch_first_conv(op.fc, s);
+        case OP_IGEMM: return launch_igemm(op.ig, s);
+        case OP_RESFINAL: return launch_resfinal(op.rf, s);
+        case OP_CTX: return launch_attn_ctx(op.cx, s);
+        case OP_MIX: return launch_attn_mix(op.mx, s);
+        case OP_FINAL: return launch_final(op.fn, s);
+        case OP_CONVTC: return launch_conv_tc(op.tc, s);
+        case OP_GNACT: return launch_gn_act(op.ga, s);
+        case OP_KVCTX: return launch_kv_ctx(op.kc, s);
+    }
+    return -1;
+}
+
+// enqueue one estimator evaluation (+ update); returns the number of launches, or -1 when a launcher refused (a
+// per-device attribute could not be set, an unsupported layout): the caller turns that into SBK_ERR_CUDA
 static int run_ops(sbk_handle* h, cudaStream_t s) {
     Plan& pl = h->plan;
     StepBeginParams sb{pl.stats, pl.n_stat_doubles, pl.step_cur, pl.step_next};
     int n = launch_step_begin(sb, s);
     for (auto& op : pl.ops) {
-        switch (op.kind) {
-            case OP_FIRST: n += launch_first_conv(op.fc, s); break;
-            case OP_IGEMM: n += launch_igemm(op.ig, s); break;
-            case OP_RESFINAL: n += launch_resfinal(op.rf, s); break;
-            case OP_CTX: n += launch_attn_ctx(op.cx, s); break;
-            case OP_MIX: n += launch_attn_mix(op.mx, s); break;
-            case OP_FINAL: n += launch_final(op.fn, s); break;
-            case OP_CONVTC: n += launch_conv_tc(op.tc, s); break;
-            case OP_GNACT: n += launch_gn_act(op.ga, s); break;
-        }
+        const int k = launch_op(op, s);
+        if (k < 0) { fail(SBK_ERR_CUDA, "launch of '%s' was refused (device attribute / layout)", op.name.c_str()); return -1; }
+        n += k;
         if (h->capture && op.dbg_ptr && op.dbg_numel > 0) {
             const size_t esz = op.dbg_fmt == 2 ? 2 : 4;
             if (!op.dbg_copy) cudaMalloc(&op.dbg_copy, op.dbg_numel * esz);
@@ -906,7 +983,7 @@ extern "C" int sbk_estimator(sbk_handle* h, const float* x, const float* mask, c
     n += time_table(h, B, s);
     set_mode(pl, 0, true, out);
     k_set_int<<<1, 1, 0, s>>>(pl.step_next, 0); ++n;
-    n += run_ops(h, s);
+    { const int k = run_ops(h, s); if (k < 0) return SBK_ERR_CUDA; n += k; }
     CU(cudaGetLastError());
     h->last_launches = n;
     return SBK_OK;
@@ -936,15 +1013,16 @@ static int run_steps(sbk_handle* h, const float* noise, int B, int T, int N, int
             if (!h->cap_stream) CU(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
             cudaGraph_t g = nullptr;
             CU(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
-            run_ops(h, h->cap_stream);
+            const int k = run_ops(h, h->cap_stream);
             CU(cudaStreamEndCapture(h->cap_stream, &g));
+            if (k < 0) { if (g) cudaGraphDestroy(g); return SBK_ERR_CUDA; }
             CU(cudaGraphInstantiate(&pl.gexec[mode], g, 0));
             CU(cudaGraphDestroy(g));
         }
         for (int i = s0; i < s1; ++i) CU(cudaGraphLaunch(pl.gexec[mode], s));
         *launches += (int64_t)(s1 - s0) * pl.launches_per_step;
     } else {
-        for (int i = s0; i < s1; ++i) *launches += run_ops(h, s);
+        for (int i = s0; i < s1; ++i) { const int k = run_ops(h, s); if (k < 0) return SBK_ERR_CUDA; *launches += k; }
     }
     CU(cudaGetLastError());
     (void)N;
@@ -1046,7 +1124,7 @@ extern "C" int sbk_reverse_diffusion_host(sbk_handle* h, const float* z, const f
 extern "C" int sbk_profile_ops(sbk_handle* h, float* ms, double* flops, double* bytes, int cap, int* n_ops) {
     if (!h || !ms || !n_ops) return fail(SBK_ERR_ARG, "sbk_profile_ops: null argument");
     Plan& pl = h->plan;
-    if (!pl.mem) return fail(SBK_ERR_STATE, "sbk_profile_ops: no plan yet (run a sampler call first)");
+    if (pl.ops.empty()) return fail(SBK_ERR_STATE, "sbk_profile_ops: no plan yet (run a sampler call first)");
     const int n = (int)pl.ops.size();
     if (cap < n) return fail(SBK_ERR_ARG, "sbk_profile_ops: need room for %d launches", n);
     CU(cudaSetDevice(h->cfg.device));
@@ -1060,17 +1138,7 @@ extern "C" int sbk_profile_ops(sbk_handle* h, float* ms, double* flops, double* 
     launch_step_begin(sb, s);
     for (int i = 0; i < n; ++i) {
         CU(cudaEventRecord(ev[i], s));
-        Op& op = pl.ops[i];
-        switch (op.kind) {
-            case OP_FIRST: launch_first_conv(op.fc, s); break;
-            case OP_IGEMM: launch_igemm(op.ig, s); break;
-            case OP_RESFINAL: launch_resfinal(op.rf, s); break;
-            case OP_CTX: launch_attn_ctx(op.cx, s); break;
-            case OP_MIX: launch_attn_mix(op.mx, s); break;
-            case OP_FINAL: launch_final(op.fn, s); break;
-            case OP_CONVTC: launch_conv_tc(op.tc, s); break;
-            case OP_GNACT: launch_gn_act(op.ga, s); break;
-        }
+        if (launch_op(pl.ops[i], s) < 0) return fail(SBK_ERR_CUDA, "sbk_profile_ops: launch of '%s' was refused", pl.ops[i].name.c_str());
     }
     CU(cudaEventRecord(ev[n], s));
     CU(cudaStreamSynchronize(s));
@@ -1146,7 +1214,7 @@ extern "C" int sbk_vc_estimator(sbk_handle* h, const float* x, const float* mask
     n += time_table(h, B, s);
     set_mode(pl, 0, true, out);
     k_set_int<<<1, 1, 0, s>>>(pl.step_next, 0); ++n;
-    n += run_ops(h, s);
+    { const int k = run_ops(h, s); if (k < 0) return SBK_ERR_CUDA; n += k; }
     CU(cudaGetLastError());
     h->last_launches = n;
     return SBK_OK;
@@ -1185,9 +1253,9 @@ extern "C" int sbk_vc_conditioning(sbk_handle* h, const float* ref, const float*
     if (!h || !ref || !ref_mask || !mean_ref || !c || !cond_out) return fail(SBK_ERR_ARG, "sbk_vc_conditioning: null argument");
     if (h->cfg.model != SBK_MODEL_DIFFVC) return fail(SBK_ERR_ARG, "sbk_vc_conditioning: this handle is not a DiffVC model");
     if (!h->is_packed) return fail(SBK_ERR_STATE, "sbk_vc_conditioning: weights not packed");
-    if (h->cfg.precision == SBK_PREC_FP32)
-        return fail(SBK_ERR_UNSUPPORTED, "sbk_vc_conditioning: the native RefBlock runs on the tensor-core path only (precision tf32); "
-                                         "in fp32 mode the binding evaluates the hoisted conditioning branch itself");
+    if (h->cfg.use_ref_t && h->cfg.dim_cond % 128 != 0) return fail(SBK_ERR_ARG, "sbk_vc_conditioning: dim_cond must be a multiple of 128");
+    // fp32-class handles (fp32x3 and the CUDA-core fp32 mode) run the RefBlock convs as 3xTF32 with exact IN / GLU
+    const bool x3 = packs_x3(h);
     if (B <= 0 || Tr <= 0 || n_timesteps < 1) return fail(SBK_ERR_ARG, "sbk_vc_conditioning: bad sizes");
     CU(cudaSetDevice(h->cfg.device));
     cudaStream_t s = (cudaStream_t)stream;
@@ -1196,10 +1264,12 @@ extern "C" int sbk_vc_conditioning(sbk_handle* h, const float* ref, const float*
     const size_t px = (size_t)B * H * Tr;
     // ---- workspace
     Arena probe;
+    float* act_lo = nullptr;
     auto carve = [&](Arena& ar, float*& xt_ref, float*& raw, float*& act, double*& st, double*& ys, float*& tb, float*& trows) {
         xt_ref = (float*)ar.take(px * sizeof(float));
         raw = (float*)ar.take(px * 8 * base * sizeof(float));
         act = (float*)ar.take(px * 4 * base * sizeof(float));
+        act_lo = x3 ? (float*)ar.take(px * 4 * base * sizeof(float)) : nullptr;
         st = (double*)ar.take((size_t)B * 8 * base * 2 * sizeof(double));
         ys = (double*)ar.take((size_t)B * dc * 2 * sizeof(double));
         tb = (float*)ar.take((size_t)N * 3 * base * sizeof(float));
@@ -1249,6 +1319,7 @@ extern "C" int sbk_vc_conditioning(sbk_handle* h, const float* ref, const float*
         p.geom = G_C3; p.in0 = act; p.c0 = cin; p.H = H; p.W = Tr; p.B = B; p.Ho = H; p.Wo = Tr;
         p.wpk = W(q + ".wtc"); p.bias = W(q + ".0.bias"); p.out = raw; p.Cout = cout; p.epi = EPI_PLAIN;
         p.mask = ref_mask; p.T = Tr; p.zero_page = h->d_zero;
+        if (x3) { p.x3 = 1; p.in0_lo = act_lo; }
         return launch_conv_tc(p, s);
     };
     auto norm_glu = [&](const char* name, int C, const float* tbias) {
@@ -1257,7 +1328,7 @@ extern "C" int sbk_vc_conditioning(sbk_handle* h, const float* ref, const float*
         int k = launch_chan_stats(cs, s);
         InGluParams g; memset(&g, 0, sizeof(g));
         g.raw = raw; g.stats = st; g.gamma = W(q + ".1.weight"); g.beta = W(q + ".1.bias"); g.tb = tbias;
-        g.mask = ref_mask; g.T = Tr; g.out = act; g.B = B; g.H = H; g.W = Tr; g.C = C;
+        g.mask = ref_mask; g.T = Tr; g.out = act; g.out_lo = act_lo; g.B = B; g.H = H; g.W = Tr; g.C = C;
         return k + launch_in_glu(g, s);
     };
     for (int i = 0; i < N; ++i) {

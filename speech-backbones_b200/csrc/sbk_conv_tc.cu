@@ -176,6 +176,13 @@ __device__ __forceinline__ float mish_fast(float x) {
 
 
 
+// fp32x3 mode: the exact closed form (mish_f of sbk_kernels.cu)
+__device__ __forceinline__ float mish_exact(float x) {
+    const float n = expf(fminf(x, 20.f));
+    const float a = n * (n + 2.f);
+    return x > 20.f ? x : x * (a / (a + 2.f));
+}
+
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
 // two floats -> packed bf16x2 (round to nearest even), `lo` in the low half = the lower channel index
@@ -253,6 +260,8 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT>::MINB) k_conv_tc(con
     const int Cin = p.c0 + p.c1;
     const int HW = p.H * p.W;
     const int ksteps = Cin / CPS;
+    // fp32x3 mode: each K stage runs three times, (x_lo, w_hi), (x, w_lo), (x, w_hi) - small terms first
+    const int ksteps_t = p.x3 ? 3 * ksteps : ksteps;
     // ---- tile space: (sample, pixel tile, N tile), N tile fastest so neighbours in time share the A tile in L2
     const int wt_w = (GEOM == G_DOWN ? p.Wo : p.W), wt_h = (GEOM == G_DOWN ? p.Ho : p.H);
     const int wtiles = (wt_w + TPX - 1) / TPX;
@@ -316,14 +325,16 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT>::MINB) k_conv_tc(con
                     sl_dst[j] = in ? (uint32_t)(k * PLANE + (r * PXP + q) * 16) : 0xFFFFFFFFu;
                 }
                 const uint32_t a0 = smem_u32(sA);
-                for (int ks = 0; ks < ksteps + LAG; ++ks) {
-                    if (ks < ksteps) {
+                for (int ks = 0; ks < ksteps_t + LAG; ++ks) {
+                    if (ks < ksteps_t) {
                         const uint32_t g = it + ks;
                         const int s = g % STAGES;
                         mbar_wait(empty(s), ((g / STAGES) & 1) ^ 1);
-                        const int ck = ks * KCH;
+                        const int kb = p.x3 ? ks / 3 : ks;
+                        const bool lo = p.x3 && ks - 3 * kb == 0;
+                        const int ck = kb * KCH;
                         const bool second = ck * EPC >= p.c0;
-                        const uint8_t* src = reinterpret_cast<const uint8_t*>(second ? p.in1 : p.in0);
+                        const uint8_t* src = reinterpret_cast<const uint8_t*>(second ? (lo ? p.in1_lo : p.in1) : (lo ? p.in0_lo : p.in0));
                         const int chs = (second ? p.c1 : p.c0) / EPC;
                         const int c0k = second ? ck - p.c0 / EPC : ck;
 #pragma unroll
@@ -342,7 +353,7 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT>::MINB) k_conv_tc(con
                         if (lane == 0) mbar_arrive(full_a((it + ks - LAG) % STAGES));
                     }
                 }
-                it += ksteps;
+                it += ksteps_t;
             }
 
             // ---- epilogue of tile t
@@ -436,7 +447,8 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT>::MINB) k_conv_tc(con
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const int cl = cb + i + e;
-                            v[i + e] += mish_fast((rr[e] - s_rg[cl]) * s_rg[NT + cl] + s_rg[2 * NT + cl]);
+                            const float xn = (rr[e] - s_rg[cl]) * s_rg[NT + cl] + s_rg[2 * NT + cl];
+                            v[i + e] += p.x3 ? mish_exact(xn) : mish_fast(xn);
                         }
                     }
                     if (cb + 32 < NT) {
@@ -479,6 +491,12 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT>::MINB) k_conv_tc(con
                     float* op = p.out + obase + (cb / 4) * cstride;
 #pragma unroll
                     for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(op + (i / 4) * cstride) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                    if (GEOM != G_C3 && p.out_lo) {
+                        float* lp = p.out_lo + obase + (cb / 4) * cstride;
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4)
+                            *reinterpret_cast<float4*>(lp + (i / 4) * cstride) = make_float4(tf32_lo(v[i]), tf32_lo(v[i + 1]), tf32_lo(v[i + 2]), tf32_lo(v[i + 3]));
+                    }
                 }
             }
             if (!SIDE && p.ostats) {
@@ -542,7 +560,7 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT>::MINB) k_conv_tc(con
                 const uint32_t tslot = tmem_base + slot * SLOT_COLS;
                 mbar_wait(tempty(slot), ((tl / NSLOT) & 1) ^ 1);        // epilogue has drained this slot
                 tc_fence_after();
-                for (int ks = 0; ks < ksteps; ++ks, ++it) {
+                for (int ks = 0; ks < ksteps_t; ++ks, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
                     if (!BULK) mbar_wait(full_a(s), ph);
@@ -608,10 +626,12 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT>::MINB) k_conv_tc(con
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 int b, h0, w0, n0, mt;
                 decode(t, b, h0, w0, n0, mt);
+                // weight image: [ntile][kstage][tap][chunk][NT][16 B]; fp32x3: [ntile][kstage][hi|lo][tap][chunk][NT][16 B]
                 const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpk) + (size_t)b * p.w_bstride_bytes +
-                                      (size_t)(n0 / NT) * ksteps * B_STAGE_BYTES;
-                for (int ks = 0; ks < ksteps; ++ks, ++it) {
+                                      (size_t)(n0 / NT) * ksteps * (p.x3 ? 2 : 1) * B_STAGE_BYTES;
+                for (int ks = 0; ks < ksteps_t; ++ks, ++it) {
                     const int s = it % STAGES;
+                    const int kb = p.x3 ? ks / 3 : ks, var = p.x3 ? ks - 3 * kb : 2;   // 0: x_lo*w_hi, 1: x*w_lo, 2: x*w_hi
                     if (lane == 0) {
                         mbar_wait(empty(s), ((it / STAGES) & 1) ^ 1);
                         uint32_t a_tx = BULK ? A_STAGE_BYTES : 0;
@@ -641,15 +661,16 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT>::MINB) k_conv_tc(con
                             a_tx -= (uint32_t)(KCH * vrows * (PXP - (qhi - qlo))) * 16u;
                         }
                         mbar_arrive_expect_tx(full_b(s), B_STAGE_BYTES + a_tx);
-                        bulk_g2s(smem_u32(sB + s * B_STAGE_BYTES), wsrc + (size_t)ks * B_STAGE_BYTES, B_STAGE_BYTES, full_b(s));
+                        bulk_g2s(smem_u32(sB + s * B_STAGE_BYTES), wsrc + (size_t)(p.x3 ? 2 * kb + (var == 1) : ks) * B_STAGE_BYTES,
+                                 B_STAGE_BYTES, full_b(s));
                     }
                     __syncwarp();
                     if (BULK && lane < KCH * HR) {
                         const uint32_t a_s = smem_u32(sA) + s * A_STAGE_BYTES;
                         const int k = lane / HR, r = lane - k * HR;
-                        const int ck = ks * KCH + k;                     // 16-byte channel chunk index over the concat
+                        const int ck = kb * KCH + k;                     // 16-byte channel chunk index over the concat
                         const bool second = ck * EPC >= p.c0;
-                        const uint8_t* src = reinterpret_cast<const uint8_t*>(second ? p.in1 : p.in0);
+                        const uint8_t* src = reinterpret_cast<const uint8_t*>(var == 0 ? (second ? p.in1_lo : p.in0_lo) : (second ? p.in1 : p.in0));
                         const int chs = (second ? p.c1 : p.c0) / EPC;
                         const int cl = second ? ck - p.c0 / EPC : ck;
                         if (GEOM == G_PW) {
@@ -688,18 +709,31 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT>::MINB) k_conv_tc(con
     }
 }
 
+// per-device launch state of one kernel instantiation: opt-in to 227 KB of dynamic shared memory + SM count
+struct DevCache {
+    static constexpr int MAXDEV = 64;
+    int sms[MAXDEV] = {};
+    int get(const void* fn) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAXDEV) return -1;
+        if (sms[dev] == 0) {
+            if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -1;
+            int n = 0;
+            if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return -1;
+            sms[dev] = n;
+        }
+        return sms[dev];
+    }
+};
+
 template <int GEOM, bool BF16, int NT, bool RES = false>
 static int launch_tc(const ConvTcParams& p, cudaStream_t s) {
     using D = Depth<GEOM, NT>;
-    static bool attr_set = false;
-    static int num_sms = 0;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_conv_tc<GEOM, BF16, NT, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-        attr_set = true;
-    }
+    // the dynamic-shared-memory opt-in is a per-device function attribute and the persistent grid is sized from the
+    // current device's SM count: both are cached per device ordinal (a process may drive several GPUs through several handles)
+    static DevCache cache;
+    const int num_sms = cache.get(reinterpret_cast<const void*>(k_conv_tc<GEOM, BF16, NT, RES>));
+    if (num_sms <= 0) return -1;
     int mt;
     if (GEOM == G_C3 || GEOM == G_UP) mt = ((p.W + TPX - 1) / TPX) * ((p.H + ROWS - 1) / ROWS);
     else if (GEOM == G_DOWN) mt = ((p.Wo + TPX - 1) / TPX) * ((p.Ho + ROWS - 1) / ROWS);
@@ -961,15 +995,9 @@ __global__ void __launch_bounds__(kvk::THREADS, 1) k_attn_kv(const ConvTcParams 
 
 template <bool BF16>
 static int launch_attn_kv(const ConvTcParams& p, cudaStream_t s) {
-    static bool attr_set = false;
-    static int num_sms = 0;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_attn_kv<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-        attr_set = true;
-    }
+    static DevCache cache;
+    const int num_sms = cache.get(reinterpret_cast<const void*>(k_attn_kv<BF16>));
+    if (num_sms <= 0) return -1;
     const long long total = (long long)p.B * ((p.H * p.W + kvk::PX - 1) / kvk::PX);
     const int grid = (int)(total < num_sms ? total : num_sms);
     k_attn_kv<BF16><<<grid, kvk::THREADS, kvk::SMEM, s>>>(p);

@@ -69,6 +69,12 @@ struct ConvTcParams {
     int bf16;
     int nt;                                         // N tile override (64) for launches with too few 128-wide tiles to fill the
                                                     // GPU (small batches); 0 = conv_tc_ntile(geom, Cout).  The weights must be packed for it.
+    // fp32-class mode (SBK_PREC_FP32X3, "3xTF32"): every operand x is carried as the pair (x, x_lo = x - trunc_tf32(x)); the
+    // tensor core reads the top 19 bits of x (= x_hi) by itself.  Weights are packed as (w_hi, w_lo) stage pairs and each
+    // K stage is issued three times: x_lo*w_hi + x*w_lo + x*w_hi, all into the same fp32 TMEM accumulator.
+    int x3;
+    const void* in0_lo; const void* in1_lo;         // the x_lo tensors, same layout as in0 / in1
+    float* out_lo;                                  // operand-form outputs (non-3x3 geometries): also write out - trunc_tf32(out)
 };
 
 // Block activation between the two convs of a ResnetBlock, written once in operand form (diffusion.py:57,76):
@@ -79,6 +85,7 @@ struct GnActParams {
     float* out; int B, H, W, C; int round_tf32;
     int chw4;
     int out_bf16;               // write the activation as bf16 [B][H][C/8][W][8] (raw stays fp32 [B][H][C/4][W][4])
+    float* out_lo;              // fp32x3 mode: out keeps the unrounded fp32 value, out_lo = out - trunc_tf32(out); exact Mish
 };
 
 struct FirstConvParams {        // Block.conv of downs.0.0.block1 on the planar stack([mu, xt(, s)]) * mask
@@ -106,11 +113,21 @@ struct ResFinalParams {         // out = Mish(GN(h2raw))*mask + res(x*mask)
     int out_mask;               // store out*mask (operand form for the next conv)
     int chw4;                   // activations are [B][H][C/4][W][4] (tensor-core modes) instead of NHWC
     int bf16;                   // x and out are bf16 [B][H][C/8][W][8]; h2raw stays fp32 [B][H][C/4][W][4]
+    float* out_lo;              // fp32x3 mode: also write out - trunc_tf32(out); exact Mish
 };
 
 struct AttnCtxParams {          // merge per-tile softmax partials -> normalised context [B][4][32][32]
     const float* kv_part; int mtiles; float* ctx; int B;
 };
+
+// fp32x3 mode: softmax-over-pixels partials + context partials from the k|v projection in HBM (CUDA cores, exact fp32).
+// kv: [B][H][256/4][W][4] fp32 (channels 0..127 = k rows head*32+d, 128..255 = v rows); one CTA per (pixel chunk, sample)
+// writes, per head, {max[32], sum[32], S[32][32]} in the k_attn_kv partial format (merged by k_attn_ctx).
+struct KvCtxParams {
+    const float* kv; float* kv_part; int B, H, W, chunk_px, nchunks;
+};
+int launch_kv_ctx(const KvCtxParams& p, cudaStream_t s);
+int kv_ctx_chunk_pixels();
 
 struct AttnMixParams {          // A_b = I + g * Wout * blockdiag(ctx^T) * Wq ; packed as [ci][co]; bias' = g*bout
     const float* ctx;           // [B][4][32][32]
@@ -124,6 +141,7 @@ struct AttnMixParams {          // A_b = I + g * Wout * blockdiag(ctx^T) * Wq ; 
     int tc_nt, tc_cps;          // != 0: write g*P only (the identity/residual is added in fp32 by the conv epilogue),
                                 // in the tcgen05 1x1 weight-stage layout, tf32-rounded
     int tc_bf16;                // ... as bf16, 8 input channels per 16-byte chunk (tc_cps = 64)
+    int tc_x3;                  // fp32x3 mode: (hi, lo) stage pairs [ntile][kstage][hi|lo][chunk][cout % NT][4]
 };
 
 struct FinalParams {            // final_block GN+Mish, final_conv 1x1 -> 1, mask, Euler(-Maruyama) update
@@ -138,6 +156,7 @@ struct FinalParams {            // final_block GN+Mish, final_conv 1x1 -> 1, mas
                                 // 3: DiffVC  xt' = (xt - ((mean-xt)*A - est*Bc + eps*sigma))*mask, coef = {A, Bc, sigma}
     int B, H, T, C;
     int chw4;
+    int exact;                  // fp32x3 mode: exact Mish (expf + IEEE division) instead of the fast intrinsics
 };
 
 struct TimeTableParams {        // SinusoidalPosEmb + mlp + the 12 per-ResnetBlock projections
@@ -181,6 +200,7 @@ struct InGluParams {             // y = mask ? tf32( IN(raw[c]) * sigmoid(IN(raw
     const float* tb;             // [C/2] time bias (mlp1 / mlp2 row of this step) or nullptr
     const float* mask; int T;    // ref_mask [B][T]
     float* out; int B, H, W, C;  // C = raw channels
+    float* out_lo;               // fp32x3 mode: out unrounded, out_lo = out - trunc_tf32(out)
 };
 struct VcCondParams {            // cond_block( [sinusoid(t) | final_conv(mean-pooled RefBlock) | c] )  (diffusion.py:62-71)
     const double* ysum;          // [B][dc][2] channel sums of the masked RefBlock output (before final_conv)
@@ -231,6 +251,9 @@ int launch_time_table(const TimeTableParams& p, cudaStream_t s);
 int launch_spk(const SpkParams& p, cudaStream_t s);
 int launch_step_begin(const StepBeginParams& p, cudaStream_t s);
 int launch_scale_mask(const float* z, const float* mask, float* out, long long n_per_b_row, int B, int H, int T, cudaStream_t s);
+
+// the part of an fp32 value the tensor core's tf32 operand path drops (low 13 mantissa bits): exact in fp32
+__device__ __forceinline__ float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
 inline int igemm_mtiles(int geom, int Hout, int Wout, int Hin, int Win) {
     const int TM = 128;

@@ -36,6 +36,9 @@ __device__ __forceinline__ float mish_fast_f(float x) {
     return x > 20.f ? x : x * __fdividef(a, a + 2.f);
 }
 
+__device__ __forceinline__ float mish_rt(float x, int exact) { return exact ? mish_f(x) : mish_fast_f(x); }
+template <bool EXACT> __device__ __forceinline__ float mish_sel(float x) { return EXACT ? mish_f(x) : mish_fast_f(x); }
+
 __device__ __forceinline__ void gn_mean_rstd(const GnRef& g, int b, int grp, float& mean, float& rstd) {
     const double s = g.stats[(b * kGroups + grp) * 2 + 0];
     const double ss = g.stats[(b * kGroups + grp) * 2 + 1];
@@ -501,6 +504,7 @@ int launch_first_conv(const FirstConvParams& p, cudaStream_t s) {
 //   out = Mish(GN(h2raw))*mask + x*mask                      (dim == dim_out)
 //   out = Mish(GN(h2raw))*mask + W_res (in*mask) + b_res     (first block, planar cin = 2|3)
 // ----------------------------------------------------------------------------------------------
+template <bool X3>
 __global__ void __launch_bounds__(256) k_resfinal(const ResFinalParams p) {
     extern __shared__ __align__(16) float sm[];
     float* mean = sm; float* scale = mean + p.C; float* beta = scale + p.C;
@@ -543,12 +547,14 @@ __global__ void __launch_bounds__(256) k_resfinal(const ResFinalParams p) {
                     if (h0 + u >= p.H) continue;
                     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (mk != 0.f) {
-                        o.x = mish_fast_f((r[u].x - pm.x) * ps.x + pb.x) + xv[u].x;
-                        o.y = mish_fast_f((r[u].y - pm.y) * ps.y + pb.y) + xv[u].y;
-                        o.z = mish_fast_f((r[u].z - pm.z) * ps.z + pb.z) + xv[u].z;
-                        o.w = mish_fast_f((r[u].w - pm.w) * ps.w + pb.w) + xv[u].w;
+                        o.x = mish_sel<X3>((r[u].x - pm.x) * ps.x + pb.x) + xv[u].x;
+                        o.y = mish_sel<X3>((r[u].y - pm.y) * ps.y + pb.y) + xv[u].y;
+                        o.z = mish_sel<X3>((r[u].z - pm.z) * ps.z + pb.z) + xv[u].z;
+                        o.w = mish_sel<X3>((r[u].w - pm.w) * ps.w + pb.w) + xv[u].w;
                     }
                     *reinterpret_cast<float4*>(outb + (long long)(h0 + u) * hstride + w * 4) = o;
+                    if (X3) *reinterpret_cast<float4*>(p.out_lo + base + (long long)(h0 + u) * hstride + w * 4) =
+                                make_float4(tf32_lo(o.x), tf32_lo(o.y), tf32_lo(o.z), tf32_lo(o.w));
                 }
             }
         }
@@ -643,13 +649,15 @@ __global__ void __launch_bounds__(256) k_resfinal(const ResFinalParams p) {
                     o.z = fmaf(mk, rx.z, fmaf(i2[u], w2.z, fmaf(i1[u], w1.z, fmaf(i0[u], w0.z, wb.z))));
                     o.w = fmaf(mk, rx.w, fmaf(i2[u], w2.w, fmaf(i1[u], w1.w, fmaf(i0[u], w0.w, wb.w))));
                     if (mk != 0.f) {
-                        o.x += mish_fast_f((r[u].x - pm.x) * ps.x + pb.x);
-                        o.y += mish_fast_f((r[u].y - pm.y) * ps.y + pb.y);
-                        o.z += mish_fast_f((r[u].z - pm.z) * ps.z + pb.z);
-                        o.w += mish_fast_f((r[u].w - pm.w) * ps.w + pb.w);
+                        o.x += mish_sel<X3>((r[u].x - pm.x) * ps.x + pb.x);
+                        o.y += mish_sel<X3>((r[u].y - pm.y) * ps.y + pb.y);
+                        o.z += mish_sel<X3>((r[u].z - pm.z) * ps.z + pb.z);
+                        o.w += mish_sel<X3>((r[u].w - pm.w) * ps.w + pb.w);
                     }
                     if (p.out_mask) { o.x *= mk; o.y *= mk; o.z *= mk; o.w *= mk; }
                     *reinterpret_cast<float4*>(outb + (long long)(h0 + u) * hstride + w * 4) = o;
+                    if (X3) *reinterpret_cast<float4*>(p.out_lo + base + (long long)(h0 + u) * hstride + w * 4) =
+                                make_float4(tf32_lo(o.x), tf32_lo(o.y), tf32_lo(o.z), tf32_lo(o.w));
                 }
             }
         }
@@ -709,6 +717,7 @@ __global__ void __launch_bounds__(256) k_resfinal(const ResFinalParams p) {
 // Block activation in operand form for the tensor-core convs:  act = mask ? Mish(GN(raw)) + tproj : 0
 // (Block.forward output * mask, then ResnetBlock's time projection, then the next Block's input mask:
 //  diffusion.py:56-58,76).  One read + one write per element; the conv's A path is then a pure copy.
+template <bool X3>
 __global__ void __launch_bounds__(256) k_gn_act(const GnActParams p) {
     extern __shared__ __align__(16) float sm[];
     float* mean = sm; float* scale = mean + p.C; float* beta = scale + p.C; float* tbv = beta + p.C;
@@ -734,6 +743,7 @@ __global__ void __launch_bounds__(256) k_gn_act(const GnActParams p) {
         const float4 pb = reinterpret_cast<const float4*>(beta)[ch], pt = reinterpret_cast<const float4*>(tbv)[ch];
         const float* rawb = p.raw + ((long long)b * n4 + (long long)ch * p.W) * 4;
         float* outb = p.out + ((long long)b * n4 + (long long)ch * p.W) * 4;
+        float* lob = X3 ? p.out_lo + ((long long)b * n4 + (long long)ch * p.W) * 4 : nullptr;
         const int hstride = c4n * p.W * 4;                               // floats between consecutive mel bins of one chunk
         for (int w = wl; w < p.W; w += tw) {
             const float mk = __ldg(p.mask + (long long)b * p.T + ((long long)w << p.lvl));
@@ -747,11 +757,11 @@ __global__ void __launch_bounds__(256) k_gn_act(const GnActParams p) {
                     if (h0 + u >= p.H) continue;
                     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (mk != 0.f) {
-                        o.x = mish_fast_f((r[u].x - pm.x) * ps.x + pb.x) + pt.x;
-                        o.y = mish_fast_f((r[u].y - pm.y) * ps.y + pb.y) + pt.y;
-                        o.z = mish_fast_f((r[u].z - pm.z) * ps.z + pb.z) + pt.z;
-                        o.w = mish_fast_f((r[u].w - pm.w) * ps.w + pb.w) + pt.w;
-                        if (p.round_tf32) {
+                        o.x = mish_sel<X3>((r[u].x - pm.x) * ps.x + pb.x) + pt.x;
+                        o.y = mish_sel<X3>((r[u].y - pm.y) * ps.y + pb.y) + pt.y;
+                        o.z = mish_sel<X3>((r[u].z - pm.z) * ps.z + pb.z) + pt.z;
+                        o.w = mish_sel<X3>((r[u].w - pm.w) * ps.w + pb.w) + pt.w;
+                        if (!X3 && p.round_tf32) {
                             uint32_t t0, t1, t2, t3;
                             asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t0) : "f"(o.x)); asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t1) : "f"(o.y));
                             asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t2) : "f"(o.z)); asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t3) : "f"(o.w));
@@ -759,6 +769,8 @@ __global__ void __launch_bounds__(256) k_gn_act(const GnActParams p) {
                         }
                     }
                     *reinterpret_cast<float4*>(outb + (long long)(h0 + u) * hstride + w * 4) = o;
+                    if (X3) *reinterpret_cast<float4*>(lob + (long long)(h0 + u) * hstride + w * 4) =
+                                make_float4(tf32_lo(o.x), tf32_lo(o.y), tf32_lo(o.z), tf32_lo(o.w));
                 }
             }
         }
@@ -1000,7 +1012,12 @@ int launch_gn_act(const GnActParams& p, cudaStream_t s) {
     if (gx < 1) gx = 1;
     if (gx > 4096) gx = 4096;
     if (p.chw4) gx = planar_ew_grid(p.H, p.W, p.C);           // must stay a multiple of C/4 (chunk = blockIdx.x % (C/4))
-    k_gn_act<<<dim3(gx, p.B), 256, 4 * p.C * sizeof(float), s>>>(p);
+    if (p.out_lo) {
+        if (!p.chw4) return -1;
+        k_gn_act<true><<<dim3(gx, p.B), 256, 4 * p.C * sizeof(float), s>>>(p);
+    } else {
+        k_gn_act<false><<<dim3(gx, p.B), 256, 4 * p.C * sizeof(float), s>>>(p);
+    }
     return 1;
 }
 
@@ -1017,7 +1034,12 @@ int launch_resfinal(const ResFinalParams& p, cudaStream_t s) {
     if (gx > 4096) gx = 4096;
     if (p.chw4) gx = planar_ew_grid(p.H, p.W, p.C);           // must stay a multiple of C/4 (chunk = blockIdx.x % (C/4))
     const size_t sm = (3 * p.C + (p.x ? 0 : (p.cin + 1) * p.C)) * sizeof(float);
-    k_resfinal<<<dim3(gx, p.B), 256, sm, s>>>(p);
+    if (p.out_lo) {
+        if (!p.chw4) return -1;
+        k_resfinal<true><<<dim3(gx, p.B), 256, sm, s>>>(p);
+    } else {
+        k_resfinal<false><<<dim3(gx, p.B), 256, sm, s>>>(p);
+    }
     return 1;
 }
 
@@ -1071,6 +1093,122 @@ __global__ void __launch_bounds__(1024) k_attn_ctx(const AttnCtxParams p) {
 
 int launch_attn_ctx(const AttnCtxParams& p, cudaStream_t s) {
     k_attn_ctx<<<dim3(kHeads, p.B), 1024, 0, s>>>(p);
+    return 1;
+}
+
+// ----------------------------------------------------------------------------------------------
+// fp32x3 mode, LinearAttention pass 1b (diffusion.py:95-96): softmax-over-pixels partials and context partials in exact
+// fp32 on CUDA cores, from the k|v projection the 3xTF32 1x1 conv left in HBM ([B][H][256/4][W][4]; rows 0..127 = k,
+// head*32+d; rows 128..255 = v).  One CTA = one chunk of KVC_CHUNK consecutive pixels (flattened H*W) of one sample, all
+// four heads; the chunk is walked in sub-tiles of KVC_PX pixels staged in shared memory with an online softmax per k row:
+//     m' = max(m, max_px k);  S[d][:] = S[d][:]*e^(m-m') + sum_px e^(k[d,px]-m') v[:,px];  z likewise.
+// Thread (head, d-quad, e-quad) owns a 4x4 block of S: per 4 pixels it reads 4+4 float4 from shared memory for 64 FMAs.
+// Output: the k_attn_kv partial format {max[32], sum[32], S[32][32]} per (sample, chunk, head), merged by k_attn_ctx.
+// ----------------------------------------------------------------------------------------------
+constexpr int KVC_PX = 64, KVC_CHUNK = 512, KVC_LD = KVC_PX + 4;
+
+__global__ void __launch_bounds__(256) k_kv_ctx(const KvCtxParams p) {
+    extern __shared__ __align__(16) float sm[];
+    float* s_k = sm;                         // [128][KVC_LD]  k, then P = exp(k - m')
+    float* s_v = s_k + 128 * KVC_LD;         // [128][KVC_LD]
+    float* s_m = s_v + 128 * KVC_LD;         // [128] running max
+    float* s_f = s_m + 128;                  // [128] rescale factor of this sub-tile
+    float* s_z = s_f + 128;                  // [128] running sum
+    const int tid = threadIdx.x, b = blockIdx.y, chunk = blockIdx.x;
+    const int HW = p.H * p.W;
+    const int m_begin = chunk * p.chunk_px, m_end = min(HW, m_begin + p.chunk_px);
+    if (tid < 128) { s_m[tid] = -INFINITY; s_z[tid] = 0.f; }
+    // S block of this thread: rows d = dq*4 + i, columns e = eq + 8*j (interleaved so that the eight threads of a
+    // quarter warp read eight different bank groups of s_v; the s_k reads are quarter-warp broadcasts)
+    const int head = tid >> 6, dq = (tid >> 3) & 7, eq = tid & 7;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int m0 = m_begin; m0 < m_end; m0 += KVC_PX) {
+        const int npx = min(KVC_PX, m_end - m0);
+        __syncthreads();                                               // previous sub-tile's readers are done
+        // ---- stage k|v: 64 channel chunks x KVC_PX pixels of float4, transposed to [channel][pixel]
+        for (int i = tid; i < 64 * KVC_PX; i += 256) {
+            const int ch = i / KVC_PX, px = i - ch * KVC_PX;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (px < npx) {
+                const int m = m0 + px, hh = m / p.W, ww = m - hh * p.W;
+                v = ldg4(p.kv + ((((long long)b * p.H + hh) * 64 + ch) * p.W + ww) * 4);
+            }
+            float* dst = (ch < 32 ? s_k : s_v) + ((ch & 31) * 4) * KVC_LD + px;
+            dst[0] = v.x; dst[KVC_LD] = v.y; dst[2 * KVC_LD] = v.z; dst[3 * KVC_LD] = v.w;
+        }
+        __syncthreads();
+        // ---- per k row: sub-tile max, new running max, rescale factor, P = exp(k - m'), running sum
+        {
+            const int row = tid >> 1, half = tid & 1;                  // two threads per row, 32 pixels each
+            float* kr = s_k + row * KVC_LD + half * 32;
+            const int n = max(0, min(32, npx - half * 32));
+            float mx = -INFINITY;
+            for (int i = 0; i < n; ++i) mx = fmaxf(mx, kr[i]);
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+            const float mo = s_m[row], mn = fmaxf(mo, mx);
+            float z = 0.f;
+            for (int i = 0; i < 32; ++i) { const float e = i < n ? expf(kr[i] - mn) : 0.f; kr[i] = e; z += e; }
+            z += __shfl_xor_sync(0xffffffffu, z, 1);
+            __syncwarp();
+            if (half == 0) {
+                const float f = mo == -INFINITY ? 0.f : expf(mo - mn);
+                s_f[row] = f; s_m[row] = mn; s_z[row] = s_z[row] * f + z;
+            }
+        }
+        __syncthreads();
+        // ---- S block update
+        {
+            const float4 f4 = *reinterpret_cast<const float4*>(s_f + head * 32 + dq * 4);
+            const float fr[4] = {f4.x, f4.y, f4.z, f4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] *= fr[i];
+            const float* pk = s_k + (head * 32 + dq * 4) * KVC_LD;
+            const float* pv = s_v + (head * 32 + eq) * KVC_LD;
+#pragma unroll 4
+            for (int px = 0; px < KVC_PX; px += 4) {
+                float4 a[4], c[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { a[i] = *reinterpret_cast<const float4*>(pk + i * KVC_LD + px); c[i] = *reinterpret_cast<const float4*>(pv + 8 * i * KVC_LD + px); }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        acc[i][j] = fmaf(a[i].x, c[j].x, acc[i][j]); acc[i][j] = fmaf(a[i].y, c[j].y, acc[i][j]);
+                        acc[i][j] = fmaf(a[i].z, c[j].z, acc[i][j]); acc[i][j] = fmaf(a[i].w, c[j].w, acc[i][j]);
+                    }
+            }
+        }
+    }
+    __syncthreads();
+    float* pt = p.kv_part + (((long long)b * p.nchunks + chunk) * kHeads + head) * kKvPartFloats;
+    if ((tid & 63) < 32) {
+        const int d = tid & 31;
+        pt[d] = s_m[head * 32 + d];
+        pt[32 + d] = s_z[head * 32 + d];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pt[64 + (dq * 4 + i) * 32 + eq + 8 * j] = acc[i][j];
+}
+
+int kv_ctx_chunk_pixels() { return KVC_CHUNK; }
+int launch_kv_ctx(const KvCtxParams& p, cudaStream_t s) {
+    const size_t smem = (size_t)(2 * 128 * KVC_LD + 3 * 128) * sizeof(float);
+    static bool attr[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
+    if (!attr[dev]) {
+        if (cudaFuncSetAttribute(k_kv_ctx, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+        attr[dev] = true;
+    }
+    k_kv_ctx<<<dim3(p.nchunks, p.B), 256, smem, s>>>(p);
     return 1;
 }
 
@@ -1140,6 +1278,17 @@ __global__ void __launch_bounds__(256) k_attn_mix(const AttnMixParams p) {
             for (int i = 0; i < 8; ++i) {
                 const int co = cb + cl0 + i;
                 float v = g * acc[i];
+                if (p.tc_x3) {
+                    // fp32x3: (hi, lo) stage pair, both tf32 (RNA): v = hi + lo to ~2^-22 relative
+                    const long long ih = (((((long long)(co / NT) * ksteps + ks) * 2) * kch + kc) * NT + (co % NT)) * 4 + e;
+                    uint32_t uh, ul;
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(uh) : "f"(v));
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(ul) : "f"(v - __uint_as_float(uh)));
+                    float* wb = p.w_eff + (long long)b * 2 * C * C;
+                    wb[ih] = __uint_as_float(uh);
+                    wb[ih + (long long)kch * NT * 4] = __uint_as_float(ul);
+                    continue;
+                }
                 const long long idx = ((((long long)(co / NT) * ksteps + ks) * kch + kc) * NT + (co % NT)) * epc + e;
                 if (p.tc_bf16) {
                     reinterpret_cast<unsigned short*>(p.w_eff)[(long long)b * C * C + idx] = (unsigned short)(pack_bf16x2_f(v, 0.f) & 0xFFFFu);
@@ -1221,10 +1370,10 @@ __global__ void __launch_bounds__(256) k_final(const FinalParams p) {
                 for (int ch = 0; ch < c4n; ++ch) {
                     const float4 r = ldg4(rp + (long long)ch * p.T * 4);
                     const int c = ch * 4;
-                    dot = fmaf(wf[c + 0], mish_fast_f((r.x - mean[c + 0]) * scale[c + 0] + beta[c + 0]), dot);
-                    dot = fmaf(wf[c + 1], mish_fast_f((r.y - mean[c + 1]) * scale[c + 1] + beta[c + 1]), dot);
-                    dot = fmaf(wf[c + 2], mish_fast_f((r.z - mean[c + 2]) * scale[c + 2] + beta[c + 2]), dot);
-                    dot = fmaf(wf[c + 3], mish_fast_f((r.w - mean[c + 3]) * scale[c + 3] + beta[c + 3]), dot);
+                    dot = fmaf(wf[c + 0], mish_rt((r.x - mean[c + 0]) * scale[c + 0] + beta[c + 0], p.exact), dot);
+                    dot = fmaf(wf[c + 1], mish_rt((r.y - mean[c + 1]) * scale[c + 1] + beta[c + 1], p.exact), dot);
+                    dot = fmaf(wf[c + 2], mish_rt((r.z - mean[c + 2]) * scale[c + 2] + beta[c + 2], p.exact), dot);
+                    dot = fmaf(wf[c + 3], mish_rt((r.w - mean[c + 3]) * scale[c + 3] + beta[c + 3], p.exact), dot);
                 }
             }
             update((long long)b * HW + m, mk, dot);
@@ -1447,12 +1596,18 @@ __global__ void __launch_bounds__(256) k_in_glu(const InGluParams p) {
                 const int c = ch * 4 + q;
                 const float xa = (av[q] - mean[c]) * scale[c] + beta[c];
                 const float xg = (gv[q] - mean[Ch + c]) * scale[Ch + c] + beta[Ch + c];
-                float y = xa * __fdividef(1.f, 1.f + __expf(-xg)) + tbv[c];
-                uint32_t t; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(y));
-                o[q] = __uint_as_float(t);
+                if (p.out_lo) {
+                    o[q] = xa * (1.f / (1.f + expf(-xg))) + tbv[c];          // fp32x3 mode: exact sigmoid, no operand rounding
+                } else {
+                    float y = xa * __fdividef(1.f, 1.f + __expf(-xg)) + tbv[c];
+                    uint32_t t; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(y));
+                    o[q] = __uint_as_float(t);
+                }
             }
         }
         *reinterpret_cast<float4*>(p.out + ((long long)b * n4 + i) * 4) = make_float4(o[0], o[1], o[2], o[3]);
+        if (p.out_lo) *reinterpret_cast<float4*>(p.out_lo + ((long long)b * n4 + i) * 4) =
+                          make_float4(tf32_lo(o[0]), tf32_lo(o[1]), tf32_lo(o[2]), tf32_lo(o[3]));
     }
 }
 int launch_in_glu(const InGluParams& p, cudaStream_t s) {

@@ -114,7 +114,7 @@ class GradLogPEstimator(BaseModule):
 
 
 class Diffusion(BaseModule):
-    def __init__(self, n_feats, dim_unet, dim_spk, use_ref_t, beta_min, beta_max, *, precision="fp32", use_graph=True):
+    def __init__(self, n_feats, dim_unet, dim_spk, use_ref_t, beta_min, beta_max, *, precision="fp32x3", use_graph=True):
         super().__init__()
         self.estimator = GradLogPEstimator(dim_unet, dim_spk, use_ref_t)
         self.n_feats, self.dim_unet, self.dim_spk, self.use_ref_t = n_feats, dim_unet, dim_spk, use_ref_t
@@ -159,21 +159,11 @@ class Diffusion(BaseModule):
     # ---- sampling (diffusion.py:164-205) ------------------------------------------------------
     @torch.no_grad()
     def conditioning_table(self, ref, ref_mask, mean_ref, c, n_timesteps):
-        """cond[i] for every step i (t_i = 1 - i/N): the hoisted conditioning branch.
-        precision="tf32": native (libsbk: RefBlock convs on tcgen05, InstanceNorm/GLU/cond_block kernels);
-        precision="fp32": the CUDA-core mode has no InstanceNorm/GLU conv path, so this 0.6 M-parameter branch is
-        evaluated with PyTorch ops on the GPU."""
-        if self.precision != "fp32":
-            with torch.cuda.device(ref.device):
-                return self.engine().vc_conditioning(ref, ref_mask, mean_ref, c, n_timesteps)
-        h = 1.0 / n_timesteps
-        rows = []
-        for i in range(n_timesteps):
-            t = 1.0 - i * h
-            xt_ref = self.compute_diffused_mean(ref, ref_mask, mean_ref, t)[:, None]
-            time = t * torch.ones(ref.shape[0], dtype=ref.dtype, device=ref.device)
-            rows.append(self.estimator.conditioning(xt_ref, ref_mask, c, time))
-        return torch.stack(rows)
+        """cond[i] for every step i (t_i = 1 - i/N): the hoisted conditioning branch, native in every precision
+        (libsbk `sbk_vc_conditioning`: RefBlock convs on tcgen05 - 3xTF32 for the fp32-class modes - plus the
+        InstanceNorm / GLU / cond_block kernels).  There is no PyTorch fallback."""
+        with torch.cuda.device(ref.device):
+            return self.engine().vc_conditioning(ref, ref_mask, mean_ref, c, n_timesteps)
 
     @torch.no_grad()
     def reverse_diffusion(self, z, mask, mean, ref, ref_mask, mean_ref, c, n_timesteps, mode):
