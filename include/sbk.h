@@ -142,6 +142,10 @@ int sbk_prior_expand(const float* mu_x, const float* w_ceil, const float* x_mask
 
 /* number of kernel launches the last sbk_estimator / sbk_reverse_* call enqueued (graph nodes count) */
 int64_t sbk_last_launch_count(const sbk_handle* h);
+/* number of HOST launches the Euler loop of the last sbk_reverse_* call took: 1 when the whole loop ran as one CUDA graph
+ * (a conditional WHILE node around one captured reverse step - the reference's Python loop, diffusion.py:258-274, issues
+ * ~350 kernel launches per step), n_steps when it fell back to one graph launch per step, n_steps * kernels without graphs */
+int sbk_last_host_launches(const sbk_handle* h);
 
 /* measurement hook: run ONE step of the current plan (the (B,T) of the last call) launch by launch with a CUDA
  * event between launches, on the library's stream, and return per-launch milliseconds plus the algorithmic
@@ -164,6 +168,37 @@ int sbk_debug_op_layout(const sbk_handle* h, const char* name);
 /* test hook: enumerate intermediate names */
 int sbk_debug_num(const sbk_handle* h);
 const char* sbk_debug_name(const sbk_handle* h, int i);
+
+/* ---- the step after the path: the HiFi-GAN generator, mel -> waveform ----------------------------
+ * Grad-TTS/hifi-gan/models.py:77-128 (Generator) with ResBlock1 (:13-49), built from Grad-TTS/checkpts/hifigan-config.json and
+ * called as `vocoder.forward(y_dec)` at Grad-TTS/inference.py:81 after `remove_weight_norm()` (:63).  The fields below are that
+ * JSON's; weights are the generator's state_dict AFTER remove_weight_norm ("conv_pre.weight" [C0,num_mels,7],
+ * "ups.i.weight" [Cin,Cout,k], "resblocks.n.convs{1,2}.j.weight" [C,C,k], "conv_post.weight" [1,C,7] and the biases).
+ * Dense contractions run on tcgen05 with tf32 operands and fp32 accumulation; everything else is fp32. */
+typedef struct sbk_vocoder sbk_vocoder;
+typedef struct sbk_vocoder_config {
+    int32_t device;
+    int32_t num_mels;                     /* 80                                                        */
+    int32_t upsample_initial_channel;     /* 512                                                       */
+    int32_t n_ups;                        /* len(upsample_rates) = 4                                   */
+    int32_t upsample_rates[4];            /* [8, 8, 2, 2]                                              */
+    int32_t upsample_kernel_sizes[4];     /* [16, 16, 4, 4]  (must be 2 * rate)                        */
+    int32_t n_kernels;                    /* len(resblock_kernel_sizes) = 3                            */
+    int32_t resblock_kernel_sizes[3];     /* [3, 7, 11]                                                */
+    int32_t resblock_dilations[3][3];     /* [[1,3,5],[1,3,5],[1,3,5]]                                 */
+} sbk_vocoder_config;
+int sbk_vocoder_create(const sbk_vocoder_config* cfg, sbk_vocoder** out);        /* Generator.__init__, models.py:78-101 */
+void sbk_vocoder_destroy(sbk_vocoder* v);
+int sbk_vocoder_num_weights(const sbk_vocoder* v);
+const char* sbk_vocoder_weight_name(const sbk_vocoder* v, int i);
+/* load_state_dict(strict) + remove_weight_norm (inference.py:61-63): one call per effective tensor, host or device fp32 */
+int sbk_vocoder_set_weight(sbk_vocoder* v, const char* name, const void* data, const int64_t* shape, int ndim);
+int sbk_vocoder_pack(sbk_vocoder* v);
+size_t sbk_vocoder_workspace_bytes(const sbk_vocoder* v, int B, int T);
+/* Generator.forward (models.py:104-119): mel [B,num_mels,T] -> wav [B,1,T*prod(upsample_rates)] in (-1,1).  Device pointers,
+ * asynchronous on `stream`. */
+int sbk_vocoder_forward(sbk_vocoder* v, const float* mel, float* wav, int B, int T, void* stream);
+int64_t sbk_vocoder_last_launch_count(const sbk_vocoder* v);
 
 const char* sbk_last_error(void);
 const char* sbk_version(void);

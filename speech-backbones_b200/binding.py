@@ -18,7 +18,7 @@ EXPORTS = [
     "sbk_workspace_bytes", "sbk_estimator", "sbk_reverse_diffusion", "sbk_reverse_steps",
     "sbk_reverse_diffusion_host", "sbk_last_launch_count", "sbk_debug_read", "sbk_debug_num",
     "sbk_debug_name", "sbk_last_error", "sbk_version", "sbk_profile_ops", "sbk_debug_capture", "sbk_debug_layout", "sbk_debug_op_layout", "sbk_vc_estimator", "sbk_vc_reverse_diffusion", "sbk_vc_conditioning",
-    "sbk_prior_expand",
+    "sbk_prior_expand", "sbk_last_host_launches",
 ]
 
 
@@ -61,6 +61,7 @@ def load_library() -> C.CDLL:
     lib.sbk_prior_expand.argtypes = [F, F, F, F, F, C.c_float, I, I, I, I, F, F, F, F, P]
     lib.sbk_last_launch_count.argtypes = [P]
     lib.sbk_last_launch_count.restype = C.c_int64
+    lib.sbk_last_host_launches.argtypes = [P]
     lib.sbk_debug_read.argtypes = [P, C.c_char_p, F, C.POINTER(C.c_int64)]
     lib.sbk_debug_num.argtypes = [P]
     lib.sbk_debug_capture.argtypes = [P, I]
@@ -139,6 +140,7 @@ class Engine:
         self.device = device
         self.n_feats = n_feats
         self.n_spks = n_spks
+        self.spk_emb_dim = spk_emb_dim
 
     def close(self):
         if getattr(self, "h", None) and self.h.value:
@@ -167,30 +169,48 @@ class Engine:
                    f"sbk_set_weight({name})")
         _check(self.lib.sbk_pack(self.h), "sbk_pack")
 
+    def _call(self, fn, what, *args):
+        """One libsbk call; if its workspace allocation ran out of memory while torch holds cached blocks (the arena is
+        raw cudaMalloc, outside torch's caching allocator), release them and retry once."""
+        rc = fn(*args)
+        if rc != 0 and b"out of memory" in self.lib.sbk_last_error():
+            torch.cuda.empty_cache()
+            rc = fn(*args)
+        _check(rc, what)
+
     def workspace_bytes(self, B, T):
         return int(self.lib.sbk_workspace_bytes(self.h, B, T))
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def _check_inputs(self, x, mask, mu, spk):
-        for n, t in (("x", x), ("mask", mask), ("mu", mu)):
-            if not t.is_cuda:
+    def _check_inputs(self, x, mask, mu, spk, t=None):
+        for n, v in (("x", x), ("mask", mask), ("mu", mu)):
+            if not v.is_cuda:
                 raise RuntimeError(f"{n} must be a CUDA tensor: the sampler has no CPU path")
         B, F, T = x.shape
         if F != self.n_feats or mu.shape != x.shape or mask.shape != (B, 1, T):
             raise RuntimeError(f"shape mismatch: x {tuple(x.shape)}, mu {tuple(mu.shape)}, mask {tuple(mask.shape)}")
         if self.n_spks > 1 and spk is None:
             raise RuntimeError("spk embedding required for a multi-speaker model")
+        # libsbk reads raw pointers on ITS device and stream: a short t / spk would be an out-of-bounds device read and a
+        # tensor on another GPU would be consumed through a peer pointer - the reference raises on both, so does this
+        for n, v in (("x", x), ("mask", mask), ("mu", mu), ("spk", spk), ("t", t)):
+            if v is not None and (not v.is_cuda or v.device.index != self.device):
+                raise RuntimeError(f"{n} lives on {v.device}, this engine on cuda:{self.device}")
+        if t is not None and tuple(t.shape) != (B,):
+            raise RuntimeError(f"t shape {tuple(t.shape)} != {(B,)}")
+        if self.n_spks > 1 and tuple(spk.shape) != (B, self.spk_emb_dim):
+            raise RuntimeError(f"spk shape {tuple(spk.shape)} != {(B, self.spk_emb_dim)}")
         return B, T
 
     def estimator(self, x, mask, mu, t, spk=None):
-        B, T = self._check_inputs(x, mask, mu, spk)
+        B, T = self._check_inputs(x, mask, mu, spk, t)
         x, mask, mu, t = _f32c(x, "x"), _f32c(mask, "mask"), _f32c(mu, "mu"), _f32c(t, "t")
         spk = _f32c(spk, "spk") if (spk is not None and self.n_spks > 1) else None
         out = torch.empty_like(x)
-        _check(self.lib.sbk_estimator(self.h, _ptr(x), _ptr(mask), _ptr(mu), _ptr(t), _ptr(spk), _ptr(out), B, T,
-                                      self._stream()), "sbk_estimator")
+        self._call(self.lib.sbk_estimator, "sbk_estimator", self.h, _ptr(x), _ptr(mask), _ptr(mu), _ptr(t), _ptr(spk), _ptr(out),
+                   B, T, self._stream())
         return out
 
     # ---- oversize batches: utterances are independent, so a batch whose workspace would not fit is run in slices
@@ -224,9 +244,8 @@ class Engine:
             if tuple(noise.shape) != (n_timesteps, B, self.n_feats, T):
                 raise RuntimeError(f"noise shape {tuple(noise.shape)} != {(n_timesteps, B, self.n_feats, T)}")
         out = torch.empty_like(z)
-        _check(self.lib.sbk_reverse_diffusion(self.h, _ptr(z), _ptr(mask), _ptr(mu), _ptr(spk),
-                                              _ptr(noise) if stoc else None, _ptr(out), B, T, int(n_timesteps),
-                                              1 if stoc else 0, self._stream()), "sbk_reverse_diffusion")
+        self._call(self.lib.sbk_reverse_diffusion, "sbk_reverse_diffusion", self.h, _ptr(z), _ptr(mask), _ptr(mu), _ptr(spk),
+                   _ptr(noise) if stoc else None, _ptr(out), B, T, int(n_timesteps), 1 if stoc else 0, self._stream())
         return out
 
     def reverse_steps(self, xt, mask, mu, n_timesteps, step_begin, step_end, stoc=False, spk=None, noise=None):
@@ -244,7 +263,7 @@ class Engine:
     VC_MODES = {"pf": 0, "em": 1, "ml": 2}
 
     def vc_estimator(self, x, mask, mean, cond, t):
-        B, T = self._check_inputs(x, mask, mean, None)
+        B, T = self._check_inputs(x, mask, mean, None, t)
         x, mask, mean, cond, t = (_f32c(v, n) for v, n in ((x, "x"), (mask, "mask"), (mean, "mean"), (cond, "cond"), (t, "t")))
         if tuple(cond.shape) != (B, self.dim_cond):
             raise RuntimeError(f"cond shape {tuple(cond.shape)} != {(B, self.dim_cond)}")
@@ -282,9 +301,9 @@ class Engine:
                 raise RuntimeError("modes 'em'/'ml' need pre-drawn noise [N,B,n_feats,T]")
             noise = _f32c(noise, "noise")
         out = torch.empty_like(z)
-        _check(self.lib.sbk_vc_reverse_diffusion(self.h, _ptr(z), _ptr(mask), _ptr(mean), _ptr(cond),
-                                                 _ptr(noise) if mode != "pf" else None, _ptr(out), B, T, int(n_timesteps),
-                                                 self.VC_MODES[mode], self._stream()), "sbk_vc_reverse_diffusion")
+        self._call(self.lib.sbk_vc_reverse_diffusion, "sbk_vc_reverse_diffusion", self.h, _ptr(z), _ptr(mask), _ptr(mean),
+                   _ptr(cond), _ptr(noise) if mode != "pf" else None, _ptr(out), B, T, int(n_timesteps),
+                   self.VC_MODES[mode], self._stream())
         return out
 
     def reverse_diffusion_host(self, z, mask, mu, n_timesteps, stoc=False, spk=None, noise=None, out=None):
@@ -305,6 +324,10 @@ class Engine:
 
     def last_launch_count(self):
         return int(self.lib.sbk_last_launch_count(self.h))
+
+    def last_host_launches(self):
+        """Host launches the Euler loop of the last sampler call took (1 = the whole loop ran as one CUDA graph)."""
+        return int(self.lib.sbk_last_host_launches(self.h))
 
     def profile_ops(self):
         """[(name, ms, flops, bytes)] for one step of the current plan, one CUDA event pair per launch."""

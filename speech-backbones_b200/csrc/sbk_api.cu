@@ -24,6 +24,14 @@ static int fail(int code, const char* fmt, ...) {
     va_end(ap);
     return code;
 }
+// shared with the other translation units of the library (sbk_vocoder.cu ...): same thread-local error text
+int sbk_set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
 #define CU(x)                                                                                          \
     do {                                                                                               \
         cudaError_t e_ = (x);                                                                          \
@@ -41,6 +49,10 @@ struct AttnInfo { std::string prefix; int c; };
 
 __global__ void k_set_int(int* p, int v) { *p = v; }
 __global__ void k_set_ptr(const float** p, const float* v) { *p = v; }
+// last node of the WHILE body: run another reverse step iff the step counter has not reached the end of the slice
+__global__ void k_loop_cond(cudaGraphConditionalHandle handle, const int* step_next, const int* step_end) {
+    cudaGraphSetConditional(handle, *step_next < *step_end ? 1u : 0u);
+}
 
 struct Arena {
     char* base = nullptr; size_t cap = 0, off = 0;
@@ -77,7 +89,12 @@ struct Plan {
     float *vc_cond = nullptr, *vc_wextra = nullptr, *vc_rextra = nullptr;   // DiffVC conditioning tables [rows][B][...]
     int first_op = -1, first_res_op = -1;
     int tb_stride = 0;
-    cudaGraphExec_t gexec[4] = {nullptr, nullptr, nullptr, nullptr};   // per FinalParams.mode
+    cudaGraphExec_t gexec[4] = {nullptr, nullptr, nullptr, nullptr};   // one reverse step, per FinalParams.mode
+    // the WHOLE loop as one graph: a conditional WHILE node whose body is one reverse step + k_loop_cond, so a sampler
+    // call is ONE host launch for any N (N = 1000 needs no 75k-node graph).  loop_state: 0 untried, 1 built, -1 unavailable
+    cudaGraphExec_t gloop[4] = {nullptr, nullptr, nullptr, nullptr};
+    int loop_state[4] = {0, 0, 0, 0};
+    int* step_end = nullptr;
     int launches_per_step = 0;
 };
 
@@ -98,6 +115,7 @@ struct sbk_handle {
     Plan plan;
     cudaStream_t cap_stream = nullptr;
     int64_t last_launches = 0;
+    int last_host_launches = 0;               // graph launches the host issued for the loop of the last sampler call
     bool capture = false;
     int tb_off[16];
     int tb_total = 0;
@@ -232,6 +250,7 @@ extern "C" int sbk_create(const sbk_config* cfg, sbk_handle** out) {
 static void free_plan(sbk_handle* h, bool release_arena = true) {
     Plan& p = h->plan;
     for (int i = 0; i < 4; ++i) if (p.gexec[i]) { cudaGraphExecDestroy(p.gexec[i]); p.gexec[i] = nullptr; }
+    for (int i = 0; i < 4; ++i) if (p.gloop[i]) { cudaGraphExecDestroy(p.gloop[i]); p.gloop[i] = nullptr; }
     for (auto& op : p.ops) if (op.dbg_copy) cudaFree(op.dbg_copy);
     void* mem = p.mem; const size_t cap = p.cap;
     if (mem && release_arena) { cudaFree(mem); mem = nullptr; }
@@ -310,7 +329,7 @@ static int pack_tc(sbk_handle* h, const std::string& src, const std::string& key
     TRY_RC(pack_tc_host(h, hs, key, cout, cin, geom, bf16));
     // 3x3 convs with >= 128 output channels also get a 64-wide N-tile image: small batches have too few 128-wide tiles to
     // fill 148 SMs (B=1, level 2: 20 tiles), so the planner switches those launches to twice as many half-width tiles
-    if (geom == G_C3 && conv_tc_ntile(geom, cout) == 128) TRY_RC(pack_tc_host(h, hs, key + "64", cout, cin, geom, bf16, 64));
+    if (geom == G_C3 && conv_tc_ntile(geom, cout) == 128 && !(packs_x3(h) && !bf16)) TRY_RC(pack_tc_host(h, hs, key + "64", cout, cin, geom, bf16, 64));
     return SBK_OK;
 }
 // k and v rows of to_qkv ('(qkv heads c)': k = rows 128.., v = rows 256..) in k_attn_kv's per-stage shared-memory image
@@ -351,10 +370,10 @@ static int pack_tc_up(sbk_handle* h, const std::string& src, const std::string& 
 }
 static int pack_tc_host(sbk_handle* h, const std::vector<float>& hs, const std::string& key, int cout, int cin, int geom, bool bf16, int nt_override) {
     const int taps = conv_tc_taps(geom);
-    const int NT = nt_override ? nt_override : conv_tc_ntile(geom, cout), CPS = conv_tc_stage_channels(geom, bf16 ? 1 : 0), EPC = bf16 ? 8 : 4, KCHK = CPS / EPC;
+    const bool x3 = !bf16 && packs_x3(h);
+    const int NT = nt_override ? nt_override : (x3 ? conv_tc_ntile_x3(geom, cout) : conv_tc_ntile(geom, cout)), CPS = conv_tc_stage_channels(geom, bf16 ? 1 : 0), EPC = bf16 ? 8 : 4, KCHK = CPS / EPC;
     const int ksteps = cin / CPS;
     const size_t esz = bf16 ? 2 : 4;
-    const bool x3 = !bf16 && packs_x3(h);
     std::vector<uint8_t> hd((size_t)cout * cin * taps * esz * (x3 ? 2 : 1));
     for (int nt = 0; nt < cout / NT; ++nt) for (int ks = 0; ks < ksteps; ++ks) for (int tap = 0; tap < taps; ++tap)
         for (int k = 0; k < KCHK; ++k) for (int col = 0; col < NT; ++col) for (int e = 0; e < EPC; ++e) {
@@ -540,6 +559,7 @@ static size_t layout(const sbk_handle* h, int B, int T, int tb_rows, Arena& ar, 
     p.coef = (float4*)ar.take((size_t)tb_rows * sizeof(float4));
     p.step_cur = (int*)ar.take(sizeof(int));
     p.step_next = (int*)ar.take(sizeof(int));
+    p.step_end = (int*)ar.take(sizeof(int));
     p.noise_pp = (const float**)ar.take(sizeof(float*));
     if (c.model == SBK_MODEL_DIFFVC) {
         p.vc_cond = f((size_t)tb_rows * B * c.dim_cond);
@@ -650,7 +670,11 @@ static int build_plan(sbk_handle* h, int B, int T, int tb_rows) {
         p.wpk = W(wkey); p.bias = bkey.empty() ? nullptr : W(bkey); p.out = out; p.Cout = cout;
         p.epi = EPI_PLAIN; p.ostats = st; p.mask = pl.mask; p.T = T; p.lvl = lvl; p.zero_page = h->d_zero;
         p.bf16 = b16 ? 1 : 0;
-        if (x3) { p.x3 = 1; p.in0_lo = LO(in0); p.in1_lo = LO(in1); p.out_lo = geom != G_C3 ? LO(out) : nullptr; }
+        if (x3) {
+            p.x3 = 1; p.in0_lo = LO(in0); p.in1_lo = LO(in1); p.out_lo = geom != G_C3 ? LO(out) : nullptr;
+            static const int flush_env = getenv("SBK_X3_FLUSH") ? atoi(getenv("SBK_X3_FLUSH")) : 0;     // measurement knob
+            p.flush = flush_env;
+        }
         if (geom == G_C3 && conv_tc_ntile(geom, cout) == 128) {
             // tiles of 2 rows x 128 pixels x 128 channels; when they cannot fill half the SMs, use 64-wide N tiles instead
             const long long tiles = (long long)B * ((Ws[lvl] + 127) / 128) * ((Hs[lvl] + 1) / 2) * (cout / 128);
@@ -797,7 +821,7 @@ static int build_plan(sbk_handle* h, int B, int T, int tb_rows) {
             p.ctx = bf.ctx; p.wq = W(a.prefix + ".fn.fn.to_qkv.weight"); p.wout = W(a.prefix + ".fn.fn.to_out.weight");
             p.bout = W(a.prefix + ".fn.fn.to_out.bias"); p.g = W(a.prefix + ".fn.g");
             p.w_eff = bf.w_eff; p.b_eff = bf.b_eff; p.B = B; p.C = a.c;
-            if (tc_apply) { p.tc_nt = conv_tc_ntile(G_PW, a.c); p.tc_cps = tc_cps1; p.tc_bf16 = b16 ? 1 : 0; p.tc_x3 = x3 ? 1 : 0; }
+            if (tc_apply) { p.tc_nt = x3 ? conv_tc_ntile_x3(G_PW, a.c) : conv_tc_ntile(G_PW, a.c); p.tc_cps = tc_cps1; p.tc_bf16 = b16 ? 1 : 0; p.tc_x3 = x3 ? 1 : 0; }
             push(op, nullptr, 0);
         }
         if (tc_apply) {
@@ -999,6 +1023,49 @@ static void step_coefs(const sbk_config& c, int n_timesteps, int i, float* t_out
     *cf = make_float4(beta, hf, sqrtf(beta * hf), 0.f);
 }
 
+// Build (once per plan and sampler mode) the single-launch loop graph.  Returns false - and the caller falls back to one
+// graph launch per step - if this driver / toolkit refuses conditional nodes; the reason is kept in sbk_last_error().
+static bool build_loop_graph(sbk_handle* h, int mode) {
+    Plan& pl = h->plan;
+    if (pl.loop_state[mode] != 0) return pl.loop_state[mode] > 0;
+    pl.loop_state[mode] = -1;
+    if (!h->cap_stream && cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking) != cudaSuccess) return false;
+    cudaGraph_t g = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    bool ok = false;
+    do {
+        if (cudaGraphCreate(&g, 0) != cudaSuccess) break;
+        cudaGraphConditionalHandle handle;
+        // default 1 at every launch: the body runs at least once (callers never launch an empty slice)
+        if (cudaGraphConditionalHandleCreate(&handle, g, 1, cudaGraphCondAssignDefault) != cudaSuccess) break;
+        cudaGraphNodeParams np = {cudaGraphNodeTypeConditional};     // (the union has no default constructor)
+        np.type = cudaGraphNodeTypeConditional;
+        np.conditional.handle = handle;
+        np.conditional.type = cudaGraphCondTypeWhile;
+        np.conditional.size = 1;
+        cudaGraphNode_t node;
+        if (cudaGraphAddNode(&node, g, nullptr, 0, &np) != cudaSuccess) break;
+        cudaGraph_t body = np.conditional.phGraph_out[0];
+        if (cudaStreamBeginCaptureToGraph(h->cap_stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) != cudaSuccess) break;
+        const int k = run_ops(h, h->cap_stream);
+        k_loop_cond<<<1, 1, 0, h->cap_stream>>>(handle, pl.step_next, pl.step_end);
+        cudaGraph_t dummy = nullptr;
+        if (cudaStreamEndCapture(h->cap_stream, &dummy) != cudaSuccess || k < 0) break;
+        if (cudaGraphInstantiate(&exec, g, 0) != cudaSuccess) break;
+        ok = true;
+    } while (0);
+    if (!ok) {
+        const cudaError_t e = cudaGetLastError();
+        fail(SBK_ERR_CUDA, "single-launch loop graph unavailable (%s): falling back to one graph launch per step", cudaGetErrorString(e));
+        if (exec) cudaGraphExecDestroy(exec);
+    } else {
+        pl.gloop[mode] = exec;
+        pl.loop_state[mode] = 1;
+    }
+    if (g) cudaGraphDestroy(g);
+    return ok;
+}
+
 static int run_steps(sbk_handle* h, const float* noise, int B, int T, int N, int s0, int s1, int stoc, cudaStream_t s, int64_t* launches) {
     Plan& pl = h->plan;
     const int mode = h->cfg.model == SBK_MODEL_DIFFVC ? 3 : (stoc ? 2 : 1);
@@ -1008,7 +1075,14 @@ static int run_steps(sbk_handle* h, const float* noise, int B, int T, int N, int
     k_set_int<<<1, 1, 0, s>>>(pl.step_next, s0);
     k_set_ptr<<<1, 1, 0, s>>>(pl.noise_pp, nbase);
     *launches += 2;
-    if (h->cfg.use_graph) {
+    h->last_host_launches = s1 - s0;
+    if (h->cfg.use_graph && s1 > s0 && build_loop_graph(h, mode)) {
+        // one host launch: WHILE(step_next < step_end) { one reverse step }
+        k_set_int<<<1, 1, 0, s>>>(pl.step_end, s1);
+        CU(cudaGraphLaunch(pl.gloop[mode], s));
+        *launches += 1 + (int64_t)(s1 - s0) * (pl.launches_per_step + 1);
+        h->last_host_launches = 1;
+    } else if (h->cfg.use_graph) {
         if (!pl.gexec[mode]) {
             if (!h->cap_stream) CU(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
             cudaGraph_t g = nullptr;
@@ -1385,6 +1459,7 @@ extern "C" int sbk_prior_expand(const float* mu_x, const float* w_ceil, const fl
 }
 
 extern "C" int64_t sbk_last_launch_count(const sbk_handle* h) { return h ? h->last_launches : 0; }
+extern "C" int sbk_last_host_launches(const sbk_handle* h) { return h ? h->last_host_launches : 0; }
 
 extern "C" int sbk_debug_capture(sbk_handle* h, int on) {
     if (!h) return fail(SBK_ERR_ARG, "sbk_debug_capture: null handle");

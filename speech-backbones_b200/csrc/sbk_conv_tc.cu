@@ -49,6 +49,14 @@ template <> struct Geo<G_DOWN> { static constexpr int HR = 2 * ROWS + 1, PXP = 2
 // all four phases are computed from one halo tile into 4*ROWS accumulators; the stage carries all 16 (kh,kw) taps.
 template <> struct Geo<G_UP> { static constexpr int HR = ROWS + 2, PXP = TPX + 2, TAPS = 16, KCH = 2, NACC = 4 * ROWS; };
 
+// Conv1d, K taps, runtime dilation d (HiFi-GAN: K in {3,7,11}, d in {1,3,5}; halo (K-1)*d <= 50 samples): ONE strip of
+// ROWS*TPX + 64 samples per channel chunk; the two M=128 accumulators are the two consecutive 128-sample halves of the strip
+// and tap t of half j is the descriptor start (j*128 + t*d) samples into it - each input sample is fetched once for all taps.
+template <int K> struct GeoC1 { static constexpr int HR = 1, PXP = ROWS * TPX + 64, TAPS = K, KCH = 2, NACC = ROWS; };
+template <> struct Geo<G_C1K3> : GeoC1<3> {};
+template <> struct Geo<G_C1K7> : GeoC1<7> {};
+template <> struct Geo<G_C1K11> : GeoC1<11> {};
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -208,14 +216,16 @@ using namespace tc;
 //   * NSLOT TMEM accumulator slots: with two slots the epilogue of tile i overlaps the loads + MMAs of tile i+1;
 //   * two CTAs per SM when smem (<= ~108 KB) and TMEM (<= 256 columns) allow, else one CTA with a deeper ring.
 constexpr int pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
-template <int GEOM, int NT> struct Depth {
+// X3 (fp32x3 mode): the epilogue warps carry the whole NT-column accumulator row in registers (chunked accumulation, see
+// k_conv_tc), so those instantiations run one CTA per SM (204 registers per thread) with two TMEM slots where they fit.
+template <int GEOM, int NT, bool X3 = false> struct Depth {
     static constexpr int STAGE_BYTES = Geo<GEOM>::KCH * Geo<GEOM>::HR * Geo<GEOM>::PXP * 16 + Geo<GEOM>::TAPS * Geo<GEOM>::KCH * NT * 16;
     static constexpr int SLOT_COLS = Geo<GEOM>::NACC * NT;
     static constexpr int FIT2 = (108 * 1024) / STAGE_BYTES;
     static constexpr int FIT1 = (220 * 1024) / STAGE_BYTES;
     // long-K 3x3 convs (NT = 128) are MMA-bound: one CTA, deep ring, two accumulator slots.  Everything else is
     // epilogue/latency-bound: two CTAs per SM double the epilogue warps; slots as TMEM (256 columns per CTA) allows.
-    static constexpr bool TWO = FIT2 >= 2 && SLOT_COLS <= 256 && !(GEOM == G_C3 && NT == 128);
+    static constexpr bool TWO = !X3 && FIT2 >= 2 && SLOT_COLS <= 256 && !(GEOM == G_C3 && NT == 128);
     static constexpr int NSLOT = TWO ? (2 * SLOT_COLS <= 256 ? 2 : 1) : (2 * SLOT_COLS <= 512 ? 2 : 1);
     static constexpr int TMEM_COLS = pow2_cols(NSLOT * SLOT_COLS);
     static constexpr int STAGES = TWO ? (FIT2 > 4 ? 4 : FIT2) : (FIT1 > 6 ? 6 : FIT1);
@@ -225,10 +235,25 @@ template <int GEOM, int NT> struct Depth {
 
 // RES: ResnetBlock-tail epilogue (1x1 res_conv + Mish(GN(h2raw)) side input), compile-time so that the plain 1x1 /
 // 3x3 instantiations do not pay its registers.
-template <int GEOM, bool BF16, int NT, bool RES = false>
-__global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT>::MINB) k_conv_tc(const ConvTcParams p) {
+//
+// X3 (fp32x3 mode, p.x3): 3xTF32 K stages AND chunked accumulation.  Measured on the B200 (profiles/r2_fp32x3_v1_*): the
+// tensor core TRUNCATES its fp32 accumulator on every MMA, a bias of ~2^-25 |acc| per instruction towards zero, so a
+// single accumulation run over the 216 ... 1728 MMAs of a 3x3 conv loses 4e-6 ... 3e-5 relative - 10-50x the fp32
+// rounding the reference's own fp32 sums have.  Here an accumulation run is therefore cut every FLUSH sub-stages (27
+// MMAs per accumulator for a 3x3 conv): the MMA issuer commits the run, the epilogue warps add the partial sums to
+// round-to-nearest fp32 REGISTER accumulators (one row of NT columns per thread) and hand the TMEM slot back, while the
+// issuer already runs the next chunk in the other slot.  The epilogue proper then works from the registers.
+template <int GEOM, bool BF16, int NT, bool RES, bool X3>
+__device__ __forceinline__ void conv_tc_body(const ConvTcParams& p) {
+    static_assert(!(X3 && BF16), "fp32x3 runs on tf32 operands");
     using G = Geo<GEOM>;
-    using D = Depth<GEOM, NT>;
+    using D = Depth<GEOM, NT, X3>;
+    // Upsample keeps its 8 accumulators (4 phases x 2 rows x 64 columns = all of TMEM) in one run: 256 register
+    // accumulators per thread do not exist, and its runs are short (4 taps: 96-192 MMAs per accumulator)
+    constexpr bool CHUNKED = X3 && GEOM != G_UP;
+    // sub-stages per accumulation run: p.flush, default 6 = two K stages of x_lo*w_hi + x*w_lo + x*w_hi (54 MMAs per
+    // accumulator for a 3x3 conv: ~1e-6 of truncation bias per conv)
+    const int FLUSH = p.flush > 0 ? p.flush : 6;
     constexpr int STAGES = D::STAGES, NSLOT = D::NSLOT, SLOT_COLS = D::SLOT_COLS;
     constexpr int LAG = STAGES >= 3 ? STAGES - 2 : 0;      // G_DOWN only: cp.async groups in flight behind the newest
     static_assert(STAGES >= 2, "need at least 2 stages");
@@ -242,6 +267,8 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT>::MINB) k_conv_tc(con
     constexpr int A_STAGE_BYTES = KCH * PLANE;
     constexpr int B_STAGE_BYTES = TAPS * KCH * NT * 16;
     constexpr bool BULK = GEOM != G_DOWN;                  // A tile = contiguous runs -> cp.async.bulk (no LSU work)
+    constexpr bool C1 = geom_is_c1(GEOM);                  // Conv1d strip geometry
+    constexpr int SPAN = C1 ? ROWS * TPX : TPX;            // output pixels per tile along W
 
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sA = smem;                                            // [STAGES][KCH][HR][PXP][16]
@@ -261,10 +288,11 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT>::MINB) k_conv_tc(con
     const int HW = p.H * p.W;
     const int ksteps = Cin / CPS;
     // fp32x3 mode: each K stage runs three times, (x_lo, w_hi), (x, w_lo), (x, w_hi) - small terms first
-    const int ksteps_t = p.x3 ? 3 * ksteps : ksteps;
+    const int ksteps_t = X3 ? 3 * ksteps : ksteps;
+    const int nchunks = CHUNKED ? (ksteps_t + FLUSH - 1) / FLUSH : 1;     // accumulation runs per tile
     // ---- tile space: (sample, pixel tile, N tile), N tile fastest so neighbours in time share the A tile in L2
     const int wt_w = (GEOM == G_DOWN ? p.Wo : p.W), wt_h = (GEOM == G_DOWN ? p.Ho : p.H);
-    const int wtiles = (wt_w + TPX - 1) / TPX;
+    const int wtiles = (wt_w + SPAN - 1) / SPAN;
     const int mtiles = GEOM == G_PW ? (HW + ROWS * TPX - 1) / (ROWS * TPX) : wtiles * ((wt_h + ROWS - 1) / ROWS);
     const int ntn = p.Cout / NT;
     const int total_tiles = p.B * mtiles * ntn;
@@ -272,7 +300,7 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT>::MINB) k_conv_tc(con
         const int nt = t % ntn; const int r = t / ntn;
         mt = r % mtiles; b = r / mtiles; n0 = nt * NT;
         if (GEOM == G_PW) { w0 = 0; h0 = mt * ROWS; }
-        else { w0 = (mt % wtiles) * TPX; h0 = (mt / wtiles) * ROWS; }
+        else { w0 = (mt % wtiles) * SPAN; h0 = (mt / wtiles) * ROWS; }
     };
 
     const uint32_t bar0 = smem_u32(bars);
@@ -302,10 +330,36 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT>::MINB) k_conv_tc(con
         // warps 0-7: (G_DOWN: cp.async A producers, then) epilogue of every tile
         // =========================================================================================================
         uint32_t it = 0;      // G_DOWN producer ring counter
-        int tl = 0;           // tile counter (accumulator slot / phase)
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
+        uint32_t ar = 0;      // accumulation-run counter (accumulator slot / phase); one run per tile unless CHUNKED
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             int b, h0, w0, n0, mt;
             decode(t, b, h0, w0, n0, mt);
+            // CHUNKED: accumulation runs of this tile are drained, in order, into register accumulators (round-to-nearest
+            // fp32 adds): this thread's TMEM lane (pixel) x the NT columns of its accumulator row
+            float accr[CHUNKED ? NT : 1];
+            int drained = 0;
+            auto drain_run = [&]() {
+                const int rs = ar % NSLOT;
+                mbar_wait(tfull(rs), (ar / NSLOT) & 1);
+                tc_fence_after();
+                const uint32_t ta = tmem_base + rs * SLOT_COLS + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * NT);
+#pragma unroll
+                for (int cb = 0; cb < (CHUNKED ? NT : 0); cb += 32) {
+                    uint32_t r[32];
+                    tmem_ld32(ta + cb, r);
+                    if (drained == 0) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) accr[cb + i] = __uint_as_float(r[i]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) accr[cb + i] += __uint_as_float(r[i]);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty(rs));
+                ++ar; ++drained;
+            };
             if (!BULK) {
                 // ---- A producers (Downsample only): 16-byte cp.async gathers that de-interleave even/odd columns
                 constexpr int SLOTS = HR * PXP * KCH;
@@ -330,8 +384,8 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT>::MINB) k_conv_tc(con
                         const uint32_t g = it + ks;
                         const int s = g % STAGES;
                         mbar_wait(empty(s), ((g / STAGES) & 1) ^ 1);
-                        const int kb = p.x3 ? ks / 3 : ks;
-                        const bool lo = p.x3 && ks - 3 * kb == 0;
+                        const int kb = X3 ? ks / 3 : ks;
+                        const bool lo = X3 && ks - 3 * kb == 0;
                         const int ck = kb * KCH;
                         const bool second = ck * EPC >= p.c0;
                         const uint8_t* src = reinterpret_cast<const uint8_t*>(second ? (lo ? p.in1_lo : p.in1) : (lo ? p.in0_lo : p.in0));
@@ -351,13 +405,23 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT>::MINB) k_conv_tc(con
                         fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor core
                         __syncwarp();
                         if (lane == 0) mbar_arrive(full_a((it + ks - LAG) % STAGES));
+                        if constexpr (CHUNKED) {
+                            // These warps are also the ones that drain the accumulation runs: a run whose last stage has
+                            // been handed to the MMA issuer completes without further production, so it is drained here -
+                            // otherwise the issuer would wait for a free TMEM slot while we wait for a free smem stage.
+                            while (drained < nchunks) {
+                                const int last = (drained + 1) * FLUSH < ksteps_t ? (drained + 1) * FLUSH - 1 : ksteps_t - 1;
+                                if (last > ks - LAG) break;
+                                drain_run();
+                            }
+                        }
                     }
                 }
                 it += ksteps_t;
             }
 
             // ---- epilogue of tile t
-            const int slot = tl % NSLOT;
+            const int slot = ar % NSLOT;                           // (!CHUNKED: the slot of this tile's only run)
             const uint32_t tslot = tmem_base + slot * SLOT_COLS;
             if constexpr (RES) {
                 asm volatile("bar.sync 1, 256;" ::: "memory");        // previous tile's readers of s_rg are done
@@ -383,6 +447,9 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT>::MINB) k_conv_tc(con
             if (GEOM == G_C3 || GEOM == G_DOWN) {
                 ho = h0 + jrow; wo = w0 + px;
                 valid = ho < Ho && wo < Wo;
+            } else if (C1) {
+                ho = 0; wo = w0 + jrow * TPX + px;
+                valid = wo < Wo;
             } else if (GEOM == G_UP) {
                 valid = (h0 + jrow) < p.H && (w0 + px) < p.W;          // per-phase coordinates are formed below
                 ho = 2 * (h0 + jrow); wo = 2 * (w0 + px);
@@ -422,15 +489,24 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT>::MINB) k_conv_tc(con
             for (int i = 0; i < 8; ++i)
                 pre[i] = pre_on ? __ldg(reinterpret_cast<const float4*>(pre_src + obase + i * cstride)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-#pragma unroll 1
+        if constexpr (CHUNKED) {
+            while (drained < nchunks) drain_run();
+            acc_ready = true;
+        }
+#pragma unroll (CHUNKED ? NT / 32 : 1)
         for (int cb = 0; cb < NT; cb += 32) {
             if (!acc_ready) {
-                mbar_wait(tfull(slot), (tl / NSLOT) & 1);
+                mbar_wait(tfull(slot), (ar / NSLOT) & 1);
                 tc_fence_after();
                 acc_ready = true;
             }
             uint32_t r[32];
-            tmem_ld32(tslot + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(acc * NT + cb), r);
+            if constexpr (CHUNKED) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(accr[cb + i]);
+            } else {
+                tmem_ld32(tslot + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(acc * NT + cb), r);
+            }
             float v[32];
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
@@ -448,7 +524,7 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT>::MINB) k_conv_tc(con
                         for (int e = 0; e < 4; ++e) {
                             const int cl = cb + i + e;
                             const float xn = (rr[e] - s_rg[cl]) * s_rg[NT + cl] + s_rg[2 * NT + cl];
-                            v[i + e] += p.x3 ? mish_exact(xn) : mish_fast(xn);
+                            v[i + e] += X3 ? mish_exact(xn) : mish_fast(xn);
                         }
                     }
                     if (cb + 32 < NT) {
@@ -480,6 +556,10 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT>::MINB) k_conv_tc(con
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] *= mo;
             }
+            if (C1 && p.act_out) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * p.slope;
+            }
             if (valid) {
                 if constexpr (OUT16) {
                     uint4* op = reinterpret_cast<uint4*>(p.out) + ochunk + (long long)(cb / 8) * Wo;
@@ -494,8 +574,16 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT>::MINB) k_conv_tc(con
                     if (GEOM != G_C3 && p.out_lo) {
                         float* lp = p.out_lo + obase + (cb / 4) * cstride;
 #pragma unroll
-                        for (int i = 0; i < 32; i += 4)
-                            *reinterpret_cast<float4*>(lp + (i / 4) * cstride) = make_float4(tf32_lo(v[i]), tf32_lo(v[i + 1]), tf32_lo(v[i + 2]), tf32_lo(v[i + 3]));
+                        for (int i = 0; i < 32; i += 4) {
+                            if (C1 && p.act_out2) {
+                                const float sl = p.slope;
+                                *reinterpret_cast<float4*>(lp + (i / 4) * cstride) =
+                                    make_float4(v[i] > 0.f ? v[i] : v[i] * sl, v[i + 1] > 0.f ? v[i + 1] : v[i + 1] * sl,
+                                                v[i + 2] > 0.f ? v[i + 2] : v[i + 2] * sl, v[i + 3] > 0.f ? v[i + 3] : v[i + 3] * sl);
+                            } else {
+                                *reinterpret_cast<float4*>(lp + (i / 4) * cstride) = make_float4(tf32_lo(v[i]), tf32_lo(v[i + 1]), tf32_lo(v[i + 2]), tf32_lo(v[i + 3]));
+                            }
+                        }
                     }
                 }
             }
@@ -530,10 +618,13 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT>::MINB) k_conv_tc(con
         }
         }
         }
-            // accumulator slot drained: hand it back to the MMA issuer
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty(slot));
+            // accumulator slot drained: hand it back to the MMA issuer (CHUNKED: every run was handed back as it was drained)
+            if constexpr (!CHUNKED) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty(slot));
+                ++ar;
+            }
             if (GEOM != G_PW && p.ostats) {
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 const int cpg = p.Cout / kGroups, gb = n0 / cpg, ng = (NT + cpg - 1) / cpg;
@@ -554,13 +645,15 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT>::MINB) k_conv_tc(con
             const uint32_t idesc = make_idesc<BF16>(TPX, NT);
             const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
             uint32_t it = 0;
-            int tl = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
-                const int slot = tl % NSLOT;
+            uint32_t ar = 0;                                             // accumulation-run counter (see the epilogue warps)
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+              for (int c = 0; c < nchunks; ++c, ++ar) {
+                const int slot = ar % NSLOT;
                 const uint32_t tslot = tmem_base + slot * SLOT_COLS;
-                mbar_wait(tempty(slot), ((tl / NSLOT) & 1) ^ 1);        // epilogue has drained this slot
+                mbar_wait(tempty(slot), ((ar / NSLOT) & 1) ^ 1);        // epilogue has drained this slot
                 tc_fence_after();
-                for (int ks = 0; ks < ksteps_t; ++ks, ++it) {
+                const int ks_lo = CHUNKED ? c * FLUSH : 0, ks_hi = CHUNKED ? (ks_lo + FLUSH < ksteps_t ? ks_lo + FLUSH : ksteps_t) : ksteps_t;
+                for (int ks = ks_lo; ks < ks_hi; ++ks, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
                     if (!BULK) mbar_wait(full_a(s), ph);
@@ -584,7 +677,7 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT>::MINB) k_conv_tc(con
 #pragma unroll
                                     for (int j = 0; j < ROWS; ++j) {
                                         const uint64_t ad = make_desc(a_st + ((1 + j + dh) * PXP + 1 + dw) * 16, PLANE, 128);
-                                        umma<BF16>(tslot + (phase * ROWS + j) * NT, ad, bd, idesc, (ks | kk | t2) != 0 ? 1u : 0u);
+                                        umma<BF16>(tslot + (phase * ROWS + j) * NT, ad, bd, idesc, ((ks - ks_lo) | kk | t2) != 0 ? 1u : 0u);
                                     }
                                 }
                             }
@@ -597,16 +690,18 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT>::MINB) k_conv_tc(con
                                 for (int j = 0; j < ROWS; ++j) {
                                     // DOWN: input row 2j+r; column tap s reads the odd plane at x (s=0) / x+1 (s=2), the even plane at x (s=1)
                                     const int aoff = GEOM == G_DOWN ? (2 * j + r) * PXP + (sx == 1 ? TPX + 1 : (sx == 2 ? 1 : 0))
-                                                                    : (r + j) * PXP + sx;
+                                                   : C1 ? j * TPX + tap * p.dil
+                                                        : (r + j) * PXP + sx;
                                     const uint64_t ad = make_desc(a_st + aoff * 16, PLANE, 128);
-                                    umma<BF16>(tslot + j * NT, ad, bd, idesc, (ks | kk | tap) != 0 ? 1u : 0u);
+                                    umma<BF16>(tslot + j * NT, ad, bd, idesc, ((ks - ks_lo) | kk | tap) != 0 ? 1u : 0u);
                                 }
                             }
                         }
                     }
                     umma_commit(empty(s));                  // frees the stage when these MMAs have read it
                 }
-                umma_commit(tfull(slot));                   // this tile's accumulators are complete
+                umma_commit(tfull(slot));                   // this run's accumulators are complete
+              }
             }
         }
     } else {
@@ -628,10 +723,10 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT>::MINB) k_conv_tc(con
                 decode(t, b, h0, w0, n0, mt);
                 // weight image: [ntile][kstage][tap][chunk][NT][16 B]; fp32x3: [ntile][kstage][hi|lo][tap][chunk][NT][16 B]
                 const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpk) + (size_t)b * p.w_bstride_bytes +
-                                      (size_t)(n0 / NT) * ksteps * (p.x3 ? 2 : 1) * B_STAGE_BYTES;
+                                      (size_t)(n0 / NT) * ksteps * (X3 ? 2 : 1) * B_STAGE_BYTES;
                 for (int ks = 0; ks < ksteps_t; ++ks, ++it) {
                     const int s = it % STAGES;
-                    const int kb = p.x3 ? ks / 3 : ks, var = p.x3 ? ks - 3 * kb : 2;   // 0: x_lo*w_hi, 1: x*w_lo, 2: x*w_hi
+                    const int kb = X3 ? ks / 3 : ks, var = X3 ? ks - 3 * kb : 2;       // 0: x_lo*w_hi, 1: x*w_lo, 2: x*w_hi
                     if (lane == 0) {
                         mbar_wait(empty(s), ((it / STAGES) & 1) ^ 1);
                         uint32_t a_tx = BULK ? A_STAGE_BYTES : 0;
@@ -640,9 +735,10 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT>::MINB) k_conv_tc(con
                             // need zeroing when this stage buffer last served a tile with a different border pattern.  With
                             // the round-robin tile order a CTA normally keeps one pattern, so this (and its proxy fence,
                             // which would otherwise serialise against the bulk copies in flight) runs a handful of times.
-                            const int wlo = w0 - 1 < 0 ? 0 : w0 - 1, whi = w0 + TPX + 1 > p.W ? p.W : w0 + TPX + 1;
-                            const int qlo = wlo - (w0 - 1), qhi = qlo + (whi - wlo);
-                            const uint32_t pat = (uint32_t)qlo | ((uint32_t)qhi << 8);
+                            const int pad = C1 ? p.pad : 1;             // Conv1d: (K-1)*dil/2 samples of halo on each side
+                            const int wlo = w0 - pad < 0 ? 0 : w0 - pad, whi = w0 + SPAN + pad > p.W ? p.W : w0 + SPAN + pad;
+                            const int qlo = wlo - (w0 - pad), qhi = qlo + (whi - wlo);
+                            const uint32_t pat = (uint32_t)qlo | ((uint32_t)qhi << 16);
                             if (stage_pat[s] != pat) {
                                 stage_pat[s] = pat;
                                 if (qlo > 0 || qhi < PXP) {
@@ -657,11 +753,11 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT>::MINB) k_conv_tc(con
                                 }
                             }
                             int vrows = 0;
-                            for (int r = 0; r < HR; ++r) { const int hi = h0 - 1 + r; vrows += (hi >= 0 && hi < p.H) ? 1 : 0; }
+                            for (int r = 0; r < HR; ++r) { const int hi = C1 ? 0 : h0 - 1 + r; vrows += (hi >= 0 && hi < p.H) ? 1 : 0; }
                             a_tx -= (uint32_t)(KCH * vrows * (PXP - (qhi - qlo))) * 16u;
                         }
                         mbar_arrive_expect_tx(full_b(s), B_STAGE_BYTES + a_tx);
-                        bulk_g2s(smem_u32(sB + s * B_STAGE_BYTES), wsrc + (size_t)(p.x3 ? 2 * kb + (var == 1) : ks) * B_STAGE_BYTES,
+                        bulk_g2s(smem_u32(sB + s * B_STAGE_BYTES), wsrc + (size_t)(X3 ? 2 * kb + (var == 1) : ks) * B_STAGE_BYTES,
                                  B_STAGE_BYTES, full_b(s));
                     }
                     __syncwarp();
@@ -688,9 +784,10 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT>::MINB) k_conv_tc(con
                             }
                             if (q < PXP) bulk_g2s(a_s + k * PLANE + (r * PXP + q) * 16, zero, (uint32_t)(PXP - q) * 16u, full_b(s));
                         } else {
-                            const int wlo = w0 - 1 < 0 ? 0 : w0 - 1, whi = w0 + TPX + 1 > p.W ? p.W : w0 + TPX + 1;
-                            const int qlo = wlo - (w0 - 1);
-                            const int hi = h0 - 1 + r;
+                            const int pad = C1 ? p.pad : 1;
+                            const int wlo = w0 - pad < 0 ? 0 : w0 - pad, whi = w0 + SPAN + pad > p.W ? p.W : w0 + SPAN + pad;
+                            const int qlo = wlo - (w0 - pad);
+                            const int hi = C1 ? 0 : h0 - 1 + r;
                             const uint32_t row_s = a_s + k * PLANE + (r * PXP) * 16;
                             if (hi < 0 || hi >= p.H) bulk_g2s(row_s, zero, PXP * 16u, full_b(s));
                             else bulk_g2s(row_s + qlo * 16, src + (((long long)(b * p.H + hi) * chs + cl) * p.W + wlo) * 16,
@@ -707,6 +804,21 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT>::MINB) k_conv_tc(con
         tc_fence_after();
         tmem_dealloc(tmem_base, D::TMEM_COLS);
     }
+}
+
+template <int GEOM, bool BF16, int NT, bool RES = false>
+__global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT, false>::MINB) k_conv_tc(const ConvTcParams p) {
+    conv_tc_body<GEOM, BF16, NT, RES, false>(p);
+}
+// fp32x3 instantiations: one CTA of 320 threads per SM.  Warps are allocated four at a time, so a 10-warp CTA is sized as
+// 384 threads and the ceiling is 65536 / 384 = 168 registers per thread (a __maxnreg__(200) build fails to launch with "too
+// many resources requested"): 128 register accumulators per thread do not fit, so every fp32x3 conv uses 64-wide N tiles
+// (64 accumulators per thread; conv_tc_ntile_x3).  The N = 64 UMMA shape costs ~20 % of the N = 128 rate on the >= 128-channel
+// convs (shared-memory operand bandwidth) - the price of fp32-class sums on a truncating accumulator.
+template <int GEOM, int NT, bool RES = false>
+__global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc_x3(const ConvTcParams p) {
+    static_assert(NT == 64, "fp32x3: 64 register accumulators per epilogue thread");
+    conv_tc_body<GEOM, false, NT, RES, true>(p);
 }
 
 // per-device launch state of one kernel instantiation: opt-in to 227 KB of dynamic shared memory + SM count
@@ -726,22 +838,27 @@ struct DevCache {
     }
 };
 
-template <int GEOM, bool BF16, int NT, bool RES = false>
+template <int GEOM, bool BF16, int NT, bool RES = false, bool X3 = false>
 static int launch_tc(const ConvTcParams& p, cudaStream_t s) {
-    using D = Depth<GEOM, NT>;
+    using D = Depth<GEOM, NT, X3>;
     // the dynamic-shared-memory opt-in is a per-device function attribute and the persistent grid is sized from the
     // current device's SM count: both are cached per device ordinal (a process may drive several GPUs through several handles)
     static DevCache cache;
-    const int num_sms = cache.get(reinterpret_cast<const void*>(k_conv_tc<GEOM, BF16, NT, RES>));
+    const void* fn;
+    if constexpr (X3) fn = reinterpret_cast<const void*>(k_conv_tc_x3<GEOM, NT, RES>);
+    else fn = reinterpret_cast<const void*>(k_conv_tc<GEOM, BF16, NT, RES>);
+    const int num_sms = cache.get(fn);
     if (num_sms <= 0) return -1;
     int mt;
-    if (GEOM == G_C3 || GEOM == G_UP) mt = ((p.W + TPX - 1) / TPX) * ((p.H + ROWS - 1) / ROWS);
+    if (geom_is_c1(GEOM)) mt = (p.W + ROWS * TPX - 1) / (ROWS * TPX);
+    else if (GEOM == G_C3 || GEOM == G_UP) mt = ((p.W + TPX - 1) / TPX) * ((p.H + ROWS - 1) / ROWS);
     else if (GEOM == G_DOWN) mt = ((p.Wo + TPX - 1) / TPX) * ((p.Ho + ROWS - 1) / ROWS);
     else mt = (p.H * p.W + ROWS * TPX - 1) / (ROWS * TPX);
     const long long total = (long long)mt * (p.Cout / NT) * p.B;
     const long long cap = (long long)num_sms * D::MINB;             // persistent: one wave of resident CTAs
     const int grid = (int)(total < cap ? total : cap);
-    k_conv_tc<GEOM, BF16, NT, RES><<<grid, NTHREADS, D::SMEM, s>>>(p);
+    if constexpr (X3) k_conv_tc_x3<GEOM, NT, RES><<<grid, NTHREADS, D::SMEM, s>>>(p);
+    else k_conv_tc<GEOM, BF16, NT, RES><<<grid, NTHREADS, D::SMEM, s>>>(p);
     return 1;
 }
 
@@ -1008,9 +1125,20 @@ int attn_kv_tile_pixels() { return kvk::PX; }
 // N tile per geometry: UP needs 8 accumulators (8*64 = all 512 TMEM columns), DOWN's de-interleaved A tile is large
 int conv_tc_ntile(int geom, int Cout) {
     if (geom == G_UP || geom == G_DOWN) return 64;
+    if (geom_is_c1(geom)) return Cout % 128 == 0 ? 128 : (Cout % 64 == 0 ? 64 : 32);
     return Cout % 128 == 0 ? 128 : 64;
 }
-int conv_tc_taps(int geom) { return geom == G_PW ? 1 : (geom == G_UP ? 16 : 9); }
+int conv_tc_ntile_x3(int, int) { return 64; }     // fp32x3: 64 register accumulators per epilogue thread (see k_conv_tc_x3)
+int conv_tc_taps(int geom) {
+    switch (geom) {
+        case G_PW: return 1;
+        case G_UP: return 16;
+        case G_C1K3: return 3;
+        case G_C1K7: return 7;
+        case G_C1K11: return 11;
+        default: return 9;
+    }
+}
 int conv_tc_stage_channels(int geom, int bf16) {
     const int epc = bf16 ? 8 : 4;
     return (geom == G_PW ? Geo<G_PW>::KCH : Geo<G_C3>::KCH) * epc;
@@ -1026,11 +1154,41 @@ static int dispatch_conv_tc(const ConvTcParams& p, cudaStream_t s) {
             if (p.epi == EPI_RES) return nt == 128 ? launch_tc<G_PW, BF16, 128, true>(p, s) : launch_tc<G_PW, BF16, 64, true>(p, s);
             return nt == 128 ? launch_tc<G_PW, BF16, 128>(p, s) : launch_tc<G_PW, BF16, 64>(p, s);
         case G_DOWN: return launch_tc<G_DOWN, BF16, 64>(p, s);
-        default:     return launch_tc<G_UP, BF16, 64>(p, s);
+        case G_UP:   return launch_tc<G_UP, BF16, 64>(p, s);
+        default:     return -1;
+    }
+}
+
+// Conv1d (vocoder): tf32 operands
+template <int GEOM>
+static int dispatch_conv1d(const ConvTcParams& p, cudaStream_t s) {
+    if (p.dil < 1 || p.pad < 0 || 2 * p.pad > 64) return -1;      // the strip carries at most 64 halo samples
+    switch (conv_tc_ntile(p.geom, p.Cout)) {
+        case 128: return launch_tc<GEOM, false, 128>(p, s);
+        case 64:  return launch_tc<GEOM, false, 64>(p, s);
+        default:  return p.Cout % 32 == 0 ? launch_tc<GEOM, false, 32>(p, s) : -1;
+    }
+}
+
+// fp32x3 mode (p.x3): tf32 operands, 3xTF32 stages, chunked accumulation
+static int dispatch_conv_tc_x3(const ConvTcParams& p, cudaStream_t s) {
+    switch (p.geom) {
+        case G_C3:   return launch_tc<G_C3, false, 64, false, true>(p, s);
+        case G_PW:
+            if (p.epi == EPI_KV) return -1;             // fp32x3 attention goes through the plain 1x1 conv + k_kv_ctx
+            if (p.epi == EPI_RES) return launch_tc<G_PW, false, 64, true, true>(p, s);
+            return launch_tc<G_PW, false, 64, false, true>(p, s);
+        case G_DOWN: return launch_tc<G_DOWN, false, 64, false, true>(p, s);
+        default:     return launch_tc<G_UP, false, 64, false, true>(p, s);
     }
 }
 
 int launch_conv_tc(const ConvTcParams& p, cudaStream_t s) {
+    if (geom_is_c1(p.geom)) {
+        if (p.x3 || p.bf16) return -1;
+        return p.geom == G_C1K3 ? dispatch_conv1d<G_C1K3>(p, s) : p.geom == G_C1K7 ? dispatch_conv1d<G_C1K7>(p, s) : dispatch_conv1d<G_C1K11>(p, s);
+    }
+    if (p.x3) return p.bf16 ? -1 : dispatch_conv_tc_x3(p, s);
     return p.bf16 ? dispatch_conv_tc<true>(p, s) : dispatch_conv_tc<false>(p, s);
 }
 

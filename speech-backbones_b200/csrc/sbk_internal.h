@@ -11,7 +11,9 @@ constexpr int kDimHead = 32;
 constexpr int kAttnHidden = 128;  // heads * dim_head
 constexpr int kKvPartFloats = 32 + 32 + 32 * 32;   // per (tile, head): max[32], sum[32], S[32][32]
 
-enum Geom { G_PW = 0, G_C3 = 1, G_DOWN = 2, G_UP = 3 };
+// G_C1K*: Conv1d with K taps and a runtime dilation over [B][1][C/4][L][4] tensors (the HiFi-GAN vocoder, sbk_vocoder.cu)
+enum Geom { G_PW = 0, G_C3 = 1, G_DOWN = 2, G_UP = 3, G_C1K3 = 4, G_C1K7 = 5, G_C1K11 = 6 };
+__host__ __device__ constexpr bool geom_is_c1(int g) { return g >= G_C1K3; }
 enum Pro { PRO_NONE = 0, PRO_MASK = 1, PRO_GN = 2 };
 enum Epi { EPI_PLAIN = 0, EPI_RES = 1, EPI_KV = 2 };
 
@@ -69,10 +71,14 @@ struct ConvTcParams {
     int bf16;
     int nt;                                         // N tile override (64) for launches with too few 128-wide tiles to fill the
                                                     // GPU (small batches); 0 = conv_tc_ntile(geom, Cout).  The weights must be packed for it.
+    // Conv1d geometries: dilation and left padding ((K-1)*dil/2) in samples; output activation LeakyReLU(slope) on `out`
+    // (act_out) and/or on the second output written through out_lo (act_out2: out_lo = lrelu(out) instead of the x_lo split)
+    int dil, pad; float slope; int act_out, act_out2;
     // fp32-class mode (SBK_PREC_FP32X3, "3xTF32"): every operand x is carried as the pair (x, x_lo = x - trunc_tf32(x)); the
     // tensor core reads the top 19 bits of x (= x_hi) by itself.  Weights are packed as (w_hi, w_lo) stage pairs and each
     // K stage is issued three times: x_lo*w_hi + x*w_lo + x*w_hi, all into the same fp32 TMEM accumulator.
     int x3;
+    int flush;                                      // sub-stages per accumulation run (0 = default 6); SBK_X3_FLUSH overrides it (measurement knob)
     const void* in0_lo; const void* in1_lo;         // the x_lo tensors, same layout as in0 / in1
     float* out_lo;                                  // operand-form outputs (non-3x3 geometries): also write out - trunc_tf32(out)
 };
@@ -239,6 +245,7 @@ int launch_igemm(const IgemmParams& p, cudaStream_t s);
 int launch_first_conv(const FirstConvParams& p, cudaStream_t s);
 int launch_conv_tc(const ConvTcParams& p, cudaStream_t s);
 int conv_tc_ntile(int geom, int Cout);
+int conv_tc_ntile_x3(int geom, int Cout);
 int conv_tc_taps(int geom);
 int conv_tc_stage_channels(int geom, int bf16);
 int launch_gn_act(const GnActParams& p, cudaStream_t s);

@@ -238,13 +238,30 @@ class Diffusion(BaseModule):
         if io_dtype != torch.float32:
             z, mask, mu = z.float(), mask.float(), mu.float()
             spk = None if spk is None else spk.float()
-        noise = None
-        if stoc:
-            # the reference draws torch.randn(z.shape) once per step, in step order (:267)
-            noise = torch.stack([torch.randn(z.shape, dtype=z.dtype, device=z.device) for _ in range(n_timesteps)])
         with torch.cuda.device(z.device):
-            out = eng.reverse_diffusion(z, mask, mu, n_timesteps, stoc, spk, noise)
+            if not stoc:
+                out = eng.reverse_diffusion(z, mask, mu, n_timesteps, False, spk, None)
+            else:
+                out = self._stochastic(eng, z, mask, mu, n_timesteps, spk)
         return out if io_dtype == torch.float32 else out.to(io_dtype)
+
+    # bytes of pre-drawn Euler-Maruyama noise resident at once (config 3: N=1000 x B=128 would be 21 GB if materialised)
+    noise_window_bytes = 256 << 20
+
+    def _stochastic(self, eng, z, mask, mu, n_timesteps, spk):
+        """stoc=True: the reference draws torch.randn(z.shape) once per step, in step order (:267).  The same draws, in the
+        same order, are made here a window of steps at a time and streamed through `sbk_reverse_steps`, so the noise
+        resident at any moment is bounded by `noise_window_bytes` instead of growing with N."""
+        per_step = z.numel() * 4
+        window = max(1, min(n_timesteps, self.noise_window_bytes // per_step))
+        draw = lambda n: torch.stack([torch.randn(z.shape, dtype=z.dtype, device=z.device) for _ in range(n)])
+        if window >= n_timesteps or len(eng.batch_slices(z.shape[0], z.shape[2])) > 1:
+            return eng.reverse_diffusion(z, mask, mu, n_timesteps, True, spk, draw(n_timesteps))
+        xt = (z * mask).contiguous()                                                # :256
+        for s0 in range(0, n_timesteps, window):
+            s1 = min(n_timesteps, s0 + window)
+            eng.reverse_steps(xt, mask, mu, n_timesteps, s0, s1, True, spk, draw(s1 - s0))
+        return xt
 
     @torch.no_grad()
     def forward(self, z, mask, mu, n_timesteps, stoc=False, spk=None):

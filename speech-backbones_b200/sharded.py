@@ -59,7 +59,11 @@ def sharded_sample(compute: Callable, z, mask, mu, n_timesteps: int, spk=None, g
     B = z.shape[0]
     lo, hi = shard_bounds(B, world, rank)
     sl = slice(lo, hi)
-    local = compute(z[sl], mask[sl], mu[sl], n_timesteps, None if spk is None else spk[sl])
+    if hi > lo:
+        local = compute(z[sl], mask[sl], mu[sl], n_timesteps, None if spk is None else spk[sl])
+    else:
+        # fewer utterances than ranks: this rank has nothing to sample but must still take part in the gather
+        local = z[sl].clone()
     if not gather:
         return local
     if B % world == 0:
