@@ -200,6 +200,29 @@ size_t sbk_vocoder_workspace_bytes(const sbk_vocoder* v, int B, int T);
 int sbk_vocoder_forward(sbk_vocoder* v, const float* mel, float* wav, int B, int T, void* stream);
 int64_t sbk_vocoder_last_launch_count(const sbk_vocoder* v);
 
+/* ---- the module in front of the glue: the Grad-TTS text encoder -------------------------------
+ * TextEncoder (Grad-TTS/model/text_encoder.py:281-326): embedding, ConvReluNorm prenet, relative-position transformer
+ * encoder, proj_m and the duration predictor; eval mode.  Called as `self.encoder(x, x_lengths, spk)` at tts.py:75; its
+ * outputs are exactly sbk_prior_expand's inputs.  Constructor arguments as in text_encoder.py:282-284 (p_dropout is
+ * irrelevant in eval mode); weights under the reference's state_dict names.  Exact fp32 arithmetic on CUDA cores. */
+typedef struct sbk_textenc sbk_textenc;
+typedef struct sbk_textenc_config {
+    int32_t device;
+    int32_t n_vocab, n_feats, n_channels, filter_channels, filter_channels_dp, n_heads, n_layers, kernel_size, window_size;
+    int32_t n_spks, spk_emb_dim;
+} sbk_textenc_config;
+int sbk_textenc_create(const sbk_textenc_config* cfg, sbk_textenc** out);
+void sbk_textenc_destroy(sbk_textenc* e);
+int sbk_textenc_num_weights(const sbk_textenc* e);
+const char* sbk_textenc_weight_name(const sbk_textenc* e, int i);
+int sbk_textenc_set_weight(sbk_textenc* e, const char* name, const void* data, const int64_t* shape, int ndim);
+int sbk_textenc_pack(sbk_textenc* e);
+/* TextEncoder.forward(x, x_lengths, spk) (:312-326): x [B,Tx] int64 token ids, x_lengths [B] int64, spk NULL or
+ * [B,spk_emb_dim] -> mu_x [B,n_feats,Tx], logw [B,1,Tx], x_mask [B,1,Tx].  Device pointers, asynchronous on `stream`. */
+int sbk_textenc_forward(sbk_textenc* e, const int64_t* x, const int64_t* x_lengths, const float* spk,
+                        float* mu_x, float* logw, float* x_mask, int B, int Tx, void* stream);
+int64_t sbk_textenc_last_launch_count(const sbk_textenc* e);
+
 const char* sbk_last_error(void);
 const char* sbk_version(void);
 

@@ -15,13 +15,15 @@ import torch
 import torch.nn.functional as F
 
 
-def param_spec(n_vocab=149, n_feats=80, ch=192, filt=768, filt_dp=256, n_layers=6, kernel=3, window=4, n_heads=2):
-    """[(name, shape)] of TextEncoder.state_dict() for n_spks = 1 (text_encoder.py:281-310)."""
+def param_spec(n_vocab=149, n_feats=80, ch=192, filt=768, filt_dp=256, n_layers=6, kernel=3, window=4, n_heads=2, spk_extra=0):
+    """[(name, shape)] of TextEncoder.state_dict() (text_encoder.py:281-310); spk_extra = spk_emb_dim when n_spks > 1 (the
+    encoder, proj_m and proj_w then run on n_channels + spk_emb_dim channels, :305-310)."""
     s = [("emb.weight", (n_vocab, ch))]
     for i in range(3):
         s += [(f"prenet.conv_layers.{i}.weight", (ch, ch, 5)), (f"prenet.conv_layers.{i}.bias", (ch,)),
               (f"prenet.norm_layers.{i}.gamma", (ch,)), (f"prenet.norm_layers.{i}.beta", (ch,))]
     s += [("prenet.proj.weight", (ch, ch, 1)), ("prenet.proj.bias", (ch,))]
+    ch = ch + spk_extra
     for i in range(n_layers):
         a = f"encoder.attn_layers.{i}"
         s += [(f"{a}.emb_rel_k", (1, 2 * window + 1, ch // n_heads)), (f"{a}.emb_rel_v", (1, 2 * window + 1, ch // n_heads))]
@@ -40,11 +42,11 @@ def param_spec(n_vocab=149, n_feats=80, ch=192, filt=768, filt_dp=256, n_layers=
     return s
 
 
-def synthetic_weights(seed):
+def synthetic_weights(seed, spk_extra=0):
     """Seeded stand-in weights (the reference ships no Grad-TTS checkpoint): 1/sqrt(fan_in) scales, LayerNorm gains near 1."""
     from speech_backbones_b200.spec import synthetic_tensor
     sd = {}
-    for name, shape in param_spec():
+    for name, shape in param_spec(spk_extra=spk_extra):
         if name.endswith(".gamma"):
             sd[name] = 1.0 + 0.1 * synthetic_tensor(seed, "textenc/" + name, shape)
         elif name.endswith((".beta", ".bias")):
@@ -89,8 +91,9 @@ def rel_attention(p, pre, x, mask, n_heads, window):
     return F.conv1d(out, p[f"{pre}.conv_o.weight"], p[f"{pre}.conv_o.bias"])
 
 
-def text_encoder(p, x, x_lengths, n_heads=2, n_layers=6, kernel=3, window=4):
-    """TextEncoder.forward (:312-326), n_spks = 1: token ids [B,Tx] -> (mu_x [B,80,Tx], logw [B,1,Tx], x_mask [B,1,Tx])."""
+def text_encoder(p, x, x_lengths, n_heads=2, n_layers=6, kernel=3, window=4, spk=None):
+    """TextEncoder.forward (:312-326): token ids [B,Tx] -> (mu_x [B,80,Tx], logw [B,1,Tx], x_mask [B,1,Tx]).  spk [B,E] for a
+    multi-speaker model: concatenated to every token after the prenet (:317-318)."""
     ch = p["emb.weight"].shape[1]
     h = (F.embedding(x, p["emb.weight"]) * math.sqrt(ch)).transpose(1, -1)
     t = h.shape[2]
@@ -101,6 +104,8 @@ def text_encoder(p, x, x_lengths, n_heads=2, n_layers=6, kernel=3, window=4):
         h = F.conv1d(h * x_mask, p[f"prenet.conv_layers.{i}.weight"], p[f"prenet.conv_layers.{i}.bias"], padding=2)
         h = torch.relu(layer_norm(h, p[f"prenet.norm_layers.{i}.gamma"], p[f"prenet.norm_layers.{i}.beta"]))
     h = (org + F.conv1d(h, p["prenet.proj.weight"], p["prenet.proj.bias"])) * x_mask
+    if spk is not None:
+        h = torch.cat([h, spk.unsqueeze(-1).repeat(1, 1, h.shape[-1])], dim=1)
     # encoder (:267-278)
     attn_mask = x_mask.unsqueeze(2) * x_mask.unsqueeze(-1)
     for i in range(n_layers):

@@ -25,7 +25,10 @@ n = len(per)
 rd = sum(p.get("dram__bytes_read.sum", 0) for p in per.values())
 wr = sum(p.get("dram__bytes_write.sum", 0) for p in per.values())
 tm = sum(p.get("gpu__time_duration.sum", 0) for p in per.values())
-res = {"source": path, "kernel_pattern": pattern, "launches": n, "dram_bytes_per_launch": (rd + wr) / max(n, 1),
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bench import csrc_digest   # ties the capture to the kernel sources it was taken from (bench.py reports it only if they match)
+res = {"csrc_digest": csrc_digest(), "source": path, "kernel_pattern": pattern, "launches": n, "dram_bytes_per_launch": (rd + wr) / max(n, 1),
        "dram_read_per_launch": rd / max(n, 1), "dram_write_per_launch": wr / max(n, 1), "ncu_seconds_per_launch": tm / max(n, 1)}
 json.dump(res, open(out, "w"), indent=1)
 print(json.dumps(res))

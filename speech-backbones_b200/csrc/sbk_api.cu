@@ -329,7 +329,7 @@ static int pack_tc(sbk_handle* h, const std::string& src, const std::string& key
     TRY_RC(pack_tc_host(h, hs, key, cout, cin, geom, bf16));
     // 3x3 convs with >= 128 output channels also get a 64-wide N-tile image: small batches have too few 128-wide tiles to
     // fill 148 SMs (B=1, level 2: 20 tiles), so the planner switches those launches to twice as many half-width tiles
-    if (geom == G_C3 && conv_tc_ntile(geom, cout) == 128 && !(packs_x3(h) && !bf16)) TRY_RC(pack_tc_host(h, hs, key + "64", cout, cin, geom, bf16, 64));
+    if (geom == G_C3 && conv_tc_ntile(geom, cout) == 128) TRY_RC(pack_tc_host(h, hs, key + "64", cout, cin, geom, bf16, 64));
     return SBK_OK;
 }
 // k and v rows of to_qkv ('(qkv heads c)': k = rows 128.., v = rows 256..) in k_attn_kv's per-stage shared-memory image

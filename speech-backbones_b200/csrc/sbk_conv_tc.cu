@@ -216,18 +216,22 @@ using namespace tc;
 //   * NSLOT TMEM accumulator slots: with two slots the epilogue of tile i overlaps the loads + MMAs of tile i+1;
 //   * two CTAs per SM when smem (<= ~108 KB) and TMEM (<= 256 columns) allow, else one CTA with a deeper ring.
 constexpr int pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
-// X3 (fp32x3 mode): the epilogue warps carry the whole NT-column accumulator row in registers (chunked accumulation, see
-// k_conv_tc), so those instantiations run one CTA per SM (204 registers per thread) with two TMEM slots where they fit.
+// X3 (fp32x3 mode), 3x3 and 1x1 convs (TMSUM): TMEM holds one accumulation-run slot per output row plus the running
+// fp32 sums of the tile, 4*NT columns in all (see conv_tc_body); Downsample keeps its running sums in registers
+// (one CTA per SM: 64 accumulators per thread); Upsample runs unchunked.
 template <int GEOM, int NT, bool X3 = false> struct Depth {
     static constexpr int STAGE_BYTES = Geo<GEOM>::KCH * Geo<GEOM>::HR * Geo<GEOM>::PXP * 16 + Geo<GEOM>::TAPS * Geo<GEOM>::KCH * NT * 16;
     static constexpr int SLOT_COLS = Geo<GEOM>::NACC * NT;
     static constexpr int FIT2 = (108 * 1024) / STAGE_BYTES;
     static constexpr int FIT1 = (220 * 1024) / STAGE_BYTES;
+    static constexpr bool TMSUM = X3 && (GEOM == G_C3 || GEOM == G_PW);
     // long-K 3x3 convs (NT = 128) are MMA-bound: one CTA, deep ring, two accumulator slots.  Everything else is
     // epilogue/latency-bound: two CTAs per SM double the epilogue warps; slots as TMEM (256 columns per CTA) allows.
-    static constexpr bool TWO = !X3 && FIT2 >= 2 && SLOT_COLS <= 256 && !(GEOM == G_C3 && NT == 128);
-    static constexpr int NSLOT = TWO ? (2 * SLOT_COLS <= 256 ? 2 : 1) : (2 * SLOT_COLS <= 512 ? 2 : 1);
-    static constexpr int TMEM_COLS = pow2_cols(NSLOT * SLOT_COLS);
+    // (TMSUM: a run's FLUSH stages stay resident for both row passes, so two CTAs need at least 3 stages each.)
+    static constexpr bool TWO = X3 ? (TMSUM && 4 * NT <= 256 && FIT2 >= 3)
+                                   : (FIT2 >= 2 && SLOT_COLS <= 256 && !(GEOM == G_C3 && NT == 128));
+    static constexpr int NSLOT = TMSUM ? 2 : (TWO ? (2 * SLOT_COLS <= 256 ? 2 : 1) : (2 * SLOT_COLS <= 512 ? 2 : 1));
+    static constexpr int TMEM_COLS = TMSUM ? 4 * NT : pow2_cols(NSLOT * SLOT_COLS);
     static constexpr int STAGES = TWO ? (FIT2 > 4 ? 4 : FIT2) : (FIT1 > 6 ? 6 : FIT1);
     static constexpr int MINB = TWO ? 2 : 1;
     static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + (3 * STAGES + 2 * NSLOT + 2) * 8 + 128 * 4 + 16 + 3 * NT * 4 + 64;
@@ -250,10 +254,21 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcParams& p) {
     using D = Depth<GEOM, NT, X3>;
     // Upsample keeps its 8 accumulators (4 phases x 2 rows x 64 columns = all of TMEM) in one run: 256 register
     // accumulators per thread do not exist, and its runs are short (4 taps: 96-192 MMAs per accumulator)
-    constexpr bool CHUNKED = X3 && GEOM != G_UP;
-    // sub-stages per accumulation run: p.flush, default 6 = two K stages of x_lo*w_hi + x*w_lo + x*w_hi (54 MMAs per
-    // accumulator for a 3x3 conv: ~1e-6 of truncation bias per conv)
-    const int FLUSH = p.flush > 0 ? p.flush : 6;
+    // Two homes for the running sums of the accumulation runs:
+    //   CHUNKED (Downsample): registers of the epilogue warps (64 per thread, one CTA per SM), two whole-tile TMEM slots;
+    //   TMSUM (3x3 and 1x1): TMEM.  Columns [0,NT) / [NT,2NT) are the RUN slots of output rows 0 / 1, [2NT,4NT) the
+    //   running sums.  The issuer walks a run row by row - row 0 over the run's FLUSH stages, then row 1 over the same,
+    //   still resident, stages - so while it computes one row the four epilogue warps of the other row fold that row's
+    //   finished run into the sums (tcgen05.ld run + ld sum, fp32 round-to-nearest add, tcgen05.st): full overlap with
+    //   one slot per row, N = 128 tiles and two CTAs per SM where they fit, which the register variant cannot do
+    //   (128 accumulators per thread spill at the 168-register ceiling of a 10-warp CTA; the N = 64 UMMA shape it forces
+    //   is operand-fetch bound: 474 vs 780 TFLOP/s of MMA issue, profiles/r2_ops_fp32x3_v2_chunked_nt64.txt).
+    constexpr bool TMSUM = D::TMSUM;
+    constexpr bool CHUNKED = X3 && GEOM == G_DOWN;
+    // sub-stages per accumulation run (p.flush overrides): Downsample 6; TMSUM 3 (= one K stage of x_lo*w_hi + x*w_lo +
+    // x*w_hi: 27 MMAs per accumulator for a 3x3 conv, ~5e-7 of truncation bias), at most STAGES - 1 resident stages
+    const int FLUSH = TMSUM ? (p.flush > 0 && p.flush < D::STAGES ? p.flush : (D::STAGES - 1 < 3 ? D::STAGES - 1 : 3))
+                            : (p.flush > 0 ? p.flush : 6);
     constexpr int STAGES = D::STAGES, NSLOT = D::NSLOT, SLOT_COLS = D::SLOT_COLS;
     constexpr int LAG = STAGES >= 3 ? STAGES - 2 : 0;      // G_DOWN only: cp.async groups in flight behind the newest
     static_assert(STAGES >= 2, "need at least 2 stages");
@@ -289,7 +304,7 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcParams& p) {
     const int ksteps = Cin / CPS;
     // fp32x3 mode: each K stage runs three times, (x_lo, w_hi), (x, w_lo), (x, w_hi) - small terms first
     const int ksteps_t = X3 ? 3 * ksteps : ksteps;
-    const int nchunks = CHUNKED ? (ksteps_t + FLUSH - 1) / FLUSH : 1;     // accumulation runs per tile
+    const int nchunks = (CHUNKED || TMSUM) ? (ksteps_t + FLUSH - 1) / FLUSH : 1;     // accumulation runs per tile
     // ---- tile space: (sample, pixel tile, N tile), N tile fastest so neighbours in time share the A tile in L2
     const int wt_w = (GEOM == G_DOWN ? p.Wo : p.W), wt_h = (GEOM == G_DOWN ? p.Ho : p.H);
     const int wtiles = (wt_w + SPAN - 1) / SPAN;
@@ -314,7 +329,8 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcParams& p) {
     // ---- one-time setup
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_a(s), NPROD / 32); mbar_init(full_b(s), 1); mbar_init(empty(s), 1); }
-        for (int a = 0; a < NSLOT; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), NPROD / 32); }
+        // (TMSUM: slot a belongs to output row a and is drained by that row's four epilogue warps)
+        for (int a = 0; a < NSLOT; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), TMSUM ? NPROD / 64 : NPROD / 32); }
         mbar_init(kv_bar, 1);
         fence_barrier_init();
     }
@@ -493,6 +509,32 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcParams& p) {
             while (drained < nchunks) drain_run();
             acc_ready = true;
         }
+        if constexpr (TMSUM) {
+            // fold every accumulation run of this row into the running sums in TMEM (this thread's lane x NT columns)
+            const uint32_t trun = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(jrow * NT);
+            const uint32_t tsum = trun + 2 * NT;
+            for (int c = 0; c < nchunks; ++c, ++ar) {
+                mbar_wait(tfull(jrow), ar & 1);
+                tc_fence_after();
+#pragma unroll 1
+                for (int cb = 0; cb < NT; cb += 32) {
+                    uint32_t r[32];
+                    tmem_ld32(trun + cb, r);
+                    if (c > 0) {
+                        uint32_t q[32];
+                        tmem_ld32(tsum + cb, q);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(q[i]));
+                    }
+                    tmem_st32(tsum + cb, r);
+                }
+                tmem_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty(jrow));
+            }
+            acc_ready = true;
+        }
 #pragma unroll (CHUNKED ? NT / 32 : 1)
         for (int cb = 0; cb < NT; cb += 32) {
             if (!acc_ready) {
@@ -504,6 +546,8 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcParams& p) {
             if constexpr (CHUNKED) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(accr[cb + i]);
+            } else if constexpr (TMSUM) {
+                tmem_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(2 * NT + acc * NT + cb), r);
             } else {
                 tmem_ld32(tslot + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(acc * NT + cb), r);
             }
@@ -619,7 +663,7 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcParams& p) {
         }
         }
             // accumulator slot drained: hand it back to the MMA issuer (CHUNKED: every run was handed back as it was drained)
-            if constexpr (!CHUNKED) {
+            if constexpr (!CHUNKED && !TMSUM) {
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tempty(slot));
@@ -646,6 +690,44 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcParams& p) {
             const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
             uint32_t it = 0;
             uint32_t ar = 0;                                             // accumulation-run counter (see the epilogue warps)
+            if constexpr (TMSUM) {
+                // row-major runs: row j of run c goes to TMEM slot j while the epilogue warps of the other row fold that
+                // row's previous run into the running sums; a stage is released after the LAST row has read it
+                for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                    for (int c = 0; c < nchunks; ++c, ++ar) {
+                        const int ks_lo = c * FLUSH, ks_hi = ks_lo + FLUSH < ksteps_t ? ks_lo + FLUSH : ksteps_t;
+#pragma unroll 1
+                        for (int j = 0; j < ROWS; ++j) {
+                            mbar_wait(tempty(j), (ar & 1) ^ 1);             // this row's slot has been folded into the sums
+                            tc_fence_after();
+                            const uint32_t tslot = tmem_base + j * NT;
+                            for (int ks = ks_lo; ks < ks_hi; ++ks) {
+                                const uint32_t itk = it + (uint32_t)(ks - ks_lo);
+                                const int s = itk % STAGES;
+                                if (j == 0) {
+                                    mbar_wait(full_b(s), (itk / STAGES) & 1);   // (row 1 re-reads stages row 0 already waited for)
+                                    tc_fence_after();
+                                }
+#pragma unroll
+                                for (int kk = 0; kk < KCH / 2; ++kk) {
+                                    const uint32_t a_st = a0 + s * A_STAGE_BYTES + kk * 2 * PLANE;
+                                    const uint32_t b_st = b0 + s * B_STAGE_BYTES + kk * 2 * (NT * 16);
+#pragma unroll
+                                    for (int tap = 0; tap < TAPS; ++tap) {
+                                        const int r = TAPS == 9 ? tap / 3 : 0, sx = TAPS == 9 ? tap % 3 : 0;
+                                        const uint64_t bd = make_desc(b_st + tap * KCH * (NT * 16), NT * 16, 128);
+                                        const uint64_t ad = make_desc(a_st + ((r + j) * PXP + sx) * 16, PLANE, 128);
+                                        umma<BF16>(tslot, ad, bd, idesc, ((ks - ks_lo) | kk | tap) != 0 ? 1u : 0u);
+                                    }
+                                }
+                                if (j == ROWS - 1) umma_commit(empty(s));   // frees the stage when both rows have read it
+                            }
+                            umma_commit(tfull(j));                          // this row's run is complete
+                        }
+                        it += (uint32_t)(ks_hi - ks_lo);
+                    }
+                }
+            } else
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
               for (int c = 0; c < nchunks; ++c, ++ar) {
                 const int slot = ar % NSLOT;
@@ -810,14 +892,11 @@ template <int GEOM, bool BF16, int NT, bool RES = false>
 __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT, false>::MINB) k_conv_tc(const ConvTcParams p) {
     conv_tc_body<GEOM, BF16, NT, RES, false>(p);
 }
-// fp32x3 instantiations: one CTA of 320 threads per SM.  Warps are allocated four at a time, so a 10-warp CTA is sized as
-// 384 threads and the ceiling is 65536 / 384 = 168 registers per thread (a __maxnreg__(200) build fails to launch with "too
-// many resources requested"): 128 register accumulators per thread do not fit, so every fp32x3 conv uses 64-wide N tiles
-// (64 accumulators per thread; conv_tc_ntile_x3).  The N = 64 UMMA shape costs ~20 % of the N = 128 rate on the >= 128-channel
-// convs (shared-memory operand bandwidth) - the price of fp32-class sums on a truncating accumulator.
+// fp32x3 instantiations.  (Warps are allocated four at a time, so a 10-warp CTA is sized as 384 threads: the ceiling is
+// 65536 / 384 = 168 registers per thread at one CTA per SM - a __maxnreg__(200) build fails to launch with "too many
+// resources requested".  That is why the running sums of the 3x3 / 1x1 convs live in TMEM, not in registers.)
 template <int GEOM, int NT, bool RES = false>
-__global__ void __launch_bounds__(NTHREADS, 1) k_conv_tc_x3(const ConvTcParams p) {
-    static_assert(NT == 64, "fp32x3: 64 register accumulators per epilogue thread");
+__global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT, true>::MINB) k_conv_tc_x3(const ConvTcParams p) {
     conv_tc_body<GEOM, false, NT, RES, true>(p);
 }
 
@@ -1128,7 +1207,7 @@ int conv_tc_ntile(int geom, int Cout) {
     if (geom_is_c1(geom)) return Cout % 128 == 0 ? 128 : (Cout % 64 == 0 ? 64 : 32);
     return Cout % 128 == 0 ? 128 : 64;
 }
-int conv_tc_ntile_x3(int, int) { return 64; }     // fp32x3: 64 register accumulators per epilogue thread (see k_conv_tc_x3)
+int conv_tc_ntile_x3(int geom, int Cout) { return conv_tc_ntile(geom, Cout); }     // (the running sums live in TMEM: same N tiles as tf32)
 int conv_tc_taps(int geom) {
     switch (geom) {
         case G_PW: return 1;
@@ -1172,12 +1251,13 @@ static int dispatch_conv1d(const ConvTcParams& p, cudaStream_t s) {
 
 // fp32x3 mode (p.x3): tf32 operands, 3xTF32 stages, chunked accumulation
 static int dispatch_conv_tc_x3(const ConvTcParams& p, cudaStream_t s) {
+    const int nt = (p.nt == 64 && p.geom == G_C3) ? 64 : conv_tc_ntile(p.geom, p.Cout);
     switch (p.geom) {
-        case G_C3:   return launch_tc<G_C3, false, 64, false, true>(p, s);
+        case G_C3:   return nt == 128 ? launch_tc<G_C3, false, 128, false, true>(p, s) : launch_tc<G_C3, false, 64, false, true>(p, s);
         case G_PW:
             if (p.epi == EPI_KV) return -1;             // fp32x3 attention goes through the plain 1x1 conv + k_kv_ctx
-            if (p.epi == EPI_RES) return launch_tc<G_PW, false, 64, true, true>(p, s);
-            return launch_tc<G_PW, false, 64, false, true>(p, s);
+            if (p.epi == EPI_RES) return nt == 128 ? launch_tc<G_PW, false, 128, true, true>(p, s) : launch_tc<G_PW, false, 64, true, true>(p, s);
+            return nt == 128 ? launch_tc<G_PW, false, 128, false, true>(p, s) : launch_tc<G_PW, false, 64, false, true>(p, s);
         case G_DOWN: return launch_tc<G_DOWN, false, 64, false, true>(p, s);
         default:     return launch_tc<G_UP, false, 64, false, true>(p, s);
     }

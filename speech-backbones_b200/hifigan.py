@@ -30,7 +30,7 @@ class SbkVocoderConfig(C.Structure):
 
 
 def _get(h, k, default=None):
-    return h[k] if isinstance(h, dict) else getattr(h, k, default)
+    return h.get(k, default) if isinstance(h, dict) else getattr(h, k, default)
 
 
 def _padding(k, d=1):

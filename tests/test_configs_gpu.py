@@ -20,21 +20,28 @@ from oracle import gradtts_oracle as O
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("precision,tol", [("bf16", 1e-2), ("fp32x3", 2e-4)])
-def test_config3_long_horizon_n1000_vs_oracle(sbk_lib, precision, tol):
-    """N = 1000 Euler steps, B=1, T=64: the GPU trajectory against the fp32 CPU oracle run to the same N."""
-    from speech_backbones_b200.binding import Engine
+@pytest.fixture(scope="module")
+def n1000_case():
+    """B=1, T=64, N=1000 on the CPU oracle - computed once (about a minute on the GPU box's host cores) for both modes."""
     cfg = UNetConfig()
     sd = synthetic_state_dict(cfg)
     z, mask, mu, _, _ = synthetic_inputs(1, 64)
+    with torch.no_grad():
+        ref = O.reverse_diffusion(sd, cfg, z, mask, mu, 1000)
+    return sd, z, mask, mu, ref
+
+
+@pytest.mark.parametrize("precision,tol", [("bf16", 1e-2), ("fp32x3", 2e-4)])
+def test_config3_long_horizon_n1000_vs_oracle(sbk_lib, n1000_case, precision, tol):
+    """N = 1000 Euler steps, B=1, T=64: the GPU trajectory against the fp32 CPU oracle run to the same N."""
+    from speech_backbones_b200.binding import Engine
+    sd, z, mask, mu, ref = n1000_case
     N = 1000
     eng = Engine(precision=precision)
     eng.load_state_dict(sd)
     y = eng.reverse_diffusion(z.cuda(), mask.cuda(), mu.cuda(), N).cpu()
     assert eng.last_host_launches() == 1                      # the whole 1000-step loop is ONE graph launch
     eng.close()
-    with torch.no_grad():
-        ref = O.reverse_diffusion(sd, cfg, z, mask, mu, N)
     err = rel_l2(y, ref)
     print(precision, "N=1000 B=1 T=64 rel_l2 vs oracle %.3e" % err)
     assert torch.isfinite(y).all()
@@ -70,7 +77,10 @@ def test_config4_diffvc_ml_n6_t256_vs_oracle(sbk_lib):
 @pytest.mark.parametrize("precision", ["fp32x3", "tf32", "bf16"])
 def test_alone_vs_in_batch_at_config_shapes(sbk_lib, precision):
     """scripts/gpu_config3.py's probe as a test: rows 5..6 of a B=8, T=512 ragged batch re-run alone (same padded T) for
-    N = 20 steps reproduce their rows bit for bit (fp64 GroupNorm statistics: no order dependence)."""
+    N = 20 steps reproduce their rows: bit for bit in the tf32 / bf16 modes (fp64 GroupNorm statistics, one TMEM
+    accumulation run per output whatever the tiling), to fp32 rounding in the fp32x3 mode (a 2-utterance batch takes the
+    64-wide N tiles, whose accumulation runs are cut every 2 sub-stages instead of 3: same sums, different fp32 rounding
+    points - measured 2.5e-7 after 20 steps)."""
     from speech_backbones_b200.binding import Engine
     cfg = UNetConfig()
     eng = Engine(precision=precision)
@@ -81,5 +91,5 @@ def test_alone_vs_in_batch_at_config_shapes(sbk_lib, precision):
     part = eng.reverse_diffusion(zd[5:7].contiguous(), md[5:7].contiguous(), mud[5:7].contiguous(), 20).cpu()
     dep = rel_l2(part, full[5:7])
     print(precision, "rows 5..6 alone vs in batch", dep)
-    assert dep == 0.0
+    assert dep == 0.0 if precision != "fp32x3" else dep < 1e-6
     eng.close()

@@ -93,7 +93,9 @@ def test_vocoder_vs_oracle_long_ragged(vocoder, hg_golden):
 @pytest.mark.gpu
 def test_vocoder_weight_norm_checkpoint_path(hg_golden):
     """inference.py:60-63 order: construct (weight norm attached) -> load a weight-norm checkpoint -> cuda -> forward works
-    both before and after remove_weight_norm() and gives the same waveform."""
+    both before and after remove_weight_norm() and gives the same waveform up to the tf32 operand rounding: the effective
+    weights g * v / ||v|| computed by this module and by torch's remove_weight_norm differ in the last fp32 bit, which
+    flips tf32 roundings of individual weights (measured 1.2e-3 between the two; the bound is the vocoder's own tolerance)."""
     g = Generator(HIFIGAN_V1).eval()
     with torch.no_grad():
         for n, p in g.named_parameters():
@@ -103,4 +105,4 @@ def test_vocoder_weight_norm_checkpoint_path(hg_golden):
     a = g(mel)
     g.remove_weight_norm()
     b = g(mel)
-    assert torch.isfinite(a).all() and rel_l2(b.cpu(), a.cpu()) < 1e-5
+    assert torch.isfinite(a).all() and rel_l2(b.cpu(), a.cpu()) <= VOC_TOL
