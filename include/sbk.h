@@ -74,7 +74,10 @@ int sbk_num_weights(const sbk_handle* h);
 const char* sbk_weight_name(const sbk_handle* h, int i);
 
 /* bytes of device workspace a (B,T) problem needs (activations, statistics, time tables) */
-size_t sbk_workspace_bytes(const sbk_handle* h, int B, int T);
+size_t sbk_workspace_bytes(const sbk_handle* h, int B, int T);          /* for n_timesteps <= 1024 */
+/* the same for a given number of steps: the per-step tables (time projections, coefficients, DiffVC conditioning vectors
+ * and folded first-conv weights) have max(64, B, n_timesteps) rows, so N = 2000 or DiffVC at large N * B needs more */
+size_t sbk_workspace_bytes_n(const sbk_handle* h, int B, int T, int n_timesteps);
 
 /* GradLogPEstimator2d.forward(x, mask, mu, t, spk) (diffusion.py:174-216).
  * x, mu, out: [B,n_feats,T]; mask: [B,1,T] in {0,1}; t: [B]; spk: NULL or [B,spk_emb_dim]. Device pointers. */
@@ -210,6 +213,8 @@ typedef struct sbk_textenc_config {
     int32_t device;
     int32_t n_vocab, n_feats, n_channels, filter_channels, filter_channels_dp, n_heads, n_layers, kernel_size, window_size;
     int32_t n_spks, spk_emb_dim;
+    int32_t kind;      /* 0: TextEncoder; 1: DiffVC MelEncoder(n_feats, channels, filters, heads, layers, kernel, dropout, window_size)
+                          (DiffVC/model/encoder.py:257-284: init_proj | prenet | encoder | term_proj; n_vocab / filter_channels_dp unused) */
 } sbk_textenc_config;
 int sbk_textenc_create(const sbk_textenc_config* cfg, sbk_textenc** out);
 void sbk_textenc_destroy(sbk_textenc* e);
@@ -221,6 +226,9 @@ int sbk_textenc_pack(sbk_textenc* e);
  * [B,spk_emb_dim] -> mu_x [B,n_feats,Tx], logw [B,1,Tx], x_mask [B,1,Tx].  Device pointers, asynchronous on `stream`. */
 int sbk_textenc_forward(sbk_textenc* e, const int64_t* x, const int64_t* x_lengths, const float* spk,
                         float* mu_x, float* logw, float* x_mask, int B, int Tx, void* stream);
+/* MelEncoder.forward(x, x_mask) (DiffVC/model/encoder.py:279-284, called at DiffVC/model/vc.py:39,45): x [B,n_feats,T],
+ * x_mask [B,1,T] in {0,1} -> out [B,n_feats,T] (the "average voice" mel; not masked, as in the reference).  kind = 1 handles. */
+int sbk_melenc_forward(sbk_textenc* e, const float* x, const float* x_mask, float* out, int B, int T, void* stream);
 int64_t sbk_textenc_last_launch_count(const sbk_textenc* e);
 
 const char* sbk_last_error(void);

@@ -125,3 +125,59 @@ def text_encoder(p, x, x_lengths, n_heads=2, n_layers=6, kernel=3, window=4, spk
     d = layer_norm(torch.relu(d), p["proj_w.norm_2.gamma"], p["proj_w.norm_2.beta"])
     logw = F.conv1d(d * x_mask, p["proj_w.proj.weight"], p["proj_w.proj.bias"]) * x_mask
     return mu, logw, x_mask
+
+
+# ---- DiffVC "average voice" mel encoder (DiffVC/model/encoder.py:257-284): the same prenet and encoder blocks around 1x1 projections
+def mel_param_spec(n_feats=80, ch=192, filt=768, n_layers=6, kernel=3, window=4, n_heads=2):
+    """[(name, shape)] of MelEncoder.state_dict() (DiffVC/model/encoder.py:258-277; DiffVC/params.py:16-22)."""
+    s = [("init_proj.weight", (ch, n_feats, 1)), ("init_proj.bias", (ch,))]
+    for i in range(3):
+        s += [(f"prenet.conv_layers.{i}.weight", (ch, ch, 5)), (f"prenet.conv_layers.{i}.bias", (ch,)),
+              (f"prenet.norm_layers.{i}.gamma", (ch,)), (f"prenet.norm_layers.{i}.beta", (ch,))]
+    s += [("prenet.proj.weight", (ch, ch, 1)), ("prenet.proj.bias", (ch,))]
+    for i in range(n_layers):
+        a = f"encoder.attn_layers.{i}"
+        s += [(f"{a}.emb_rel_k", (1, 2 * window + 1, ch // n_heads)), (f"{a}.emb_rel_v", (1, 2 * window + 1, ch // n_heads))]
+        for c in ("conv_q", "conv_k", "conv_v", "conv_o"):
+            s += [(f"{a}.{c}.weight", (ch, ch, 1)), (f"{a}.{c}.bias", (ch,))]
+        s += [(f"encoder.norm_layers_1.{i}.gamma", (ch,)), (f"encoder.norm_layers_1.{i}.beta", (ch,)),
+              (f"encoder.ffn_layers.{i}.conv_1.weight", (filt, ch, kernel)), (f"encoder.ffn_layers.{i}.conv_1.bias", (filt,)),
+              (f"encoder.ffn_layers.{i}.conv_2.weight", (ch, filt, kernel)), (f"encoder.ffn_layers.{i}.conv_2.bias", (ch,)),
+              (f"encoder.norm_layers_2.{i}.gamma", (ch,)), (f"encoder.norm_layers_2.{i}.beta", (ch,))]
+    s += [("term_proj.weight", (n_feats, ch, 1)), ("term_proj.bias", (n_feats,))]
+    return s
+
+
+def mel_synthetic_weights(seed):
+    from speech_backbones_b200.spec import synthetic_tensor
+    sd = {}
+    for name, shape in mel_param_spec():
+        if name.endswith(".gamma"):
+            sd[name] = 1.0 + 0.1 * synthetic_tensor(seed, "melenc/" + name, shape)
+        elif name.endswith((".beta", ".bias")):
+            sd[name] = 0.05 * synthetic_tensor(seed, "melenc/" + name, shape)
+        else:
+            fan_in = shape[1] * (shape[2] if len(shape) > 2 else 1) if "emb_rel" not in name else shape[-1]
+            sd[name] = synthetic_tensor(seed, "melenc/" + name, shape) / fan_in ** 0.5
+    return sd
+
+
+def mel_encoder(p, x, x_mask, n_heads=2, n_layers=6, kernel=3, window=4):
+    """MelEncoder.forward (DiffVC/model/encoder.py:279-284): mel [B,80,T], x_mask [B,1,T] -> "average voice" mel [B,80,T]."""
+    h = F.conv1d(x * x_mask, p["init_proj.weight"], p["init_proj.bias"])
+    org = h
+    for i in range(3):                                                          # ConvReluNorm (:62-69)
+        h = F.conv1d(h * x_mask, p[f"prenet.conv_layers.{i}.weight"], p[f"prenet.conv_layers.{i}.bias"], padding=2)
+        h = torch.relu(layer_norm(h, p[f"prenet.norm_layers.{i}.gamma"], p[f"prenet.norm_layers.{i}.beta"]))
+    h = (org + F.conv1d(h, p["prenet.proj.weight"], p["prenet.proj.bias"])) * x_mask
+    attn_mask = x_mask.unsqueeze(2) * x_mask.unsqueeze(-1)
+    for i in range(n_layers):                                                   # Encoder (:243-254)
+        h = h * x_mask
+        y = rel_attention(p, f"encoder.attn_layers.{i}", h, attn_mask, n_heads, window)
+        h = layer_norm(h + y, p[f"encoder.norm_layers_1.{i}.gamma"], p[f"encoder.norm_layers_1.{i}.beta"])
+        y = F.conv1d(h * x_mask, p[f"encoder.ffn_layers.{i}.conv_1.weight"], p[f"encoder.ffn_layers.{i}.conv_1.bias"], padding=kernel // 2)
+        y = F.conv1d(torch.relu(y) * x_mask, p[f"encoder.ffn_layers.{i}.conv_2.weight"], p[f"encoder.ffn_layers.{i}.conv_2.bias"],
+                     padding=kernel // 2) * x_mask
+        h = layer_norm(h + y, p[f"encoder.norm_layers_2.{i}.gamma"], p[f"encoder.norm_layers_2.{i}.beta"])
+    h = h * x_mask
+    return F.conv1d(h * x_mask, p["term_proj.weight"], p["term_proj.bias"])

@@ -18,7 +18,7 @@ EXPORTS = [
     "sbk_workspace_bytes", "sbk_estimator", "sbk_reverse_diffusion", "sbk_reverse_steps",
     "sbk_reverse_diffusion_host", "sbk_last_launch_count", "sbk_debug_read", "sbk_debug_num",
     "sbk_debug_name", "sbk_last_error", "sbk_version", "sbk_profile_ops", "sbk_debug_capture", "sbk_debug_layout", "sbk_debug_op_layout", "sbk_vc_estimator", "sbk_vc_reverse_diffusion", "sbk_vc_conditioning",
-    "sbk_prior_expand", "sbk_last_host_launches",
+    "sbk_prior_expand", "sbk_last_host_launches", "sbk_workspace_bytes_n",
 ]
 
 
@@ -51,6 +51,8 @@ def load_library() -> C.CDLL:
     lib.sbk_weight_name.restype = C.c_char_p
     lib.sbk_workspace_bytes.argtypes = [P, I, I]
     lib.sbk_workspace_bytes.restype = C.c_size_t
+    lib.sbk_workspace_bytes_n.argtypes = [P, I, I, I]
+    lib.sbk_workspace_bytes_n.restype = C.c_size_t
     lib.sbk_estimator.argtypes = [P, F, F, F, F, F, F, I, I, P]
     lib.sbk_reverse_diffusion.argtypes = [P, F, F, F, F, F, F, I, I, I, I, P]
     lib.sbk_vc_estimator.argtypes = [P, F, F, F, F, F, F, I, I, P]
@@ -178,8 +180,8 @@ class Engine:
             rc = fn(*args)
         _check(rc, what)
 
-    def workspace_bytes(self, B, T):
-        return int(self.lib.sbk_workspace_bytes(self.h, B, T))
+    def workspace_bytes(self, B, T, n_timesteps=1024):
+        return int(self.lib.sbk_workspace_bytes_n(self.h, B, T, int(n_timesteps)))
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -216,11 +218,11 @@ class Engine:
     # ---- oversize batches: utterances are independent, so a batch whose workspace would not fit is run in slices
     max_workspace_bytes = None      # default: 60 % of the device memory
 
-    def batch_slices(self, B, T):
+    def batch_slices(self, B, T, n_timesteps=1024):
         limit = self.max_workspace_bytes
         if limit is None:
             limit = 0.6 * torch.cuda.get_device_properties(self.device).total_memory
-        need = self.workspace_bytes(B, T)
+        need = self.workspace_bytes(B, T, n_timesteps)
         if need <= limit or B == 1:
             return [(0, B)]
         per = need / B
@@ -229,7 +231,7 @@ class Engine:
 
     def reverse_diffusion(self, z, mask, mu, n_timesteps, stoc=False, spk=None, noise=None):
         B, T = self._check_inputs(z, mask, mu, spk)
-        sl = self.batch_slices(B, T)
+        sl = self.batch_slices(B, T, n_timesteps)
         if len(sl) > 1:
             outs = [self.reverse_diffusion(z[a:b], mask[a:b], mu[a:b], n_timesteps, stoc,
                                            None if spk is None else spk[a:b],
@@ -288,7 +290,7 @@ class Engine:
 
     def vc_reverse_diffusion(self, z, mask, mean, cond, n_timesteps, mode, noise=None):
         B, T = self._check_inputs(z, mask, mean, None)
-        sl = self.batch_slices(B, T)
+        sl = self.batch_slices(B, T, n_timesteps)
         if len(sl) > 1:
             outs = [self.vc_reverse_diffusion(z[a:b], mask[a:b], mean[a:b], cond[:, a:b].contiguous(), n_timesteps, mode,
                                               None if noise is None else noise[:, a:b].contiguous()) for a, b in sl]

@@ -569,11 +569,15 @@ static size_t layout(const sbk_handle* h, int B, int T, int tb_rows, Arena& ar, 
     return ar.off + 256;
 }
 
-extern "C" size_t sbk_workspace_bytes(const sbk_handle* h, int B, int T) {
-    if (!h || B <= 0 || T <= 0 || T % 4 != 0) return 0;
+// rows of the per-step tables (time projections, coefficients, DiffVC conditioning): the same rule ensure_plan uses
+static int table_rows(int B, int n_timesteps) { const int r = B > n_timesteps ? B : n_timesteps; return r < 64 ? 64 : r; }
+
+extern "C" size_t sbk_workspace_bytes_n(const sbk_handle* h, int B, int T, int n_timesteps) {
+    if (!h || B <= 0 || T <= 0 || T % 4 != 0 || n_timesteps < 1) return 0;
     Arena ar;
-    return layout(h, B, T, B > 1024 ? B : 1024, ar, nullptr, nullptr);
+    return layout(h, B, T, table_rows(B, n_timesteps), ar, nullptr, nullptr);
 }
+extern "C" size_t sbk_workspace_bytes(const sbk_handle* h, int B, int T) { return sbk_workspace_bytes_n(h, B, T, 1024); }
 
 static int build_plan(sbk_handle* h, int B, int T, int tb_rows) {
     free_plan(h, false);
@@ -918,7 +922,10 @@ static int launch_op(const Op& op, cudaStream_t s) {
         case OP_FINAL: return launch_final(op.fn, s);
         case OP_CONVTC: return launch_conv_tc(op.tc, s);
         case OP_GNACT: return launch_gn_act(op.ga, s);
-        case OP_KVCTX: return launch_kv_ctx(op.kc, s);
+        case OP_KVCTX: {
+            static const bool ffma = getenv("SBK_KVCTX_FFMA") != nullptr;       // measurement / cross-check knob
+            return ffma ? launch_kv_ctx(op.kc, s) : launch_kv_ctx_tc(op.kc, s);
+        }
     }
     return -1;
 }

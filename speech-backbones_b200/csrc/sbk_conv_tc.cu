@@ -211,6 +211,23 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 
 using namespace tc;
 
+// per-device launch state of one kernel instantiation: opt-in to 227 KB of dynamic shared memory + SM count
+struct DevCache {
+    static constexpr int MAXDEV = 64;
+    int sms[MAXDEV] = {};
+    int get(const void* fn) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAXDEV) return -1;
+        if (sms[dev] == 0) {
+            if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -1;
+            int n = 0;
+            if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return -1;
+            sms[dev] = n;
+        }
+        return sms[dev];
+    }
+};
+
 // Residency / pipeline / accumulator configuration.
 //   * persistent CTAs: each CTA loops over output tiles (round-robin), every role keeps its own ring / slot counters;
 //   * NSLOT TMEM accumulator slots: with two slots the epilogue of tile i overlaps the loads + MMAs of tile i+1;
@@ -900,23 +917,6 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT, true>::MINB) k_conv_
     conv_tc_body<GEOM, false, NT, RES, true>(p);
 }
 
-// per-device launch state of one kernel instantiation: opt-in to 227 KB of dynamic shared memory + SM count
-struct DevCache {
-    static constexpr int MAXDEV = 64;
-    int sms[MAXDEV] = {};
-    int get(const void* fn) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAXDEV) return -1;
-        if (sms[dev] == 0) {
-            if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -1;
-            int n = 0;
-            if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return -1;
-            sms[dev] = n;
-        }
-        return sms[dev];
-    }
-};
-
 template <int GEOM, bool BF16, int NT, bool RES = false, bool X3 = false>
 static int launch_tc(const ConvTcParams& p, cudaStream_t s) {
     using D = Depth<GEOM, NT, X3>;
@@ -1200,6 +1200,152 @@ static int launch_attn_kv(const ConvTcParams& p, cudaStream_t s) {
     return 1;
 }
 int attn_kv_tile_pixels() { return kvk::PX; }
+
+// =================================================================================================================
+// fp32x3 mode, LinearAttention pass 1b on the tensor cores (diffusion.py:95-96): softmax-over-pixels partials and context
+// partials S[d][e] = sum_px P[d,px] V[e,px] from the k|v projection the 3xTF32 1x1 conv left in HBM ([B][H][64][W][4] fp32,
+// rows 0..127 = k, 128..255 = v).  One CTA = one chunk of pixels of one sample, walked in sub-tiles of 32 pixels with an
+// online softmax per k row (thread d < 128 owns k row d, thread 128+e owns v row e):
+//     m' = max(m, max_px k);  P = exp(k - m');  operands P_hi|P_lo, V_hi|V_lo (tf32 each, x = hi + lo to 2^-22) are written
+//     to shared memory in the UMMA K-major layout [4-pixel chunk][row][16 B];  S_sub = P_lo V_hi^T + P_hi V_lo^T + P_hi V_hi^T
+//     is 12 UMMAs (M = N = 128, K = 8 pixels) into a FRESH TMEM accumulator;  thread d then adds its head's 32 columns into
+//     fp32 registers: acc = acc * e^(m - m') + S_sub[d][32h .. 32h+31].
+// A run is 12 MMAs, so the tensor core's truncating accumulator costs nothing here, and the fp32 running sums are
+// round-to-nearest.  (The CUDA-core version of this pass, k_kv_ctx, ran at 12 TFLOP/s: 1.8 ms of an 19 ms step.)
+// Output: the k_attn_kv partial format {max[32], sum[32], S[32][32]} per (sample, chunk, head), merged by k_attn_ctx.
+// =================================================================================================================
+namespace kvx {
+constexpr int PXS = 32;                              // pixels per sub-tile (K extent of one S_sub)
+constexpr int LD = PXS + 4;                          // staging row stride (floats): 16-byte aligned, conflict-free float4 rows
+constexpr int OPB = (PXS / 4) * 128 * 16;            // one operand image [pixel chunk][row][16 B]
+constexpr size_t SMEM = (size_t)2 * 128 * LD * 4 + 4 * OPB + 64;
+}
+
+__global__ void __launch_bounds__(256, 2) k_kv_ctx_tc(const KvCtxParams p) {
+    using namespace kvx;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    float* s_k = reinterpret_cast<float*>(smem);                     // [128][LD]
+    float* s_v = s_k + 128 * LD;                                     // [128][LD]
+    uint8_t* op = reinterpret_cast<uint8_t*>(s_v + 128 * LD);        // P_hi | P_lo | V_hi | V_lo
+    uint64_t* bar = reinterpret_cast<uint64_t*>(op + 4 * OPB);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, b = blockIdx.y, chunk = blockIdx.x;
+    const int HW = p.H * p.W;
+    const int m_begin = chunk * p.chunk_px, m_end = min(HW, m_begin + p.chunk_px);
+    const uint32_t mbar = smem_u32(bar);
+    if (tid == 0) { mbar_init(mbar, 1); fence_barrier_init(); }
+    if (warp == 4) tmem_alloc(smem_u32(s_tmem), 128);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *s_tmem;
+    const bool krow = tid < 128;                                     // this thread owns k row `row` (else v row `row`)
+    const int row = tid & 127;
+    float m_run = -INFINITY, z_run = 0.f;
+    float acc[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+    const uint32_t idesc = make_idesc<false>(128, 128);
+    const uint32_t op0 = smem_u32(op);
+    uint32_t phase = 0;
+    for (int m0 = m_begin; m0 < m_end; m0 += PXS) {
+        const int npx = min(PXS, m_end - m0);
+        // ---- stage k|v: 64 channel chunks x PXS pixels of float4 (coalesced), transposed to [channel][pixel]
+        for (int i = tid; i < 64 * PXS; i += 256) {
+            const int ch = i / PXS, px = i - ch * PXS;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (px < npx) {
+                const int m = m0 + px, hh = m / p.W, ww = m - hh * p.W;
+                v = __ldg(reinterpret_cast<const float4*>(p.kv + ((((long long)b * p.H + hh) * 64 + ch) * p.W + ww) * 4));
+            }
+            float* dst = (ch < 32 ? s_k : s_v) + ((ch & 31) * 4) * LD + px;
+            dst[0] = v.x; dst[LD] = v.y; dst[2 * LD] = v.z; dst[3 * LD] = v.w;
+        }
+        __syncthreads();                                             // staging visible; the previous sub-tile's MMAs were awaited below
+        float f = 1.f;
+        {
+            const float* src = (krow ? s_k : s_v) + row * LD;
+            float x[PXS];
+#pragma unroll
+            for (int i = 0; i < PXS; i += 4) { const float4 t = *reinterpret_cast<const float4*>(src + i); x[i] = t.x; x[i + 1] = t.y; x[i + 2] = t.z; x[i + 3] = t.w; }
+            if (krow) {
+                float mx = -INFINITY;
+#pragma unroll
+                for (int i = 0; i < PXS; ++i) if (i < npx) mx = fmaxf(mx, x[i]);
+                const float mn = fmaxf(m_run, mx);
+                f = m_run == -INFINITY ? 0.f : expf(m_run - mn);
+                float z = 0.f;
+#pragma unroll
+                for (int i = 0; i < PXS; ++i) { x[i] = i < npx ? expf(x[i] - mn) : 0.f; z += x[i]; }
+                m_run = mn; z_run = z_run * f + z;
+            }
+            // hi | lo split (both tf32, round to nearest) written as K-major operand chunks [pixel chunk][row][16 B]
+            uint8_t* ohi = op + (krow ? 0 : 2 * OPB) + row * 16;
+            uint8_t* olo = ohi + OPB;
+#pragma unroll
+            for (int j = 0; j < PXS / 4; ++j) {
+                uint32_t h[4], l[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h[e]) : "f"(x[4 * j + e]));
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l[e]) : "f"(x[4 * j + e] - __uint_as_float(h[e])));
+                }
+                *reinterpret_cast<uint4*>(ohi + (size_t)j * 128 * 16) = make_uint4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<uint4*>(olo + (size_t)j * 128 * 16) = make_uint4(l[0], l[1], l[2], l[3]);
+            }
+        }
+        fence_proxy_async();                                         // generic-proxy operand writes -> visible to the tensor core
+        tc_fence_before();
+        __syncthreads();
+        // One lane of warp 4 issues; its 31 siblings park at the __syncwarp instead of spinning in the mbarrier wait below
+        // (a spinning sibling path starves the issuing lane: the first version issued from tid 0 and ran 15k clocks per
+        // sub-tile, slower than the CUDA-core kernel).
+        if (warp == 4) {
+          if (lane == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {                            // P_lo V_hi^T, P_hi V_lo^T, P_hi V_hi^T
+                const uint32_t pa = op0 + (t == 0 ? OPB : 0), vb = op0 + 2 * OPB + (t == 1 ? OPB : 0);
+#pragma unroll
+                for (int kk = 0; kk < PXS / 8; ++kk) {
+                    const uint64_t ad = make_desc(pa + kk * 2 * (128 * 16), 128 * 16, 128);
+                    const uint64_t bd = make_desc(vb + kk * 2 * (128 * 16), 128 * 16, 128);
+                    umma<false>(tmem, ad, bd, idesc, (t | kk) != 0 ? 1u : 0u);
+                }
+            }
+            umma_commit(mbar);
+          }
+          __syncwarp();
+        }
+        mbar_wait(mbar, phase);                                      // S_sub complete (and the operand images free again)
+        phase ^= 1;
+        tc_fence_after();
+        if (krow) {
+            uint32_t r[32];
+            tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(warp * 32), r);     // lanes 32w.., columns of head w
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[i] = fmaf(acc[i], f, __uint_as_float(r[i]));
+        }
+        tc_fence_before();
+        __syncthreads();                                             // TMEM read out before the next sub-tile's MMAs overwrite it
+    }
+    if (krow) {
+        float* pt = p.kv_part + (((long long)b * p.nchunks + chunk) * kHeads + warp) * kKvPartFloats;
+        pt[lane] = m_run;
+        pt[32 + lane] = z_run;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(pt + 64 + lane * 32 + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+    }
+    __syncthreads();
+    if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem, 128); }
+}
+
+int launch_kv_ctx_tc(const KvCtxParams& p, cudaStream_t s) {
+    static DevCache cache;
+    if (cache.get(reinterpret_cast<const void*>(k_kv_ctx_tc)) <= 0) return -1;
+    k_kv_ctx_tc<<<dim3(p.nchunks, p.B), 256, kvx::SMEM, s>>>(p);
+    return 1;
+}
 
 // N tile per geometry: UP needs 8 accumulators (8*64 = all 512 TMEM columns), DOWN's de-interleaved A tile is large
 int conv_tc_ntile(int geom, int Cout) {

@@ -132,7 +132,8 @@ struct AttnCtxParams {          // merge per-tile softmax partials -> normalised
 struct KvCtxParams {
     const float* kv; float* kv_part; int B, H, W, chunk_px, nchunks;
 };
-int launch_kv_ctx(const KvCtxParams& p, cudaStream_t s);
+int launch_kv_ctx(const KvCtxParams& p, cudaStream_t s);      // CUDA cores (kept as a second opinion: SBK_KVCTX_FFMA=1)
+int launch_kv_ctx_tc(const KvCtxParams& p, cudaStream_t s);   // tensor cores, 3xTF32 (sbk_conv_tc.cu)
 int kv_ctx_chunk_pixels();
 
 struct AttnMixParams {          // A_b = I + g * Wout * blockdiag(ctx^T) * Wq ; packed as [ci][co]; bias' = g*bout

@@ -44,7 +44,8 @@ constexpr int TE_TOK = 8;            // tokens per CTA of k_te_conv
 constexpr int TE_MAXCO = 3;          // output channels per thread (Cout <= 768)
 
 struct TeConvParams {
-    const float* in; int Cin;        // [B][T][Cin]
+    const float* in; int Cin;        // [B][T][Cin], or the reference's planar [B][Cin][T] when in_planar
+    int in_planar;
     const float* spk; int E;         // optional: Cin..Cin+E-1 are the speaker embedding [B][E], constant over T (:317-318)
     const float* w;                  // packed [K][Cin+E][Cout]
     const float* bias;               // [Cout]
@@ -85,7 +86,8 @@ __global__ void __launch_bounds__(256) k_te_conv(const TeConvParams p) {
         const int pos = i / Ci, ci = i - pos * Ci, t = t0 + pos - pad;
         float v = 0.f;
         if (t >= 0 && t < p.T) {
-            v = ci < p.Cin ? p.in[((long long)b * p.T + t) * p.Cin + ci] : p.spk[(long long)b * p.E + ci - p.Cin];
+            v = ci >= p.Cin ? p.spk[(long long)b * p.E + ci - p.Cin]
+                : p.in_planar ? p.in[((long long)b * p.Cin + ci) * p.T + t] : p.in[((long long)b * p.T + t) * p.Cin + ci];
             if (p.in_mask) v *= p.mask[(long long)b * p.T + t];
         }
         s_in[i] = v;
@@ -277,7 +279,10 @@ extern "C" int sbk_textenc_create(const sbk_textenc_config* cfg, sbk_textenc** o
     e->cfg = *cfg;
     auto add = [&](const std::string& n, std::vector<int64_t> s) { e->spec.push_back({n, s}); };
     const int F = cfg->filter_channels, Fd = cfg->filter_channels_dp, K = cfg->kernel_size, d = Ce / cfg->n_heads, nrel = 2 * cfg->window_size + 1;
-    add("emb.weight", {cfg->n_vocab, C});
+    const bool mel = cfg->kind == 1;         // DiffVC MelEncoder (DiffVC/model/encoder.py:257-284): init_proj | prenet | encoder | term_proj
+    if (mel && cfg->n_spks > 1) { delete e; return sbk_set_error(SBK_ERR_ARG, "sbk_textenc_create: the mel encoder has no speaker input"); }
+    if (mel) { add("init_proj.weight", {C, cfg->n_feats, 1}); add("init_proj.bias", {C}); }
+    else add("emb.weight", {cfg->n_vocab, C});
     for (int i = 0; i < 3; ++i) {
         const std::string p = "prenet.";
         add(p + "conv_layers." + std::to_string(i) + ".weight", {C, C, 5}); add(p + "conv_layers." + std::to_string(i) + ".bias", {C});
@@ -293,12 +298,16 @@ extern "C" int sbk_textenc_create(const sbk_textenc_config* cfg, sbk_textenc** o
         add("encoder.ffn_layers." + n + ".conv_2.weight", {Ce, F, K}); add("encoder.ffn_layers." + n + ".conv_2.bias", {Ce});
         add("encoder.norm_layers_2." + n + ".gamma", {Ce}); add("encoder.norm_layers_2." + n + ".beta", {Ce});
     }
-    add("proj_m.weight", {cfg->n_feats, Ce, 1}); add("proj_m.bias", {cfg->n_feats});
-    add("proj_w.conv_1.weight", {Fd, Ce, K}); add("proj_w.conv_1.bias", {Fd});
-    add("proj_w.norm_1.gamma", {Fd}); add("proj_w.norm_1.beta", {Fd});
-    add("proj_w.conv_2.weight", {Fd, Fd, K}); add("proj_w.conv_2.bias", {Fd});
-    add("proj_w.norm_2.gamma", {Fd}); add("proj_w.norm_2.beta", {Fd});
-    add("proj_w.proj.weight", {1, Fd, 1}); add("proj_w.proj.bias", {1});
+    if (mel) {
+        add("term_proj.weight", {cfg->n_feats, C, 1}); add("term_proj.bias", {cfg->n_feats});
+    } else {
+        add("proj_m.weight", {cfg->n_feats, Ce, 1}); add("proj_m.bias", {cfg->n_feats});
+        add("proj_w.conv_1.weight", {Fd, Ce, K}); add("proj_w.conv_1.bias", {Fd});
+        add("proj_w.norm_1.gamma", {Fd}); add("proj_w.norm_1.beta", {Fd});
+        add("proj_w.conv_2.weight", {Fd, Fd, K}); add("proj_w.conv_2.bias", {Fd});
+        add("proj_w.norm_2.gamma", {Fd}); add("proj_w.norm_2.beta", {Fd});
+        add("proj_w.proj.weight", {1, Fd, 1}); add("proj_w.proj.bias", {1});
+    }
     *out = e;
     return SBK_OK;
 }
@@ -384,17 +393,22 @@ extern "C" int sbk_textenc_pack(sbk_textenc* e) {
         TTRY(te_pack(e, {"encoder.ffn_layers." + n + ".conv_1.weight"}, "ffn" + n + ".1", false));
         TTRY(te_pack(e, {"encoder.ffn_layers." + n + ".conv_2.weight"}, "ffn" + n + ".2", false));
     }
-    TTRY(te_pack(e, {"proj_m.weight"}, "proj_m", false));
-    TTRY(te_pack(e, {"proj_w.conv_1.weight"}, "dp.1", false));
-    TTRY(te_pack(e, {"proj_w.conv_2.weight"}, "dp.2", false));
-    TTRY(te_pack(e, {"proj_w.proj.weight"}, "dp.p", false));
+    if (e->cfg.kind == 1) {
+        TTRY(te_pack(e, {"init_proj.weight"}, "init_proj", false));
+        TTRY(te_pack(e, {"term_proj.weight"}, "term_proj", false));
+    } else {
+        TTRY(te_pack(e, {"proj_m.weight"}, "proj_m", false));
+        TTRY(te_pack(e, {"proj_w.conv_1.weight"}, "dp.1", false));
+        TTRY(te_pack(e, {"proj_w.conv_2.weight"}, "dp.2", false));
+        TTRY(te_pack(e, {"proj_w.proj.weight"}, "dp.p", false));
+    }
     e->is_packed = true;
     return SBK_OK;
 }
 
-extern "C" int sbk_textenc_forward(sbk_textenc* e, const int64_t* x, const int64_t* x_lengths, const float* spk,
-                                   float* mu_x, float* logw, float* x_mask, int B, int Tx, void* stream) {
-    if (!e || !x || !x_lengths || !mu_x || !logw || !x_mask) return sbk_set_error(SBK_ERR_ARG, "sbk_textenc_forward: null argument");
+// shared body of TextEncoder.forward (x, x_lengths given; mel == nullptr) and MelEncoder.forward (mel, mask_in given)
+static int te_forward(sbk_textenc* e, const int64_t* x, const int64_t* x_lengths, const float* spk, const float* mel, const float* mask_in,
+                      float* mu_x, float* logw, float* x_mask, int B, int Tx, void* stream) {
     if (!e->is_packed) return sbk_set_error(SBK_ERR_STATE, "sbk_textenc_forward: weights not packed");
     if (B <= 0 || Tx <= 0) return sbk_set_error(SBK_ERR_ARG, "sbk_textenc_forward: B and Tx must be positive");
     const sbk_textenc_config& c = e->cfg;
@@ -417,9 +431,9 @@ extern "C" int sbk_textenc_forward(sbk_textenc* e, const int64_t* x, const int64
     int64_t n = 0;
     auto conv = [&](const float* in, int Cin, const float* spk_in, int E, const std::string& wkey, const std::string& bkey, int Kk, int Cout,
                     int in_mask, int relu1, int mask1, const float* res, int res_mask, const std::string& ln, int relu2, int mask2,
-                    float* out, int planar) {
+                    float* out, int planar, int in_planar = 0) {
         TeConvParams p; memset(&p, 0, sizeof(p));
-        p.in = in; p.Cin = Cin; p.spk = spk_in; p.E = E; p.w = W(wkey); p.bias = W(bkey); p.K = Kk; p.Cout = Cout; p.B = B; p.T = Tx;
+        p.in = in; p.Cin = Cin; p.in_planar = in_planar; p.spk = spk_in; p.E = E; p.w = W(wkey); p.bias = W(bkey); p.K = Kk; p.Cout = Cout; p.B = B; p.T = Tx;
         p.mask = x_mask; p.in_mask = in_mask; p.relu1 = relu1; p.mask1 = mask1; p.res = res; p.res_mask = res_mask;
         if (!ln.empty()) { p.ln_g = W(ln + ".gamma"); p.ln_b = W(ln + ".beta"); }
         p.relu2 = relu2; p.mask2 = mask2; p.out = out; p.out_planar = planar;
@@ -433,8 +447,14 @@ extern "C" int sbk_textenc_forward(sbk_textenc* e, const int64_t* x, const int64
         TCU(cudaFuncSetAttribute(k_te_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_done[c.device] = true;
     }
-    k_te_mask<<<(B * Tx + 255) / 256, 256, 0, s>>>(reinterpret_cast<const long long*>(x_lengths), x_mask, B, Tx); ++n;
-    k_te_embed<<<(int)std::min<size_t>((ntok * (C / 4) + 255) / 256, 148 * 8), 256, 0, s>>>(reinterpret_cast<const long long*>(x), W("emb.weight"), h0, (int)ntok, C, c.n_vocab, sqrtf((float)C)); ++n;
+    if (mel) {
+        // MelEncoder (DiffVC/model/encoder.py:279-284): x = init_proj(x * x_mask); the caller's mask is used as is
+        x_mask = const_cast<float*>(mask_in);
+        conv(mel, c.n_feats, nullptr, 0, "init_proj", "init_proj.bias", 1, C, 1, 0, 0, nullptr, 0, "", 0, 0, h0, 0, 1);
+    } else {
+        k_te_mask<<<(B * Tx + 255) / 256, 256, 0, s>>>(reinterpret_cast<const long long*>(x_lengths), x_mask, B, Tx); ++n;
+        k_te_embed<<<(int)std::min<size_t>((ntok * (C / 4) + 255) / 256, 148 * 8), 256, 0, s>>>(reinterpret_cast<const long long*>(x), W("emb.weight"), h0, (int)ntok, C, c.n_vocab, sqrtf((float)C)); ++n;
+    }
     // ---- prenet (ConvReluNorm, :57-64): x = relu(LN(conv5(x * mask))) x3; x = (x_org + proj(x)) * mask
     const float* cur = h0; float* pp[2] = {h1, h2};
     for (int i = 0; i < 3; ++i) {
@@ -467,6 +487,13 @@ extern "C" int sbk_textenc_forward(sbk_textenc* e, const int64_t* x, const int64
         conv(wa, F, nullptr, 0, "ffn" + nn + ".2", "encoder.ffn_layers." + nn + ".conv_2.bias", K, Ce, 0, 0, 1, other[0], 0, "encoder.norm_layers_2." + nn, 0, 0, other[1], 0);
         float* t = h; h = other[1]; other[1] = t;
     }
+    if (mel) {
+        // x = term_proj(x * x_mask): no output mask (DiffVC/model/encoder.py:283)
+        conv(h, Ce, nullptr, 0, "term_proj", "term_proj.bias", 1, c.n_feats, 1, 0, 0, nullptr, 0, "", 0, 0, mu_x, 1);
+        TCU(cudaGetLastError());
+        e->last_launches = n;
+        return SBK_OK;
+    }
     // ---- x = x * mask; mu = proj_m(x) * mask; logw = DurationPredictor(x, mask)  (:278, :321-324, :83-93)
     conv(h, Ce, nullptr, 0, "proj_m", "proj_m.bias", 1, c.n_feats, 1, 0, 0, nullptr, 0, "", 0, 1, mu_x, 1);
     conv(h, Ce, nullptr, 0, "dp.1", "proj_w.conv_1.bias", K, Fd, 1, 1, 0, nullptr, 0, "proj_w.norm_1", 0, 0, wa, 0);
@@ -475,6 +502,20 @@ extern "C" int sbk_textenc_forward(sbk_textenc* e, const int64_t* x, const int64
     TCU(cudaGetLastError());
     e->last_launches = n;
     return SBK_OK;
+}
+
+extern "C" int sbk_textenc_forward(sbk_textenc* e, const int64_t* x, const int64_t* x_lengths, const float* spk,
+                                   float* mu_x, float* logw, float* x_mask, int B, int Tx, void* stream) {
+    if (!e || !x || !x_lengths || !mu_x || !logw || !x_mask) return sbk_set_error(SBK_ERR_ARG, "sbk_textenc_forward: null argument");
+    if (e->cfg.kind != 0) return sbk_set_error(SBK_ERR_ARG, "sbk_textenc_forward: this handle is a mel encoder, use sbk_melenc_forward");
+    return te_forward(e, x, x_lengths, spk, nullptr, nullptr, mu_x, logw, x_mask, B, Tx, stream);
+}
+
+// MelEncoder.forward(x, x_mask) (DiffVC/model/encoder.py:279-284): x [B,n_feats,T], x_mask [B,1,T] -> out [B,n_feats,T]
+extern "C" int sbk_melenc_forward(sbk_textenc* e, const float* x, const float* x_mask, float* out, int B, int T, void* stream) {
+    if (!e || !x || !x_mask || !out) return sbk_set_error(SBK_ERR_ARG, "sbk_melenc_forward: null argument");
+    if (e->cfg.kind != 1) return sbk_set_error(SBK_ERR_ARG, "sbk_melenc_forward: this handle is a text encoder, use sbk_textenc_forward");
+    return te_forward(e, nullptr, nullptr, nullptr, x, x_mask, out, nullptr, nullptr, B, T, stream);
 }
 
 extern "C" int64_t sbk_textenc_last_launch_count(const sbk_textenc* e) { return e ? e->last_launches : 0; }

@@ -19,7 +19,7 @@ from .gradtts import BaseModule
 
 class SbkTextEncConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("device", "n_vocab", "n_feats", "n_channels", "filter_channels", "filter_channels_dp",
-                                         "n_heads", "n_layers", "kernel_size", "window_size", "n_spks", "spk_emb_dim")]
+                                         "n_heads", "n_layers", "kernel_size", "window_size", "n_spks", "spk_emb_dim", "kind")]
 
 
 class _ChanNorm(BaseModule):                     # reference name: LayerNorm (text_encoder.py:11-29)
@@ -75,7 +75,7 @@ class _DurationPredictor(BaseModule):            # reference name: DurationPredi
 class TextEncEngine:
     """One sbk_textenc handle."""
 
-    def __init__(self, m: "TextEncoder", device):
+    def __init__(self, m, device, kind=0):
         self.lib = load_library()
         P, I = C.c_void_p, C.c_int
         L = self.lib
@@ -90,8 +90,9 @@ class TextEncEngine:
         L.sbk_textenc_forward.argtypes = [P, P, P, P, P, P, P, I, I, P]
         L.sbk_textenc_last_launch_count.argtypes = [P]
         L.sbk_textenc_last_launch_count.restype = C.c_int64
+        L.sbk_melenc_forward.argtypes = [P, P, P, P, I, I, P]
         cfg = SbkTextEncConfig(device, m.n_vocab, m.n_feats, m.n_channels, m.filter_channels, m.filter_channels_dp, m.n_heads,
-                               m.n_layers, m.kernel_size, m.window_size, m.n_spks, m.spk_emb_dim)
+                               m.n_layers, m.kernel_size, m.window_size, m.n_spks, m.spk_emb_dim, kind)
         self.h = C.c_void_p()
         _check(L.sbk_textenc_create(C.byref(cfg), C.byref(self.h)), "sbk_textenc_create")
         self.device, self.n_feats, self.n_spks, self.spk_emb_dim = device, m.n_feats, m.n_spks, m.spk_emb_dim
@@ -143,8 +144,66 @@ class TextEncEngine:
                                                 B, Tx, stream), "sbk_textenc_forward")
         return mu, logw, mask
 
+    def forward_mel(self, x, x_mask):
+        for n, v in (("x", x), ("x_mask", x_mask)):
+            if not v.is_cuda or v.device.index != self.device:
+                raise RuntimeError(f"{n} lives on {v.device}; the mel encoder runs only on cuda:{self.device} (no CPU path)")
+        B, Fm, T = x.shape
+        if Fm != self.n_feats or tuple(x_mask.shape) != (B, 1, T) or x.dtype != torch.float32:
+            raise RuntimeError(f"expected x [B,{self.n_feats},T] float32 and x_mask [B,1,T], got {tuple(x.shape)} {x.dtype}, {tuple(x_mask.shape)}")
+        x, x_mask = x.contiguous(), x_mask.to(torch.float32).contiguous()
+        out = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+            _check(self.lib.sbk_melenc_forward(self.h, _ptr(x), _ptr(x_mask), _ptr(out), B, T, stream), "sbk_melenc_forward")
+        return out
+
     def last_launch_count(self):
         return int(self.lib.sbk_textenc_last_launch_count(self.h))
+
+
+class MelEncoder(BaseModule):
+    """Drop-in for DiffVC's "average voice" encoder (DiffVC/model/encoder.py:257-284, built at DiffVC/model/vc.py:32 and
+    called at :39,45 / :106,108): `MelEncoder(n_feats, channels, filters, heads, layers, kernel, dropout, window_size)`,
+    the reference's state_dict (init_proj | prenet | encoder | term_proj, 6,841,232 parameters), `forward(x, x_mask)` in
+    libsbk (`sbk_melenc_forward`: the text encoder's kernels, with a 1x1 projection at either end)."""
+
+    def __init__(self, n_feats, channels, filters, heads, layers, kernel, dropout, window_size=None):
+        super().__init__()
+        if window_size is None:
+            raise ValueError("the sm_100a mel encoder implements relative-position attention (DiffVC uses window_size=4)")
+        self.n_feats, self.channels, self.filters, self.heads, self.layers = n_feats, channels, filters, heads, layers
+        self.kernel, self.dropout, self.window_size = kernel, dropout, window_size
+        # the engine reads the text encoder's attribute names
+        self.n_vocab, self.n_channels, self.filter_channels, self.filter_channels_dp = 1, channels, filters, 4
+        self.n_heads, self.n_layers, self.kernel_size, self.n_spks, self.spk_emb_dim = heads, layers, kernel, 1, 64
+        self.init_proj = nn.Conv1d(n_feats, channels, 1)
+        self.prenet = _Prenet(channels)
+        self.encoder = _Encoder(channels, filters, heads, layers, kernel, window_size)
+        self.term_proj = nn.Conv1d(channels, n_feats, 1)
+        self._engine = None
+        self._engine_sig = None
+
+    def engine(self) -> TextEncEngine:
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("the mel encoder runs only on a CUDA device (sm_100a); move the module with .cuda() first - "
+                               "there is no CPU fallback")
+        sig = (dev.index,) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if self._engine is None or self._engine.device != dev.index:
+            if self._engine is not None:
+                self._engine.close()
+            self._engine = TextEncEngine(self, dev.index, kind=1)
+            self._engine_sig = None
+        if sig != self._engine_sig:
+            with torch.cuda.device(dev):
+                self._engine.load_state_dict(self.state_dict())
+            self._engine_sig = sig
+        return self._engine
+
+    @torch.no_grad()
+    def forward(self, x, x_mask):
+        return self.engine().forward_mel(x, x_mask)
 
 
 class TextEncoder(BaseModule):

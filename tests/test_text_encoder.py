@@ -96,3 +96,44 @@ def test_text_encoder_multispeaker_vs_oracle():
     e_mu, e_w = rel_l2(mu.cpu(), mu_r), rel_l2(logw.cpu(), w_r)
     print("text encoder n_spks=4 mu %.3e logw %.3e" % (e_mu, e_w))
     assert e_mu <= TE_TOL and e_w <= TE_TOL
+
+
+# ---- DiffVC's mel encoder (DiffVC/model/encoder.py:257-284): the same kernels behind `MelEncoder`
+@pytest.fixture(scope="module")
+def mel_golden():
+    return torch.load(os.path.join(ROOT, "tests", "golden", "mel_encoder_golden.pt"), weights_only=False)
+
+
+def test_mel_encoder_parameter_tree(sbk_lib):
+    from speech_backbones_b200.text_encoder import MelEncoder
+    m = MelEncoder(80, 192, 768, 2, 6, 3, 0.1, window_size=4)
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == dict(T.mel_param_spec())
+    assert m.nparams == 6_841_232
+    assert hasattr(sbk_lib, "sbk_melenc_forward")
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(1, 80, 8), torch.ones(1, 1, 8))
+
+
+def test_mel_oracle_matches_reference_golden(mel_golden):
+    sd = T.mel_synthetic_weights(mel_golden["seed"])
+    for c in mel_golden["cases"]:
+        x = torch.randn(c["B"], 80, c["T"], generator=torch.Generator().manual_seed(mel_golden["seed"] + c["T"]))
+        mask = (torch.arange(c["T"])[None, :] < torch.tensor(c["lengths"])[:, None]).float()[:, None]
+        with torch.no_grad():
+            assert torch.allclose(T.mel_encoder(sd, x, mask), c["out"], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("idx", range(3))
+def test_mel_encoder_matches_reference_golden(mel_golden, idx):
+    from speech_backbones_b200.text_encoder import MelEncoder
+    c = mel_golden["cases"][idx]
+    m = MelEncoder(80, 192, 768, 2, 6, 3, 0.1, window_size=4).eval()
+    m.load_state_dict(T.mel_synthetic_weights(mel_golden["seed"]), strict=True)
+    m = m.cuda()
+    x = torch.randn(c["B"], 80, c["T"], generator=torch.Generator().manual_seed(mel_golden["seed"] + c["T"]))
+    mask = (torch.arange(c["T"])[None, :] < torch.tensor(c["lengths"])[:, None]).float()[:, None]
+    y = m(x.cuda(), mask.cuda()).cpu()
+    err = rel_l2(y, c["out"])
+    print("mel encoder golden", idx, "B=%d T=%d rel_l2 %.3e" % (c["B"], c["T"], err), "launches", m.engine().last_launch_count())
+    assert err <= TE_TOL
