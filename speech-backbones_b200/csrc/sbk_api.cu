@@ -4,6 +4,7 @@
 #include "../../include/sbk.h"
 #include "sbk_internal.h"
 
+#include <cuda_fp16.h>
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -313,6 +314,13 @@ static uint32_t f32_to_tf32_rna(float x) {
     if ((u & 0x7F800000u) != 0x7F800000u) u += 0x1000u;     // round to nearest, ties away (cvt.rna.tf32.f32)
     return u & 0xFFFFE000u;
 }
+static uint16_t f32_to_f16_rn(float x) {              // saturating, like the device side's cvt.rn.satfinite.f16x2.f32
+    if (x > 65504.f) x = 65504.f;
+    if (x < -65504.f) x = -65504.f;
+    const __half h = __float2half_rn(x);
+    uint16_t u; memcpy(&u, &h, 2);
+    return u;
+}
 static uint16_t f32_to_bf16_rn(float x) {
     uint32_t u; memcpy(&u, &x, 4);
     if ((u & 0x7FFFFFFFu) > 0x7F800000u) return (uint16_t)((u >> 16) | 0x40);
@@ -380,12 +388,16 @@ static int pack_tc_host(sbk_handle* h, const std::vector<float>& hs, const std::
             const int co = nt * NT + col, ci = ks * CPS + k * EPC + e;
             const float w = hs[((size_t)co * cin + ci) * taps + tap];
             if (x3) {
-                // [ntile][kstage][hi|lo][tap][chunk][co % NT][4]: w = hi + lo, both tf32 (RNA), residual ~2^-22 |w|
+                // [ntile][kstage][hi|correction][tap][chunk][co % NT][16 B]: the main image holds w_hi = tf32(w) (RNA), the
+                // correction image the fp16 chunk {w[c0..c3], (w - w_hi)[c0..c3] * 2^12} that pairs with the activations'
+                // {x_lo, x * 2^-12} chunk in one kind::f16 MMA (sbk_internal.h: corr_chunk)
                 const size_t ih = ((((((size_t)nt * ksteps + ks) * 2) * taps + tap) * KCHK + k) * NT + col) * EPC + e;
                 const uint32_t uh = f32_to_tf32_rna(w);
                 float fh; memcpy(&fh, &uh, 4);
                 reinterpret_cast<uint32_t*>(hd.data())[ih] = uh;
-                reinterpret_cast<uint32_t*>(hd.data())[ih + (size_t)taps * KCHK * NT * EPC] = f32_to_tf32_rna(w - fh);
+                uint16_t* cc = reinterpret_cast<uint16_t*>(hd.data()) + 2 * ((ih - e) + (size_t)taps * KCHK * NT * EPC);   // this (chunk, co)'s 8 halfs
+                cc[e] = f32_to_f16_rn(w);
+                cc[4 + e] = f32_to_f16_rn((w - fh) * 4096.f);
                 continue;
             }
             const size_t idx = (((((size_t)nt * ksteps + ks) * taps + tap) * KCHK + k) * NT + col) * EPC + e;

@@ -28,6 +28,7 @@
 #include <cuda_bf16.h>
 #include <math.h>
 #include <stdint.h>
+#include <type_traits>
 
 namespace sbk {
 
@@ -113,17 +114,44 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
     return d;                 // base_offset = 0, lbo_mode = 0, layout_type = SWIZZLE_NONE (0)
 }
 
+// The descriptor split into its two 32-bit words: the high word (SBO, version) is a constant of the layout, the low word is
+// start address | LBO - so stepping to another tap / K chunk of the same tile is ONE 32-bit add on the low word (in 16-byte
+// units; the 14-bit address field cannot carry into LBO below 256 KB of shared memory).
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+    return ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ constexpr uint32_t desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14); }
+__device__ __forceinline__ uint64_t desc_pack(uint32_t lo, uint32_t hi) {
+    uint64_t d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+    return d;
+}
+
+// One lane of a fully converged warp.  The MMA-issuing warps run their loops with ALL 32 lanes and put only the
+// tcgen05.mma / tcgen05.commit instructions under this predicate: inside an `if (lane == 0)` region the compiler cannot
+// prove that a single thread is active and wraps every uniform-datapath instruction (UTCHMMA, UTCBAR) in a per-lane
+// ELECT / R2UR / BRA.U.ANY loop with the descriptors rebuilt from vector registers - ~15 dependent instructions, ~100
+// clocks per MMA against the 64 (N = 128) or 32 (N = 64) clocks the MMA itself takes: the issuing thread, not the tensor
+// pipe, bounded every conv (profiles/r2_ncu_issue_bound.md: 86 % of the issuer warp's samples in issue code, tensor pipe
+// 62 % / 47 % active).  With elect.sync the SASS is one UIADD3 per descriptor and back-to-back UTCHMMAs.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xffffffff;\n\t@px mov.s32 %0, 1;\n\t}" : "+r"(pred));
+    return pred != 0;
+}
+
 // instruction descriptor (UMMA::InstrDescriptor): c=F32, a/b format, K-major both, N>>3 at [17,23), M>>4 at [24,29)
-template <bool BF16>
-__device__ __forceinline__ uint32_t make_idesc(int M, int N) {
+__device__ __forceinline__ uint32_t make_idesc_fmt(uint32_t fmt, int M, int N) {     // fmt: F16 = 0, BF16 = 1, TF32 = 2
     uint32_t d = 0;
     d |= 1u << 4;                           // c_format = F32
-    d |= (BF16 ? 1u : 2u) << 7;             // a_format: BF16 = 1, TF32 = 2
-    d |= (BF16 ? 1u : 2u) << 10;            // b_format
+    d |= fmt << 7;                          // a_format
+    d |= fmt << 10;                         // b_format
     d |= (uint32_t)(N >> 3) << 17;
     d |= (uint32_t)(M >> 4) << 24;
     return d;
 }
+template <bool BF16>
+__device__ __forceinline__ uint32_t make_idesc(int M, int N) { return make_idesc_fmt(BF16 ? 1u : 2u, M, N); }
 
 template <bool BF16>
 __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -319,8 +347,9 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcParams& p) {
     const int Cin = p.c0 + p.c1;
     const int HW = p.H * p.W;
     const int ksteps = Cin / CPS;
-    // fp32x3 mode: each K stage runs three times, (x_lo, w_hi), (x, w_lo), (x, w_hi) - small terms first
-    const int ksteps_t = X3 ? 3 * ksteps : ksteps;
+    // fp32x3 mode: each K stage runs twice - the kind::f16 correction sub-stage (x_lo*w + x*w_lo from the packed fp16
+    // chunks, sbk_internal.h: corr_chunk) first, then the kind::tf32 main sub-stage (x_hi*w_hi): small terms first
+    const int ksteps_t = X3 ? 2 * ksteps : ksteps;
     const int nchunks = (CHUNKED || TMSUM) ? (ksteps_t + FLUSH - 1) / FLUSH : 1;     // accumulation runs per tile
     // ---- tile space: (sample, pixel tile, N tile), N tile fastest so neighbours in time share the A tile in L2
     const int wt_w = (GEOM == G_DOWN ? p.Wo : p.W), wt_h = (GEOM == G_DOWN ? p.Ho : p.H);
@@ -417,8 +446,8 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcParams& p) {
                         const uint32_t g = it + ks;
                         const int s = g % STAGES;
                         mbar_wait(empty(s), ((g / STAGES) & 1) ^ 1);
-                        const int kb = X3 ? ks / 3 : ks;
-                        const bool lo = X3 && ks - 3 * kb == 0;
+                        const int kb = X3 ? ks / 2 : ks;
+                        const bool lo = X3 && (ks & 1) == 0;
                         const int ck = kb * KCH;
                         const bool second = ck * EPC >= p.c0;
                         const uint8_t* src = reinterpret_cast<const uint8_t*>(second ? (lo ? p.in1_lo : p.in1) : (lo ? p.in0_lo : p.in0));
@@ -642,7 +671,7 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcParams& p) {
                                     make_float4(v[i] > 0.f ? v[i] : v[i] * sl, v[i + 1] > 0.f ? v[i + 1] : v[i + 1] * sl,
                                                 v[i + 2] > 0.f ? v[i + 2] : v[i + 2] * sl, v[i + 3] > 0.f ? v[i + 3] : v[i + 3] * sl);
                             } else {
-                                *reinterpret_cast<float4*>(lp + (i / 4) * cstride) = make_float4(tf32_lo(v[i]), tf32_lo(v[i + 1]), tf32_lo(v[i + 2]), tf32_lo(v[i + 3]));
+                                *reinterpret_cast<float4*>(lp + (i / 4) * cstride) = corr_chunk(v[i], v[i + 1], v[i + 2], v[i + 3]);
                             }
                         }
                     }
@@ -700,11 +729,13 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcParams& p) {
         }
     } else if (warp == NPROD / 32) {
         // =========================================================================================================
-        // MMA issuer (one thread)
+        // MMA issuer: the whole warp runs the loops and the barrier waits; one elected lane issues (see elect_one)
         // =========================================================================================================
-        if (lane == 0) {
+        {
             const uint32_t idesc = make_idesc<BF16>(TPX, NT);
+            const uint32_t idesc_c = make_idesc_fmt(0u, TPX, NT);        // fp32x3 correction sub-stages: fp16 operands
             const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+            constexpr uint32_t D_HI = desc_hi(128);                      // SBO = 128 B for both operands
             uint32_t it = 0;
             uint32_t ar = 0;                                             // accumulation-run counter (see the epilogue warps)
             if constexpr (TMSUM) {
@@ -725,21 +756,28 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcParams& p) {
                                     mbar_wait(full_b(s), (itk / STAGES) & 1);   // (row 1 re-reads stages row 0 already waited for)
                                     tc_fence_after();
                                 }
+                                const uint32_t a_lo = desc_lo(a0 + s * A_STAGE_BYTES + (j * PXP) * 16, PLANE);
+                                const uint32_t b_lo = desc_lo(b0 + s * B_STAGE_BYTES, NT * 16);
+                                if (elect_one()) {
+                                    auto issue = [&](auto kind16, const uint32_t idk) {
 #pragma unroll
-                                for (int kk = 0; kk < KCH / 2; ++kk) {
-                                    const uint32_t a_st = a0 + s * A_STAGE_BYTES + kk * 2 * PLANE;
-                                    const uint32_t b_st = b0 + s * B_STAGE_BYTES + kk * 2 * (NT * 16);
+                                        for (int kk = 0; kk < KCH / 2; ++kk) {
 #pragma unroll
-                                    for (int tap = 0; tap < TAPS; ++tap) {
-                                        const int r = TAPS == 9 ? tap / 3 : 0, sx = TAPS == 9 ? tap % 3 : 0;
-                                        const uint64_t bd = make_desc(b_st + tap * KCH * (NT * 16), NT * 16, 128);
-                                        const uint64_t ad = make_desc(a_st + ((r + j) * PXP + sx) * 16, PLANE, 128);
-                                        umma<BF16>(tslot, ad, bd, idesc, ((ks - ks_lo) | kk | tap) != 0 ? 1u : 0u);
-                                    }
+                                            for (int tap = 0; tap < TAPS; ++tap) {
+                                                const int r = TAPS == 9 ? tap / 3 : 0, sx = TAPS == 9 ? tap % 3 : 0;
+                                                umma<decltype(kind16)::value>(tslot, desc_pack(a_lo + (uint32_t)(kk * 2 * (PLANE / 16) + r * PXP + sx), D_HI),
+                                                                              desc_pack(b_lo + (uint32_t)((kk * 2 + tap * KCH) * NT), D_HI), idk,
+                                                                              ((ks - ks_lo) | kk | tap) != 0 ? 1u : 0u);
+                                            }
+                                        }
+                                    };
+                                    if ((ks & 1) == 0) issue(std::true_type{}, idesc_c);      // correction sub-stage: kind::f16 on the fp16 chunks
+                                    else issue(std::false_type{}, idesc);                     // main sub-stage: kind::tf32
+                                    if (j == ROWS - 1) umma_commit(empty(s));   // frees the stage when both rows have read it
+                                    if (ks == ks_hi - 1) umma_commit(tfull(j)); // this row's run is complete
                                 }
-                                if (j == ROWS - 1) umma_commit(empty(s));   // frees the stage when both rows have read it
+                                __syncwarp();
                             }
-                            umma_commit(tfull(j));                          // this row's run is complete
                         }
                         it += (uint32_t)(ks_hi - ks_lo);
                     }
@@ -758,48 +796,56 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcParams& p) {
                     if (!BULK) mbar_wait(full_a(s), ph);
                     mbar_wait(full_b(s), ph);               // weights (+ the A runs when they are bulk copies)
                     tc_fence_after();
+                    const uint32_t a_lo = desc_lo(a0 + s * A_STAGE_BYTES, PLANE);
+                    const uint32_t b_lo = desc_lo(b0 + s * B_STAGE_BYTES, NT * 16);
+                    const uint32_t dil = C1 ? (uint32_t)p.dil : 0u;
+                    if (elect_one()) {
+                      auto issue = [&](auto kind16, const uint32_t idk) {
+                        constexpr bool K16 = decltype(kind16)::value;
 #pragma unroll
-                    for (int kk = 0; kk < KCH / 2; ++kk) {
-                        const uint32_t a_st = a0 + s * A_STAGE_BYTES + kk * 2 * PLANE;
-                        const uint32_t b_st = b0 + s * B_STAGE_BYTES + kk * 2 * (NT * 16);
-                        if (GEOM == G_UP) {
-                            // ho = 2*hi - 1 + kh: parity ph uses (kh=1,dh=0),(kh=3,dh=-1) if ph=0 and (kh=0,dh=+1),(kh=2,dh=0) if ph=1
+                        for (int kk = 0; kk < KCH / 2; ++kk) {
+                            const uint32_t a_k = a_lo + (uint32_t)(kk * 2 * (PLANE / 16)), b_k = b_lo + (uint32_t)(kk * 2 * NT);
+                            if (GEOM == G_UP) {
+                                // ho = 2*hi - 1 + kh: parity ph uses (kh=1,dh=0),(kh=3,dh=-1) if ph=0 and (kh=0,dh=+1),(kh=2,dh=0) if ph=1
 #pragma unroll
-                            for (int phase = 0; phase < 4; ++phase) {
-                                const int pph = phase >> 1, pw = phase & 1;
+                                for (int phase = 0; phase < 4; ++phase) {
+                                    const int pph = phase >> 1, pw = phase & 1;
 #pragma unroll
-                                for (int t2 = 0; t2 < 4; ++t2) {
-                                    const int a = t2 >> 1, bb = t2 & 1;
-                                    const int kh = pph ? (a ? 2 : 0) : (a ? 3 : 1), kw = pw ? (bb ? 2 : 0) : (bb ? 3 : 1);
-                                    const int dh = pph ? (a ? 0 : 1) : (a ? -1 : 0), dw = pw ? (bb ? 0 : 1) : (bb ? -1 : 0);
-                                    const uint64_t bd = make_desc(b_st + (kh * 4 + kw) * KCH * (NT * 16), NT * 16, 128);
+                                    for (int t2 = 0; t2 < 4; ++t2) {
+                                        const int a = t2 >> 1, bb = t2 & 1;
+                                        const int kh = pph ? (a ? 2 : 0) : (a ? 3 : 1), kw = pw ? (bb ? 2 : 0) : (bb ? 3 : 1);
+                                        const int dh = pph ? (a ? 0 : 1) : (a ? -1 : 0), dw = pw ? (bb ? 0 : 1) : (bb ? -1 : 0);
+                                        const uint64_t bd = desc_pack(b_k + (uint32_t)((kh * 4 + kw) * KCH * NT), D_HI);
+#pragma unroll
+                                        for (int j = 0; j < ROWS; ++j)
+                                            umma<K16>(tslot + (phase * ROWS + j) * NT, desc_pack(a_k + (uint32_t)((1 + j + dh) * PXP + 1 + dw), D_HI), bd,
+                                                      idk, ((ks - ks_lo) | kk | t2) != 0 ? 1u : 0u);
+                                    }
+                                }
+                            } else {
+#pragma unroll
+                                for (int tap = 0; tap < TAPS; ++tap) {
+                                    const int r = TAPS == 9 ? tap / 3 : 0, sx = TAPS == 9 ? tap % 3 : 0;
+                                    const uint64_t bd = desc_pack(b_k + (uint32_t)(tap * KCH * NT), D_HI);
 #pragma unroll
                                     for (int j = 0; j < ROWS; ++j) {
-                                        const uint64_t ad = make_desc(a_st + ((1 + j + dh) * PXP + 1 + dw) * 16, PLANE, 128);
-                                        umma<BF16>(tslot + (phase * ROWS + j) * NT, ad, bd, idesc, ((ks - ks_lo) | kk | t2) != 0 ? 1u : 0u);
+                                        // DOWN: input row 2j+r; column tap s reads the odd plane at x (s=0) / x+1 (s=2), the even plane at x (s=1)
+                                        const uint32_t aoff = GEOM == G_DOWN ? (uint32_t)((2 * j + r) * PXP + (sx == 1 ? TPX + 1 : (sx == 2 ? 1 : 0)))
+                                                            : C1 ? (uint32_t)(j * TPX) + (uint32_t)tap * dil
+                                                                 : (uint32_t)((r + j) * PXP + sx);
+                                        umma<K16>(tslot + j * NT, desc_pack(a_k + aoff, D_HI), bd, idk, ((ks - ks_lo) | kk | tap) != 0 ? 1u : 0u);
                                     }
                                 }
                             }
-                        } else {
-#pragma unroll
-                            for (int tap = 0; tap < TAPS; ++tap) {
-                                const int r = TAPS == 9 ? tap / 3 : 0, sx = TAPS == 9 ? tap % 3 : 0;
-                                const uint64_t bd = make_desc(b_st + tap * KCH * (NT * 16), NT * 16, 128);
-#pragma unroll
-                                for (int j = 0; j < ROWS; ++j) {
-                                    // DOWN: input row 2j+r; column tap s reads the odd plane at x (s=0) / x+1 (s=2), the even plane at x (s=1)
-                                    const int aoff = GEOM == G_DOWN ? (2 * j + r) * PXP + (sx == 1 ? TPX + 1 : (sx == 2 ? 1 : 0))
-                                                   : C1 ? j * TPX + tap * p.dil
-                                                        : (r + j) * PXP + sx;
-                                    const uint64_t ad = make_desc(a_st + aoff * 16, PLANE, 128);
-                                    umma<BF16>(tslot + j * NT, ad, bd, idesc, ((ks - ks_lo) | kk | tap) != 0 ? 1u : 0u);
-                                }
-                            }
                         }
+                      };
+                        if (X3 && (ks & 1) == 0) issue(std::true_type{}, idesc_c);          // fp32x3 correction sub-stage: kind::f16
+                        else issue(std::integral_constant<bool, BF16>{}, idesc);
+                        umma_commit(empty(s));                  // frees the stage when these MMAs have read it
+                        if (ks == ks_hi - 1) umma_commit(tfull(slot));   // this run's accumulators are complete
                     }
-                    umma_commit(empty(s));                  // frees the stage when these MMAs have read it
+                    __syncwarp();
                 }
-                umma_commit(tfull(slot));                   // this run's accumulators are complete
               }
             }
         }
@@ -820,12 +866,12 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcParams& p) {
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 int b, h0, w0, n0, mt;
                 decode(t, b, h0, w0, n0, mt);
-                // weight image: [ntile][kstage][tap][chunk][NT][16 B]; fp32x3: [ntile][kstage][hi|lo][tap][chunk][NT][16 B]
+                // weight image: [ntile][kstage][tap][chunk][NT][16 B]; fp32x3: [ntile][kstage][hi|correction][tap][chunk][NT][16 B]
                 const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpk) + (size_t)b * p.w_bstride_bytes +
                                       (size_t)(n0 / NT) * ksteps * (X3 ? 2 : 1) * B_STAGE_BYTES;
                 for (int ks = 0; ks < ksteps_t; ++ks, ++it) {
                     const int s = it % STAGES;
-                    const int kb = X3 ? ks / 3 : ks, var = X3 ? ks - 3 * kb : 2;       // 0: x_lo*w_hi, 1: x*w_lo, 2: x*w_hi
+                    const int kb = X3 ? ks / 2 : ks, var = X3 ? (ks & 1) : 1;          // 0: correction (fp16 chunks), 1: main (x, w_hi)
                     if (lane == 0) {
                         mbar_wait(empty(s), ((it / STAGES) & 1) ^ 1);
                         uint32_t a_tx = BULK ? A_STAGE_BYTES : 0;
@@ -856,7 +902,7 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcParams& p) {
                             a_tx -= (uint32_t)(KCH * vrows * (PXP - (qhi - qlo))) * 16u;
                         }
                         mbar_arrive_expect_tx(full_b(s), B_STAGE_BYTES + a_tx);
-                        bulk_g2s(smem_u32(sB + s * B_STAGE_BYTES), wsrc + (size_t)(X3 ? 2 * kb + (var == 1) : ks) * B_STAGE_BYTES,
+                        bulk_g2s(smem_u32(sB + s * B_STAGE_BYTES), wsrc + (size_t)(X3 ? 2 * kb + (var == 0) : ks) * B_STAGE_BYTES,
                                  B_STAGE_BYTES, full_b(s));
                     }
                     __syncwarp();
@@ -1100,10 +1146,11 @@ __global__ void __launch_bounds__(kvk::THREADS, 1) k_attn_kv(const ConvTcParams 
         }
         if (tl > 0) finish(tl - 1);
     } else if (warp == EPW) {
-        // ---------------------------------------------------------------- projection UMMA issuer
-        if (lane == 0) {
+        // ---------------------------------------------------------------- projection UMMA issuer (whole warp + elect_one)
+        {
             const uint32_t idesc = make_idesc<BF16>(128, PX);
             const uint32_t s0 = smem_u32(sS);
+            constexpr uint32_t D_HI = desc_hi(128);
             uint32_t it = 0;
             int tl = 0;
             for (int t = blockIdx.x; t < total; t += gridDim.x, ++tl) {
@@ -1115,37 +1162,41 @@ __global__ void __launch_bounds__(kvk::THREADS, 1) k_attn_kv(const ConvTcParams 
                     const int s = it % STAGES;
                     mbar_wait(full(s), (it / STAGES) & 1);
                     tc_fence_after();
-                    const uint32_t xs = s0 + s * STAGE, wk = xs + XS, wv = wk + KCH * 128 * 16;
+                    const uint32_t xs = s0 + s * STAGE;
+                    const uint32_t x_lo = desc_lo(xs, PX * 16), k_lo = desc_lo(xs + XS, 128 * 16), v_lo = desc_lo(xs + XS + KCH * 128 * 16, 128 * 16);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int kk = 0; kk < KCH / 2; ++kk) {
-                        const uint64_t xd = make_desc(xs + kk * 2 * (PX * 16), PX * 16, 128);
-                        const uint64_t kd = make_desc(wk + kk * 2 * (128 * 16), 128 * 16, 128);
-                        const uint64_t vd = make_desc(wv + kk * 2 * (128 * 16), 128 * 16, 128);
-                        umma<BF16>(tslot, kd, xd, idesc, (ks | kk) != 0 ? 1u : 0u);
-                        umma<BF16>(tslot + 128, vd, xd, idesc, (ks | kk) != 0 ? 1u : 0u);
+                        for (int kk = 0; kk < KCH / 2; ++kk) {
+                            const uint64_t xd = desc_pack(x_lo + (uint32_t)(kk * 2 * PX), D_HI);
+                            umma<BF16>(tslot, desc_pack(k_lo + (uint32_t)(kk * 2 * 128), D_HI), xd, idesc, (ks | kk) != 0 ? 1u : 0u);
+                            umma<BF16>(tslot + 128, desc_pack(v_lo + (uint32_t)(kk * 2 * 128), D_HI), xd, idesc, (ks | kk) != 0 ? 1u : 0u);
+                        }
+                        umma_commit(empty(s));
+                        if (ks == ksteps - 1) umma_commit(tfull(slot));
                     }
-                    umma_commit(empty(s));
+                    __syncwarp();
                 }
-                umma_commit(tfull(slot));
             }
         }
     } else if (warp == EPW + 2) {
         // ---------------------------------------------------------------- context UMMA issuer: S = P * V^T
-        if (lane == 0) {
+        {
             const uint32_t idesc2 = make_idesc<false>(128, 128);
-            const uint32_t vt0 = smem_u32(vt);
+            const uint32_t v_lo = desc_lo(smem_u32(vt), 128 * 16);
+            constexpr uint32_t D_HI = desc_hi(128);
             int tl = 0;
             for (int t = blockIdx.x; t < total; t += gridDim.x, ++tl) {
                 const int slot = tl & 1;
                 const uint32_t tslot = tmem_base + slot * SLOT_COLS;
                 mbar_wait(pready(slot), (tl >> 1) & 1);
                 tc_fence_after();
+                if (elect_one()) {
 #pragma unroll
-                for (int kk = 0; kk < PX / 8; ++kk) {              // K = 8 pixels (32 bytes) per UMMA
-                    const uint64_t bd = make_desc(vt0 + kk * 2 * (128 * 16), 128 * 16, 128);
-                    umma_ts_tf32(tslot + 128, tslot + kk * 8, bd, idesc2, kk != 0 ? 1u : 0u);
+                    for (int kk = 0; kk < PX / 8; ++kk)                // K = 8 pixels (32 bytes) per UMMA
+                        umma_ts_tf32(tslot + 128, tslot + kk * 8, desc_pack(v_lo + (uint32_t)(kk * 2 * 128), D_HI), idesc2, kk != 0 ? 1u : 0u);
+                    umma_commit(kvdone(slot));
                 }
-                umma_commit(kvdone(slot));
+                __syncwarp();
             }
         }
     } else {
@@ -1297,25 +1348,22 @@ __global__ void __launch_bounds__(256, 2) k_kv_ctx_tc(const KvCtxParams p) {
         fence_proxy_async();                                         // generic-proxy operand writes -> visible to the tensor core
         tc_fence_before();
         __syncthreads();
-        // One lane of warp 4 issues; its 31 siblings park at the __syncwarp instead of spinning in the mbarrier wait below
-        // (a spinning sibling path starves the issuing lane: the first version issued from tid 0 and ran 15k clocks per
-        // sub-tile, slower than the CUDA-core kernel).
+        // Warp 4 issues (one elected lane, see elect_one); the other warps go straight to the mbarrier wait below.
         if (warp == 4) {
-          if (lane == 0) {
             tc_fence_after();
+            constexpr uint32_t D_HI = desc_hi(128);
+            const uint32_t o_lo = desc_lo(op0, 128 * 16);
+            if (elect_one()) {
 #pragma unroll
-            for (int t = 0; t < 3; ++t) {                            // P_lo V_hi^T, P_hi V_lo^T, P_hi V_hi^T
-                const uint32_t pa = op0 + (t == 0 ? OPB : 0), vb = op0 + 2 * OPB + (t == 1 ? OPB : 0);
+                for (int t = 0; t < 3; ++t) {                            // P_lo V_hi^T, P_hi V_lo^T, P_hi V_hi^T
+                    const uint32_t pa = o_lo + (t == 0 ? OPB / 16 : 0), vb = o_lo + 2 * (OPB / 16) + (t == 1 ? OPB / 16 : 0);
 #pragma unroll
-                for (int kk = 0; kk < PXS / 8; ++kk) {
-                    const uint64_t ad = make_desc(pa + kk * 2 * (128 * 16), 128 * 16, 128);
-                    const uint64_t bd = make_desc(vb + kk * 2 * (128 * 16), 128 * 16, 128);
-                    umma<false>(tmem, ad, bd, idesc, (t | kk) != 0 ? 1u : 0u);
+                    for (int kk = 0; kk < PXS / 8; ++kk)
+                        umma<false>(tmem, desc_pack(pa + (uint32_t)(kk * 2 * 128), D_HI), desc_pack(vb + (uint32_t)(kk * 2 * 128), D_HI), idesc, (t | kk) != 0 ? 1u : 0u);
                 }
+                umma_commit(mbar);
             }
-            umma_commit(mbar);
-          }
-          __syncwarp();
+            __syncwarp();
         }
         mbar_wait(mbar, phase);                                      // S_sub complete (and the operand images free again)
         phase ^= 1;

@@ -74,13 +74,14 @@ struct ConvTcParams {
     // Conv1d geometries: dilation and left padding ((K-1)*dil/2) in samples; output activation LeakyReLU(slope) on `out`
     // (act_out) and/or on the second output written through out_lo (act_out2: out_lo = lrelu(out) instead of the x_lo split)
     int dil, pad; float slope; int act_out, act_out2;
-    // fp32-class mode (SBK_PREC_FP32X3, "3xTF32"): every operand x is carried as the pair (x, x_lo = x - trunc_tf32(x)); the
-    // tensor core reads the top 19 bits of x (= x_hi) by itself.  Weights are packed as (w_hi, w_lo) stage pairs and each
-    // K stage is issued three times: x_lo*w_hi + x*w_lo + x*w_hi, all into the same fp32 TMEM accumulator.
+    // fp32-class mode (SBK_PREC_FP32X3): every operand x is carried as the pair (x, correction chunks - see corr_chunk
+    // below); the tensor core reads the top 19 bits of x (= x_hi) by itself.  Weights are packed as (w_hi, correction)
+    // stage pairs and each K stage is issued twice into the same fp32 TMEM accumulator: the kind::f16 correction MMAs
+    // (x_lo*w + x*w_lo) first, then the kind::tf32 main MMAs (x_hi*w_hi).
     int x3;
-    int flush;                                      // sub-stages per accumulation run (0 = default 6); SBK_X3_FLUSH overrides it (measurement knob)
-    const void* in0_lo; const void* in1_lo;         // the x_lo tensors, same layout as in0 / in1
-    float* out_lo;                                  // operand-form outputs (non-3x3 geometries): also write out - trunc_tf32(out)
+    int flush;                                      // sub-stages per accumulation run (0 = default); SBK_X3_FLUSH overrides it (measurement knob)
+    const void* in0_lo; const void* in1_lo;         // the correction tensors, same chunk layout as in0 / in1
+    float* out_lo;                                  // operand-form outputs (non-3x3 geometries): also write the correction chunks
 };
 
 // Block activation between the two convs of a ResnetBlock, written once in operand form (diffusion.py:57,76):
@@ -262,6 +263,28 @@ int launch_scale_mask(const float* z, const float* mask, float* out, long long n
 
 // the part of an fp32 value the tensor core's tf32 operand path drops (low 13 mantissa bits): exact in fp32
 __device__ __forceinline__ float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+// ---- fp32x3 mode: the correction operand ------------------------------------------------------------------------------
+// x*w = x_hi*w_hi + (x_lo*w + x*w_lo) + O(2^-23): the first product runs on kind::tf32 from the fp32 tensor itself (the
+// tensor core reads the top 19 bits = x_hi), the bracket is ONE kind::f16 MMA over a packed correction operand.  For every
+// 16-byte chunk of 4 channels the producers write, next to the fp32 chunk, a second 16-byte chunk of eight fp16 values
+//     { x_lo[c0..c3] , x[c0..c3] * 2^-12 }            with x_lo = x - trunc_tf32(x)  (|x_lo| <= 2^-10 |x|)
+// and the weight packers write the matching K order { w[c0..c3] , w_lo[c0..c3] * 2^12 } (w_lo = w - tf32(w)), so one
+// K = 16 fp16 MMA over two chunks adds x_lo*w + x*w_lo for 8 channels.  fp16 carries the same 11 significant bits as tf32;
+// the exact 2^-12 / 2^12 scaling keeps x in fp16's range up to |x| = 2.7e8 and keeps w_lo (~2^-12 |w|) out of its subnormals.
+// The stored chunk has the same address and size as the old fp32 x_lo chunk.  Two MMAs per algorithmic MAC instead of the
+// three of a 3xTF32 split, at the same modelled accuracy (CPU operand-rounding model: 1.1e-6 vs 1.2e-6 per estimator call).
+constexpr float kCorrDown = 1.f / 4096.f;     // 2^-12 (activation side)
+constexpr float kCorrUp = 4096.f;             // 2^12  (weight side)
+__device__ __forceinline__ uint32_t f16x2_sat(float e0, float e1) {     // e0 in the low half (= the lower K index)
+    uint32_t d;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(e1), "f"(e0));
+    return d;
+}
+__device__ __forceinline__ float4 corr_chunk(float x0, float x1, float x2, float x3) {
+    return make_float4(__uint_as_float(f16x2_sat(tf32_lo(x0), tf32_lo(x1))), __uint_as_float(f16x2_sat(tf32_lo(x2), tf32_lo(x3))),
+                       __uint_as_float(f16x2_sat(x0 * kCorrDown, x1 * kCorrDown)), __uint_as_float(f16x2_sat(x2 * kCorrDown, x3 * kCorrDown)));
+}
 
 inline int igemm_mtiles(int geom, int Hout, int Wout, int Hin, int Win) {
     const int TM = 128;

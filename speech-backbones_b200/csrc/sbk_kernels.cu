@@ -554,7 +554,7 @@ __global__ void __launch_bounds__(256) k_resfinal(const ResFinalParams p) {
                     }
                     *reinterpret_cast<float4*>(outb + (long long)(h0 + u) * hstride + w * 4) = o;
                     if (X3) *reinterpret_cast<float4*>(p.out_lo + base + (long long)(h0 + u) * hstride + w * 4) =
-                                make_float4(tf32_lo(o.x), tf32_lo(o.y), tf32_lo(o.z), tf32_lo(o.w));
+                                corr_chunk(o.x, o.y, o.z, o.w);
                 }
             }
         }
@@ -657,7 +657,7 @@ __global__ void __launch_bounds__(256) k_resfinal(const ResFinalParams p) {
                     if (p.out_mask) { o.x *= mk; o.y *= mk; o.z *= mk; o.w *= mk; }
                     *reinterpret_cast<float4*>(outb + (long long)(h0 + u) * hstride + w * 4) = o;
                     if (X3) *reinterpret_cast<float4*>(p.out_lo + base + (long long)(h0 + u) * hstride + w * 4) =
-                                make_float4(tf32_lo(o.x), tf32_lo(o.y), tf32_lo(o.z), tf32_lo(o.w));
+                                corr_chunk(o.x, o.y, o.z, o.w);
                 }
             }
         }
@@ -770,7 +770,7 @@ __global__ void __launch_bounds__(256) k_gn_act(const GnActParams p) {
                     }
                     *reinterpret_cast<float4*>(outb + (long long)(h0 + u) * hstride + w * 4) = o;
                     if (X3) *reinterpret_cast<float4*>(lob + (long long)(h0 + u) * hstride + w * 4) =
-                                make_float4(tf32_lo(o.x), tf32_lo(o.y), tf32_lo(o.z), tf32_lo(o.w));
+                                corr_chunk(o.x, o.y, o.z, o.w);
                 }
             }
         }
@@ -1279,14 +1279,16 @@ __global__ void __launch_bounds__(256) k_attn_mix(const AttnMixParams p) {
                 const int co = cb + cl0 + i;
                 float v = g * acc[i];
                 if (p.tc_x3) {
-                    // fp32x3: (hi, lo) stage pair, both tf32 (RNA): v = hi + lo to ~2^-22 relative
+                    // fp32x3: (w_hi, correction) stage pair - tf32 (RNA) main image and the fp16 chunk {w[c0..c3], w_lo[c0..c3] * 2^12}
+                    // of the kind::f16 correction MMA (sbk_internal.h: corr_chunk)
                     const long long ih = (((((long long)(co / NT) * ksteps + ks) * 2) * kch + kc) * NT + (co % NT)) * 4 + e;
-                    uint32_t uh, ul;
+                    uint32_t uh;
                     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(uh) : "f"(v));
-                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(ul) : "f"(v - __uint_as_float(uh)));
                     float* wb = p.w_eff + (long long)b * 2 * C * C;
                     wb[ih] = __uint_as_float(uh);
-                    wb[ih + (long long)kch * NT * 4] = __uint_as_float(ul);
+                    unsigned short* cb16 = reinterpret_cast<unsigned short*>(wb + (ih - e) + (long long)kch * NT * 4);   // the chunk of (kc, co)
+                    cb16[e] = (unsigned short)(f16x2_sat(v, 0.f) & 0xFFFFu);
+                    cb16[4 + e] = (unsigned short)(f16x2_sat((v - __uint_as_float(uh)) * kCorrUp, 0.f) & 0xFFFFu);
                     continue;
                 }
                 const long long idx = ((((long long)(co / NT) * ksteps + ks) * kch + kc) * NT + (co % NT)) * epc + e;
@@ -1607,7 +1609,7 @@ __global__ void __launch_bounds__(256) k_in_glu(const InGluParams p) {
         }
         *reinterpret_cast<float4*>(p.out + ((long long)b * n4 + i) * 4) = make_float4(o[0], o[1], o[2], o[3]);
         if (p.out_lo) *reinterpret_cast<float4*>(p.out_lo + ((long long)b * n4 + i) * 4) =
-                          make_float4(tf32_lo(o[0]), tf32_lo(o[1]), tf32_lo(o[2]), tf32_lo(o[3]));
+                          corr_chunk(o[0], o[1], o[2], o[3]);
     }
 }
 int launch_in_glu(const InGluParams& p, cudaStream_t s) {
