@@ -1299,19 +1299,36 @@ __global__ void __launch_bounds__(256, 2) k_kv_ctx_tc(const KvCtxParams p) {
     const uint32_t idesc = make_idesc<false>(128, 128);
     const uint32_t op0 = smem_u32(op);
     uint32_t phase = 0;
+    // Staging: thread (px = tid % 32, ch0 = tid / 32) owns the float4 chunks ch0 + 8j, j < 8, of pixel px.  All eight loads of a
+    // sub-tile are issued back to back and one sub-tile AHEAD, into registers, so their global latency hides under the
+    // previous sub-tile's softmax / MMA / read-out.  (The first version loaded and stored chunk by chunk: eight serialised
+    // global round trips per 32 pixels, 46 % of the kernel's stall samples on the dependent STS - profiles/r2_ncu_kvctx.md.)
+    static_assert(PXS == 32, "staging maps one warp lane to one pixel of the sub-tile");
+    const int spx = tid & 31, ch0 = tid >> 5;
+    float4 pre[8];
+    auto load_sub = [&](int m0) {
+        const int m = m0 + spx;
+        if (m < m_end) {
+            const int hh = m / p.W, ww = m - hh * p.W;
+            const float4* src = reinterpret_cast<const float4*>(p.kv) + (((long long)b * p.H + hh) * 64 + ch0) * p.W + ww;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) pre[j] = __ldg(src + (long long)j * 8 * p.W);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) pre[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    load_sub(m_begin);
     for (int m0 = m_begin; m0 < m_end; m0 += PXS) {
         const int npx = min(PXS, m_end - m0);
-        // ---- stage k|v: 64 channel chunks x PXS pixels of float4 (coalesced), transposed to [channel][pixel]
-        for (int i = tid; i < 64 * PXS; i += 256) {
-            const int ch = i / PXS, px = i - ch * PXS;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (px < npx) {
-                const int m = m0 + px, hh = m / p.W, ww = m - hh * p.W;
-                v = __ldg(reinterpret_cast<const float4*>(p.kv + ((((long long)b * p.H + hh) * 64 + ch) * p.W + ww) * 4));
-            }
-            float* dst = (ch < 32 ? s_k : s_v) + ((ch & 31) * 4) * LD + px;
-            dst[0] = v.x; dst[LD] = v.y; dst[2 * LD] = v.z; dst[3 * LD] = v.w;
+        // ---- stage k|v: transposed to [channel][pixel]
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int ch = ch0 + 8 * j;
+            float* dst = (ch < 32 ? s_k : s_v) + ((ch & 31) * 4) * LD + spx;
+            dst[0] = pre[j].x; dst[LD] = pre[j].y; dst[2 * LD] = pre[j].z; dst[3 * LD] = pre[j].w;
         }
+        if (m0 + PXS < m_end) load_sub(m0 + PXS);                    // next sub-tile: in flight until the top of the next iteration
         __syncthreads();                                             // staging visible; the previous sub-tile's MMAs were awaited below
         float f = 1.f;
         {
