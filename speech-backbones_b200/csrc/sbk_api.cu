@@ -11,6 +11,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <map>
 #include <string>
 #include <vector>
@@ -307,6 +308,14 @@ static int repack(sbk_handle* h, const std::string& src, const std::string& key,
     return SBK_OK;
 }
 
+// k_attn_kv_x3: items (64 pixels) per chunk = per partial.  A constant, so that an utterance is cut at the same pixels
+// whatever batch it sits in (alone-vs-in-batch results stay at the rounding level of the partial merge), and short enough
+// that a single utterance still spreads over the GPU (B=1, T=512, level 0: 160 chunks for 148 SMs).
+static int attn_x3_chunk_items(int items_per_sample, int B) {
+    (void)items_per_sample; (void)B;
+    return 4;
+}
+
 // Pack a 3x3 conv weight [co][ci][3][3] into the tcgen05 kernel's per-stage shared-memory image
 // [ntile][kstage][tap][16-byte chunk][co % NT][elements]: tf32-rounded fp32 (4 per chunk) or bf16 (8 per chunk).
 static uint32_t f32_to_tf32_rna(float x) {
@@ -360,13 +369,28 @@ static int pack_tc_kv(sbk_handle* h, const std::string& src, const std::string& 
     CU(cudaMemcpy(d, m.data(), m.size(), cudaMemcpyHostToDevice));
     return SBK_OK;
 }
-// fp32x3 mode: the k|v rows of to_qkv (rows 128..383) as a plain 1x1 conv [256][C] for the 3xTF32 conv kernel; its fp32
-// output [B][H][64][W][4] feeds k_kv_ctx
+// fp32x3 mode: the same k and v rows for k_attn_kv_x3 (sbk_attn_x3.cu): per 32-channel stage a (w_hi, correction) pair of
+// images [k|v][16-byte chunk][row][16 B] - tf32 (RNA) w_hi, and the fp16 chunks {w[c0..c3], (w - w_hi)[c0..c3] * 2^12}
 static int pack_tc_kvx(sbk_handle* h, const std::string& src, const std::string& key, int C) {
     std::vector<float> q((size_t)384 * C);
     CU(cudaMemcpy(q.data(), h->raw[src], q.size() * sizeof(float), cudaMemcpyDeviceToHost));
-    std::vector<float> kv(q.begin() + (size_t)128 * C, q.end());
-    return pack_tc_host(h, kv, key, 256, C, G_PW, false);
+    std::vector<uint8_t> m((size_t)2 * 256 * C * 4);
+    for (int ks = 0; ks < C / 32; ++ks) for (int kv = 0; kv < 2; ++kv) for (int k = 0; k < 8; ++k)
+        for (int row = 0; row < 128; ++row) for (int e = 0; e < 4; ++e) {
+            const size_t chunk_hi = (((((size_t)ks * 2 + 0) * 2 + kv) * 8 + k) * 128 + row) * 4;      // in 4-byte units
+            const size_t chunk_c = (((((size_t)ks * 2 + 1) * 2 + kv) * 8 + k) * 128 + row) * 4;
+            const float w = q[(size_t)(128 + kv * 128 + row) * C + ks * 32 + k * 4 + e];
+            const uint32_t uh = f32_to_tf32_rna(w);
+            float fh; memcpy(&fh, &uh, 4);
+            reinterpret_cast<uint32_t*>(m.data())[chunk_hi + e] = uh;
+            uint16_t* cc = reinterpret_cast<uint16_t*>(m.data()) + 2 * chunk_c;
+            cc[e] = f32_to_f16_rn(w);
+            cc[4 + e] = f32_to_f16_rn((w - fh) * 4096.f);
+        }
+    float*& d = h->packed[key];
+    if (!d) { CU(cudaMalloc(&d, m.size())); h->owned.push_back(d); }
+    CU(cudaMemcpy(d, m.data(), m.size(), cudaMemcpyHostToDevice));
+    return SBK_OK;
 }
 // ConvTranspose2d weight [ci][co][4][4] -> logical [co][ci][kh*4+kw]
 static int pack_tc_up(sbk_handle* h, const std::string& src, const std::string& key, int C, bool bf16) {
@@ -552,12 +576,20 @@ static size_t layout(const sbk_handle* h, int B, int T, int tb_rows, Arena& ar, 
         b.D[l] = l > 0 ? fo((size_t)B * P[l] * C[l - 1]) : nullptr;
     }
     b.U1 = fo((size_t)B * P[1] * C[1]);
-    const size_t mt0 = (P[0] + 127) / 128;
+    size_t mt0 = (P[0] + 127) / 128;
+    if (x3) {
+        mt0 = 0;                                    // the chunk length depends on the level's item count: take the largest chunk count
+        for (int l = 0; l < 3; ++l) {
+            const int items = (int)((P[l] + attn_kv_x3_item_pixels() - 1) / attn_kv_x3_item_pixels());
+            const int ci = attn_x3_chunk_items(items, B);
+            mt0 = std::max(mt0, (size_t)((items + ci - 1) / ci));
+        }
+    }
     b.kv_part = f((size_t)B * mt0 * kHeads * kKvPartFloats);
     b.ctx = f((size_t)B * kHeads * 1024);
     b.w_eff = f((size_t)B * C[2] * C[2] * (x3 ? 2 : 1));
     b.b_eff = f(C[2]);
-    b.kvraw = x3 ? f((size_t)B * P[0] * 256) : nullptr;
+    b.kvraw = nullptr;
     if (bf) *bf = b;
     Plan dummy;
     Plan& p = pl ? *pl : dummy;
@@ -799,17 +831,17 @@ static int build_plan(sbk_handle* h, int B, int T, int tb_rows) {
         int mt = igemm_mtiles(G_PW, Hs[lvl], Ws[lvl], Hs[lvl], Ws[lvl]);
         const bool tc_apply = use_tc && a.c % tc_cps1 == 0;
         if (tc_apply && x3) {
-            // fp32-class attention: k|v projection as a 3xTF32 1x1 conv (fp32 result in HBM), then the softmax / context
-            // partials in exact fp32 on CUDA cores (k_kv_ctx): a tf32 P*V^T product would leave a 2^-12-class error in ctx
-            Op op = tc_conv(a.prefix + ".kvraw", G_PW, a.prefix + ".kvx.wtc", "", lvl, x, a.c, nullptr, 0, 256, bf.kvraw, nullptr);
-            op.bytes = 4.0 * npix(lvl) * (a.c * 2.0 + 256.0);
+            // fp32-class attention, fused (k_attn_kv_x3): k|v projection (tf32 + fp16 correction), online softmax over the
+            // items of a chunk, context partials - k and v never reach HBM.  One partial per chunk of `chunk_items` 64-pixel
+            // items; the chunk length keeps >= ~2 chunks per SM in flight for small batches.
+            Op op = tc_conv(a.prefix + ".kvpart", G_PW, a.prefix + ".kvx.wtc", "", lvl, x, a.c, nullptr, 0, 256, nullptr, nullptr);
+            const int items = (Hs[lvl] * Ws[lvl] + attn_kv_x3_item_pixels() - 1) / attn_kv_x3_item_pixels();
+            const int chunk_items = attn_x3_chunk_items(items, B);
+            mt = (items + chunk_items - 1) / chunk_items;
+            op.tc.epi = EPI_KV; op.tc.kv_part = bf.kv_part; op.tc.Ho = chunk_items; op.tc.Wo = mt;
+            op.bytes = 8.0 * npix(lvl) * a.c;
+            op.flops += 2.0 * npix(lvl) * 4096.0;
             push(op, nullptr, 0);
-            Op kc; kc.kind = OP_KVCTX; kc.name = a.prefix + ".kvpart";
-            mt = (Hs[lvl] * Ws[lvl] + kv_ctx_chunk_pixels() - 1) / kv_ctx_chunk_pixels();
-            kc.kc.kv = bf.kvraw; kc.kc.kv_part = bf.kv_part; kc.kc.B = B; kc.kc.H = Hs[lvl]; kc.kc.W = Ws[lvl];
-            kc.kc.chunk_px = kv_ctx_chunk_pixels(); kc.kc.nchunks = mt;
-            kc.flops = 2.0 * npix(lvl) * 4096.0; kc.bytes = 4.0 * npix(lvl) * 256.0;
-            push(kc, nullptr, 0);
         } else if (tc_apply) {
             // k/v projection + softmax partials on tensor cores (k_attn_kv): items of 128 pixels x 4 heads
             Op op = tc_conv(a.prefix + ".kvpart", G_PW, a.prefix + ".kv.wtc", "", lvl, x, a.c, nullptr, 0, 256, nullptr, nullptr);

@@ -23,11 +23,8 @@
 // Pipeline.  STAGES-deep ring with full_a / full_b / empty mbarriers; one thread issues tcgen05.mma and frees
 // stages with tcgen05.commit; the epilogue (the eight producer warps) reads the accumulators with tcgen05.ld.
 // All waits are bounded spins that trap instead of hanging the GPU.
-#include "sbk_internal.h"
+#include "sbk_tc.cuh"
 
-#include <cuda_bf16.h>
-#include <math.h>
-#include <stdint.h>
 #include <type_traits>
 
 namespace sbk {
@@ -58,203 +55,10 @@ template <> struct Geo<G_C1K3> : GeoC1<3> {};
 template <> struct Geo<G_C1K7> : GeoC1<7> {};
 template <> struct Geo<G_C1K11> : GeoC1<11> {};
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok != 0;
-}
-// bounded spin: a protocol bug must trap, not hang the GPU
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 24)) __trap();
-    }
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-
-// shared-memory matrix descriptor, K-major, SWIZZLE_NONE ("interleaved"): element (row m, 16-byte K chunk c)
-// lives at start + (m%8)*16 + (m/8)*SBO + c*LBO  (cute/arch/mma_sm100_desc.hpp SmemDescriptor; version_=1).
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-    d |= (uint64_t)1 << 46;   // version = 1 (Blackwell)
-    return d;                 // base_offset = 0, lbo_mode = 0, layout_type = SWIZZLE_NONE (0)
-}
-
-// The descriptor split into its two 32-bit words: the high word (SBO, version) is a constant of the layout, the low word is
-// start address | LBO - so stepping to another tap / K chunk of the same tile is ONE 32-bit add on the low word (in 16-byte
-// units; the 14-bit address field cannot carry into LBO below 256 KB of shared memory).
-__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
-    return ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
-}
-__device__ __forceinline__ constexpr uint32_t desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14); }
-__device__ __forceinline__ uint64_t desc_pack(uint32_t lo, uint32_t hi) {
-    uint64_t d;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
-    return d;
-}
-
-// One lane of a fully converged warp.  The MMA-issuing warps run their loops with ALL 32 lanes and put only the
-// tcgen05.mma / tcgen05.commit instructions under this predicate: inside an `if (lane == 0)` region the compiler cannot
-// prove that a single thread is active and wraps every uniform-datapath instruction (UTCHMMA, UTCBAR) in a per-lane
-// ELECT / R2UR / BRA.U.ANY loop with the descriptors rebuilt from vector registers - ~15 dependent instructions, ~100
-// clocks per MMA against the 64 (N = 128) or 32 (N = 64) clocks the MMA itself takes: the issuing thread, not the tensor
-// pipe, bounded every conv (profiles/r2_ncu_issue_bound.md: 86 % of the issuer warp's samples in issue code, tensor pipe
-// 62 % / 47 % active).  With elect.sync the SASS is one UIADD3 per descriptor and back-to-back UTCHMMAs.
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred = 0;
-    asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xffffffff;\n\t@px mov.s32 %0, 1;\n\t}" : "+r"(pred));
-    return pred != 0;
-}
-
-// instruction descriptor (UMMA::InstrDescriptor): c=F32, a/b format, K-major both, N>>3 at [17,23), M>>4 at [24,29)
-__device__ __forceinline__ uint32_t make_idesc_fmt(uint32_t fmt, int M, int N) {     // fmt: F16 = 0, BF16 = 1, TF32 = 2
-    uint32_t d = 0;
-    d |= 1u << 4;                           // c_format = F32
-    d |= fmt << 7;                          // a_format
-    d |= fmt << 10;                         // b_format
-    d |= (uint32_t)(N >> 3) << 17;
-    d |= (uint32_t)(M >> 4) << 24;
-    return d;
-}
-template <bool BF16>
-__device__ __forceinline__ uint32_t make_idesc(int M, int N) { return make_idesc_fmt(BF16 ? 1u : 2u, M, N); }
-
-template <bool BF16>
-__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    if (BF16) {
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                     "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                     ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-    } else {
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                     "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                     ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-    }
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-        :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
-           "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
-           "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
-           "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-        : "memory");
-}
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-// D[tmem] (+)= A[tmem] * B[smem]: the A operand is read from tensor memory (lanes = M rows, one 32-bit column per K element)
-__device__ __forceinline__ void umma_ts_tf32(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-                 ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-
-__device__ __forceinline__ float mish_fast(float x) {
-    // same closed form as mish_f (sbk_kernels.cu); exp via ex2.approx and an approximate reciprocal:
-    // relative error ~1e-6, far below the tf32/bf16 operand rounding this path already applies.
-    const float n = __expf(fminf(x, 20.f));
-    const float a = n * (n + 2.f);
-    return x > 20.f ? x : x * __fdividef(a, a + 2.f);
-}
-
-
-
-// fp32x3 mode: the exact closed form (mish_f of sbk_kernels.cu)
-__device__ __forceinline__ float mish_exact(float x) {
-    const float n = expf(fminf(x, 20.f));
-    const float a = n * (n + 2.f);
-    return x > 20.f ? x : x * (a / (a + 2.f));
-}
-
-__device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
-__device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
-// two floats -> packed bf16x2 (round to nearest even), `lo` in the low half = the lower channel index
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-    uint32_t d;
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
-    return d;
-}
-
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-
 }  // namespace tc
 
 using namespace tc;
 
-// per-device launch state of one kernel instantiation: opt-in to 227 KB of dynamic shared memory + SM count
-struct DevCache {
-    static constexpr int MAXDEV = 64;
-    int sms[MAXDEV] = {};
-    int get(const void* fn) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAXDEV) return -1;
-        if (sms[dev] == 0) {
-            if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -1;
-            int n = 0;
-            if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return -1;
-            sms[dev] = n;
-        }
-        return sms[dev];
-    }
-};
 
 // Residency / pipeline / accumulator configuration.
 //   * persistent CTAs: each CTA loops over output tiles (round-robin), every role keeps its own ring / slot counters;
@@ -1466,7 +1270,7 @@ static int dispatch_conv_tc_x3(const ConvTcParams& p, cudaStream_t s) {
     switch (p.geom) {
         case G_C3:   return nt == 128 ? launch_tc<G_C3, false, 128, false, true>(p, s) : launch_tc<G_C3, false, 64, false, true>(p, s);
         case G_PW:
-            if (p.epi == EPI_KV) return -1;             // fp32x3 attention goes through the plain 1x1 conv + k_kv_ctx
+            if (p.epi == EPI_KV) return launch_attn_kv_x3(p, s);      // fused projection + softmax + context (sbk_attn_x3.cu)
             if (p.epi == EPI_RES) return nt == 128 ? launch_tc<G_PW, false, 128, true, true>(p, s) : launch_tc<G_PW, false, 64, true, true>(p, s);
             return nt == 128 ? launch_tc<G_PW, false, 128, false, true>(p, s) : launch_tc<G_PW, false, 64, false, true>(p, s);
         case G_DOWN: return launch_tc<G_DOWN, false, 64, false, true>(p, s);

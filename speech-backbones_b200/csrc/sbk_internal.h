@@ -254,6 +254,10 @@ int launch_gn_act(const GnActParams& p, cudaStream_t s);
 int launch_resfinal(const ResFinalParams& p, cudaStream_t s);
 int launch_attn_ctx(const AttnCtxParams& p, cudaStream_t s);
 int attn_kv_tile_pixels();
+// fp32x3 mode: fused k|v projection + online softmax + context partials (sbk_attn_x3.cu); p.Ho = items per chunk, p.Wo = chunks
+// per sample, p.kv_part = [B][chunks per sample][4][kKvPartFloats]
+int launch_attn_kv_x3(const ConvTcParams& p, cudaStream_t s);
+int attn_kv_x3_item_pixels();
 int launch_attn_mix(const AttnMixParams& p, cudaStream_t s);
 int launch_final(const FinalParams& p, cudaStream_t s);
 int launch_time_table(const TimeTableParams& p, cudaStream_t s);
