@@ -66,11 +66,10 @@ struct Arena {
     }
 };
 
-enum OpKind { OP_FIRST, OP_IGEMM, OP_RESFINAL, OP_CTX, OP_MIX, OP_FINAL, OP_CONVTC, OP_GNACT, OP_KVCTX };
+enum OpKind { OP_FIRST, OP_IGEMM, OP_RESFINAL, OP_CTX, OP_MIX, OP_FINAL, OP_CONVTC, OP_GNACT };
 struct Op {
     OpKind kind; std::string name;
     FirstConvParams fc; IgemmParams ig; ConvTcParams tc; GnActParams ga; ResFinalParams rf; AttnCtxParams cx; AttnMixParams mx; FinalParams fn;
-    KvCtxParams kc;
     const float* dbg_ptr = nullptr; int64_t dbg_numel = 0;
     int dbg_fmt = 0;               // layout of the named output: 0 NHWC fp32, 1 [B][H][C/4][W][4] fp32, 2 [B][H][C/8][W][8] bf16
     double flops = 0, bytes = 0;   // algorithmic work of this launch
@@ -346,7 +345,10 @@ static int pack_tc(sbk_handle* h, const std::string& src, const std::string& key
     TRY_RC(pack_tc_host(h, hs, key, cout, cin, geom, bf16));
     // 3x3 convs with >= 128 output channels also get a 64-wide N-tile image: small batches have too few 128-wide tiles to
     // fill 148 SMs (B=1, level 2: 20 tiles), so the planner switches those launches to twice as many half-width tiles
+    // ... and that half-width image is also what a CTA pair stages: each CTA of a cta_group::2 pair holds half of the N tile
+    // (sbk_conv_tc.cu, PAIR).  64-channel convs (level 0) get a 32-wide image for the same purpose.
     if (geom == G_C3 && conv_tc_ntile(geom, cout) == 128) TRY_RC(pack_tc_host(h, hs, key + "64", cout, cin, geom, bf16, 64));
+    if (geom == G_C3 && conv_tc_ntile(geom, cout) == 64) TRY_RC(pack_tc_host(h, hs, key + "32", cout, cin, geom, bf16, 32));
     return SBK_OK;
 }
 // k and v rows of to_qkv ('(qkv heads c)': k = rows 128.., v = rows 256..) in k_attn_kv's per-stage shared-memory image
@@ -549,7 +551,6 @@ namespace {
 struct Bufs {
     float *A[3], *Bf[3], *X[3], *Y[3], *S[3], *D[3], *U1;
     float *kv_part, *ctx, *w_eff, *b_eff;
-    float* kvraw;                              // fp32x3: the k|v projection [B][H0][64][W0][4]
     std::map<const void*, float*> lo;          // fp32x3: operand tensor -> its x_lo twin
 };
 }
@@ -589,7 +590,6 @@ static size_t layout(const sbk_handle* h, int B, int T, int tb_rows, Arena& ar, 
     b.ctx = f((size_t)B * kHeads * 1024);
     b.w_eff = f((size_t)B * C[2] * C[2] * (x3 ? 2 : 1));
     b.b_eff = f(C[2]);
-    b.kvraw = nullptr;
     if (bf) *bf = b;
     Plan dummy;
     Plan& p = pl ? *pl : dummy;
@@ -727,6 +727,16 @@ static int build_plan(sbk_handle* h, int B, int T, int tb_rows) {
             // tiles of 2 rows x 128 pixels x 128 channels; when they cannot fill half the SMs, use 64-wide N tiles instead
             const long long tiles = (long long)B * ((Ws[lvl] + 127) / 128) * ((Hs[lvl] + 1) / 2) * (cout / 128);
             if (tiles * 2 <= num_sms && h->packed.count(wkey + "64")) { p.nt = 64; p.wpk = W(wkey + "64"); }
+        }
+        if (geom == G_C3 && !p.nt) {
+            // CTA pairs (cta_group::2) when there are enough 4-row pair tiles to fill every SM pair; the pair kernel reads the
+            // weight image packed for half-width N tiles.  SBK_NO_PAIR=1 keeps the single-CTA kernels (measurement knob).
+            static const bool no_pair = getenv("SBK_NO_PAIR") != nullptr;
+            const int ntile = conv_tc_ntile(geom, cout);
+            const std::string half = wkey + (ntile == 128 ? "64" : "32");
+            const long long ptiles = (long long)B * conv_tc_pair_tiles(Hs[lvl], Ws[lvl]) * (cout / ntile);
+            // (bf16 mode: measured 2 % slower on pairs - its MMAs are half as long, the pair's cross-CTA handshakes are not)
+            if (!no_pair && !b16 && ptiles >= num_sms / 2 && h->packed.count(half)) { p.pair = 1; p.wpk = W(half); }
         }
         const double taps = geom == G_PW ? 1.0 : (geom == G_UP ? 4.0 : 9.0);
         op.flops = 2.0 * B * Hs[lvl] * Ws[lvl] * cout * (c0 + c1) * taps;
@@ -966,10 +976,6 @@ static int launch_op(const Op& op, cudaStream_t s) {
         case OP_FINAL: return launch_final(op.fn, s);
         case OP_CONVTC: return launch_conv_tc(op.tc, s);
         case OP_GNACT: return launch_gn_act(op.ga, s);
-        case OP_KVCTX: {
-            static const bool ffma = getenv("SBK_KVCTX_FFMA") != nullptr;       // measurement / cross-check knob
-            return ffma ? launch_kv_ctx(op.kc, s) : launch_kv_ctx_tc(op.kc, s);
-        }
     }
     return -1;
 }

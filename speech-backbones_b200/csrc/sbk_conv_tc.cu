@@ -68,8 +68,11 @@ constexpr int pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ?
 // X3 (fp32x3 mode), 3x3 and 1x1 convs (TMSUM): TMEM holds one accumulation-run slot per output row plus the running
 // fp32 sums of the tile, 4*NT columns in all (see conv_tc_body); Downsample keeps its running sums in registers
 // (one CTA per SM: 64 accumulators per thread); Upsample runs unchunked.
-template <int GEOM, int NT, bool X3 = false> struct Depth {
-    static constexpr int STAGE_BYTES = Geo<GEOM>::KCH * Geo<GEOM>::HR * Geo<GEOM>::PXP * 16 + Geo<GEOM>::TAPS * Geo<GEOM>::KCH * NT * 16;
+// PAIR (3x3 convs only): the CTA is one half of a cta_group::2 pair - it stages its own two output rows' A tile and HALF of
+// the weight tile (NT/2 output channels); see conv_tc_body.
+template <int GEOM, int NT, bool X3 = false, bool PAIR = false> struct Depth {
+    static constexpr int NB = PAIR ? NT / 2 : NT;           // weight rows (output channels) staged by this CTA
+    static constexpr int STAGE_BYTES = Geo<GEOM>::KCH * Geo<GEOM>::HR * Geo<GEOM>::PXP * 16 + Geo<GEOM>::TAPS * Geo<GEOM>::KCH * NB * 16;
     static constexpr int SLOT_COLS = Geo<GEOM>::NACC * NT;
     static constexpr int FIT2 = (108 * 1024) / STAGE_BYTES;
     static constexpr int FIT1 = (220 * 1024) / STAGE_BYTES;
@@ -96,11 +99,25 @@ template <int GEOM, int NT, bool X3 = false> struct Depth {
 // MMAs per accumulator for a 3x3 conv): the MMA issuer commits the run, the epilogue warps add the partial sums to
 // round-to-nearest fp32 REGISTER accumulators (one row of NT columns per thread) and hand the TMEM slot back, while the
 // issuer already runs the next chunk in the other slot.  The epilogue proper then works from the registers.
-template <int GEOM, bool BF16, int NT, bool RES, bool X3>
+//
+// PAIR (cta_group::2, G_C3 only).  Every UMMA reads its A tile (4 KB) and its B tile (NT x 32 B) from shared memory: at
+// M = N = 128 that is 8 KB per 64-clock instruction = the whole 128 B/clk of the SM's shared memory, with nothing left for
+// the bulk copies that refill the ring - the convs sat at ~75 % of that shared-memory bound (profiles/r2_smem_bound.md).
+// A CTA pair halves the weight traffic: the two CTAs of a 2-CTA cluster own the two halves of a 4-row tile (2 rows = 2
+// M = 128 row-tiles each) and each stages only HALF of the weight tile; one tcgen05.mma.cta_group::2 (M = 256) issued by
+// the leader CTA computes row j of both CTAs, reading each CTA's A tile locally and the B halves from both shared
+// memories (6 KB instead of 8 KB per instruction and SM, and half the weight bytes through L2 -> smem).  Protocol:
+//   * both loaders fill their own ring; the peer's MMA warp relays "my stage s is full" to the leader's full barrier
+//     (remote mbarrier arrive), so the leader's issuer waits on ONE barrier per stage (count 2: local expect_tx + relay);
+//   * tcgen05.commit.cta_group::2 multicasts stage-empty / accumulator-full arrivals to the same barrier in both CTAs;
+//   * the epilogue warps of both CTAs (each reads its own TMEM: its 128 pixel rows) arrive on the LEADER's tempty barrier.
+template <int GEOM, bool BF16, int NT, bool RES, bool X3, bool PAIR = false>
 __device__ __forceinline__ void conv_tc_body(const ConvTcParams& p) {
     static_assert(!(X3 && BF16), "fp32x3 runs on tf32 operands");
+    static_assert(!PAIR || (GEOM == G_C3 && !RES), "CTA pairs: 3x3 convs only");
     using G = Geo<GEOM>;
-    using D = Depth<GEOM, NT, X3>;
+    using D = Depth<GEOM, NT, X3, PAIR>;
+    constexpr int NB = D::NB;
     // Upsample keeps its 8 accumulators (4 phases x 2 rows x 64 columns = all of TMEM) in one run: 256 register
     // accumulators per thread do not exist, and its runs are short (4 taps: 96-192 MMAs per accumulator)
     // Two homes for the running sums of the accumulation runs:
@@ -114,10 +131,9 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcParams& p) {
     //   is operand-fetch bound: 474 vs 780 TFLOP/s of MMA issue, profiles/r2_ops_fp32x3_v2_chunked_nt64.txt).
     constexpr bool TMSUM = D::TMSUM;
     constexpr bool CHUNKED = X3 && GEOM == G_DOWN;
-    // sub-stages per accumulation run (p.flush overrides): Downsample 6; TMSUM 3 (= one K stage of x_lo*w_hi + x*w_lo +
-    // x*w_hi: 27 MMAs per accumulator for a 3x3 conv, ~5e-7 of truncation bias), at most STAGES - 1 resident stages
-    const int FLUSH = TMSUM ? (p.flush > 0 && p.flush < D::STAGES ? p.flush : (D::STAGES - 1 < 3 ? D::STAGES - 1 : 3))
-                            : (p.flush > 0 ? p.flush : 6);
+    // sub-stages per accumulation run (p.flush overrides): 6 = three K stages of correction + main sub-stage, 54 MMAs per
+    // accumulator for a 3x3 conv (~1e-6 of truncation bias; 4 gave 2.1e-6 per estimator call, 6 gives 2.4e-6 and 5 % less time)
+    const int FLUSH = p.flush > 0 ? p.flush : 6;
     constexpr int STAGES = D::STAGES, NSLOT = D::NSLOT, SLOT_COLS = D::SLOT_COLS;
     constexpr int LAG = STAGES >= 3 ? STAGES - 2 : 0;      // G_DOWN only: cp.async groups in flight behind the newest
     static_assert(STAGES >= 2, "need at least 2 stages");
@@ -129,7 +145,7 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcParams& p) {
     constexpr bool OUT16 = BF16 && GEOM != G_C3;
     constexpr int PLANE = HR * PXP * 16;                   // bytes between K chunks of the A tile
     constexpr int A_STAGE_BYTES = KCH * PLANE;
-    constexpr int B_STAGE_BYTES = TAPS * KCH * NT * 16;
+    constexpr int B_STAGE_BYTES = TAPS * KCH * NB * 16;
     constexpr bool BULK = GEOM != G_DOWN;                  // A tile = contiguous runs -> cp.async.bulk (no LSU work)
     constexpr bool C1 = geom_is_c1(GEOM);                  // Conv1d strip geometry
     constexpr int SPAN = C1 ? ROWS * TPX : TPX;            // output pixels per tile along W
@@ -158,14 +174,17 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcParams& p) {
     // ---- tile space: (sample, pixel tile, N tile), N tile fastest so neighbours in time share the A tile in L2
     const int wt_w = (GEOM == G_DOWN ? p.Wo : p.W), wt_h = (GEOM == G_DOWN ? p.Ho : p.H);
     const int wtiles = (wt_w + SPAN - 1) / SPAN;
-    const int mtiles = GEOM == G_PW ? (HW + ROWS * TPX - 1) / (ROWS * TPX) : wtiles * ((wt_h + ROWS - 1) / ROWS);
+    constexpr int TROWS = PAIR ? 2 * ROWS : ROWS;           // output rows per (pair) tile
+    const int mtiles = GEOM == G_PW ? (HW + ROWS * TPX - 1) / (ROWS * TPX) : wtiles * ((wt_h + TROWS - 1) / TROWS);
     const int ntn = p.Cout / NT;
     const int total_tiles = p.B * mtiles * ntn;
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;   // PAIR: rank 0 = leader (issues the MMAs), rank 1 = peer
+    const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, tstep = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     auto decode = [&](int t, int& b, int& h0, int& w0, int& n0, int& mt) {
         const int nt = t % ntn; const int r = t / ntn;
         mt = r % mtiles; b = r / mtiles; n0 = nt * NT;
         if (GEOM == G_PW) { w0 = 0; h0 = mt * ROWS; }
-        else { w0 = (mt % wtiles) * SPAN; h0 = (mt / wtiles) * ROWS; }
+        else { w0 = (mt % wtiles) * SPAN; h0 = (mt / wtiles) * TROWS + (int)rank * ROWS; }
     };
 
     const uint32_t bar0 = smem_u32(bars);
@@ -178,17 +197,23 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcParams& p) {
 
     // ---- one-time setup
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(full_a(s), NPROD / 32); mbar_init(full_b(s), 1); mbar_init(empty(s), 1); }
+        // PAIR: the leader's full barrier also takes the peer's relay arrival; its tempty barriers take both CTAs' epilogue warps
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_a(s), NPROD / 32); mbar_init(full_b(s), (PAIR && rank == 0) ? 2 : 1); mbar_init(empty(s), 1); }
         // (TMSUM: slot a belongs to output row a and is drained by that row's four epilogue warps)
-        for (int a = 0; a < NSLOT; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), TMSUM ? NPROD / 64 : NPROD / 32); }
+        for (int a = 0; a < NSLOT; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), (TMSUM ? NPROD / 64 : NPROD / 32) * (PAIR ? 2 : 1)); }
         mbar_init(kv_bar, 1);
         fence_barrier_init();
     }
-    if (warp == NPROD / 32) tmem_alloc(smem_u32(s_tmem), D::TMEM_COLS);
+    if (warp == NPROD / 32) { if constexpr (PAIR) tmem_alloc2(smem_u32(s_tmem), D::TMEM_COLS); else tmem_alloc(smem_u32(s_tmem), D::TMEM_COLS); }
     if (tid < 128) s_st[tid] = 0.f;
     tc_fence_before();
-    __syncthreads();
+    if constexpr (PAIR) cluster_sync_all(); else __syncthreads();    // (pair: the peer's barriers must exist before any remote arrival)
     tc_fence_after();
+    const uint32_t lead_bar0 = PAIR ? mapa_shared(bar0, 0u) : bar0;  // the leader CTA's barrier block (cluster address)
+    auto tempty_arrive = [&](int a) {                                 // one epilogue warp done with accumulator slot a
+        if constexpr (PAIR) mbar_arrive_cluster(lead_bar0 + 8u * (2 * STAGES + NSLOT + a));
+        else mbar_arrive(tempty(a));
+    };
     const uint32_t tmem_base = *s_tmem;
 
     if (warp < NPROD / 32) {
@@ -197,7 +222,7 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcParams& p) {
         // =========================================================================================================
         uint32_t it = 0;      // G_DOWN producer ring counter
         uint32_t ar = 0;      // accumulation-run counter (accumulator slot / phase); one run per tile unless CHUNKED
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        for (int t = tile0; t < total_tiles; t += tstep) {
             int b, h0, w0, n0, mt;
             decode(t, b, h0, w0, n0, mt);
             // CHUNKED: accumulation runs of this tile are drained, in order, into register accumulators (round-to-nearest
@@ -223,7 +248,7 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcParams& p) {
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(tempty(rs));
+                if (lane == 0) tempty_arrive(rs);
                 ++ar; ++drained;
             };
             if (!BULK) {
@@ -381,7 +406,7 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcParams& p) {
                 tmem_wait_st();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(tempty(jrow));
+                if (lane == 0) tempty_arrive(jrow);
             }
             acc_ready = true;
         }
@@ -516,7 +541,7 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcParams& p) {
             if constexpr (!CHUNKED && !TMSUM) {
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(tempty(slot));
+                if (lane == 0) tempty_arrive(slot);
                 ++ar;
             }
             if (GEOM != G_PW && p.ostats) {
@@ -535,33 +560,54 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcParams& p) {
         // =========================================================================================================
         // MMA issuer: the whole warp runs the loops and the barrier waits; one elected lane issues (see elect_one)
         // =========================================================================================================
-        {
-            const uint32_t idesc = make_idesc<BF16>(TPX, NT);
-            const uint32_t idesc_c = make_idesc_fmt(0u, TPX, NT);        // fp32x3 correction sub-stages: fp16 operands
+        if (PAIR && rank != 0) {
+            // peer CTA of a pair: no MMAs to issue - relay "stage s of MY ring is full" to the leader's full barrier, in ring order
+            const uint32_t lead_full0 = lead_bar0;                       // full_b(s) = bar0 + 8 s
+            uint32_t it = 0;
+            for (int t = tile0; t < total_tiles; t += tstep)
+                for (int ks = 0; ks < ksteps_t; ++ks, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(full_b(s), (it / STAGES) & 1);
+                    if (lane == 0) mbar_arrive_cluster(lead_full0 + 8u * s);
+                    __syncwarp();
+                }
+        } else {
+            const uint32_t idesc = make_idesc<BF16>(PAIR ? 2 * TPX : TPX, NT);
+            const uint32_t idesc_c = make_idesc_fmt(0u, PAIR ? 2 * TPX : TPX, NT);   // fp32x3 correction sub-stages: fp16 operands
             const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+            auto mma = [&](auto kind16, uint32_t d, uint64_t ad, uint64_t bd, uint32_t idk, uint32_t acc) {
+                if constexpr (PAIR) umma2<decltype(kind16)::value>(d, ad, bd, idk, acc);
+                else umma<decltype(kind16)::value>(d, ad, bd, idk, acc);
+            };
+            auto commit = [&](uint32_t bar) { if constexpr (PAIR) umma_commit2(bar); else umma_commit(bar); };
+            auto wait_full = [&](uint32_t bar, uint32_t ph) { if constexpr (PAIR) mbar_wait_cluster(bar, ph); else mbar_wait(bar, ph); };
             constexpr uint32_t D_HI = desc_hi(128);                      // SBO = 128 B for both operands
             uint32_t it = 0;
             uint32_t ar = 0;                                             // accumulation-run counter (see the epilogue warps)
             if constexpr (TMSUM) {
-                // row-major runs: row j of run c goes to TMEM slot j while the epilogue warps of the other row fold that
-                // row's previous run into the running sums; a stage is released after the LAST row has read it
-                for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                // Both rows advance together through the sub-stages of a run - row 0's taps, then row 1's, on every stage - so a
+                // stage is released as soon as both rows have read it (18 MMAs), and each row's run is committed separately:
+                // row 0's fold into the running sums overlaps row 1's last stage, row 1's fold overlaps row 0's first stage
+                // of the next run (whose MMAs only wait for row 0's fold).  (The first version walked a run row by row over
+                // RESIDENT stages so that one row's fold hid under the other row's whole run; holding 3 of the 4 stages for
+                // two passes left the ring one stage of prefetch, and the activation loads - ~2 us from HBM - were exposed:
+                // 39 % of the conv time, profiles/r2_x3_ring.md.)
+                for (int t = tile0; t < total_tiles; t += tstep) {
                     for (int c = 0; c < nchunks; ++c, ++ar) {
                         const int ks_lo = c * FLUSH, ks_hi = ks_lo + FLUSH < ksteps_t ? ks_lo + FLUSH : ksteps_t;
-#pragma unroll 1
-                        for (int j = 0; j < ROWS; ++j) {
-                            mbar_wait(tempty(j), (ar & 1) ^ 1);             // this row's slot has been folded into the sums
+                        for (int ks = ks_lo; ks < ks_hi; ++ks, ++it) {
+                            const int s = it % STAGES;
+                            wait_full(full_b(s), (it / STAGES) & 1);
                             tc_fence_after();
-                            const uint32_t tslot = tmem_base + j * NT;
-                            for (int ks = ks_lo; ks < ks_hi; ++ks) {
-                                const uint32_t itk = it + (uint32_t)(ks - ks_lo);
-                                const int s = itk % STAGES;
-                                if (j == 0) {
-                                    mbar_wait(full_b(s), (itk / STAGES) & 1);   // (row 1 re-reads stages row 0 already waited for)
+                            const uint32_t b_lo = desc_lo(b0 + s * B_STAGE_BYTES, NB * 16);
+#pragma unroll
+                            for (int j = 0; j < ROWS; ++j) {
+                                if (ks == ks_lo) {
+                                    wait_full(tempty(j), (ar & 1) ^ 1);     // this row's previous run has been folded into the sums
                                     tc_fence_after();
                                 }
+                                const uint32_t tslot = tmem_base + j * NT;
                                 const uint32_t a_lo = desc_lo(a0 + s * A_STAGE_BYTES + (j * PXP) * 16, PLANE);
-                                const uint32_t b_lo = desc_lo(b0 + s * B_STAGE_BYTES, NT * 16);
                                 if (elect_one()) {
                                     auto issue = [&](auto kind16, const uint32_t idk) {
 #pragma unroll
@@ -569,46 +615,44 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcParams& p) {
 #pragma unroll
                                             for (int tap = 0; tap < TAPS; ++tap) {
                                                 const int r = TAPS == 9 ? tap / 3 : 0, sx = TAPS == 9 ? tap % 3 : 0;
-                                                umma<decltype(kind16)::value>(tslot, desc_pack(a_lo + (uint32_t)(kk * 2 * (PLANE / 16) + r * PXP + sx), D_HI),
-                                                                              desc_pack(b_lo + (uint32_t)((kk * 2 + tap * KCH) * NT), D_HI), idk,
-                                                                              ((ks - ks_lo) | kk | tap) != 0 ? 1u : 0u);
+                                                mma(kind16, tslot, desc_pack(a_lo + (uint32_t)(kk * 2 * (PLANE / 16) + r * PXP + sx), D_HI),
+                                                    desc_pack(b_lo + (uint32_t)((kk * 2 + tap * KCH) * NB), D_HI), idk,
+                                                    ((ks - ks_lo) | kk | tap) != 0 ? 1u : 0u);
                                             }
                                         }
                                     };
                                     if ((ks & 1) == 0) issue(std::true_type{}, idesc_c);      // correction sub-stage: kind::f16 on the fp16 chunks
                                     else issue(std::false_type{}, idesc);                     // main sub-stage: kind::tf32
-                                    if (j == ROWS - 1) umma_commit(empty(s));   // frees the stage when both rows have read it
-                                    if (ks == ks_hi - 1) umma_commit(tfull(j)); // this row's run is complete
+                                    if (j == ROWS - 1) commit(empty(s));        // frees the stage: both rows have read it
+                                    if (ks == ks_hi - 1) commit(tfull(j));      // this row's run is complete
                                 }
                                 __syncwarp();
                             }
                         }
-                        it += (uint32_t)(ks_hi - ks_lo);
                     }
                 }
             } else
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            for (int t = tile0; t < total_tiles; t += tstep) {
               for (int c = 0; c < nchunks; ++c, ++ar) {
                 const int slot = ar % NSLOT;
                 const uint32_t tslot = tmem_base + slot * SLOT_COLS;
-                mbar_wait(tempty(slot), ((ar / NSLOT) & 1) ^ 1);        // epilogue has drained this slot
+                wait_full(tempty(slot), ((ar / NSLOT) & 1) ^ 1);        // epilogue has drained this slot
                 tc_fence_after();
                 const int ks_lo = CHUNKED ? c * FLUSH : 0, ks_hi = CHUNKED ? (ks_lo + FLUSH < ksteps_t ? ks_lo + FLUSH : ksteps_t) : ksteps_t;
                 for (int ks = ks_lo; ks < ks_hi; ++ks, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
                     if (!BULK) mbar_wait(full_a(s), ph);
-                    mbar_wait(full_b(s), ph);               // weights (+ the A runs when they are bulk copies)
+                    wait_full(full_b(s), ph);               // weights (+ the A runs when they are bulk copies)
                     tc_fence_after();
                     const uint32_t a_lo = desc_lo(a0 + s * A_STAGE_BYTES, PLANE);
-                    const uint32_t b_lo = desc_lo(b0 + s * B_STAGE_BYTES, NT * 16);
+                    const uint32_t b_lo = desc_lo(b0 + s * B_STAGE_BYTES, NB * 16);
                     const uint32_t dil = C1 ? (uint32_t)p.dil : 0u;
                     if (elect_one()) {
                       auto issue = [&](auto kind16, const uint32_t idk) {
-                        constexpr bool K16 = decltype(kind16)::value;
 #pragma unroll
                         for (int kk = 0; kk < KCH / 2; ++kk) {
-                            const uint32_t a_k = a_lo + (uint32_t)(kk * 2 * (PLANE / 16)), b_k = b_lo + (uint32_t)(kk * 2 * NT);
+                            const uint32_t a_k = a_lo + (uint32_t)(kk * 2 * (PLANE / 16)), b_k = b_lo + (uint32_t)(kk * 2 * NB);
                             if (GEOM == G_UP) {
                                 // ho = 2*hi - 1 + kh: parity ph uses (kh=1,dh=0),(kh=3,dh=-1) if ph=0 and (kh=0,dh=+1),(kh=2,dh=0) if ph=1
 #pragma unroll
@@ -619,25 +663,25 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcParams& p) {
                                         const int a = t2 >> 1, bb = t2 & 1;
                                         const int kh = pph ? (a ? 2 : 0) : (a ? 3 : 1), kw = pw ? (bb ? 2 : 0) : (bb ? 3 : 1);
                                         const int dh = pph ? (a ? 0 : 1) : (a ? -1 : 0), dw = pw ? (bb ? 0 : 1) : (bb ? -1 : 0);
-                                        const uint64_t bd = desc_pack(b_k + (uint32_t)((kh * 4 + kw) * KCH * NT), D_HI);
+                                        const uint64_t bd = desc_pack(b_k + (uint32_t)((kh * 4 + kw) * KCH * NB), D_HI);
 #pragma unroll
                                         for (int j = 0; j < ROWS; ++j)
-                                            umma<K16>(tslot + (phase * ROWS + j) * NT, desc_pack(a_k + (uint32_t)((1 + j + dh) * PXP + 1 + dw), D_HI), bd,
-                                                      idk, ((ks - ks_lo) | kk | t2) != 0 ? 1u : 0u);
+                                            mma(kind16, tslot + (phase * ROWS + j) * NT, desc_pack(a_k + (uint32_t)((1 + j + dh) * PXP + 1 + dw), D_HI), bd,
+                                                idk, ((ks - ks_lo) | kk | t2) != 0 ? 1u : 0u);
                                     }
                                 }
                             } else {
 #pragma unroll
                                 for (int tap = 0; tap < TAPS; ++tap) {
                                     const int r = TAPS == 9 ? tap / 3 : 0, sx = TAPS == 9 ? tap % 3 : 0;
-                                    const uint64_t bd = desc_pack(b_k + (uint32_t)(tap * KCH * NT), D_HI);
+                                    const uint64_t bd = desc_pack(b_k + (uint32_t)(tap * KCH * NB), D_HI);
 #pragma unroll
                                     for (int j = 0; j < ROWS; ++j) {
                                         // DOWN: input row 2j+r; column tap s reads the odd plane at x (s=0) / x+1 (s=2), the even plane at x (s=1)
                                         const uint32_t aoff = GEOM == G_DOWN ? (uint32_t)((2 * j + r) * PXP + (sx == 1 ? TPX + 1 : (sx == 2 ? 1 : 0)))
                                                             : C1 ? (uint32_t)(j * TPX) + (uint32_t)tap * dil
                                                                  : (uint32_t)((r + j) * PXP + sx);
-                                        umma<K16>(tslot + j * NT, desc_pack(a_k + aoff, D_HI), bd, idk, ((ks - ks_lo) | kk | tap) != 0 ? 1u : 0u);
+                                        mma(kind16, tslot + j * NT, desc_pack(a_k + aoff, D_HI), bd, idk, ((ks - ks_lo) | kk | tap) != 0 ? 1u : 0u);
                                     }
                                 }
                             }
@@ -645,8 +689,8 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcParams& p) {
                       };
                         if (X3 && (ks & 1) == 0) issue(std::true_type{}, idesc_c);          // fp32x3 correction sub-stage: kind::f16
                         else issue(std::integral_constant<bool, BF16>{}, idesc);
-                        umma_commit(empty(s));                  // frees the stage when these MMAs have read it
-                        if (ks == ks_hi - 1) umma_commit(tfull(slot));   // this run's accumulators are complete
+                        commit(empty(s));                       // frees the stage when these MMAs have read it
+                        if (ks == ks_hi - 1) commit(tfull(slot));        // this run's accumulators are complete
                     }
                     __syncwarp();
                 }
@@ -667,12 +711,13 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcParams& p) {
             uint32_t stage_pat[STAGES];
 #pragma unroll
             for (int i = 0; i < STAGES; ++i) stage_pat[i] = 0xFFFFFFFFu;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            for (int t = tile0; t < total_tiles; t += tstep) {
                 int b, h0, w0, n0, mt;
                 decode(t, b, h0, w0, n0, mt);
                 // weight image: [ntile][kstage][tap][chunk][NT][16 B]; fp32x3: [ntile][kstage][hi|correction][tap][chunk][NT][16 B]
+                // (PAIR: the image is packed for NT/2-wide tiles; this CTA stages half `rank` of the N tile)
                 const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpk) + (size_t)b * p.w_bstride_bytes +
-                                      (size_t)(n0 / NT) * ksteps * (X3 ? 2 : 1) * B_STAGE_BYTES;
+                                      (size_t)(PAIR ? 2 * (n0 / NT) + (int)rank : n0 / NT) * ksteps * (X3 ? 2 : 1) * B_STAGE_BYTES;
                 for (int ks = 0; ks < ksteps_t; ++ks, ++it) {
                     const int s = it % STAGES;
                     const int kb = X3 ? ks / 2 : ks, var = X3 ? (ks & 1) : 1;          // 0: correction (fp16 chunks), 1: main (x, w_hi)
@@ -748,10 +793,10 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcParams& p) {
         }
     }
 
-    __syncthreads();
+    if constexpr (PAIR) cluster_sync_all(); else __syncthreads();    // (pair: neither CTA may exit or free TMEM while the other still uses it)
     if (warp == NPROD / 32) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, D::TMEM_COLS);
+        if constexpr (PAIR) tmem_dealloc2(tmem_base, D::TMEM_COLS); else tmem_dealloc(tmem_base, D::TMEM_COLS);
     }
 }
 
@@ -765,6 +810,15 @@ __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT, false>::MINB) k_conv
 template <int GEOM, int NT, bool RES = false>
 __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT, true>::MINB) k_conv_tc_x3(const ConvTcParams p) {
     conv_tc_body<GEOM, false, NT, RES, true>(p);
+}
+// CTA-pair instantiations (3x3 convs; launched as 2-CTA clusters)
+template <bool BF16, int NT>
+__global__ void __launch_bounds__(NTHREADS, Depth<G_C3, NT, false, true>::MINB) k_conv_tc_pair(const ConvTcParams p) {
+    conv_tc_body<G_C3, BF16, NT, false, false, true>(p);
+}
+template <int NT>
+__global__ void __launch_bounds__(NTHREADS, Depth<G_C3, NT, true, true>::MINB) k_conv_tc_x3_pair(const ConvTcParams p) {
+    conv_tc_body<G_C3, false, NT, false, true, true>(p);
 }
 
 template <int GEOM, bool BF16, int NT, bool RES = false, bool X3 = false>
@@ -789,6 +843,30 @@ static int launch_tc(const ConvTcParams& p, cudaStream_t s) {
     if constexpr (X3) k_conv_tc_x3<GEOM, NT, RES><<<grid, NTHREADS, D::SMEM, s>>>(p);
     else k_conv_tc<GEOM, BF16, NT, RES><<<grid, NTHREADS, D::SMEM, s>>>(p);
     return 1;
+}
+
+// 3x3 conv on CTA pairs: persistent grid of 2-CTA clusters, one pair tile = 4 rows x 128 pixels x NT channels
+template <bool BF16, int NT, bool X3>
+static int launch_tc_pair(const ConvTcParams& p, cudaStream_t s) {
+    using D = Depth<G_C3, NT, X3, true>;
+    static DevCache cache;
+    const void* fn;
+    if constexpr (X3) fn = reinterpret_cast<const void*>(k_conv_tc_x3_pair<NT>);
+    else fn = reinterpret_cast<const void*>(k_conv_tc_pair<BF16, NT>);
+    const int num_sms = cache.get(fn);
+    if (num_sms <= 0) return -1;
+    const long long total = (long long)conv_tc_pair_tiles(p.H, p.W) * (p.Cout / NT) * p.B;
+    const long long cap = (long long)(num_sms / 2) * D::MINB;       // clusters resident at once
+    const unsigned clusters = (unsigned)(total < cap ? total : cap);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters, 1, 1); cfg.blockDim = dim3(NTHREADS, 1, 1); cfg.dynamicSmemBytes = D::SMEM; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t e;
+    if constexpr (X3) e = cudaLaunchKernelEx(&cfg, k_conv_tc_x3_pair<NT>, p);
+    else e = cudaLaunchKernelEx(&cfg, k_conv_tc_pair<BF16, NT>, p);
+    return e == cudaSuccess ? 1 : -1;
 }
 
 // =================================================================================================================
@@ -1056,172 +1134,14 @@ static int launch_attn_kv(const ConvTcParams& p, cudaStream_t s) {
 }
 int attn_kv_tile_pixels() { return kvk::PX; }
 
-// =================================================================================================================
-// fp32x3 mode, LinearAttention pass 1b on the tensor cores (diffusion.py:95-96): softmax-over-pixels partials and context
-// partials S[d][e] = sum_px P[d,px] V[e,px] from the k|v projection the 3xTF32 1x1 conv left in HBM ([B][H][64][W][4] fp32,
-// rows 0..127 = k, 128..255 = v).  One CTA = one chunk of pixels of one sample, walked in sub-tiles of 32 pixels with an
-// online softmax per k row (thread d < 128 owns k row d, thread 128+e owns v row e):
-//     m' = max(m, max_px k);  P = exp(k - m');  operands P_hi|P_lo, V_hi|V_lo (tf32 each, x = hi + lo to 2^-22) are written
-//     to shared memory in the UMMA K-major layout [4-pixel chunk][row][16 B];  S_sub = P_lo V_hi^T + P_hi V_lo^T + P_hi V_hi^T
-//     is 12 UMMAs (M = N = 128, K = 8 pixels) into a FRESH TMEM accumulator;  thread d then adds its head's 32 columns into
-//     fp32 registers: acc = acc * e^(m - m') + S_sub[d][32h .. 32h+31].
-// A run is 12 MMAs, so the tensor core's truncating accumulator costs nothing here, and the fp32 running sums are
-// round-to-nearest.  (The CUDA-core version of this pass, k_kv_ctx, ran at 12 TFLOP/s: 1.8 ms of an 19 ms step.)
-// Output: the k_attn_kv partial format {max[32], sum[32], S[32][32]} per (sample, chunk, head), merged by k_attn_ctx.
-// =================================================================================================================
-namespace kvx {
-constexpr int PXS = 32;                              // pixels per sub-tile (K extent of one S_sub)
-constexpr int LD = PXS + 4;                          // staging row stride (floats): 16-byte aligned, conflict-free float4 rows
-constexpr int OPB = (PXS / 4) * 128 * 16;            // one operand image [pixel chunk][row][16 B]
-constexpr size_t SMEM = (size_t)2 * 128 * LD * 4 + 4 * OPB + 64;
-}
-
-__global__ void __launch_bounds__(256, 2) k_kv_ctx_tc(const KvCtxParams p) {
-    using namespace kvx;
-    extern __shared__ __align__(1024) uint8_t smem[];
-    float* s_k = reinterpret_cast<float*>(smem);                     // [128][LD]
-    float* s_v = s_k + 128 * LD;                                     // [128][LD]
-    uint8_t* op = reinterpret_cast<uint8_t*>(s_v + 128 * LD);        // P_hi | P_lo | V_hi | V_lo
-    uint64_t* bar = reinterpret_cast<uint64_t*>(op + 4 * OPB);
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar + 1);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, b = blockIdx.y, chunk = blockIdx.x;
-    const int HW = p.H * p.W;
-    const int m_begin = chunk * p.chunk_px, m_end = min(HW, m_begin + p.chunk_px);
-    const uint32_t mbar = smem_u32(bar);
-    if (tid == 0) { mbar_init(mbar, 1); fence_barrier_init(); }
-    if (warp == 4) tmem_alloc(smem_u32(s_tmem), 128);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = *s_tmem;
-    const bool krow = tid < 128;                                     // this thread owns k row `row` (else v row `row`)
-    const int row = tid & 127;
-    float m_run = -INFINITY, z_run = 0.f;
-    float acc[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-    const uint32_t idesc = make_idesc<false>(128, 128);
-    const uint32_t op0 = smem_u32(op);
-    uint32_t phase = 0;
-    // Staging: thread (px = tid % 32, ch0 = tid / 32) owns the float4 chunks ch0 + 8j, j < 8, of pixel px.  All eight loads of a
-    // sub-tile are issued back to back and one sub-tile AHEAD, into registers, so their global latency hides under the
-    // previous sub-tile's softmax / MMA / read-out.  (The first version loaded and stored chunk by chunk: eight serialised
-    // global round trips per 32 pixels, 46 % of the kernel's stall samples on the dependent STS - profiles/r2_ncu_kvctx.md.)
-    static_assert(PXS == 32, "staging maps one warp lane to one pixel of the sub-tile");
-    const int spx = tid & 31, ch0 = tid >> 5;
-    float4 pre[8];
-    auto load_sub = [&](int m0) {
-        const int m = m0 + spx;
-        if (m < m_end) {
-            const int hh = m / p.W, ww = m - hh * p.W;
-            const float4* src = reinterpret_cast<const float4*>(p.kv) + (((long long)b * p.H + hh) * 64 + ch0) * p.W + ww;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) pre[j] = __ldg(src + (long long)j * 8 * p.W);
-        } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) pre[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-    };
-    load_sub(m_begin);
-    for (int m0 = m_begin; m0 < m_end; m0 += PXS) {
-        const int npx = min(PXS, m_end - m0);
-        // ---- stage k|v: transposed to [channel][pixel]
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int ch = ch0 + 8 * j;
-            float* dst = (ch < 32 ? s_k : s_v) + ((ch & 31) * 4) * LD + spx;
-            dst[0] = pre[j].x; dst[LD] = pre[j].y; dst[2 * LD] = pre[j].z; dst[3 * LD] = pre[j].w;
-        }
-        if (m0 + PXS < m_end) load_sub(m0 + PXS);                    // next sub-tile: in flight until the top of the next iteration
-        __syncthreads();                                             // staging visible; the previous sub-tile's MMAs were awaited below
-        float f = 1.f;
-        {
-            const float* src = (krow ? s_k : s_v) + row * LD;
-            float x[PXS];
-#pragma unroll
-            for (int i = 0; i < PXS; i += 4) { const float4 t = *reinterpret_cast<const float4*>(src + i); x[i] = t.x; x[i + 1] = t.y; x[i + 2] = t.z; x[i + 3] = t.w; }
-            if (krow) {
-                float mx = -INFINITY;
-#pragma unroll
-                for (int i = 0; i < PXS; ++i) if (i < npx) mx = fmaxf(mx, x[i]);
-                const float mn = fmaxf(m_run, mx);
-                f = m_run == -INFINITY ? 0.f : expf(m_run - mn);
-                float z = 0.f;
-#pragma unroll
-                for (int i = 0; i < PXS; ++i) { x[i] = i < npx ? expf(x[i] - mn) : 0.f; z += x[i]; }
-                m_run = mn; z_run = z_run * f + z;
-            }
-            // hi | lo split (both tf32, round to nearest) written as K-major operand chunks [pixel chunk][row][16 B]
-            uint8_t* ohi = op + (krow ? 0 : 2 * OPB) + row * 16;
-            uint8_t* olo = ohi + OPB;
-#pragma unroll
-            for (int j = 0; j < PXS / 4; ++j) {
-                uint32_t h[4], l[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h[e]) : "f"(x[4 * j + e]));
-                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l[e]) : "f"(x[4 * j + e] - __uint_as_float(h[e])));
-                }
-                *reinterpret_cast<uint4*>(ohi + (size_t)j * 128 * 16) = make_uint4(h[0], h[1], h[2], h[3]);
-                *reinterpret_cast<uint4*>(olo + (size_t)j * 128 * 16) = make_uint4(l[0], l[1], l[2], l[3]);
-            }
-        }
-        fence_proxy_async();                                         // generic-proxy operand writes -> visible to the tensor core
-        tc_fence_before();
-        __syncthreads();
-        // Warp 4 issues (one elected lane, see elect_one); the other warps go straight to the mbarrier wait below.
-        if (warp == 4) {
-            tc_fence_after();
-            constexpr uint32_t D_HI = desc_hi(128);
-            const uint32_t o_lo = desc_lo(op0, 128 * 16);
-            if (elect_one()) {
-#pragma unroll
-                for (int t = 0; t < 3; ++t) {                            // P_lo V_hi^T, P_hi V_lo^T, P_hi V_hi^T
-                    const uint32_t pa = o_lo + (t == 0 ? OPB / 16 : 0), vb = o_lo + 2 * (OPB / 16) + (t == 1 ? OPB / 16 : 0);
-#pragma unroll
-                    for (int kk = 0; kk < PXS / 8; ++kk)
-                        umma<false>(tmem, desc_pack(pa + (uint32_t)(kk * 2 * 128), D_HI), desc_pack(vb + (uint32_t)(kk * 2 * 128), D_HI), idesc, (t | kk) != 0 ? 1u : 0u);
-                }
-                umma_commit(mbar);
-            }
-            __syncwarp();
-        }
-        mbar_wait(mbar, phase);                                      // S_sub complete (and the operand images free again)
-        phase ^= 1;
-        tc_fence_after();
-        if (krow) {
-            uint32_t r[32];
-            tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(warp * 32), r);     // lanes 32w.., columns of head w
-#pragma unroll
-            for (int i = 0; i < 32; ++i) acc[i] = fmaf(acc[i], f, __uint_as_float(r[i]));
-        }
-        tc_fence_before();
-        __syncthreads();                                             // TMEM read out before the next sub-tile's MMAs overwrite it
-    }
-    if (krow) {
-        float* pt = p.kv_part + (((long long)b * p.nchunks + chunk) * kHeads + warp) * kKvPartFloats;
-        pt[lane] = m_run;
-        pt[32 + lane] = z_run;
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(pt + 64 + lane * 32 + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
-    }
-    __syncthreads();
-    if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem, 128); }
-}
-
-int launch_kv_ctx_tc(const KvCtxParams& p, cudaStream_t s) {
-    static DevCache cache;
-    if (cache.get(reinterpret_cast<const void*>(k_kv_ctx_tc)) <= 0) return -1;
-    k_kv_ctx_tc<<<dim3(p.nchunks, p.B), 256, kvx::SMEM, s>>>(p);
-    return 1;
-}
-
 // N tile per geometry: UP needs 8 accumulators (8*64 = all 512 TMEM columns), DOWN's de-interleaved A tile is large
 int conv_tc_ntile(int geom, int Cout) {
     if (geom == G_UP || geom == G_DOWN) return 64;
     if (geom_is_c1(geom)) return Cout % 128 == 0 ? 128 : (Cout % 64 == 0 ? 64 : 32);
     return Cout % 128 == 0 ? 128 : 64;
 }
+// pair tiles (4 rows x 128 pixels) of one sample's grid
+int conv_tc_pair_tiles(int H, int W) { return ((W + TPX - 1) / TPX) * ((H + 2 * ROWS - 1) / (2 * ROWS)); }
 int conv_tc_ntile_x3(int geom, int Cout) { return conv_tc_ntile(geom, Cout); }     // (the running sums live in TMEM: same N tiles as tf32)
 int conv_tc_taps(int geom) {
     switch (geom) {
@@ -1242,7 +1162,9 @@ template <bool BF16>
 static int dispatch_conv_tc(const ConvTcParams& p, cudaStream_t s) {
     const int nt = (p.nt == 64 && p.geom == G_C3) ? 64 : conv_tc_ntile(p.geom, p.Cout);
     switch (p.geom) {
-        case G_C3:   return nt == 128 ? launch_tc<G_C3, BF16, 128>(p, s) : launch_tc<G_C3, BF16, 64>(p, s);
+        case G_C3:
+            if (p.pair) return nt == 128 ? launch_tc_pair<BF16, 128, false>(p, s) : launch_tc_pair<BF16, 64, false>(p, s);
+            return nt == 128 ? launch_tc<G_C3, BF16, 128>(p, s) : launch_tc<G_C3, BF16, 64>(p, s);
         case G_PW:
             if (p.epi == EPI_KV) return launch_attn_kv<BF16>(p, s);
             if (p.epi == EPI_RES) return nt == 128 ? launch_tc<G_PW, BF16, 128, true>(p, s) : launch_tc<G_PW, BF16, 64, true>(p, s);
@@ -1268,7 +1190,9 @@ static int dispatch_conv1d(const ConvTcParams& p, cudaStream_t s) {
 static int dispatch_conv_tc_x3(const ConvTcParams& p, cudaStream_t s) {
     const int nt = (p.nt == 64 && p.geom == G_C3) ? 64 : conv_tc_ntile(p.geom, p.Cout);
     switch (p.geom) {
-        case G_C3:   return nt == 128 ? launch_tc<G_C3, false, 128, false, true>(p, s) : launch_tc<G_C3, false, 64, false, true>(p, s);
+        case G_C3:
+            if (p.pair) return nt == 128 ? launch_tc_pair<false, 128, true>(p, s) : launch_tc_pair<false, 64, true>(p, s);
+            return nt == 128 ? launch_tc<G_C3, false, 128, false, true>(p, s) : launch_tc<G_C3, false, 64, false, true>(p, s);
         case G_PW:
             if (p.epi == EPI_KV) return launch_attn_kv_x3(p, s);      // fused projection + softmax + context (sbk_attn_x3.cu)
             if (p.epi == EPI_RES) return nt == 128 ? launch_tc<G_PW, false, 128, true, true>(p, s) : launch_tc<G_PW, false, 64, true, true>(p, s);

@@ -78,6 +78,7 @@ struct ConvTcParams {
     // below); the tensor core reads the top 19 bits of x (= x_hi) by itself.  Weights are packed as (w_hi, correction)
     // stage pairs and each K stage is issued twice into the same fp32 TMEM accumulator: the kind::f16 correction MMAs
     // (x_lo*w + x*w_lo) first, then the kind::tf32 main MMAs (x_hi*w_hi).
+    int pair;                                       // G_C3: run on CTA pairs (cta_group::2); wpk is then the image packed for NT/2-wide tiles
     int x3;
     int flush;                                      // sub-stages per accumulation run (0 = default); SBK_X3_FLUSH overrides it (measurement knob)
     const void* in0_lo; const void* in1_lo;         // the correction tensors, same chunk layout as in0 / in1
@@ -126,16 +127,6 @@ struct ResFinalParams {         // out = Mish(GN(h2raw))*mask + res(x*mask)
 struct AttnCtxParams {          // merge per-tile softmax partials -> normalised context [B][4][32][32]
     const float* kv_part; int mtiles; float* ctx; int B;
 };
-
-// fp32x3 mode: softmax-over-pixels partials + context partials from the k|v projection in HBM (CUDA cores, exact fp32).
-// kv: [B][H][256/4][W][4] fp32 (channels 0..127 = k rows head*32+d, 128..255 = v rows); one CTA per (pixel chunk, sample)
-// writes, per head, {max[32], sum[32], S[32][32]} in the k_attn_kv partial format (merged by k_attn_ctx).
-struct KvCtxParams {
-    const float* kv; float* kv_part; int B, H, W, chunk_px, nchunks;
-};
-int launch_kv_ctx(const KvCtxParams& p, cudaStream_t s);      // CUDA cores (kept as a second opinion: SBK_KVCTX_FFMA=1)
-int launch_kv_ctx_tc(const KvCtxParams& p, cudaStream_t s);   // tensor cores, 3xTF32 (sbk_conv_tc.cu)
-int kv_ctx_chunk_pixels();
 
 struct AttnMixParams {          // A_b = I + g * Wout * blockdiag(ctx^T) * Wq ; packed as [ci][co]; bias' = g*bout
     const float* ctx;           // [B][4][32][32]
@@ -248,6 +239,7 @@ int launch_first_conv(const FirstConvParams& p, cudaStream_t s);
 int launch_conv_tc(const ConvTcParams& p, cudaStream_t s);
 int conv_tc_ntile(int geom, int Cout);
 int conv_tc_ntile_x3(int geom, int Cout);
+int conv_tc_pair_tiles(int H, int W);
 int conv_tc_taps(int geom);
 int conv_tc_stage_channels(int geom, int bf16);
 int launch_gn_act(const GnActParams& p, cudaStream_t s);

@@ -1096,121 +1096,6 @@ int launch_attn_ctx(const AttnCtxParams& p, cudaStream_t s) {
     return 1;
 }
 
-// ----------------------------------------------------------------------------------------------
-// fp32x3 mode, LinearAttention pass 1b (diffusion.py:95-96): softmax-over-pixels partials and context partials in exact
-// fp32 on CUDA cores, from the k|v projection the 3xTF32 1x1 conv left in HBM ([B][H][256/4][W][4]; rows 0..127 = k,
-// head*32+d; rows 128..255 = v).  One CTA = one chunk of KVC_CHUNK consecutive pixels (flattened H*W) of one sample, all
-// four heads; the chunk is walked in sub-tiles of KVC_PX pixels staged in shared memory with an online softmax per k row:
-//     m' = max(m, max_px k);  S[d][:] = S[d][:]*e^(m-m') + sum_px e^(k[d,px]-m') v[:,px];  z likewise.
-// Thread (head, d-quad, e-quad) owns a 4x4 block of S: per 4 pixels it reads 4+4 float4 from shared memory for 64 FMAs.
-// Output: the k_attn_kv partial format {max[32], sum[32], S[32][32]} per (sample, chunk, head), merged by k_attn_ctx.
-// ----------------------------------------------------------------------------------------------
-constexpr int KVC_PX = 64, KVC_CHUNK = 512, KVC_LD = KVC_PX + 4;
-
-__global__ void __launch_bounds__(256) k_kv_ctx(const KvCtxParams p) {
-    extern __shared__ __align__(16) float sm[];
-    float* s_k = sm;                         // [128][KVC_LD]  k, then P = exp(k - m')
-    float* s_v = s_k + 128 * KVC_LD;         // [128][KVC_LD]
-    float* s_m = s_v + 128 * KVC_LD;         // [128] running max
-    float* s_f = s_m + 128;                  // [128] rescale factor of this sub-tile
-    float* s_z = s_f + 128;                  // [128] running sum
-    const int tid = threadIdx.x, b = blockIdx.y, chunk = blockIdx.x;
-    const int HW = p.H * p.W;
-    const int m_begin = chunk * p.chunk_px, m_end = min(HW, m_begin + p.chunk_px);
-    if (tid < 128) { s_m[tid] = -INFINITY; s_z[tid] = 0.f; }
-    // S block of this thread: rows d = dq*4 + i, columns e = eq + 8*j (interleaved so that the eight threads of a
-    // quarter warp read eight different bank groups of s_v; the s_k reads are quarter-warp broadcasts)
-    const int head = tid >> 6, dq = (tid >> 3) & 7, eq = tid & 7;
-    float acc[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    for (int m0 = m_begin; m0 < m_end; m0 += KVC_PX) {
-        const int npx = min(KVC_PX, m_end - m0);
-        __syncthreads();                                               // previous sub-tile's readers are done
-        // ---- stage k|v: 64 channel chunks x KVC_PX pixels of float4, transposed to [channel][pixel]
-        for (int i = tid; i < 64 * KVC_PX; i += 256) {
-            const int ch = i / KVC_PX, px = i - ch * KVC_PX;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (px < npx) {
-                const int m = m0 + px, hh = m / p.W, ww = m - hh * p.W;
-                v = ldg4(p.kv + ((((long long)b * p.H + hh) * 64 + ch) * p.W + ww) * 4);
-            }
-            float* dst = (ch < 32 ? s_k : s_v) + ((ch & 31) * 4) * KVC_LD + px;
-            dst[0] = v.x; dst[KVC_LD] = v.y; dst[2 * KVC_LD] = v.z; dst[3 * KVC_LD] = v.w;
-        }
-        __syncthreads();
-        // ---- per k row: sub-tile max, new running max, rescale factor, P = exp(k - m'), running sum
-        {
-            const int row = tid >> 1, half = tid & 1;                  // two threads per row, 32 pixels each
-            float* kr = s_k + row * KVC_LD + half * 32;
-            const int n = max(0, min(32, npx - half * 32));
-            float mx = -INFINITY;
-            for (int i = 0; i < n; ++i) mx = fmaxf(mx, kr[i]);
-            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-            const float mo = s_m[row], mn = fmaxf(mo, mx);
-            float z = 0.f;
-            for (int i = 0; i < 32; ++i) { const float e = i < n ? expf(kr[i] - mn) : 0.f; kr[i] = e; z += e; }
-            z += __shfl_xor_sync(0xffffffffu, z, 1);
-            __syncwarp();
-            if (half == 0) {
-                const float f = mo == -INFINITY ? 0.f : expf(mo - mn);
-                s_f[row] = f; s_m[row] = mn; s_z[row] = s_z[row] * f + z;
-            }
-        }
-        __syncthreads();
-        // ---- S block update
-        {
-            const float4 f4 = *reinterpret_cast<const float4*>(s_f + head * 32 + dq * 4);
-            const float fr[4] = {f4.x, f4.y, f4.z, f4.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] *= fr[i];
-            const float* pk = s_k + (head * 32 + dq * 4) * KVC_LD;
-            const float* pv = s_v + (head * 32 + eq) * KVC_LD;
-#pragma unroll 4
-            for (int px = 0; px < KVC_PX; px += 4) {
-                float4 a[4], c[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) { a[i] = *reinterpret_cast<const float4*>(pk + i * KVC_LD + px); c[i] = *reinterpret_cast<const float4*>(pv + 8 * i * KVC_LD + px); }
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        acc[i][j] = fmaf(a[i].x, c[j].x, acc[i][j]); acc[i][j] = fmaf(a[i].y, c[j].y, acc[i][j]);
-                        acc[i][j] = fmaf(a[i].z, c[j].z, acc[i][j]); acc[i][j] = fmaf(a[i].w, c[j].w, acc[i][j]);
-                    }
-            }
-        }
-    }
-    __syncthreads();
-    float* pt = p.kv_part + (((long long)b * p.nchunks + chunk) * kHeads + head) * kKvPartFloats;
-    if ((tid & 63) < 32) {
-        const int d = tid & 31;
-        pt[d] = s_m[head * 32 + d];
-        pt[32 + d] = s_z[head * 32 + d];
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) pt[64 + (dq * 4 + i) * 32 + eq + 8 * j] = acc[i][j];
-}
-
-int kv_ctx_chunk_pixels() { return KVC_CHUNK; }
-int launch_kv_ctx(const KvCtxParams& p, cudaStream_t s) {
-    const size_t smem = (size_t)(2 * 128 * KVC_LD + 3 * 128) * sizeof(float);
-    static bool attr[64] = {};
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
-    if (!attr[dev]) {
-        if (cudaFuncSetAttribute(k_kv_ctx, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-        attr[dev] = true;
-    }
-    k_kv_ctx<<<dim3(p.nchunks, p.B), 256, smem, s>>>(p);
-    return 1;
-}
 
 // out = to_out(context^T q) is linear in q = Wq x, so for each sample the whole second half of
 // LinearAttention + Rezero + Residual (diffusion.py:45-46,97-100,108-110) collapses to a per-sample
