@@ -34,10 +34,12 @@ enum { SBK_PREC_FP32 = 0,   /* CUDA-core FFMA, fp32 operands (bit-faithful class
        SBK_PREC_BF16 = 2,   /* tcgen05 kind::f16 on bf16 operand tensors (conv inputs + weights stored as bf16),
                                fp32 accumulate; raw conv outputs, GN statistics, softmax, sampler state fp32
                                (BASELINE config 3); both models                                             */
-       SBK_PREC_FP32X3 = 3 };/* fp32-class arithmetic on tcgen05 ("3xTF32"): every operand is split x = x_hi + x_lo
-                               (tf32 each), x_lo*w_hi + x_hi*w_lo + x_hi*w_hi accumulated in fp32 in TMEM; softmax /
-                               context / Mish / GN exact fp32.  The default of the drop-in modules: matches the
-                               reference's fp32 CPU arithmetic to ~1e-6 per estimator call                   */
+       SBK_PREC_FP32X3 = 3 };/* fp32-class arithmetic on tcgen05: x*w = x_hi*w_hi (kind::tf32, the tensor core reads
+                               the top 19 bits of x) + (x_lo*w + x*w_lo) as ONE kind::f16 MMA over packed fp16
+                               correction chunks - two MMAs per MAC; fp32 accumulation in TMEM, cut into short runs
+                               that are summed in round-to-nearest fp32 (the tensor core truncates its accumulator);
+                               softmax / Mish / GN exact fp32.  The default of the drop-in modules: matches the
+                               reference's fp32 CPU arithmetic to ~2e-6 per estimator call                   */
 
 enum { SBK_MODEL_GRADTTS = 0, SBK_MODEL_DIFFVC = 1 };
 

@@ -12,14 +12,16 @@ path, prec = sys.argv[1], sys.argv[2]
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
 HBM = pk.get("hbm_gbs", 6569.6)
-TEN = pk.get("bf16_tflops_sustained", 1386.8) * (1.0 if prec == "bf16" else 0.5)
+# tensor peak per ALGORITHMIC flop: bf16 = the cuBLAS bf16 rate, tf32 = half of it, fp32x3 = a quarter (two tensor-core passes
+# at the tf32 instruction rate per MAC: one tf32 MMA + one fp16 correction MMA)
+TEN = pk.get("bf16_tflops_sustained", 1386.8) * {"bf16": 1.0, "tf32": 0.5, "fp32x3": 0.25}[prec]
 
 
 def klass(n):
     if n.endswith("block1.raw") and "downs.0.0." in n: return "first conv (CUDA cores, 2->64)"
     if n.endswith(".raw"): return "3x3 conv (tcgen05) + GN partials"
     if n.endswith(".act"): return "k_gn_act: GN + Mish + time bias -> operand"
-    if "kvpart" in n: return "k_attn_kv: k/v projection + softmax partials + P V^T"
+    if "kvpart" in n: return "k_attn_kv(_x3): k/v projection + softmax partials + P V^T"
     if n.endswith(".ctx"): return "k_attn_ctx: merge partials"
     if n.endswith(".mix"): return "k_attn_mix: fold to_out ctx^T W_q"
     if re.search(r"\.2\.out|mid_attn.out", n): return "attention apply 1x1 (+ residual)"
@@ -41,7 +43,9 @@ for line in open(path):
     a[0] += 1; a[1] += ms; a[2] += tf * ms * 1e-3; a[3] += gb * ms * 1e-3      # TFLOP and GB totals
 tot = sum(a[1] for a in agg.values())
 print(f"# Roofline per kernel class, {prec}, B=32 T=512 ({'; '.join(head)})\n")
-print(f"Peaks: HBM {HBM:.0f} GB/s, tensor {TEN:.0f} TFLOP/s ({'cuBLAS bf16 sustained' if prec == 'bf16' else 'half the cuBLAS bf16 sustained rate'}, MEASURED_PEAKS.json).")
+PEAK_NOTE = {"bf16": "cuBLAS bf16 sustained", "tf32": "half the cuBLAS bf16 sustained rate",
+             "fp32x3": "a quarter of the cuBLAS bf16 sustained rate: two tf32-rate passes per MAC"}[prec]
+print(f"Peaks: HBM {HBM:.0f} GB/s, tensor {TEN:.0f} TFLOP/s ({PEAK_NOTE}, MEASURED_PEAKS.json).")
 print("`frac` = achieved / peak of the BINDING resource (the larger of the two fractions).\n")
 print("| class | launches | ms | share | TFLOP/s | GB/s (algorithmic) | tensor frac | HBM frac | bound |")
 print("|---|---:|---:|---:|---:|---:|---:|---:|---|")

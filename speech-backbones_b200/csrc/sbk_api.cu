@@ -507,7 +507,7 @@ extern "C" int sbk_pack(sbk_handle* h) {
         for (int k = 0; k < 5; ++k) {
             const std::string q = std::string("estimator.ref_block.") + nm[k];
             // the hoisted RefBlock branch (sbk_vc_conditioning) runs once per call outside the loop, on the tensor cores in
-            // every precision: tf32 operands with fp32 activations for the tf32 / bf16 handles, 3xTF32 (hi, lo) pairs for
+            // every precision: tf32 operands with fp32 activations for the tf32 / bf16 handles, (w_hi, correction) image pairs for
             // the fp32-class handles (fp32x3 and the CUDA-core fp32 mode, whose U-Net kernels have no InstanceNorm/GLU path)
             TRY(pack_tc(h, q + ".0.weight", q + ".wtc", co[k], ci[k], G_C3, false));
         }
@@ -1385,7 +1385,7 @@ extern "C" int sbk_vc_conditioning(sbk_handle* h, const float* ref, const float*
     if (h->cfg.model != SBK_MODEL_DIFFVC) return fail(SBK_ERR_ARG, "sbk_vc_conditioning: this handle is not a DiffVC model");
     if (!h->is_packed) return fail(SBK_ERR_STATE, "sbk_vc_conditioning: weights not packed");
     if (h->cfg.use_ref_t && h->cfg.dim_cond % 128 != 0) return fail(SBK_ERR_ARG, "sbk_vc_conditioning: dim_cond must be a multiple of 128");
-    // fp32-class handles (fp32x3 and the CUDA-core fp32 mode) run the RefBlock convs as 3xTF32 with exact IN / GLU
+    // fp32-class handles (fp32x3 and the CUDA-core fp32 mode) run the RefBlock convs with the tf32 + fp16-correction split and exact IN / GLU
     const bool x3 = packs_x3(h);
     if (B <= 0 || Tr <= 0 || n_timesteps < 1) return fail(SBK_ERR_ARG, "sbk_vc_conditioning: bad sizes");
     CU(cudaSetDevice(h->cfg.device));

@@ -92,21 +92,21 @@ template <int GEOM, int NT, bool X3 = false, bool PAIR = false> struct Depth {
 // RES: ResnetBlock-tail epilogue (1x1 res_conv + Mish(GN(h2raw)) side input), compile-time so that the plain 1x1 /
 // 3x3 instantiations do not pay its registers.
 //
-// X3 (fp32x3 mode, p.x3): 3xTF32 K stages AND chunked accumulation.  Measured on the B200 (profiles/r2_fp32x3_v1_*): the
-// tensor core TRUNCATES its fp32 accumulator on every MMA, a bias of ~2^-25 |acc| per instruction towards zero, so a
-// single accumulation run over the 216 ... 1728 MMAs of a 3x3 conv loses 4e-6 ... 3e-5 relative - 10-50x the fp32
-// rounding the reference's own fp32 sums have.  Here an accumulation run is therefore cut every FLUSH sub-stages (27
-// MMAs per accumulator for a 3x3 conv): the MMA issuer commits the run, the epilogue warps add the partial sums to
-// round-to-nearest fp32 REGISTER accumulators (one row of NT columns per thread) and hand the TMEM slot back, while the
-// issuer already runs the next chunk in the other slot.  The epilogue proper then works from the registers.
+// X3 (fp32x3 mode, p.x3): two sub-stages per K stage (the kind::f16 correction MMAs over the packed fp16 chunks, then the
+// kind::tf32 main MMAs - sbk_internal.h: corr_chunk) AND chunked accumulation.  Measured on the B200
+// (profiles/r2_fp32x3_v1_*): the tensor core TRUNCATES its fp32 accumulator on every MMA, a bias of ~2^-25 |acc| per
+// instruction towards zero, so a single accumulation run over the hundreds of MMAs of a 3x3 conv loses 4e-6 ... 3e-5
+// relative - 10-50x the fp32 rounding the reference's own fp32 sums have.  An accumulation run is therefore cut every
+// FLUSH sub-stages and the partial sums are added in round-to-nearest fp32 outside the MMA pipe (below: where they live).
 //
-// PAIR (cta_group::2, G_C3 only).  Every UMMA reads its A tile (4 KB) and its B tile (NT x 32 B) from shared memory: at
-// M = N = 128 that is 8 KB per 64-clock instruction = the whole 128 B/clk of the SM's shared memory, with nothing left for
-// the bulk copies that refill the ring - the convs sat at ~75 % of that shared-memory bound (profiles/r2_smem_bound.md).
-// A CTA pair halves the weight traffic: the two CTAs of a 2-CTA cluster own the two halves of a 4-row tile (2 rows = 2
-// M = 128 row-tiles each) and each stages only HALF of the weight tile; one tcgen05.mma.cta_group::2 (M = 256) issued by
-// the leader CTA computes row j of both CTAs, reading each CTA's A tile locally and the B halves from both shared
-// memories (6 KB instead of 8 KB per instruction and SM, and half the weight bytes through L2 -> smem).  Protocol:
+// PAIR (cta_group::2, G_C3 only).  Every SS-form UMMA reads its A tile (4 KB) and its B tile (NT x 32 B) from shared
+// memory: at M = N = 128 that is 8 KB per 64-clock instruction, the SM's whole shared-memory bandwidth.  A CTA pair cuts
+// the weight side in half: the two CTAs of a 2-CTA cluster own the two halves of a 4-row tile (2 rows = 2 M = 128
+// row-tiles each) and each stages only HALF of the weight tile; one tcgen05.mma.cta_group::2 (M = 256) issued by the
+// leader CTA computes row j of both CTAs, reading each CTA's A tile locally and the B halves from both shared memories
+// (6 KB instead of 8 KB per instruction and SM, and half the weight bytes through L2 -> smem).  Measured: a pure MMA
+// stream runs 11 % faster on pairs, the whole conv 0-10 % (fp32x3 level 0: 0.426 -> 0.385 ms; profiles/r2_experiments.md, 3-4).
+// Protocol:
 //   * both loaders fill their own ring; the peer's MMA warp relays "my stage s is full" to the leader's full barrier
 //     (remote mbarrier arrive), so the leader's issuer waits on ONE barrier per stage (count 2: local expect_tx + relay);
 //   * tcgen05.commit.cta_group::2 multicasts stage-empty / accumulator-full arrivals to the same barrier in both CTAs;
@@ -123,12 +123,11 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcParams& p) {
     // Two homes for the running sums of the accumulation runs:
     //   CHUNKED (Downsample): registers of the epilogue warps (64 per thread, one CTA per SM), two whole-tile TMEM slots;
     //   TMSUM (3x3 and 1x1): TMEM.  Columns [0,NT) / [NT,2NT) are the RUN slots of output rows 0 / 1, [2NT,4NT) the
-    //   running sums.  The issuer walks a run row by row - row 0 over the run's FLUSH stages, then row 1 over the same,
-    //   still resident, stages - so while it computes one row the four epilogue warps of the other row fold that row's
-    //   finished run into the sums (tcgen05.ld run + ld sum, fp32 round-to-nearest add, tcgen05.st): full overlap with
-    //   one slot per row, N = 128 tiles and two CTAs per SM where they fit, which the register variant cannot do
-    //   (128 accumulators per thread spill at the 168-register ceiling of a 10-warp CTA; the N = 64 UMMA shape it forces
-    //   is operand-fetch bound: 474 vs 780 TFLOP/s of MMA issue, profiles/r2_ops_fp32x3_v2_chunked_nt64.txt).
+    //   running sums.  The four epilogue warps of a row fold that row's finished run into its sums (tcgen05.ld run + ld
+    //   sum, fp32 round-to-nearest add, tcgen05.st) while the issuer works on the other row / the next run (see the
+    //   issuer): N = 128 tiles and two CTAs per SM where they fit, which the register variant cannot do (128
+    //   accumulators per thread spill at the 168-register ceiling of a 10-warp CTA; the N = 64 UMMA shape it forces ran at
+    //   474 vs 780 TFLOP/s of MMA issue, profiles/r2_ops_fp32x3_v2_chunked_nt64.txt).
     constexpr bool TMSUM = D::TMSUM;
     constexpr bool CHUNKED = X3 && GEOM == G_DOWN;
     // sub-stages per accumulation run (p.flush overrides): 6 = three K stages of correction + main sub-stage, 54 MMAs per
@@ -591,7 +590,7 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcParams& p) {
                 // of the next run (whose MMAs only wait for row 0's fold).  (The first version walked a run row by row over
                 // RESIDENT stages so that one row's fold hid under the other row's whole run; holding 3 of the 4 stages for
                 // two passes left the ring one stage of prefetch, and the activation loads - ~2 us from HBM - were exposed:
-                // 39 % of the conv time, profiles/r2_x3_ring.md.)
+                // 39 % of the conv time, profiles/r2_experiments.md, 4-5.)
                 for (int t = tile0; t < total_tiles; t += tstep) {
                     for (int c = 0; c < nchunks; ++c, ++ar) {
                         const int ks_lo = c * FLUSH, ks_hi = ks_lo + FLUSH < ksteps_t ? ks_lo + FLUSH : ksteps_t;
@@ -1186,7 +1185,7 @@ static int dispatch_conv1d(const ConvTcParams& p, cudaStream_t s) {
     }
 }
 
-// fp32x3 mode (p.x3): tf32 operands, 3xTF32 stages, chunked accumulation
+// fp32x3 mode (p.x3): correction + main sub-stages, chunked accumulation
 static int dispatch_conv_tc_x3(const ConvTcParams& p, cudaStream_t s) {
     const int nt = (p.nt == 64 && p.geom == G_C3) ? 64 : conv_tc_ntile(p.geom, p.Cout);
     switch (p.geom) {

@@ -85,7 +85,7 @@ __device__ __forceinline__ uint64_t desc_pack(uint32_t lo, uint32_t hi) {
 // prove that a single thread is active and wraps every uniform-datapath instruction (UTCHMMA, UTCBAR) in a per-lane
 // ELECT / R2UR / BRA.U.ANY loop with the descriptors rebuilt from vector registers - ~15 dependent instructions, ~100
 // clocks per MMA against the 64 (N = 128) or 32 (N = 64) clocks the MMA itself takes: the issuing thread, not the tensor
-// pipe, bounded every conv (profiles/r2_ncu_issue_bound.md: 86 % of the issuer warp's samples in issue code, tensor pipe
+// pipe, bounded every conv (profiles/r2_ncu_x3_before.md: 86 % of the issuer warp's samples in issue code, tensor pipe
 // 62 % / 47 % active).  With elect.sync the SASS is one UIADD3 per descriptor and back-to-back UTCHMMAs.
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred = 0;

@@ -160,7 +160,7 @@ class Diffusion(BaseModule):
     @torch.no_grad()
     def conditioning_table(self, ref, ref_mask, mean_ref, c, n_timesteps):
         """cond[i] for every step i (t_i = 1 - i/N): the hoisted conditioning branch, native in every precision
-        (libsbk `sbk_vc_conditioning`: RefBlock convs on tcgen05 - 3xTF32 for the fp32-class modes - plus the
+        (libsbk `sbk_vc_conditioning`: RefBlock convs on tcgen05 - tf32 + fp16 correction for the fp32-class modes - plus the
         InstanceNorm / GLU / cond_block kernels).  There is no PyTorch fallback."""
         with torch.cuda.device(ref.device):
             return self.engine().vc_conditioning(ref, ref_mask, mean_ref, c, n_timesteps)

@@ -188,7 +188,7 @@ def get_noise(t, beta_init, beta_term, cumulative=False):
 
 class Diffusion(BaseModule):
     """Score-based decoder.  `precision`/`use_graph` are extra, keyword-only engine knobs.  The default precision
-    "fp32x3" is fp32-class arithmetic on the tensor cores (3xTF32 operand splits, exact fp32 everywhere else): it matches
+    "fp32x3" is fp32-class arithmetic on the tensor cores (tf32 main product + one fp16 correction product per MAC, exact fp32 everywhere else): it matches
     the reference's fp32 path to ~1e-6 per estimator call.  "tf32" is what PyTorch's own GPU convs compute by default
     (~1.5e-3 per call), "bf16" is config 3's arithmetic, "fp32" the CUDA-core FFMA path."""
 

@@ -14,7 +14,7 @@ from speech_backbones_b200.spec import DiffVCConfig, diffvc_param_spec, syntheti
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # bf16: the U-Net runs on bf16 operand tensors (the hoisted conditioning branch stays tf32)
-# fp32x3: the fp32-class tensor-core mode (3xTF32 splits; the modules' default); fp32: the CUDA-core FFMA path
+# fp32x3: the fp32-class tensor-core mode (tf32 + fp16-correction splits; the modules' default); fp32: the CUDA-core FFMA path
 # (DiffVC's 3x3 convs run K up to 9 x 2048: fp32x3 measures 1.05e-5 per call, the CUDA-core fp32 mode 2-3e-6)
 TOL = {"fp32": (1e-4, 2e-3), "fp32x3": (2e-5, 2e-4), "tf32": (4e-3, 1e-2), "bf16": (3e-2, 4e-2)}   # (estimator call, trajectory)
 COND_TOL = {"fp32": 1e-5, "fp32x3": 1e-5, "tf32": 4e-3, "bf16": 4e-3}          # the hoisted RefBlock + cond_block branch
@@ -89,7 +89,7 @@ def test_vc_samplers_vs_reference_golden(vc_engines, vc_golden, precision):
 @pytest.mark.parametrize("precision", ["fp32", "fp32x3", "tf32", "bf16"])
 def test_vc_native_conditioning_vs_oracle(vc_engines, vc_golden, precision):
     """RefBlock + cond_block natively in EVERY precision: sbk_vc_conditioning vs the CPU oracle,
-    every step.  The fp32-class handles (fp32x3, and the CUDA-core fp32 mode) run the RefBlock convs as 3xTF32."""
+    every step.  The fp32-class handles (fp32x3, and the CUDA-core fp32 mode) run the RefBlock convs with the tf32 + fp16-correction split."""
     eng, cfg, sd = vc_engines(precision)
     c = next(c for c in vc_golden["cases"] if c["kind"] == "traj" and c["mode"] == "ml" and c["B"] == 2)
     z, mask, mean, r, rmask, mean_ref, spk = _inputs(vc_golden, c)

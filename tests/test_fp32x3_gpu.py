@@ -1,6 +1,7 @@
 """GPU parity of the fp32-class tensor-core mode (precision="fp32x3", the drop-in modules' default).
 
-Every dense contraction runs on tcgen05 as a 3xTF32 split (x_lo*w_hi + x_hi*w_lo + x_hi*w_hi, fp32 accumulation in TMEM);
+Every dense contraction runs on tcgen05 as x_hi*w_hi (kind::tf32) + (x_lo*w + x*w_lo) (one kind::f16 MMA over packed fp16
+correction chunks), fp32 accumulation in TMEM with the runs folded in round-to-nearest fp32;
 GroupNorm, Mish, softmax, the attention context and the Euler update are exact fp32.  The reference computes in fp32
 (Grad-TTS/model/diffusion.py:174-216,254-275 on the CPU), so this mode is held to an fp32-class bound against the
 committed outputs of the unmodified reference:
