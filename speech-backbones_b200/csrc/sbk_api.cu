@@ -723,7 +723,7 @@ static int build_plan(sbk_handle* h, int B, int T, int tb_rows) {
             static const int flush_env = getenv("SBK_X3_FLUSH") ? atoi(getenv("SBK_X3_FLUSH")) : 0;     // measurement knob
             p.flush = flush_env;
         }
-        if (geom == G_C3 && conv_tc_ntile(geom, cout) == 128) {
+        if (geom == G_C3 && conv_tc_ntile(geom, cout) == 128 && getenv("SBK_FORCE_PAIR") == nullptr) {
             // tiles of 2 rows x 128 pixels x 128 channels; when they cannot fill half the SMs, use 64-wide N tiles instead
             const long long tiles = (long long)B * ((Ws[lvl] + 127) / 128) * ((Hs[lvl] + 1) / 2) * (cout / 128);
             if (tiles * 2 <= num_sms && h->packed.count(wkey + "64")) { p.nt = 64; p.wpk = W(wkey + "64"); }
@@ -731,12 +731,14 @@ static int build_plan(sbk_handle* h, int B, int T, int tb_rows) {
         if (geom == G_C3 && !p.nt) {
             // CTA pairs (cta_group::2) when there are enough 4-row pair tiles to fill every SM pair; the pair kernel reads the
             // weight image packed for half-width N tiles.  SBK_NO_PAIR=1 keeps the single-CTA kernels (measurement knob).
-            static const bool no_pair = getenv("SBK_NO_PAIR") != nullptr;
+            // SBK_FORCE_PAIR=1 uses them for every shape (the parity tests run the small ragged goldens through the pair kernels).
+            // Both are read when a plan is built, so a test can switch them between engines.
+            const bool no_pair = getenv("SBK_NO_PAIR") != nullptr, force_pair = getenv("SBK_FORCE_PAIR") != nullptr;
             const int ntile = conv_tc_ntile(geom, cout);
             const std::string half = wkey + (ntile == 128 ? "64" : "32");
             const long long ptiles = (long long)B * conv_tc_pair_tiles(Hs[lvl], Ws[lvl]) * (cout / ntile);
             // (bf16 mode: measured 2 % slower on pairs - its MMAs are half as long, the pair's cross-CTA handshakes are not)
-            if (!no_pair && !b16 && ptiles >= num_sms / 2 && h->packed.count(half)) { p.pair = 1; p.wpk = W(half); }
+            if (!no_pair && h->packed.count(half) && (force_pair || (!b16 && ptiles >= num_sms / 2))) { p.pair = 1; p.wpk = W(half); }
         }
         const double taps = geom == G_PW ? 1.0 : (geom == G_UP ? 4.0 : 9.0);
         op.flops = 2.0 * B * Hs[lvl] * Ws[lvl] * cout * (c0 + c1) * taps;

@@ -123,3 +123,31 @@ def test_default_module_is_fp32_class(golden):
     dec = dec.cuda()
     y = dec(z.cuda(), mask.cuda(), mu.cuda(), n_timesteps=10).cpu()
     assert rel_l2(y, c["out"]) <= X3_TRAJ_TOL
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32x3", X3_EST_TOL), ("tf32", 4e-3)])
+def test_cta_pair_kernels_on_small_ragged_shapes(sbk_lib, golden, monkeypatch, precision, tol):
+    """The 3x3 convs run on CTA pairs (cta_group::2) only when a launch has enough 4-row pair tiles to fill the GPU, i.e. never
+    on the small goldens.  SBK_FORCE_PAIR=1 (read when a plan is built) routes every 3x3 conv of a fresh engine through the
+    pair kernels, so the ragged cases (W not a multiple of 128, masked tails, B = 1..3, 1 and 4 speakers) check them
+    against the committed outputs of the reference too."""
+    from speech_backbones_b200.binding import Engine
+    monkeypatch.setenv("SBK_FORCE_PAIR", "1")
+    engines = {}
+    try:
+        for idx, c in _golden_cases("est"):
+            if c["scale"] != 1.0:
+                continue
+            cfg, sd, z, mask, mu, spk = case_inputs(golden, c)
+            if c["n_spks"] not in engines:
+                e = Engine(n_spks=c["n_spks"], precision=precision)
+                e.load_state_dict(synthetic_state_dict(UNetConfig(n_spks=c["n_spks"]), 1234))
+                engines[c["n_spks"]] = e
+            eng = engines[c["n_spks"]]
+            y = eng.estimator((z * mask).cuda(), mask.cuda(), mu.cuda(), torch.tensor(c["t"]).cuda(), None if spk is None else spk.cuda()).cpu()
+            err = rel_l2(y, c["out"])
+            print("forced pairs", precision, case_id(c), "rel_l2 %.3e" % err)
+            assert err <= tol, (case_id(c), err)
+    finally:
+        for e in engines.values():
+            e.close()
