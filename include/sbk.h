@@ -39,7 +39,7 @@ enum { SBK_PREC_FP32 = 0,   /* CUDA-core FFMA, fp32 operands (bit-faithful class
                                correction chunks - two MMAs per MAC; fp32 accumulation in TMEM, cut into short runs
                                that are summed in round-to-nearest fp32 (the tensor core truncates its accumulator);
                                softmax / Mish / GN exact fp32.  The default of the drop-in modules: matches the
-                               reference's fp32 CPU arithmetic to ~2e-6 per estimator call                   */
+                               reference's fp32 CPU arithmetic to 2-3e-6 per estimator call                   */
 
 enum { SBK_MODEL_GRADTTS = 0, SBK_MODEL_DIFFVC = 1 };
 

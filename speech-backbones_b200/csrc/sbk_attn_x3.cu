@@ -1,7 +1,7 @@
 // fp32x3 mode, LinearAttention pass 1 fused (Grad-TTS/model/diffusion.py:93-96): k|v projection, softmax-over-pixels
 // statistics and the context partials S[d][e] = sum_px P[d,px] V[e,px] in ONE persistent tcgen05 kernel - k and v never
 // reach HBM.  (The first fp32-class version wrote the projection to HBM as a 256-channel fp32 tensor, 1.3 GB per call at
-// B=32 x T=512, and re-read it in k_kv_ctx_tc: 0.44 + 0.62 ms at level 0 for 0.2 ms of algorithmic work.)
+// B=32 x T=512, and re-read it in a second kernel: 0.44 + 0.62 ms at level 0 for 0.2 ms of algorithmic work.)
 //
 // Roles are swapped relative to the convs, as in the tf32 kernel k_attn_kv (sbk_conv_tc.cu): the weights are the M operand,
 // so a TMEM lane is a k (or v) channel and a column is a pixel of the current 64-pixel ITEM:

@@ -131,7 +131,7 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcParams& p) {
     constexpr bool TMSUM = D::TMSUM;
     constexpr bool CHUNKED = X3 && GEOM == G_DOWN;
     // sub-stages per accumulation run (p.flush overrides): 6 = three K stages of correction + main sub-stage, 54 MMAs per
-    // accumulator for a 3x3 conv (~1e-6 of truncation bias; 4 gave 2.1e-6 per estimator call, 6 gives 2.4e-6 and 5 % less time)
+    // accumulator for a 3x3 conv (~1e-6 of truncation bias; 4 gave 2.0-2.5e-6 per estimator call on the goldens, 6 gives 2.2-2.9e-6 and 2-5 % less time)
     const int FLUSH = p.flush > 0 ? p.flush : 6;
     constexpr int STAGES = D::STAGES, NSLOT = D::NSLOT, SLOT_COLS = D::SLOT_COLS;
     constexpr int LAG = STAGES >= 3 ? STAGES - 2 : 0;      // G_DOWN only: cp.async groups in flight behind the newest
