@@ -111,10 +111,21 @@ template <int GEOM, int NT, bool X3 = false, bool PAIR = false> struct Depth {
 //     (remote mbarrier arrive), so the leader's issuer waits on ONE barrier per stage (count 2: local expect_tx + relay);
 //   * tcgen05.commit.cta_group::2 multicasts stage-empty / accumulator-full arrivals to the same barrier in both CTAs;
 //   * the epilogue warps of both CTAs (each reads its own TMEM: its 128 pixel rows) arrive on the LEADER's tempty barrier.
-template <int GEOM, bool BF16, int NT, bool RES, bool X3, bool PAIR = false>
+//
+// RS ("row-shared" issue order, 64-output-channel 3x3 convs = level 0).  An N = 64 instruction still reads its whole 4 KB A
+// tile for half the math of an N = 128 one: with one MMA per (tap, output row) the 18 instructions of a stage read 108 KB
+// of operands in 576 clocks = 187 B/clk against the SM's 128 - the level-0 convs were shared-memory bound (tensor pipe 47-61 %).
+// Input-stationary order instead: ONE MMA per (input halo row, column tap) updates every output row that input row feeds.
+// Input row i feeds output row i+1 through kernel row 0, row i through kernel row 1 and row i-1 through kernel row 2, and
+// the two output rows' accumulators are adjacent TMEM columns, so with the weights of a column tap packed as
+// [kr=2 | kr=1 | kr=0] x 64 channels the middle halo rows are single N = 128 instructions (B = [W1|W0] resp. [W2|W1], D = both
+// rows) and the outer halo rows N = 64 ones: 12 instructions per stage instead of 18, the same MMA time, 84 KB of operand
+// reads instead of 108.  (The two N = 64 instructions come first in a run: they are the ones that may start an accumulator.)
+template <int GEOM, bool BF16, int NT, bool RES, bool X3, bool PAIR = false, bool RS = false>
 __device__ __forceinline__ void conv_tc_body(const ConvTcParams& p) {
     static_assert(!(X3 && BF16), "fp32x3 runs on tf32 operands");
     static_assert(!PAIR || (GEOM == G_C3 && !RES), "CTA pairs: 3x3 convs only");
+    static_assert(!RS || (GEOM == G_C3 && NT == 64 && !RES && !PAIR), "row-shared issue order: 64-channel 3x3 convs on single CTAs");
     using G = Geo<GEOM>;
     using D = Depth<GEOM, NT, X3, PAIR>;
     constexpr int NB = D::NB;
@@ -574,13 +585,30 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcParams& p) {
             const uint32_t idesc = make_idesc<BF16>(PAIR ? 2 * TPX : TPX, NT);
             const uint32_t idesc_c = make_idesc_fmt(0u, PAIR ? 2 * TPX : TPX, NT);   // fp32x3 correction sub-stages: fp16 operands
             const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+            constexpr uint32_t D_HI = desc_hi(128);                      // SBO = 128 B for both operands
             auto mma = [&](auto kind16, uint32_t d, uint64_t ad, uint64_t bd, uint32_t idk, uint32_t acc) {
                 if constexpr (PAIR) umma2<decltype(kind16)::value>(d, ad, bd, idk, acc);
                 else umma<decltype(kind16)::value>(d, ad, bd, idk, acc);
             };
             auto commit = [&](uint32_t bar) { if constexpr (PAIR) umma_commit2(bar); else umma_commit(bar); };
             auto wait_full = [&](uint32_t bar, uint32_t ph) { if constexpr (PAIR) mbar_wait_cluster(bar, ph); else mbar_wait(bar, ph); };
-            constexpr uint32_t D_HI = desc_hi(128);                      // SBO = 128 B for both operands
+            // RS: the 12 MMAs of one (sub-)stage into the two adjacent row accumulators at tbase / tbase + NT; `first` = this stage
+            // starts an accumulation run.  Weight stage image: [column tap sx][chunk][kr=2 | kr=1 | kr=0][NT rows][16 B].
+            auto issue_rs = [&](auto kind16, const uint32_t id64, const uint32_t id128, const uint32_t tbase, const uint32_t a_st, const uint32_t b_st, const bool first) {
+                constexpr uint32_t BL = 3 * NT;                                 // weight rows per (sx, chunk)
+#pragma unroll
+                for (int sx = 0; sx < 3; ++sx) {
+                    const uint32_t bs = b_st + (uint32_t)(sx * KCH) * BL;       // (KCH = 2: one K step of two chunks per stage)
+                    const uint32_t acc0 = (first && sx == 0) ? 0u : 1u;
+                    // halo row 0 (input h0-1) -> output row 0 through kernel row 0;  halo row 3 (input h0+2) -> output row 1 through kr 2
+                    mma(kind16, tbase, desc_pack(a_st + (uint32_t)(0 * PXP + sx), D_HI), desc_pack(bs + 2 * NT, D_HI), id64, acc0);
+                    mma(kind16, tbase + NT, desc_pack(a_st + (uint32_t)(3 * PXP + sx), D_HI), desc_pack(bs, D_HI), id64, acc0);
+                    // halo row 1 (input h0): [W1 | W0] -> rows 0, 1;  halo row 2 (input h0+1): [W2 | W1] -> rows 0, 1
+                    mma(kind16, tbase, desc_pack(a_st + (uint32_t)(1 * PXP + sx), D_HI), desc_pack(bs + NT, D_HI), id128, 1u);
+                    mma(kind16, tbase, desc_pack(a_st + (uint32_t)(2 * PXP + sx), D_HI), desc_pack(bs, D_HI), id128, 1u);
+                }
+            };
+            const uint32_t idesc_w = make_idesc<BF16>(TPX, 2 * NT), idesc_cw = make_idesc_fmt(0u, TPX, 2 * NT);   // RS: the N = 128 instructions
             uint32_t it = 0;
             uint32_t ar = 0;                                             // accumulation-run counter (see the epilogue warps)
             if constexpr (TMSUM) {
@@ -598,6 +626,22 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcParams& p) {
                             const int s = it % STAGES;
                             wait_full(full_b(s), (it / STAGES) & 1);
                             tc_fence_after();
+                            if constexpr (RS) {
+                                if (ks == ks_lo) {                              // both rows' previous runs folded (every MMA may touch both)
+                                    wait_full(tempty(0), (ar & 1) ^ 1);
+                                    wait_full(tempty(1), (ar & 1) ^ 1);
+                                    tc_fence_after();
+                                }
+                                const uint32_t a_st = desc_lo(a0 + s * A_STAGE_BYTES, PLANE), b_st = desc_lo(b0 + s * B_STAGE_BYTES, 3 * NT * 16);
+                                if (elect_one()) {
+                                    if ((ks & 1) == 0) issue_rs(std::true_type{}, idesc_c, idesc_cw, tmem_base, a_st, b_st, ks == ks_lo);
+                                    else issue_rs(std::false_type{}, idesc, idesc_w, tmem_base, a_st, b_st, ks == ks_lo);
+                                    commit(empty(s));
+                                    if (ks == ks_hi - 1) { commit(tfull(0)); commit(tfull(1)); }
+                                }
+                                __syncwarp();
+                                continue;
+                            }
                             const uint32_t b_lo = desc_lo(b0 + s * B_STAGE_BYTES, NB * 16);
 #pragma unroll
                             for (int j = 0; j < ROWS; ++j) {
@@ -644,6 +688,16 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcParams& p) {
                     if (!BULK) mbar_wait(full_a(s), ph);
                     wait_full(full_b(s), ph);               // weights (+ the A runs when they are bulk copies)
                     tc_fence_after();
+                    if constexpr (RS) {
+                        const uint32_t a_st = desc_lo(a0 + s * A_STAGE_BYTES, PLANE), b_st = desc_lo(b0 + s * B_STAGE_BYTES, 3 * NT * 16);
+                        if (elect_one()) {
+                            issue_rs(std::integral_constant<bool, BF16>{}, idesc, idesc_w, tslot, a_st, b_st, ks == ks_lo);
+                            commit(empty(s));
+                            if (ks == ks_hi - 1) commit(tfull(slot));
+                        }
+                        __syncwarp();
+                        continue;
+                    }
                     const uint32_t a_lo = desc_lo(a0 + s * A_STAGE_BYTES, PLANE);
                     const uint32_t b_lo = desc_lo(b0 + s * B_STAGE_BYTES, NB * 16);
                     const uint32_t dil = C1 ? (uint32_t)p.dil : 0u;
@@ -810,6 +864,14 @@ template <int GEOM, int NT, bool RES = false>
 __global__ void __launch_bounds__(NTHREADS, Depth<GEOM, NT, true>::MINB) k_conv_tc_x3(const ConvTcParams p) {
     conv_tc_body<GEOM, false, NT, RES, true>(p);
 }
+// row-shared issue order (64-channel 3x3 convs, single CTAs)
+template <bool BF16>
+__global__ void __launch_bounds__(NTHREADS, Depth<G_C3, 64, false>::MINB) k_conv_tc_rs(const ConvTcParams p) {
+    conv_tc_body<G_C3, BF16, 64, false, false, false, true>(p);
+}
+__global__ void __launch_bounds__(NTHREADS, Depth<G_C3, 64, true>::MINB) k_conv_tc_x3_rs(const ConvTcParams p) {
+    conv_tc_body<G_C3, false, 64, false, true, false, true>(p);
+}
 // CTA-pair instantiations (3x3 convs; launched as 2-CTA clusters)
 template <bool BF16, int NT>
 __global__ void __launch_bounds__(NTHREADS, Depth<G_C3, NT, false, true>::MINB) k_conv_tc_pair(const ConvTcParams p) {
@@ -820,14 +882,16 @@ __global__ void __launch_bounds__(NTHREADS, Depth<G_C3, NT, true, true>::MINB) k
     conv_tc_body<G_C3, false, NT, false, true, true>(p);
 }
 
-template <int GEOM, bool BF16, int NT, bool RES = false, bool X3 = false>
+template <int GEOM, bool BF16, int NT, bool RES = false, bool X3 = false, bool RS = false>
 static int launch_tc(const ConvTcParams& p, cudaStream_t s) {
     using D = Depth<GEOM, NT, X3>;
     // the dynamic-shared-memory opt-in is a per-device function attribute and the persistent grid is sized from the
     // current device's SM count: both are cached per device ordinal (a process may drive several GPUs through several handles)
     static DevCache cache;
     const void* fn;
-    if constexpr (X3) fn = reinterpret_cast<const void*>(k_conv_tc_x3<GEOM, NT, RES>);
+    if constexpr (RS && X3) fn = reinterpret_cast<const void*>(k_conv_tc_x3_rs);
+    else if constexpr (RS) fn = reinterpret_cast<const void*>(k_conv_tc_rs<BF16>);
+    else if constexpr (X3) fn = reinterpret_cast<const void*>(k_conv_tc_x3<GEOM, NT, RES>);
     else fn = reinterpret_cast<const void*>(k_conv_tc<GEOM, BF16, NT, RES>);
     const int num_sms = cache.get(fn);
     if (num_sms <= 0) return -1;
@@ -839,7 +903,9 @@ static int launch_tc(const ConvTcParams& p, cudaStream_t s) {
     const long long total = (long long)mt * (p.Cout / NT) * p.B;
     const long long cap = (long long)num_sms * D::MINB;             // persistent: one wave of resident CTAs
     const int grid = (int)(total < cap ? total : cap);
-    if constexpr (X3) k_conv_tc_x3<GEOM, NT, RES><<<grid, NTHREADS, D::SMEM, s>>>(p);
+    if constexpr (RS && X3) k_conv_tc_x3_rs<<<grid, NTHREADS, D::SMEM, s>>>(p);
+    else if constexpr (RS) k_conv_tc_rs<BF16><<<grid, NTHREADS, D::SMEM, s>>>(p);
+    else if constexpr (X3) k_conv_tc_x3<GEOM, NT, RES><<<grid, NTHREADS, D::SMEM, s>>>(p);
     else k_conv_tc<GEOM, BF16, NT, RES><<<grid, NTHREADS, D::SMEM, s>>>(p);
     return 1;
 }
@@ -1162,6 +1228,7 @@ static int dispatch_conv_tc(const ConvTcParams& p, cudaStream_t s) {
     const int nt = (p.nt == 64 && p.geom == G_C3) ? 64 : conv_tc_ntile(p.geom, p.Cout);
     switch (p.geom) {
         case G_C3:
+            if (p.rs) return nt == 64 ? launch_tc<G_C3, BF16, 64, false, false, true>(p, s) : -1;
             if (p.pair) return nt == 128 ? launch_tc_pair<BF16, 128, false>(p, s) : launch_tc_pair<BF16, 64, false>(p, s);
             return nt == 128 ? launch_tc<G_C3, BF16, 128>(p, s) : launch_tc<G_C3, BF16, 64>(p, s);
         case G_PW:
@@ -1190,6 +1257,7 @@ static int dispatch_conv_tc_x3(const ConvTcParams& p, cudaStream_t s) {
     const int nt = (p.nt == 64 && p.geom == G_C3) ? 64 : conv_tc_ntile(p.geom, p.Cout);
     switch (p.geom) {
         case G_C3:
+            if (p.rs) return nt == 64 ? launch_tc<G_C3, false, 64, false, true, true>(p, s) : -1;
             if (p.pair) return nt == 128 ? launch_tc_pair<false, 128, true>(p, s) : launch_tc_pair<false, 64, true>(p, s);
             return nt == 128 ? launch_tc<G_C3, false, 128, false, true>(p, s) : launch_tc<G_C3, false, 64, false, true>(p, s);
         case G_PW:

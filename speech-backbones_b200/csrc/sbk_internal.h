@@ -78,6 +78,7 @@ struct ConvTcParams {
     // below); the tensor core reads the top 19 bits of x (= x_hi) by itself.  Weights are packed as (w_hi, correction)
     // stage pairs and each K stage is issued twice into the same fp32 TMEM accumulator: the kind::f16 correction MMAs
     // (x_lo*w + x*w_lo) first, then the kind::tf32 main MMAs (x_hi*w_hi).
+    int rs;                                         // G_C3, 64 output channels: row-shared issue order; wpk is then the [sx][chunk][kr2|kr1|kr0] image
     int pair;                                       // G_C3: run on CTA pairs (cta_group::2); wpk is then the image packed for NT/2-wide tiles
     int x3;
     int flush;                                      // sub-stages per accumulation run (0 = default); SBK_X3_FLUSH overrides it (measurement knob)

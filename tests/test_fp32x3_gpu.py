@@ -151,3 +151,25 @@ def test_cta_pair_kernels_on_small_ragged_shapes(sbk_lib, golden, monkeypatch, p
     finally:
         for e in engines.values():
             e.close()
+
+
+def test_row_shared_issue_order_in_fp32x3(sbk_lib, golden, monkeypatch):
+    """The 64-channel (level 0) 3x3 convs of the tf32 / bf16 modes use the row-shared issue order (one N = 128 MMA per input
+    halo row and column tap updates both output rows); the fp32x3 mode keeps CTA pairs there.  SBK_FORCE_RS=1 routes the
+    fp32x3 level-0 convs through it as well, so its correction + main sub-stages and both-row accumulation runs are checked
+    at fp32-class tolerance against the committed reference outputs."""
+    from speech_backbones_b200.binding import Engine
+    monkeypatch.setenv("SBK_FORCE_RS", "1")
+    eng = Engine(precision="fp32x3")
+    try:
+        eng.load_state_dict(synthetic_state_dict(UNetConfig(), 1234))
+        for idx, c in _golden_cases("est"):
+            if c["scale"] != 1.0 or c["n_spks"] != 1:
+                continue
+            cfg, sd, z, mask, mu, spk = case_inputs(golden, c)
+            y = eng.estimator((z * mask).cuda(), mask.cuda(), mu.cuda(), torch.tensor(c["t"]).cuda(), None).cpu()
+            err = rel_l2(y, c["out"])
+            print("forced row-shared fp32x3", case_id(c), "rel_l2 %.3e" % err)
+            assert err <= X3_EST_TOL, (case_id(c), err)
+    finally:
+        eng.close()
