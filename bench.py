@@ -449,6 +449,9 @@ def run_ours(args, wl):
         "kernel": "conv3x3 implicit GEMM (25 launches/step)", "bound": "tensor", "achieved": achieved, "peak": tensor_peak,
         "unit": "TFLOP/s", "frac": achieved / tensor_peak, "traffic": traffic, "traffic_source": traffic_src,
         "algorithmic_bytes_per_launch": conv_by / max(1, len(conv)),
+        "traffic_note": ("fp32x3 reads every conv input twice by design (the fp32 tensor + its 16-byte-per-4-channels correction "
+                         "chunks): expected DRAM bytes = algorithmic (4 B in + 4 B out per element) + the input bytes once more"
+                         if args.precision == "fp32x3" else None),
         "peak_note": (f"{peaks['src']} cuBLAS bf16 sustained (MEASURED_PEAKS.json)" if args.precision == "bf16" else
                       f"tf32 MMA rate = max(0.5 x {peaks['src']} cuBLAS bf16 sustained = {peaks['bf16'] * 0.5:.1f}, cuBLAS TF32 matmul 8192^3 "
                       f"sustained measured in this run = {tf32_here:.1f}) TFLOP/s, divided by {per_mac} tensor-core pass(es) at the tf32 instruction rate per algorithmic MAC in mode {args.precision}"),
